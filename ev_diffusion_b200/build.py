@@ -1,0 +1,146 @@
+"""Build helpers: nvcc for sm_100a, in-tree outputs.
+
+Replaces the make -> xsltproc -> nvcc chain of ``tools/common.mk:252-451``:
+
+  build_runtime()            csrc/fgpu_rt.cu              -> _lib/libfgpu_rt.so
+  build_model(xml, name)     XMLModelFile.xml+functions.c -> _lib/models/<name>.so
+
+All outputs are git-ignored ``.so`` files inside the package, so they travel
+with the repository snapshot to the GPU box.  Nothing is JIT-compiled at run
+time; a missing library is an error, never a fallback.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from typing import List, Optional
+
+from . import codegen, xmml
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+INCLUDE = os.path.join(ROOT, "include")
+LIB = os.path.join(PKG, "_lib")
+GEN = os.path.join(PKG, "_gen")
+MODELS = os.path.join(PKG, "models")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared",
+          "-Xlinker", "-rpath=/usr/local/cuda/lib64", "-diag-suppress", "20012,177,550"]
+
+
+class BuildError(RuntimeError):
+    pass
+
+
+def _run(cmd: List[str], log: Optional[str] = None) -> str:
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if log:
+        with open(log, "w") as fh:
+            fh.write(" ".join(cmd) + "\n" + proc.stdout)
+    if proc.returncode != 0:
+        raise BuildError("command failed: %s\n%s" % (" ".join(cmd), proc.stdout[-6000:]))
+    return proc.stdout
+
+
+def _stamp(paths: List[str], extra: str = "") -> str:
+    h = hashlib.sha256(extra.encode())
+    for p in sorted(paths):
+        with open(p, "rb") as fh:
+            h.update(p.encode())
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def _fresh(out: str, stamp: str) -> bool:
+    sp = out + ".stamp"
+    return os.path.exists(out) and os.path.exists(sp) and open(sp).read() == stamp
+
+
+def _mark(out: str, stamp: str) -> None:
+    with open(out + ".stamp", "w") as fh:
+        fh.write(stamp)
+
+
+def runtime_path() -> str:
+    return os.path.join(LIB, "libfgpu_rt.so")
+
+
+def model_path(name: str) -> str:
+    return os.path.join(LIB, "models", name + ".so")
+
+
+def build_runtime(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(LIB, exist_ok=True)
+    srcs = [os.path.join(CSRC, f) for f in ("fgpu_rt.cu", "fgpu_kernels.cuh")]
+    hdrs = [os.path.join(INCLUDE, f) for f in ("fgpu.h", "fgpu_model.h")]
+    out = runtime_path()
+    extra = []
+    cmd = [NVCC] + ARCH_FLAGS + COMMON + ["-Xptxas", "-v", "-I", INCLUDE, "-I", CSRC] + extra + \
+          [os.path.join(CSRC, "fgpu_rt.cu"), "-o", out, "-ldl"]
+    stamp = _stamp(srcs + hdrs, " ".join(cmd))
+    if not force and _fresh(out, stamp):
+        return out
+    text = _run(cmd, log=out + ".log")
+    if verbose:
+        print(text)
+    _mark(out, stamp)
+    return out
+
+
+def build_model(xml_path: str, name: str, fmad: bool = True, force: bool = False, verbose: bool = False,
+                function_files: Optional[List[str]] = None) -> str:
+    """Generate and compile the plugin of one model.
+
+    ``fmad=False`` builds the exact-arithmetic variant (no FMA contraction) whose
+    float results are bit-comparable with the host oracle compiled with
+    ``-ffp-contract=off``.
+    """
+    model = xmml.parse_model(xml_path)
+    mdir = os.path.dirname(os.path.abspath(xml_path))
+    if function_files is None:
+        function_files = [os.path.join(mdir, f) for f in model.function_files]
+    for f in function_files:
+        if not os.path.exists(f):
+            raise BuildError(f"function file {f} not found")
+    gen = os.path.join(GEN, name)
+    files = codegen.emit_cuda(model, function_files, gen)
+    os.makedirs(os.path.join(LIB, "models"), exist_ok=True)
+    out = model_path(name)
+    cmd = [NVCC] + ARCH_FLAGS + COMMON + ["-Xptxas", "-v", "-fmad=" + ("true" if fmad else "false"),
+                                          "-I", gen, "-I", INCLUDE, "-I", CSRC, "-I", mdir,
+                                          files["model_glue.cu"], "-o", out]
+    deps = [files["header.h"], files["model_glue.cu"], os.path.join(CSRC, "fgpu_device.cuh"),
+            os.path.join(CSRC, "fgpu_glm.h"), os.path.join(INCLUDE, "fgpu_model.h")] + list(function_files)
+    stamp = _stamp(deps, " ".join(cmd))
+    if not force and _fresh(out, stamp):
+        return out
+    text = _run(cmd, log=out + ".log")
+    if verbose:
+        print(text)
+    _mark(out, stamp)
+    return out
+
+
+def write_scaled_xml(src_xml: str, dst_xml: str, replacements: dict) -> str:
+    """XML-only scaling of a model (bufferSize, bounds, radius, constants): plain
+    text substitution of ``<tag>old</tag>`` pairs, the functions.c is untouched."""
+    text = open(src_xml).read()
+    for old, new in replacements.items():
+        if old not in text:
+            raise BuildError(f"scaling: '{old}' not found in {src_xml}")
+        text = text.replace(old, new)
+    os.makedirs(os.path.dirname(dst_xml), exist_ok=True)
+    if not os.path.exists(dst_xml) or open(dst_xml).read() != text:
+        with open(dst_xml, "w") as fh:
+            fh.write(text)
+    return dst_xml
+
+
+if __name__ == "__main__":
+    build_runtime(force="--force" in sys.argv, verbose=True)

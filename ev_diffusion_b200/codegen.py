@@ -1,0 +1,657 @@
+"""Glue generator: XMML -> header.h + model plugin source.
+
+This is the build-time replacement for the reference's XSLT templates
+(`FLAMEGPU/templates/header.xslt`, `FLAMEGPU_kernals.xslt`, `simulation.xslt`).
+It emits only *thin* code: the model API header that ``functions.c`` compiles
+against unchanged, one wrapper kernel per ``<gpu:function>`` and the C
+descriptor table of ``include/fgpu_model.h``.  Everything that executes per
+iteration apart from the user's agent scripts lives in the model-agnostic
+runtime (``csrc/fgpu_rt.cu``).
+
+Two back ends share the model walk:
+  * ``emit_cuda``   -- sm_100a plugin (device proxies, packed message records);
+  * ``emit_oracle`` -- host-C++ restatement with the reference's own struct
+    layouts and cursor logic (used only by tests / the CPU baseline).
+"""
+from __future__ import annotations
+
+import os
+import re
+from typing import Dict, List, Optional, Set, Tuple
+
+from .xmml import Agent, Function, Message, Model, ModelError, Variable, _f32
+
+# --------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------
+
+
+def _float_lit(v: float) -> str:
+    """A C float literal that round-trips the binary32 value."""
+    f = _f32(v)
+    s = repr(float(f))
+    if "e" not in s and "." not in s and "inf" not in s and "nan" not in s:
+        s += ".0"
+    return s + "f"
+
+
+def _cast_lit(ctype: str, literal: str) -> str:
+    return f"({ctype})({literal})"
+
+
+def record_layout(msg: Message) -> Tuple[Dict[str, int], int]:
+    """Byte offset of each message variable inside the packed record and the
+    number of 16-byte quads.  XML order, natural alignment."""
+    off = 0
+    offsets = {}
+    for v in msg.variables:
+        sz = v.size
+        off = (off + sz - 1) // sz * sz
+        offsets[v.name] = off
+        off += sz
+    quads = max(1, (off + 15) // 16)
+    return offsets, quads
+
+
+def agent_list_offsets(agent: Agent) -> Tuple[Dict[str, int], int]:
+    """offsetof() of each column in xmachine_memory_<A>_list (header.xslt:187-194)."""
+    n = agent.buffer_size
+    off = 8 * n  # int _position[MAX]; int _scan_input[MAX];
+    offsets = {}
+    maxalign = 4
+    for v in agent.variables:
+        sz = v.size
+        maxalign = max(maxalign, sz)
+        off = (off + sz - 1) // sz * sz
+        offsets[v.name] = off
+        off += sz * n * max(1, v.array_length)
+    total = (off + maxalign - 1) // maxalign * maxalign
+    return offsets, total
+
+
+# --------------------------------------------------------------------------
+# functions.c analysis: which agent variables does a script write?
+# --------------------------------------------------------------------------
+
+_COMMENT_RE = re.compile(r"//[^\n]*|/\*.*?\*/", re.S)
+_STRING_RE = re.compile(r'"(?:\\.|[^"\\])*"|\'(?:\\.|[^\'\\])*\'')
+
+
+def _strip(src: str) -> str:
+    src = _COMMENT_RE.sub(" ", src)
+    return _STRING_RE.sub('""', src)
+
+
+def find_function_body(src: str, fname: str) -> Optional[Tuple[str, str]]:
+    """Return (parameter list text, body text) of ``int fname(...) {...}``."""
+    for m in re.finditer(r"\bint\s+" + re.escape(fname) + r"\s*\(", src):
+        i = m.end()
+        depth = 1
+        while i < len(src) and depth:
+            depth += {"(": 1, ")": -1}.get(src[i], 0)
+            i += 1
+        params = src[m.end():i - 1]
+        j = i
+        while j < len(src) and src[j] in " \t\r\n":
+            j += 1
+        if j >= len(src) or src[j] != "{":
+            continue  # a prototype
+        k = j + 1
+        depth = 1
+        while k < len(src) and depth:
+            depth += {"{": 1, "}": -1}.get(src[k], 0)
+            k += 1
+        return params, src[j:k]
+    return None
+
+
+def written_variables(func: Function, agent: Agent, sources: List[str]) -> Set[str]:
+    """Conservative write set of an agent script.  The reference scatters every
+    variable back (krn:1383-1384); we only store those the script can modify.
+    Anything we cannot prove read-only is treated as written."""
+    allv = {v.name for v in agent.variables}
+    for raw in sources:
+        src = _strip(raw)
+        # a macro that hides a member access defeats the textual analysis
+        if re.search(r"#\s*define[^\n]*->", src):
+            return allv
+        found = find_function_body(src, func.name)
+        if not found:
+            continue
+        params, body = found
+        first = params.split(",")[0].strip()
+        pm = re.search(r"([A-Za-z_]\w*)\s*$", first)
+        if not pm:
+            return allv
+        p = pm.group(1)
+        # the pointer escapes (passed on, dereferenced whole, reassigned)
+        for use in re.finditer(r"\b" + re.escape(p) + r"\b", body):
+            tail = body[use.end():use.end() + 8].lstrip()
+            if not tail.startswith("->"):
+                return allv
+        written = set()
+        assign = r"\s*(?:\[[^\]]*\])?\s*(?:=(?!=)|\+=|-=|\*=|/=|%=|&=|\|=|\^=|<<=|>>=|\+\+|--)"
+        for v in agent.variables:
+            ref = r"\b" + re.escape(p) + r"\s*->\s*" + re.escape(v.name) + r"\b"
+            if (re.search(ref + assign, body) or re.search(r"(?:\+\+|--)\s*" + ref, body)
+                    or re.search(r"&\s*" + ref, body) or v.array_length):
+                written.add(v.name)
+        return written
+    return allv
+
+
+# --------------------------------------------------------------------------
+# shared header pieces
+# --------------------------------------------------------------------------
+
+_COLOURS = """
+#define FLAME_GPU_VISUALISATION_COLOUR_BLACK 0
+#define FLAME_GPU_VISUALISATION_COLOUR_RED 1
+#define FLAME_GPU_VISUALISATION_COLOUR_GREEN 2
+#define FLAME_GPU_VISUALISATION_COLOUR_BLUE 3
+#define FLAME_GPU_VISUALISATION_COLOUR_YELLOW 4
+#define FLAME_GPU_VISUALISATION_COLOUR_CYAN 5
+#define FLAME_GPU_VISUALISATION_COLOUR_MAGENTA 6
+#define FLAME_GPU_VISUALISATION_COLOUR_WHITE 7
+#define FLAME_GPU_VISUALISATION_COLOUR_BROWN 8
+"""
+
+
+def _common_defs(model: Model) -> str:
+    out = []
+    out.append("#define THREADS_PER_TILE 64")
+    out.append("#define USE_CUDA_STREAMS")
+    out.append("#define FLAME_GPU_MAJOR_VERSION 1\n#define FLAME_GPU_MINOR_VERSION 5\n#define FLAME_GPU_PATCH_VERSION 0")
+    out.append("#define MAX_FILEPATH_LENGTH 4096")
+    out.append("typedef unsigned int uint;")
+    for n in ("vec2", "vec3", "vec4", "ivec2", "ivec3", "ivec4", "uvec2", "uvec3", "uvec4", "dvec2", "dvec3", "dvec4"):
+        out.append(f"typedef glm::{n} {n};")
+    for n in ("2", "3", "4"):
+        out.append(f"typedef glm::vec{n} fvec{n};")
+    if any(v.type == "double" for a in model.agents for v in a.variables) or \
+            any(v.type == "double" for m in model.messages for v in m.variables):
+        out.append("#define _DOUBLE_SUPPORT_REQUIRED_")
+    out.append(f"#define buffer_size_MAX {model.buffer_size_max}")
+    for a in model.agents:
+        out.append(f"#define xmachine_memory_{a.name}_MAX {a.buffer_size}")
+        for v in a.variables:
+            if v.array_length:
+                out.append(f"#define xmachine_memory_{a.name}_{v.name}_LENGTH {v.array_length}")
+    for m in model.messages:
+        out.append(f"#define xmachine_message_{m.name}_MAX {m.buffer_size}")
+        tag = {"spatial": "partitioningSpatial", "none": "partitioningNone"}[m.partitioning]
+        out.append(f"#define xmachine_message_{m.name}_{tag}")
+        if m.partitioning == "spatial":
+            out.append(f"#define xmachine_message_{m.name}_grid_size {m.grid_size()}")
+    out.append(_COLOURS)
+    out.append("enum MESSAGE_OUTPUT{\n\tsingle_message,\n\toptional_message,\n};")
+    out.append("enum AGENT_TYPE{\n\tCONTINUOUS,\n\tDISCRETE_2D\n};")
+    return "\n".join(out) + "\n"
+
+
+def _agent_structs(model: Model, align: str) -> str:
+    out = []
+    for a in model.agents:
+        out.append(f"struct {align} xmachine_memory_{a.name}\n{{")
+        for v in a.variables:
+            star = "*" if v.array_length else ""
+            out.append(f"    {v.type} {star}{v.name};")
+        out.append("};\n")
+        out.append(f"struct xmachine_memory_{a.name}_list\n{{")
+        out.append(f"    int _position [xmachine_memory_{a.name}_MAX];")
+        out.append(f"    int _scan_input [xmachine_memory_{a.name}_MAX];")
+        for v in a.variables:
+            mul = f"*{v.array_length}" if v.array_length else ""
+            out.append(f"    {v.type} {v.name} [xmachine_memory_{a.name}_MAX{mul}];")
+        out.append("};\n")
+    return "\n".join(out)
+
+
+def _function_signature(model: Model, f: Function, prefix: str = "") -> str:
+    """Agent script signature rule (header.xslt:375-378)."""
+    args = [f"xmachine_memory_{f.agent}* agent"]
+    if f.xagent_output:
+        args.append(f"xmachine_memory_{f.xagent_output}_list* {f.xagent_output}_agents")
+    if f.input_message:
+        args.append(f"xmachine_message_{f.input_message}_list* {f.input_message}_messages")
+        if model.message(f.input_message).partitioning == "spatial":
+            args.append(f"xmachine_message_{f.input_message}_PBM* partition_matrix")
+    if f.output_message:
+        args.append(f"xmachine_message_{f.output_message}_list* {f.output_message}_messages")
+    if f.rng:
+        args.append("RNG_rand48* rand48")
+    return f"{prefix}int {f.name}({', '.join(args)})"
+
+
+def _msg_args(m: Message) -> str:
+    return ", ".join(f"{v.type} {v.name}" for v in m.variables)
+
+
+def _agent_args(a: Agent) -> str:
+    return ", ".join(f"{v.type} {v.name}" for v in a.variables if not v.array_length)
+
+
+# --------------------------------------------------------------------------
+# CUDA back end
+# --------------------------------------------------------------------------
+
+def _cuda_message_api(m: Message) -> str:
+    name = m.name
+    T = f"fgpu_traits_{name}"
+    S = f"xmachine_message_{name}"
+    out = []
+    # user-visible message struct == the record stored in HBM (payload only; the
+    # cursor lives in the proxy).  __align__(16) pads sizeof to a 16-byte multiple.
+    out.append(f"struct __align__(16) {S}\n{{")
+    for v in m.variables:
+        out.append(f"    {v.type} {v.name};")
+    out.append("};")
+    out.append(f"struct {T} {{")
+    out.append(f"    static constexpr int MAX = {m.buffer_size};")
+    out.append(f"    static constexpr int NQ = (int)(sizeof({S}) / 16);")
+    if m.partitioning == "spatial":
+        dx, dy, dz = m.partition_dims()
+        out.append(f"    static constexpr int DIMX = {dx}, DIMY = {dy}, DIMZ = {dz};")
+        out.append(f"    static constexpr bool IS2D = {'true' if m.is_2d() else 'false'};")
+        for ax, lo, hi in zip("XYZ", m.min_literals, m.max_literals):
+            out.append(f"    static constexpr float MIN{ax} = (float){lo}, MAX{ax} = (float){hi};")
+    else:
+        out.append("    static constexpr int DIMX = 1, DIMY = 1, DIMZ = 1;")
+        out.append("    static constexpr bool IS2D = false;")
+        for ax in "XYZ":
+            out.append(f"    static constexpr float MIN{ax} = 0.0f, MAX{ax} = 1.0f;")
+    out.append("};")
+    out.append(f"struct {S}_list : fgpu::MessageProxy<{S}, {T}> {{}};")
+    if m.partitioning == "spatial":
+        out.append(f"struct {S}_PBM {{ int _unused; }};")
+    # add_<M>_message (krn:382-404) fused with the cell hash (krn:899-911 / 944-953)
+    out.append(f"FGPU_DEV void add_{name}_message({S}_list* messages, {_msg_args(m)}){{")
+    out.append(f"    union {{ {S} m; uint4 q[{T}::NQ]; }} r;")
+    out.append(f"    for (int _q = 0; _q < {T}::NQ; ++_q) r.q[_q] = make_uint4(0u, 0u, 0u, 0u);")
+    for v in m.variables:
+        out.append(f"    r.m.{v.name} = {v.name};")
+    out.append(f"    uint4* _dst = (uint4*)(messages->out_recs + messages->out_index);")
+    out.append(f"    for (int _q = 0; _q < {T}::NQ; ++_q) _dst[_q] = r.q[_q];")
+    if m.partitioning == "spatial":
+        out.append("    int _cx, _cy, _cz;")
+        out.append(f"    fgpu::grid_position<{T}>((float)x, (float)y, (float)z, _cx, _cy, _cz);")
+        out.append(f"    messages->out_keys[messages->out_index] = fgpu::cell_hash<{T}>(_cx, _cy, _cz);")
+    out.append("}")
+    if m.partitioning == "spatial":
+        out.append(f"""FGPU_DEV {S}* get_first_{name}_message({S}_list* messages, {S}_PBM* partition_matrix, float x, float y, float z){{
+    (void)partition_matrix;
+    if (messages->in_count == 0) return nullptr;   /* krn:1117 */
+    fgpu::grid_position<{T}>(x, y, z, messages->cx, messages->cy, messages->cz);
+    messages->step = 0;
+    return const_cast<{S}*>(fgpu::open_next_range<{S}, {T}>(messages));
+}}
+FGPU_DEV {S}* get_next_{name}_message({S}* current, {S}_list* messages, {S}_PBM* partition_matrix){{
+    (void)partition_matrix;
+    const {S}* nxt = current + 1;
+    if (nxt >= messages->end) nxt = fgpu::open_next_range<{S}, {T}>(messages);
+    return const_cast<{S}*>(nxt);
+}}""")
+    else:
+        out.append(f"""FGPU_DEV {S}* get_first_{name}_message({S}_list* messages){{
+    if (messages->in_count == 0) return nullptr;
+    messages->end = messages->in_recs + messages->in_count;
+    return const_cast<{S}*>(messages->in_recs);
+}}
+FGPU_DEV {S}* get_next_{name}_message({S}* current, {S}_list* messages){{
+    const {S}* nxt = current + 1;
+    return (nxt >= messages->end) ? nullptr : const_cast<{S}*>(nxt);
+}}""")
+    return "\n".join(out) + "\n"
+
+
+def _cuda_agent_api(a: Agent) -> str:
+    scal = [v for v in a.variables if not v.array_length]
+    out = [f"""template <int AGENT_TYPE>
+FGPU_DEV void add_{a.name}_agent(xmachine_memory_{a.name}_list* agents, {_agent_args(a)}){{
+    /* krn:287-314: newborn of parent k goes to sparse slot k of d_{a.name}s_new, flag = 1 */
+    const fgpu::NewAgentProxy* _p = (const fgpu::NewAgentProxy*)(const void*)agents;
+    xmachine_memory_{a.name}_list* _l = (xmachine_memory_{a.name}_list*)_p->list;
+    const int index = _p->index;
+    _l->_position[index] = 0;
+    _l->_scan_input[index] = 1;"""]
+    for v in scal:
+        out.append(f"    _l->{v.name}[index] = {v.name};")
+    out.append("}")
+    out.append(f"FGPU_DEV void add_{a.name}_agent(xmachine_memory_{a.name}_list* agents, {_agent_args(a)}){{")
+    out.append(f"    add_{a.name}_agent<DISCRETE_2D>(agents, {', '.join(v.name for v in scal)});\n}}")
+    if any(v.array_length for v in a.variables):
+        out.append(f"""template<typename T> FGPU_DEV T get_{a.name}_agent_array_value(T *array, uint index){{
+    return array[(size_t)index * xmachine_memory_{a.name}_MAX];
+}}
+template<typename T> FGPU_DEV void set_{a.name}_agent_array_value(T *array, uint index, T value){{
+    array[(size_t)index * xmachine_memory_{a.name}_MAX] = value;
+}}""")
+    return "\n".join(out) + "\n"
+
+
+def emit_cuda_header(model: Model) -> str:
+    out = ["/* generated by ev_diffusion_b200.codegen -- model API header (replaces header.xslt output) */",
+           "#ifndef __HEADER\n#define __HEADER",
+           "#include <cuda_runtime.h>",
+           '#include "fgpu_glm.h"',
+           '#include "fgpu_device.cuh"',
+           "#define __FLAME_GPU_FUNC__ __device__",
+           "#define __FLAME_GPU_INIT_FUNC__\n#define __FLAME_GPU_STEP_FUNC__\n#define __FLAME_GPU_EXIT_FUNC__",
+           "#define __FLAME_GPU_HOST_FUNC__ __host__",
+           "#define FGPU_B200 1"]
+    out.append(_common_defs(model))
+    out.append(_agent_structs(model, "__align__(16)"))
+    for m in model.messages:
+        out.append(_cuda_message_api(m))
+    out.append("struct RNG_rand48 : fgpu::Rand48Proxy {};")
+    out.append("""template <int AGENT_TYPE> FGPU_DEV float rnd(RNG_rand48* rand48){ return fgpu::rand48_draw(rand48); }
+FGPU_DEV float rnd(RNG_rand48* rand48){ return fgpu::rand48_draw(rand48); }""")
+    for a in model.agents:
+        out.append(_cuda_agent_api(a))
+    out.append("/* Agent function prototypes (header.xslt:364-378) */")
+    for f in model.all_functions():
+        out.append(_function_signature(model, f, "__FLAME_GPU_FUNC__ ") + ";")
+    out.append("/* environment constants (header.xslt:763-773) */")
+    for c in model.constants:
+        dim = f"[{c.array_length}]" if c.array_length else ""
+        out.append(f"__constant__ {c.type} {c.name}{dim};")
+        out.append(f"extern {c.type} h_env_{c.name}{dim};")
+        out.append(f"void set_{c.name}({c.type}* h_{c.name});")
+        out.append(f"const {c.type}* get_{c.name}();")
+    out.append(_host_api_decls(model))
+    out.append("#endif /* __HEADER */")
+    return "\n".join(out) + "\n"
+
+
+def _host_api_decls(model: Model) -> str:
+    """Face-2 names (header.xslt:531-645) implemented by the generated shim on
+    top of libfgpu_rt."""
+    out = ["/* host API (header.xslt:531-645) -- implemented by the plugin shim over libfgpu_rt */",
+           "extern unsigned int getIterationNumber();",
+           "extern void initialise(char * input);",
+           "extern void cleanup();",
+           "extern void singleIteration();",
+           "extern void set_exit_early();",
+           "extern bool get_exit_early();"]
+    for a in model.agents:
+        out.append(f"extern int get_agent_{a.name}_MAX_count();")
+        for s in a.states:
+            out.append(f"extern int get_agent_{a.name}_{s}_count();")
+            out.append(f"extern void reset_{a.name}_{s}_count();")
+            out.append(f"extern xmachine_memory_{a.name}_list* get_device_{a.name}_{s}_agents();")
+            for v in a.variables:
+                if not v.array_length:
+                    out.append(f"{v.type} get_{a.name}_{s}_variable_{v.name}(unsigned int index);")
+    return "\n".join(out)
+
+
+def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
+    a = model.agent(f.agent)
+    A = a.name
+    bs = 128 if f.input_message else 256
+    out = [f"/* GPUFLAME_{f.name} (krn:1320-1387) */",
+           f"__global__ void __launch_bounds__({bs}) fgpu_k_{f.name}(const fgpu_launch L)\n{{",
+           "    const int t = blockIdx.x * blockDim.x + threadIdx.x;",
+           "    if (t >= L.n) return;",
+           "    const int index = L.order ? (int)__ldg(L.order + t) : t;",
+           f"    xmachine_memory_{A}_list* __restrict__ agents = (xmachine_memory_{A}_list*)L.agents;",
+           f"    xmachine_memory_{A} agent;"]
+    for v in a.variables:
+        if v.array_length:
+            out.append(f"    agent.{v.name} = &(agents->{v.name}[index]);")
+        else:
+            out.append(f"    agent.{v.name} = agents->{v.name}[index];")
+    call = ["&agent"]
+    if f.xagent_output:
+        out.append("    fgpu::NewAgentProxy newp; newp.list = L.new_agents; newp.index = index;")
+        call.append(f"(xmachine_memory_{f.xagent_output}_list*)(void*)&newp")
+    if f.input_message:
+        M = f.input_message
+        out.append(f"    xmachine_message_{M}_list inp;")
+        out.append(f"    inp.in_recs = (const xmachine_message_{M}*)L.in_recs; inp.cell_start = L.in_cell_start; inp.in_count = L.in_count;")
+        out.append("    inp.out_recs = nullptr; inp.out_keys = nullptr; inp.out_index = 0; inp.end = nullptr; inp.step = 0;")
+        call.append("&inp")
+        if model.message(M).partitioning == "spatial":
+            call.append(f"(xmachine_message_{M}_PBM*)nullptr")
+    if f.output_message:
+        M = f.output_message
+        if f.input_message == M:
+            raise ModelError(f"function '{f.name}' reads and writes message '{M}'")
+        out.append(f"    xmachine_message_{M}_list outp;")
+        out.append("    outp.in_recs = nullptr; outp.cell_start = nullptr; outp.in_count = 0; outp.end = nullptr; outp.step = 0;")
+        out.append(f"    outp.out_recs = (xmachine_message_{M}*)L.out_recs; outp.out_keys = L.out_keys; outp.out_index = L.out_base + index;")
+        call.append("&outp")
+    if f.rng:
+        out.append("    RNG_rand48 rng; rng.Ax = L.Ax; rng.Ay = L.Ay; rng.Cx = L.Cx; rng.Cy = L.Cy;")
+        out.append("    { const uint2 s = ((const uint2*)L.seeds)[index]; rng.sx = s.x; rng.sy = s.y; }")
+        call.append("&rng")
+    out.append(f"    const int dead = !{f.name}({', '.join(call)});")
+    if f.reallocate:
+        out.append("    agents->_scan_input[index] = dead;   /* krn:1381: flag 1 = keep */")
+    else:
+        out.append("    (void)dead;")
+    for v in a.variables:
+        if not v.array_length and v.name in written:
+            out.append(f"    agents->{v.name}[index] = agent.{v.name};")
+    if f.rng:
+        out.append("    ((uint2*)L.seeds)[index] = make_uint2(rng.sx, rng.sy);")
+    out.append("}")
+    out.append(f"""static void fgpu_launch_{f.name}(const fgpu_launch* a, void* stream){{
+    if (a->n <= 0) return;
+    const int grid = (a->n + {bs} - 1) / {bs};
+    fgpu_k_{f.name}<<<grid, {bs}, 0, (cudaStream_t)stream>>>(*a);
+}}""")
+    return "\n".join(out) + "\n"
+
+
+def _cuda_filter(model: Model, f: Function) -> str:
+    a = model.agent(f.agent)
+    A = a.name
+    if f.condition is not None:
+        expr = f.condition.c_expr("currentState->{0}[index]")
+        copies = "\n".join(
+            (f"        for (int i = 0; i < {v.array_length}; i++) nextState->{v.name}[(i*xmachine_memory_{A}_MAX)+index] = currentState->{v.name}[(i*xmachine_memory_{A}_MAX)+index];"
+             if v.array_length else f"        nextState->{v.name}[index] = currentState->{v.name}[index];")
+            for v in a.variables)
+        return f"""/* {f.name}_function_filter (krn:162-184); also performs the two
+ * reset_{A}_scan_input launches of simulation.xslt:1447-1452 by writing both flags */
+__global__ void __launch_bounds__(256) fgpu_filter_{f.name}(const fgpu_filter F)
+{{
+    const int index = blockIdx.x * blockDim.x + threadIdx.x;
+    if (index >= F.n) return;
+    xmachine_memory_{A}_list* __restrict__ currentState = (xmachine_memory_{A}_list*)F.current;
+    xmachine_memory_{A}_list* __restrict__ nextState = (xmachine_memory_{A}_list*)F.working;
+    if {expr}
+    {{
+{copies}
+        nextState->_scan_input[index] = 1;
+        currentState->_scan_input[index] = 0;
+    }}
+    else
+    {{
+        nextState->_scan_input[index] = 0;
+        currentState->_scan_input[index] = 1;
+    }}
+}}
+static void fgpu_launch_filter_{f.name}(const fgpu_filter* a, void* stream){{
+    if (a->n <= 0) return;
+    fgpu_filter_{f.name}<<<(a->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*a);
+}}
+"""
+    expr = f.global_condition.c_expr("currentState->{0}[index]")
+    return f"""/* {f.name}_function_filter, global condition (krn:192-210) */
+__global__ void __launch_bounds__(256) fgpu_filter_{f.name}(const fgpu_filter F)
+{{
+    const int index = blockIdx.x * blockDim.x + threadIdx.x;
+    if (index >= F.n) return;
+    xmachine_memory_{A}_list* __restrict__ currentState = (xmachine_memory_{A}_list*)F.current;
+    if {expr}
+        currentState->_scan_input[index] = 1;
+    else
+        currentState->_scan_input[index] = 0;
+}}
+static void fgpu_launch_filter_{f.name}(const fgpu_filter* a, void* stream){{
+    if (a->n <= 0) return;
+    fgpu_filter_{f.name}<<<(a->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*a);
+}}
+"""
+
+
+def _descriptor_tables(model: Model, mode: str, launch_prefix: str) -> str:
+    """The fgpu_model tables (shared by both back ends; the oracle passes its
+    own thunks in place of kernel launchers)."""
+    out = []
+    aidx = {a.name: i for i, a in enumerate(model.agents)}
+    midx = {m.name: i for i, m in enumerate(model.messages)}
+    for a in model.agents:
+        rows = []
+        for v in a.variables:
+            dv = v.default_literal()
+            rows.append(f'    {{"{v.name}", "{v.type}", {v.size}, {1 if v.type in ("float", "double") else 0}, '
+                        f'offsetof(xmachine_memory_{a.name}_list, {v.name}), (double)({dv})}},')
+        out.append(f"static const fgpu_var fgpu_vars_agent_{a.name}[] = {{\n" + "\n".join(rows) + "\n};")
+        states = ", ".join(f'"{s}"' for s in a.states)
+        out.append(f"static const char* const fgpu_states_{a.name}[] = {{{states}}};")
+    for m in model.messages:
+        rows = []
+        for v in m.variables:
+            rows.append(f'    {{"{v.name}", "{v.type}", {v.size}, {1 if v.type in ("float", "double") else 0}, '
+                        f'offsetof(xmachine_message_{m.name}{"_list" if mode == "oracle" else ""}, {v.name}), 0.0}},')
+        out.append(f"static const fgpu_var fgpu_vars_message_{m.name}[] = {{\n" + "\n".join(rows) + "\n};")
+    rows = []
+    for a in model.agents:
+        rows.append(f'    {{"{a.name}", {a.buffer_size}, {len(a.variables)}, fgpu_vars_agent_{a.name}, {len(a.states)}, '
+                    f'fgpu_states_{a.name}, {a.states.index(a.initial_state)}, sizeof(xmachine_memory_{a.name}_list), '
+                    f'offsetof(xmachine_memory_{a.name}_list, _position), offsetof(xmachine_memory_{a.name}_list, _scan_input)}},')
+    out.append("static const fgpu_agent fgpu_agents[] = {\n" + "\n".join(rows) + "\n};")
+    rows = []
+    for m in model.messages:
+        quads = f"(int)(sizeof(xmachine_message_{m.name}) / 16)"
+        names = [v.name for v in m.variables]
+        if m.partitioning == "spatial":
+            dx, dy, dz = m.partition_dims()
+            mn = ", ".join(f"(float){x}" for x in m.min_literals)
+            mx = ", ".join(f"(float){x}" for x in m.max_literals)
+            rows.append(f'    {{"{m.name}", {m.buffer_size}, {len(m.variables)}, fgpu_vars_message_{m.name}, {quads}, FGPU_PART_SPATIAL, '
+                        f'(float){m.radius_literal}, {{{mn}}}, {{{mx}}}, {{{dx}, {dy}, {dz}}}, {m.grid_size()}, {1 if m.is_2d() else 0}, '
+                        f'{m.radix_bits()}, {names.index("x")}, {names.index("y")}, {names.index("z")}}},')
+        else:
+            rows.append(f'    {{"{m.name}", {m.buffer_size}, {len(m.variables)}, fgpu_vars_message_{m.name}, {quads}, FGPU_PART_NONE, '
+                        f'0.0f, {{0,0,0}}, {{0,0,0}}, {{1,1,1}}, 1, 0, 1, -1, -1, -1}},')
+    if rows:
+        out.append("static const fgpu_message fgpu_messages[] = {\n" + "\n".join(rows) + "\n};")
+    else:
+        out.append("static const fgpu_message* const fgpu_messages = nullptr;")
+    funcs = model.all_functions()
+    fidx = {f.name: i for i, f in enumerate(funcs)}
+    rows = []
+    for f in funcs:
+        a = model.agent(f.agent)
+        cond = "FGPU_COND_FUNCTION" if f.condition is not None else ("FGPU_COND_GLOBAL" if f.global_condition is not None else "FGPU_COND_NONE")
+        # the literal test of simulation.xslt:1945 (note gpu:reallocate='false' is a string compare)
+        swappable = int(f.current_state == f.next_state and f.condition is None and f.global_condition is None
+                        and f.reallocate_literal == "false" and f.xagent_output is None)
+        filt = f"{launch_prefix}filter_{f.name}" if cond != "FGPU_COND_NONE" else "nullptr"
+        rows.append(
+            f'    {{"{f.name}", {aidx[f.agent]}, {a.states.index(f.current_state)}, {a.states.index(f.next_state)}, '
+            f'{midx[f.input_message] if f.input_message else -1}, {midx[f.output_message] if f.output_message else -1}, '
+            f'{"FGPU_OUT_OPTIONAL" if f.output_type == "optional_message" else "FGPU_OUT_SINGLE"}, '
+            f'{aidx[f.xagent_output] if f.xagent_output else -1}, '
+            f'{model.agent(f.xagent_output).states.index(f.xagent_output_state) if f.xagent_output else -1}, '
+            f'{int(f.reallocate)}, {swappable}, {int(f.rng)}, {cond}, {f.gc_max_iterations}, {int(f.gc_must_evaluate_to)}, '
+            f'{launch_prefix}{f.name}, {filt}, {128 if f.input_message else 256}}},')
+    out.append("static const fgpu_function fgpu_functions[] = {\n" + "\n".join(rows) + "\n};")
+    lrows = []
+    for i, layer in enumerate(model.layers):
+        out.append(f"static const int fgpu_layer_{i}[] = {{{', '.join(str(fidx[n]) for n in layer)}}};")
+        lrows.append(f"    {{{len(layer)}, fgpu_layer_{i}}},")
+    out.append("static const fgpu_layer fgpu_layers[] = {\n" + "\n".join(lrows) + "\n};")
+    return "\n".join(out) + "\n"
+
+
+def _constants_code(model: Model, cuda: bool) -> str:
+    out = []
+    rows = []
+    for c in model.constants:
+        dim = f"[{c.array_length}]" if c.array_length else ""
+        n = max(1, c.array_length)
+        out.append(f"{c.type} h_env_{c.name}{dim};")
+        if cuda:
+            out.append(f"void set_{c.name}({c.type}* h_{c.name}){{\n"
+                       f"    cudaMemcpyToSymbol({c.name}, h_{c.name}, sizeof({c.type})*{n});\n"
+                       f"    memcpy(&h_env_{c.name}, h_{c.name}, sizeof({c.type})*{n});\n}}")
+        else:
+            out.append(f"void set_{c.name}({c.type}* h_{c.name}){{\n"
+                       f"    memcpy(&{c.name}, h_{c.name}, sizeof({c.type})*{n});\n"
+                       f"    memcpy(&h_env_{c.name}, h_{c.name}, sizeof({c.type})*{n});\n}}")
+        out.append(f"const {c.type}* get_{c.name}(){{ return {'h_env_' + c.name if c.array_length else '&h_env_' + c.name}; }}")
+        out.append(f"static void fgpu_cset_{c.name}(const void* v){{ set_{c.name}(({c.type}*)v); }}")
+        out.append(f"static const void* fgpu_cget_{c.name}(void){{ return (const void*)get_{c.name}(); }}")
+        rows.append(f'    {{"{c.name}", "{c.type}", (int)sizeof({c.type}), {n}, fgpu_cset_{c.name}, fgpu_cget_{c.name}}},')
+    # initEnvVars (io.xslt:201-209): T t = (T)<literal>; set_<c>(&t)
+    out.append("static void fgpu_init_constants(void){")
+    for c in model.constants:
+        if c.default is not None and c.default != "" and not c.array_length:
+            out.append(f"    {{ {c.type} t = ({c.type}){c.default}; set_{c.name}(&t); }}")
+        elif not c.array_length:
+            out.append(f"    {{ {c.type} t = ({c.type})0; set_{c.name}(&t); }}")
+    out.append("}")
+    if rows:
+        out.append("static const fgpu_constant fgpu_constants[] = {\n" + "\n".join(rows) + "\n};")
+    else:
+        out.append("static const fgpu_constant* const fgpu_constants = nullptr;")
+    return "\n".join(out) + "\n"
+
+
+def _model_struct(model: Model) -> str:
+    def fnlist(kind, names):
+        if not names:
+            return f"static void (*const *fgpu_{kind}_functions)(void) = nullptr;"
+        return f"static void (*const fgpu_{kind}_functions[])(void) = {{{', '.join(names)}}};"
+    out = [fnlist("init", model.init_functions), fnlist("step", model.step_functions), fnlist("exit", model.exit_functions)]
+    safe = model.name.replace('"', "'")
+    out.append(f"""static const fgpu_model fgpu_the_model = {{
+    FGPU_MODEL_ABI_VERSION, "{safe}", {model.buffer_size_max},
+    {len(model.agents)}, fgpu_agents,
+    {len(model.messages)}, fgpu_messages,
+    {len(model.all_functions())}, fgpu_functions,
+    {len(model.layers)}, fgpu_layers,
+    {len(model.constants)}, fgpu_constants,
+    fgpu_init_constants,
+    {len(model.init_functions)}, fgpu_init_functions,
+    {len(model.step_functions)}, fgpu_step_functions,
+    {len(model.exit_functions)}, fgpu_exit_functions
+}};
+extern "C" const fgpu_model* fgpu_model_get(void){{ return &fgpu_the_model; }}
+""")
+    return "\n".join(out)
+
+
+def emit_cuda_glue(model: Model, function_files: List[str]) -> str:
+    sources = [open(p, "r", errors="replace").read() for p in function_files]
+    out = ["/* generated by ev_diffusion_b200.codegen -- model plugin for sm_100a */",
+           "#include <cstddef>\n#include <cstring>\n#include <cstdio>\n#include <cmath>",
+           '#include "header.h"',
+           '#include "fgpu_model.h"']
+    for p in function_files:
+        out.append(f'#include "{os.path.abspath(p)}"')
+    for f in model.all_functions():
+        a = model.agent(f.agent)
+        out.append(_cuda_kernel(model, f, written_variables(f, a, sources)))
+        if f.condition is not None or f.global_condition is not None:
+            out.append(_cuda_filter(model, f))
+    out.append(_constants_code(model, cuda=True))
+    out.append(_descriptor_tables(model, "cuda", "fgpu_launch_"))
+    out.append(_model_struct(model))
+    return "\n".join(out) + "\n"
+
+
+def emit_cuda(model: Model, function_files: List[str], outdir: str) -> Dict[str, str]:
+    os.makedirs(outdir, exist_ok=True)
+    files = {"header.h": emit_cuda_header(model), "model_glue.cu": emit_cuda_glue(model, function_files)}
+    for name, text in files.items():
+        path = os.path.join(outdir, name)
+        if not os.path.exists(path) or open(path).read() != text:
+            with open(path, "w") as fh:
+                fh.write(text)
+    return {k: os.path.join(outdir, k) for k in files}

@@ -1,0 +1,1247 @@
+/*
+ * fgpu_rt.cu -- host runtime of the B200-native FLAME GPU 1.5 simulation step
+ * and its C ABI (include/fgpu.h).
+ *
+ * This is the model-agnostic replacement for the XSLT-generated simulation.cu:
+ *   initialise()            simulation.xslt:472-747   -> fgpu_sim_create / load_states
+ *   singleIteration()       simulation.xslt:878-975   -> fgpu_sim_step
+ *   <Agent>_<func>(stream)  simulation.xslt:1402-1974 -> Sim::run_function
+ * The list / pointer discipline of the reference (working list d_<A>s, swap,
+ * new, one list per state; pointer swaps, stable compaction, append) is kept
+ * exactly, because list order defines rand48 stream ownership and message
+ * order.  What changes is the mechanism underneath:
+ *   - no per-launch cudaMemcpyToSymbol / texture binding / occupancy queries;
+ *     everything a kernel needs travels in one by-value argument struct;
+ *   - models without conditions / death / birth replay one captured CUDA graph
+ *     per iteration (zero host round trips);
+ *   - spatial message build = fused cell hash in add_<M>_message, hand-written
+ *     LSD radix sort, fused gather + CSR partition boundary matrix;
+ *   - message consumers process agents in cell order when the consuming list
+ *     is the list that produced the messages (locality only, never semantics).
+ */
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "fgpu.h"
+#include "fgpu_kernels.cuh"
+
+using namespace fgpu;
+
+/* ------------------------------------------------------------------------- */
+/* errors                                                                     */
+/* ------------------------------------------------------------------------- */
+static thread_local char g_err[1024] = "";
+
+static int set_err(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char *fgpu_last_error(void) { return g_err; }
+
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return set_err(FGPU_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+/* ------------------------------------------------------------------------- */
+/* runtime objects                                                            */
+/* ------------------------------------------------------------------------- */
+struct AgentRT {
+    const fgpu_agent *d = nullptr;
+    char *work = nullptr;  /* d_<A>s */
+    char *swap = nullptr;  /* d_<A>s_swap */
+    char *newl = nullptr;  /* d_<A>s_new */
+    std::vector<char *> state; /* d_<A>s_<state> */
+    int h_count = 0;           /* h_xmachine_memory_<A>_count */
+    std::vector<int> h_state_count;
+    ColSet cols;
+    unsigned int *block_sums = nullptr;
+    int *d_total = nullptr;
+};
+
+struct MsgRT {
+    const fgpu_message *d = nullptr;
+    uint4 *unsorted = nullptr; /* staging written by add_<M>_message */
+    uint4 *sorted = nullptr;   /* cell-ordered list read by get_first/next */
+    unsigned int *keys_in = nullptr; /* cell key of each unsorted message (written by add_<M>_message) */
+    unsigned int *keys[2] = {nullptr, nullptr}; /* radix ping-pong */
+    unsigned int *vals[2] = {nullptr, nullptr};
+    unsigned int *cell_start = nullptr; /* CSR, grid_size + 1 */
+    unsigned int *scratch = nullptr;    /* hist | tickets | gap_count | status */
+    size_t scratch_bytes = 0;
+    unsigned int *gap_queue = nullptr;
+    int max_tiles = 0;
+    int h_count = 0; /* h_message_<M>_count */
+    /* which list produced the current contents (for cell-coherent consumers) */
+    const char *producer_buf = nullptr;
+    unsigned long long producer_epoch = 0;
+    int producers = 0;
+    int sorted_in = 0; /* index of keys/vals buffer holding the final sorted pairs */
+    bool built = false;
+};
+
+struct ProfEntry {
+    std::string name;
+    cudaEvent_t a, b;
+};
+
+struct fgpu_sim {
+    const fgpu_model *model = nullptr;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<AgentRT> agents;
+    std::vector<MsgRT> msgs;
+    std::vector<int> gc_count; /* h_<f>_condition_count */
+    uint2 *seeds = nullptr;
+    unsigned int Ax = 0, Ay = 0, Cx = 0, Cy = 0;
+    unsigned int iteration = 0;
+    long long launches = 0;
+    float last_ms = 0.f;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::map<const char *, unsigned long long> epoch; /* last structural modification per list buffer */
+    unsigned long long epoch_counter = 1;
+    /* options */
+    int opt_order = 1;
+    int opt_graph = 1;
+    int opt_radix_bits = 8;
+    /* CUDA graph of one iteration (static models) */
+    bool is_static = false;
+    cudaGraphExec_t graph = nullptr;
+    std::vector<int> graph_counts; /* counts baked into the graph */
+    long long graph_launches = 0;
+    bool capturing = false;
+    /* profiling */
+    bool profiling = false;
+    std::vector<ProfEntry> prof;
+    std::vector<std::string> prof_names;
+    std::vector<float> prof_ms;
+    unsigned int *unpack_tmp = nullptr;
+    size_t unpack_tmp_n = 0;
+
+    void touch(const char *buf) { epoch[buf] = ++epoch_counter; }
+    unsigned long long epoch_of(const char *buf) {
+        auto it = epoch.find(buf);
+        return it == epoch.end() ? 0ull : it->second;
+    }
+    void prof_begin(const std::string &name) {
+        if (!profiling) return;
+        ProfEntry e;
+        e.name = name;
+        cudaEventCreate(&e.a);
+        cudaEventCreate(&e.b);
+        cudaEventRecord(e.a, stream);
+        prof.push_back(e);
+    }
+    void prof_end() {
+        if (!profiling) return;
+        cudaEventRecord(prof.back().b, stream);
+    }
+};
+
+static size_t msg_plane_bytes(const fgpu_message *m) { return (size_t)m->rec_quads * m->buffer_size * sizeof(uint4); }
+
+/* ------------------------------------------------------------------------- */
+/* model plugins                                                              */
+/* ------------------------------------------------------------------------- */
+extern "C" const fgpu_model *fgpu_model_load(const char *plugin_path) {
+    if (!plugin_path) {
+        set_err(FGPU_ERR_ARG, "fgpu_model_load: null path");
+        return nullptr;
+    }
+    void *h = dlopen(plugin_path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) {
+        set_err(FGPU_ERR_MODEL, "dlopen(%s): %s", plugin_path, dlerror());
+        return nullptr;
+    }
+    typedef const fgpu_model *(*get_fn)(void);
+    get_fn get = (get_fn)dlsym(h, "fgpu_model_get");
+    if (!get) {
+        set_err(FGPU_ERR_MODEL, "%s does not export fgpu_model_get", plugin_path);
+        return nullptr;
+    }
+    const fgpu_model *m = get();
+    if (!m || m->abi_version != FGPU_MODEL_ABI_VERSION) {
+        set_err(FGPU_ERR_MODEL, "%s: plugin ABI %d, runtime ABI %d", plugin_path, m ? m->abi_version : -1,
+                FGPU_MODEL_ABI_VERSION);
+        return nullptr;
+    }
+    return m;
+}
+
+/* ------------------------------------------------------------------------- */
+/* create / destroy                                                           */
+/* ------------------------------------------------------------------------- */
+static int sort_passes(int radix_bits, int max_bits) { return (radix_bits + max_bits - 1) / max_bits; }
+
+static int sim_alloc(fgpu_sim *s) {
+    const fgpu_model *m = s->model;
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&s->ev0));
+    CU(cudaEventCreate(&s->ev1));
+    s->agents.resize(m->nagents);
+    for (int a = 0; a < m->nagents; ++a) {
+        AgentRT &A = s->agents[a];
+        A.d = &m->agents[a];
+        if (A.d->nvars > MAX_COLS) return set_err(FGPU_ERR_MODEL, "agent %s has more than %d variables", A.d->name, MAX_COLS);
+        CU(cudaMalloc(&A.work, A.d->list_bytes));
+        CU(cudaMalloc(&A.swap, A.d->list_bytes));
+        CU(cudaMalloc(&A.newl, A.d->list_bytes));
+        CU(cudaMemsetAsync(A.work, 0, A.d->list_bytes, s->stream));
+        CU(cudaMemsetAsync(A.swap, 0, A.d->list_bytes, s->stream));
+        CU(cudaMemsetAsync(A.newl, 0, A.d->list_bytes, s->stream));
+        A.state.resize(A.d->nstates);
+        A.h_state_count.assign(A.d->nstates, 0);
+        for (int st = 0; st < A.d->nstates; ++st) {
+            CU(cudaMalloc(&A.state[st], A.d->list_bytes));
+            CU(cudaMemsetAsync(A.state[st], 0, A.d->list_bytes, s->stream));
+        }
+        A.cols.ncols = A.d->nvars;
+        for (int v = 0; v < A.d->nvars; ++v) {
+            A.cols.size[v] = A.d->vars[v].size;
+            A.cols.off[v] = A.d->vars[v].list_offset;
+        }
+        const int nb = (A.d->buffer_size + COMPACT_THREADS - 1) / COMPACT_THREADS;
+        CU(cudaMalloc(&A.block_sums, sizeof(unsigned int) * (size_t)(nb + 1)));
+        CU(cudaMalloc(&A.d_total, sizeof(int)));
+    }
+    s->msgs.resize(m->nmessages);
+    for (int i = 0; i < m->nmessages; ++i) {
+        MsgRT &M = s->msgs[i];
+        M.d = &m->messages[i];
+        CU(cudaMalloc(&M.unsorted, msg_plane_bytes(M.d)));
+        if (M.d->partitioning == FGPU_PART_SPATIAL) {
+            CU(cudaMalloc(&M.sorted, msg_plane_bytes(M.d)));
+            CU(cudaMalloc(&M.keys_in, sizeof(unsigned int) * (size_t)M.d->buffer_size));
+            for (int k = 0; k < 2; ++k) {
+                CU(cudaMalloc(&M.keys[k], sizeof(unsigned int) * (size_t)M.d->buffer_size));
+                CU(cudaMalloc(&M.vals[k], sizeof(unsigned int) * (size_t)M.d->buffer_size));
+            }
+            CU(cudaMalloc(&M.cell_start, sizeof(unsigned int) * ((size_t)M.d->grid_size + 1)));
+            CU(cudaMemsetAsync(M.cell_start, 0, sizeof(unsigned int) * ((size_t)M.d->grid_size + 1), s->stream));
+            M.max_tiles = (M.d->buffer_size + SORT_TILE - 1) / SORT_TILE;
+            /* scratch: hist[4][256] | tickets[4] | gap_count[1] | pad | status[4][tiles][256] */
+            M.scratch_bytes = sizeof(unsigned int) * ((size_t)SORT_MAX_PASSES * SORT_BINS + 8 +
+                                                      (size_t)SORT_MAX_PASSES * M.max_tiles * SORT_BINS);
+            CU(cudaMalloc(&M.scratch, M.scratch_bytes));
+            CU(cudaMalloc(&M.gap_queue, sizeof(unsigned int) * 3 * ((size_t)M.d->grid_size / GAP_INLINE + 8)));
+        }
+    }
+    s->gc_count.assign(m->nfunctions, 0);
+
+    /* rand48 seeding, simulation.xslt:661-688 */
+    const unsigned int N = (unsigned int)m->buffer_size_max;
+    CU(cudaMalloc(&s->seeds, sizeof(uint2) * (size_t)N));
+    {
+        static const unsigned long long a = 0x5DEECE66DULL, c = 0xB;
+        const unsigned long long M48 = (1ULL << 48) - 1ULL;
+        unsigned long long A = 1ULL, C = 0ULL;
+        for (unsigned int i = 0; i < N; ++i) {
+            C += A * c;
+            A *= a;
+        }
+        s->Ax = (unsigned int)(A & 0xFFFFFFULL);
+        s->Ay = (unsigned int)((A >> 24) & 0xFFFFFFULL);
+        s->Cx = (unsigned int)(C & 0xFFFFFFULL);
+        s->Cy = (unsigned int)((C >> 24) & 0xFFFFFFULL);
+        std::vector<uint2> h(N);
+        unsigned long long x = (((unsigned long long)123) << 16) | 0x330E;
+        for (unsigned int i = 0; i < N; ++i) {
+            x = a * x + c;
+            h[i].x = (unsigned int)(x & 0xFFFFFFULL);
+            h[i].y = (unsigned int)((x >> 24) & 0xFFFFFFULL);
+        }
+        (void)M48;
+        CU(cudaMemcpyAsync(s->seeds, h.data(), sizeof(uint2) * (size_t)N, cudaMemcpyHostToDevice, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    /* static model: every function is an in-place pointer-swap function with single-message output */
+    s->is_static = (m->nstep_functions == 0);
+    for (int f = 0; f < m->nfunctions; ++f) {
+        const fgpu_function &F = m->functions[f];
+        if (!F.swappable || F.output_type != FGPU_OUT_SINGLE) s->is_static = false;
+    }
+    if (m->init_constants) m->init_constants();
+    CU(cudaStreamSynchronize(s->stream));
+    return FGPU_OK;
+}
+
+extern "C" fgpu_sim *fgpu_sim_create(const fgpu_model *model, int device) {
+    if (!model) {
+        set_err(FGPU_ERR_ARG, "fgpu_sim_create: null model");
+        return nullptr;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_err(FGPU_ERR_CUDA, "fgpu_sim_create: no CUDA device (this runtime has no CPU path)");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) {
+        set_err(FGPU_ERR_ARG, "fgpu_sim_create: device %d out of range (%d devices)", device, ndev);
+        return nullptr;
+    }
+    fgpu_sim *s = new fgpu_sim();
+    s->model = model;
+    s->device = device;
+    if (sim_alloc(s) != FGPU_OK) {
+        fgpu_sim_destroy(s);
+        return nullptr;
+    }
+    return s;
+}
+
+extern "C" void fgpu_sim_destroy(fgpu_sim *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->graph) cudaGraphExecDestroy(s->graph);
+    for (AgentRT &A : s->agents) {
+        cudaFree(A.work);
+        cudaFree(A.swap);
+        cudaFree(A.newl);
+        for (char *p : A.state) cudaFree(p);
+        cudaFree(A.block_sums);
+        cudaFree(A.d_total);
+    }
+    for (MsgRT &M : s->msgs) {
+        cudaFree(M.unsorted);
+        cudaFree(M.sorted);
+        cudaFree(M.keys_in);
+        for (int k = 0; k < 2; ++k) {
+            cudaFree(M.keys[k]);
+            cudaFree(M.vals[k]);
+        }
+        cudaFree(M.cell_start);
+        cudaFree(M.scratch);
+        cudaFree(M.gap_queue);
+    }
+    cudaFree(s->seeds);
+    cudaFree(s->unpack_tmp);
+    for (ProfEntry &e : s->prof) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+/* ------------------------------------------------------------------------- */
+/* state upload / download                                                    */
+/* ------------------------------------------------------------------------- */
+static void invalidate_graph(fgpu_sim *s) {
+    if (s->graph) {
+        cudaGraphExecDestroy(s->graph);
+        s->graph = nullptr;
+    }
+}
+
+static int upload_columns(fgpu_sim *s, int agent, int state, int offset, int count, const void *const *columns) {
+    if (agent < 0 || agent >= (int)s->agents.size()) return set_err(FGPU_ERR_ARG, "bad agent index %d", agent);
+    AgentRT &A = s->agents[agent];
+    if (state < 0 || state >= A.d->nstates) return set_err(FGPU_ERR_ARG, "bad state index %d", state);
+    if (count < 0 || offset + count > A.d->buffer_size)
+        return set_err(FGPU_ERR_OVERFLOW, "ERROR: MAX Buffer size (%i) for agent %s exceeded whilst reading data",
+                       A.d->buffer_size, A.d->name); /* io.xslt:406, without its off-by-one */
+    CU(cudaSetDevice(s->device));
+    char *list = A.state[state];
+    for (int v = 0; v < A.d->nvars; ++v) {
+        const fgpu_var &V = A.d->vars[v];
+        char *dst = list + V.list_offset + (size_t)offset * V.size;
+        if (columns && columns[v]) {
+            CU(cudaMemcpyAsync(dst, columns[v], (size_t)count * V.size, cudaMemcpyHostToDevice, s->stream));
+        } else {
+            /* defaultValue or 0 (io.xslt:276-291) */
+            std::vector<char> tmp((size_t)count * V.size);
+            for (int i = 0; i < count; ++i) {
+                if (V.size == 8) {
+                    if (V.is_float) ((double *)tmp.data())[i] = V.default_value;
+                    else ((long long *)tmp.data())[i] = (long long)V.default_value;
+                } else {
+                    if (V.is_float) ((float *)tmp.data())[i] = (float)V.default_value;
+                    else if (!strcmp(V.ctype, "unsigned int")) ((unsigned int *)tmp.data())[i] = (unsigned int)V.default_value;
+                    else ((int *)tmp.data())[i] = (int)V.default_value;
+                }
+            }
+            CU(cudaMemcpyAsync(dst, tmp.data(), tmp.size(), cudaMemcpyHostToDevice, s->stream));
+            CU(cudaStreamSynchronize(s->stream));
+        }
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    A.h_state_count[state] = offset + count;
+    s->touch(list);
+    invalidate_graph(s);
+    return FGPU_OK;
+}
+
+extern "C" int fgpu_sim_set_agents(fgpu_sim *s, int agent, int state, int count, const void *const *columns) {
+    if (!s) return set_err(FGPU_ERR_ARG, "null sim");
+    return upload_columns(s, agent, state, 0, count, columns);
+}
+
+extern "C" int fgpu_sim_add_agents(fgpu_sim *s, int agent, int state, int count, const void *const *columns) {
+    if (!s) return set_err(FGPU_ERR_ARG, "null sim");
+    if (agent < 0 || agent >= (int)s->agents.size()) return set_err(FGPU_ERR_ARG, "bad agent index %d", agent);
+    if (state < 0 || state >= s->agents[agent].d->nstates) return set_err(FGPU_ERR_ARG, "bad state index %d", state);
+    return upload_columns(s, agent, state, s->agents[agent].h_state_count[state], count, columns);
+}
+
+extern "C" int fgpu_sim_agent_count(fgpu_sim *s, int agent, int state) {
+    if (!s || agent < 0 || agent >= (int)s->agents.size()) return set_err(FGPU_ERR_ARG, "bad agent index");
+    AgentRT &A = s->agents[agent];
+    if (state < 0 || state >= A.d->nstates) return set_err(FGPU_ERR_ARG, "bad state index");
+    return A.h_state_count[state];
+}
+
+extern "C" int fgpu_sim_read_agent_var(fgpu_sim *s, int agent, int state, int var, void *dst, int count) {
+    if (!s || !dst || agent < 0 || agent >= (int)s->agents.size()) return set_err(FGPU_ERR_ARG, "bad argument");
+    AgentRT &A = s->agents[agent];
+    if (state < 0 || state >= A.d->nstates || var < 0 || var >= A.d->nvars) return set_err(FGPU_ERR_ARG, "bad index");
+    if (count < 0 || count > A.d->buffer_size) return set_err(FGPU_ERR_ARG, "bad count");
+    CU(cudaSetDevice(s->device));
+    const fgpu_var &V = A.d->vars[var];
+    CU(cudaMemcpyAsync(dst, A.state[state] + V.list_offset, (size_t)count * V.size, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FGPU_OK;
+}
+
+extern "C" void *fgpu_sim_device_agents(fgpu_sim *s, int agent, int state) {
+    if (!s || agent < 0 || agent >= (int)s->agents.size()) return nullptr;
+    AgentRT &A = s->agents[agent];
+    if (state < 0 || state >= A.d->nstates) return nullptr;
+    return A.state[state];
+}
+
+extern "C" int fgpu_sim_message_count(fgpu_sim *s, int message) {
+    if (!s || message < 0 || message >= (int)s->msgs.size()) return set_err(FGPU_ERR_ARG, "bad message index");
+    return s->msgs[message].h_count;
+}
+
+static int ensure_tmp(fgpu_sim *s, size_t n) {
+    if (s->unpack_tmp_n >= n) return FGPU_OK;
+    if (s->unpack_tmp) cudaFree(s->unpack_tmp);
+    s->unpack_tmp = nullptr;
+    s->unpack_tmp_n = 0;
+    CU(cudaMalloc(&s->unpack_tmp, n * sizeof(unsigned int)));
+    s->unpack_tmp_n = n;
+    return FGPU_OK;
+}
+
+extern "C" int fgpu_sim_read_message_var(fgpu_sim *s, int message, int var, void *dst, int count) {
+    if (!s || !dst || message < 0 || message >= (int)s->msgs.size()) return set_err(FGPU_ERR_ARG, "bad argument");
+    MsgRT &M = s->msgs[message];
+    if (var < 0 || var >= M.d->nvars || count < 0 || count > M.d->buffer_size) return set_err(FGPU_ERR_ARG, "bad index");
+    if (count == 0) return FGPU_OK;
+    CU(cudaSetDevice(s->device));
+    const fgpu_var &V = M.d->vars[var];
+    const uint4 *src = (M.d->partitioning == FGPU_PART_SPATIAL) ? M.sorted : M.unsorted;
+    int rc = ensure_tmp(s, (size_t)count);
+    if (rc) return rc;
+    const int words = V.size / 4;
+    std::vector<unsigned int> tmp((size_t)count);
+    for (int w = 0; w < words; ++w) {
+        k_unpack_words<<<(count + 255) / 256, 256, 0, s->stream>>>((const unsigned int *)src, M.d->rec_quads * 4, count,
+                                                                  (int)(V.list_offset / 4) + w, s->unpack_tmp);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(tmp.data(), s->unpack_tmp, (size_t)count * 4, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        if (words == 1) {
+            memcpy(dst, tmp.data(), (size_t)count * 4);
+        } else {
+            unsigned int *d = (unsigned int *)dst;
+            for (int i = 0; i < count; ++i) d[2 * (size_t)i + w] = tmp[i];
+        }
+    }
+    return FGPU_OK;
+}
+
+extern "C" int fgpu_sim_read_pbm(fgpu_sim *s, int message, int *start, int *count) {
+    if (!s || !start || !count || message < 0 || message >= (int)s->msgs.size()) return set_err(FGPU_ERR_ARG, "bad argument");
+    MsgRT &M = s->msgs[message];
+    if (M.d->partitioning != FGPU_PART_SPATIAL) return set_err(FGPU_ERR_ARG, "message %s is not spatially partitioned", M.d->name);
+    CU(cudaSetDevice(s->device));
+    const int cells = M.d->grid_size;
+    std::vector<unsigned int> h((size_t)cells + 1, 0u);
+    if (M.h_count > 0 && M.built) {
+        CU(cudaMemcpyAsync(h.data(), M.cell_start, sizeof(unsigned int) * ((size_t)cells + 1), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    for (int c = 0; c < cells; ++c) {
+        start[c] = (int)h[c];
+        count[c] = (int)(h[c + 1] - h[c]);
+    }
+    return FGPU_OK;
+}
+
+extern "C" int fgpu_sim_read_message_keys(fgpu_sim *s, int message, unsigned int *keys, int count) {
+    if (!s || !keys || message < 0 || message >= (int)s->msgs.size()) return set_err(FGPU_ERR_ARG, "bad argument");
+    MsgRT &M = s->msgs[message];
+    if (M.d->partitioning != FGPU_PART_SPATIAL || count < 0 || count > M.d->buffer_size) return set_err(FGPU_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(keys, M.keys_in, sizeof(unsigned int) * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FGPU_OK;
+}
+
+extern "C" int fgpu_sim_read_message_order(fgpu_sim *s, int message, unsigned int *order, int count) {
+    if (!s || !order || message < 0 || message >= (int)s->msgs.size()) return set_err(FGPU_ERR_ARG, "bad argument");
+    MsgRT &M = s->msgs[message];
+    if (M.d->partitioning != FGPU_PART_SPATIAL || count < 0 || count > M.d->buffer_size) return set_err(FGPU_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(order, M.vals[M.sorted_in], sizeof(unsigned int) * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FGPU_OK;
+}
+
+extern "C" int fgpu_sim_read_seeds(fgpu_sim *s, unsigned int *dst_xy, int count) {
+    if (!s || !dst_xy || count < 0 || count > s->model->buffer_size_max) return set_err(FGPU_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(dst_xy, s->seeds, sizeof(uint2) * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FGPU_OK;
+}
+
+extern "C" int fgpu_sim_rand48_constants(fgpu_sim *s, unsigned int *out) {
+    if (!s || !out) return set_err(FGPU_ERR_ARG, "bad argument");
+    out[0] = s->Ax;
+    out[1] = s->Ay;
+    out[2] = s->Cx;
+    out[3] = s->Cy;
+    return FGPU_OK;
+}
+
+extern "C" int fgpu_sim_set_constant(fgpu_sim *s, const char *name, const void *value) {
+    if (!s || !name || !value) return set_err(FGPU_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(s->device));
+    for (int i = 0; i < s->model->nconstants; ++i)
+        if (!strcmp(s->model->constants[i].name, name)) {
+            CU(cudaStreamSynchronize(s->stream));
+            s->model->constants[i].set(value);
+            CU(cudaDeviceSynchronize());
+            return FGPU_OK;
+        }
+    return set_err(FGPU_ERR_ARG, "unknown environment constant '%s'", name);
+}
+
+extern "C" int fgpu_sim_get_constant(fgpu_sim *s, const char *name, void *value) {
+    if (!s || !name || !value) return set_err(FGPU_ERR_ARG, "bad argument");
+    for (int i = 0; i < s->model->nconstants; ++i)
+        if (!strcmp(s->model->constants[i].name, name)) {
+            const fgpu_constant &c = s->model->constants[i];
+            memcpy(value, c.get(), (size_t)c.size * c.length);
+            return FGPU_OK;
+        }
+    return set_err(FGPU_ERR_ARG, "unknown environment constant '%s'", name);
+}
+
+/* ------------------------------------------------------------------------- */
+/* 0.xml reader -- character stream, same tag rules as io.xslt:336-583        */
+/* ------------------------------------------------------------------------- */
+namespace {
+struct XmlAgentBuf {
+    std::vector<std::vector<char>> cols; /* per variable, raw bytes */
+    int count = 0;
+};
+
+void store_value(const fgpu_var &V, const char *text, char *dst) {
+    if (V.is_float) {
+        if (V.size == 4) *(float *)dst = (float)atof(text);      /* fgpu_atof */
+        else *(double *)dst = strtod(text, nullptr);             /* fpgu_strtod */
+    } else if (V.size == 4) {
+        if (!strcmp(V.ctype, "unsigned int")) *(unsigned int *)dst = (unsigned int)strtoul(text, nullptr, 0);
+        else *(int *)dst = (int)strtol(text, nullptr, 0);        /* fpgu_strtol(.., 0) */
+    } else {
+        if (!strncmp(V.ctype, "unsigned", 8)) *(unsigned long long *)dst = strtoull(text, nullptr, 0);
+        else *(long long *)dst = strtoll(text, nullptr, 0);
+    }
+}
+
+void default_value(const fgpu_var &V, char *dst) {
+    if (V.is_float) {
+        if (V.size == 4) *(float *)dst = (float)V.default_value;
+        else *(double *)dst = V.default_value;
+    } else if (V.size == 4) {
+        if (!strcmp(V.ctype, "unsigned int")) *(unsigned int *)dst = (unsigned int)V.default_value;
+        else *(int *)dst = (int)V.default_value;
+    } else {
+        *(long long *)dst = (long long)V.default_value;
+    }
+}
+}  // namespace
+
+extern "C" int fgpu_sim_load_states(fgpu_sim *s, const char *xml_path) {
+    if (!s || !xml_path) return set_err(FGPU_ERR_ARG, "bad argument");
+    const fgpu_model *m = s->model;
+    CU(cudaSetDevice(s->device));
+    if (m->init_constants) m->init_constants(); /* initEnvVars(), io.xslt:254-255 */
+    FILE *file = fopen(xml_path, "r");
+    if (!file) return set_err(FGPU_ERR_IO, "Could not open input file %s", xml_path);
+
+    std::vector<XmlAgentBuf> bufs(m->nagents);
+    /* current values per agent type per variable, reset to defaults after each </xagent> */
+    std::vector<std::vector<std::vector<char>>> cur(m->nagents);
+    auto reset_cur = [&]() {
+        for (int a = 0; a < m->nagents; ++a) {
+            cur[a].resize(m->agents[a].nvars);
+            for (int v = 0; v < m->agents[a].nvars; ++v) {
+                cur[a][v].assign(8, 0);
+                default_value(m->agents[a].vars[v], cur[a][v].data());
+            }
+        }
+    };
+    reset_cur();
+    for (int a = 0; a < m->nagents; ++a) bufs[a].cols.resize(m->agents[a].nvars);
+
+    std::string buffer, agentname;
+    bool in_tag = false, in_comment = false, in_itno = false, in_env = false, in_xagent = false, in_name = false;
+    bool reading = true;
+    std::string open_var; /* the variable tag we are inside of, matched by bare name (io.xslt:458-459) */
+    int rc = FGPU_OK;
+    int ch;
+    while (reading && (ch = fgetc(file)) != EOF) {
+        const char c = (char)ch;
+        if (buffer.size() >= 10000) {
+            rc = set_err(FGPU_ERR_IO, "Error: XML Parsing failed Tag name or content too long (> 10000 characters)");
+            break;
+        }
+        if (in_comment) {
+            if (c == '-') buffer.push_back(c);
+            else if (c == '>' && buffer.size() >= 2) { in_comment = false; buffer.clear(); }
+            else buffer.clear();
+        } else if (c == '>') {
+            const std::string &tag = buffer;
+            if (tag == "/states") reading = false;
+            if (tag == "itno") in_itno = true;
+            if (tag == "/itno") in_itno = false;
+            if (tag == "environment") in_env = true;
+            if (tag == "/environment") in_env = false;
+            if (tag == "name") in_name = true;
+            if (tag == "/name") in_name = false;
+            if (tag == "xagent") in_xagent = true;
+            if (tag == "/xagent") {
+                int a = -1;
+                for (int k = 0; k < m->nagents; ++k)
+                    if (agentname == m->agents[k].name) a = k;
+                if (a < 0) {
+                    fprintf(stdout, "Warning: agent name undefined - '%s'\n", agentname.c_str());
+                } else {
+                    if (bufs[a].count >= m->agents[a].buffer_size) {
+                        rc = set_err(FGPU_ERR_OVERFLOW, "ERROR: MAX Buffer size (%i) for agent %s exceeded whilst reading data",
+                                     m->agents[a].buffer_size, m->agents[a].name);
+                        break;
+                    }
+                    for (int v = 0; v < m->agents[a].nvars; ++v) {
+                        const int sz = m->agents[a].vars[v].size;
+                        bufs[a].cols[v].insert(bufs[a].cols[v].end(), cur[a][v].data(), cur[a][v].data() + sz);
+                    }
+                    bufs[a].count++;
+                }
+                reset_cur();
+                in_xagent = false;
+            }
+            if (!tag.empty() && tag[0] == '/') {
+                if (open_var == tag.substr(1)) open_var.clear();
+            } else {
+                open_var = tag;
+            }
+            in_tag = false;
+            buffer.clear();
+        } else if (c == '<') {
+            in_tag = true;
+            if (in_itno) { /* parsed into a dead local by the reference (io.xslt:478) */ }
+            if (in_name) {
+                agentname = buffer;
+            } else if (in_xagent) {
+                /* every agent type that has a variable of this name receives the value */
+                for (int a = 0; a < m->nagents; ++a)
+                    for (int v = 0; v < m->agents[a].nvars; ++v)
+                        if (open_var == m->agents[a].vars[v].name) store_value(m->agents[a].vars[v], buffer.c_str(), cur[a][v].data());
+            } else if (in_env) {
+                for (int k = 0; k < m->nconstants; ++k)
+                    if (open_var == m->constants[k].name && m->constants[k].length == 1) {
+                        fgpu_var V;
+                        V.ctype = m->constants[k].ctype;
+                        V.size = m->constants[k].size;
+                        V.is_float = (!strcmp(V.ctype, "float") || !strcmp(V.ctype, "double"));
+                        char tmp[8];
+                        store_value(V, buffer.c_str(), tmp);
+                        m->constants[k].set(tmp);
+                    }
+            }
+            buffer.clear();
+        } else if (in_tag) {
+            if (buffer.size() == 2 && c == '-' && buffer[1] == '-' && buffer[0] == '!') {
+                in_comment = true;
+                buffer.clear();
+            }
+            buffer.push_back(c);
+        } else {
+            buffer.push_back(c);
+        }
+    }
+    fclose(file);
+    if (rc != FGPU_OK) return rc;
+    for (int a = 0; a < m->nagents; ++a) {
+        std::vector<const void *> cols(m->agents[a].nvars);
+        for (int v = 0; v < m->agents[a].nvars; ++v) cols[v] = bufs[a].cols[v].data();
+        /* other states start empty */
+        for (int st = 0; st < m->agents[a].nstates; ++st) s->agents[a].h_state_count[st] = 0;
+        rc = upload_columns(s, a, m->agents[a].initial_state, 0, bufs[a].count, bufs[a].count ? cols.data() : nullptr);
+        if (rc != FGPU_OK) return rc;
+    }
+    CU(cudaDeviceSynchronize());
+    return FGPU_OK;
+}
+
+/* ------------------------------------------------------------------------- */
+/* building blocks                                                            */
+/* ------------------------------------------------------------------------- */
+#define LAUNCH_CHECK()                                                                       \
+    do {                                                                                     \
+        s->launches++;                                                                       \
+        cudaError_t e_ = cudaGetLastError();                                                 \
+        if (e_ != cudaSuccess)                                                               \
+            return set_err(FGPU_ERR_CUDA, "%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+
+/* Stable compaction of the flagged agents of `src` into `dst` at dst_offset.
+ * With count_out != nullptr the survivor count is read back (blocking, like
+ * the two 4-byte D2H copies after every cub scan, e.g. simulation.xslt:1476). */
+static int compact(fgpu_sim *s, AgentRT &A, const char *src, char *dst, int dst_offset, int n, const int *flags,
+                   bool scatter, int *count_out) {
+    if (n <= 0) {
+        if (count_out) *count_out = 0;
+        return FGPU_OK;
+    }
+    const int nb = (n + COMPACT_THREADS - 1) / COMPACT_THREADS;
+    k_flag_blocksum<<<nb, COMPACT_THREADS, 0, s->stream>>>(flags, n, A.block_sums);
+    LAUNCH_CHECK();
+    k_scan_blocksums<<<1, 1024, 0, s->stream>>>(A.block_sums, nb, A.d_total);
+    LAUNCH_CHECK();
+    if (count_out) {
+        CU(cudaMemcpyAsync(count_out, A.d_total, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    if (scatter) {
+        k_compact_scatter<<<nb, COMPACT_THREADS, 0, s->stream>>>(src, dst, A.cols, flags, A.block_sums, dst_offset, n);
+        LAUNCH_CHECK();
+        s->touch(dst);
+    }
+    return FGPU_OK;
+}
+
+static int choose_digit_bits(int radix_bits, int max_bits, int *passes_out) {
+    const int passes = std::max(1, sort_passes(radix_bits, max_bits));
+    *passes_out = passes;
+    return (radix_bits + passes - 1) / passes; /* balanced digits */
+}
+
+/* Spatial message build for h_count messages (simulation.xslt:1831-1892). */
+static int build_spatial(fgpu_sim *s, MsgRT &M) {
+    const int n = M.h_count;
+    M.built = true;
+    if (n <= 0) return FGPU_OK;
+    int passes = 1;
+    const int max_bits = std::min(std::max(s->opt_radix_bits, 4), SORT_MAXBITS);
+    const int digit_bits = choose_digit_bits(M.d->radix_bits, max_bits, &passes);
+    if (passes > SORT_MAX_PASSES) return set_err(FGPU_ERR_MODEL, "partition grid of %s needs %d radix passes", M.d->name, passes);
+    const int tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    unsigned int *hist = M.scratch;
+    unsigned int *tickets = M.scratch + SORT_MAX_PASSES * SORT_BINS;
+    unsigned int *gap_count = tickets + 4;
+    unsigned int *status = M.scratch + SORT_MAX_PASSES * SORT_BINS + 8;
+    const size_t zero_bytes = sizeof(unsigned int) * ((size_t)SORT_MAX_PASSES * SORT_BINS + 8 + (size_t)passes * tiles * SORT_BINS);
+
+    s->prof_begin(std::string("sort:") + M.d->name);
+    CU(cudaMemsetAsync(M.scratch, 0, zero_bytes, s->stream));
+    {
+        const int blocks = std::min((n + 255) / 256, 148 * 8);
+        k_radix_hist<<<blocks, 256, 0, s->stream>>>(M.keys_in, n, hist, passes, digit_bits);
+        LAUNCH_CHECK();
+    }
+    for (int p = 0; p < passes; ++p) {
+        const unsigned int *kin = p == 0 ? M.keys_in : M.keys[(p - 1) & 1];
+        const unsigned int *vin = p == 0 ? nullptr : M.vals[(p - 1) & 1];
+        k_radix_pass<<<tiles, SORT_THREADS, 0, s->stream>>>(kin, vin, M.keys[p & 1], M.vals[p & 1], n, p * digit_bits,
+                                                            digit_bits, hist + p * SORT_BINS,
+                                                            status + (size_t)p * tiles * SORT_BINS, tickets + p);
+        LAUNCH_CHECK();
+    }
+    s->prof_end();
+    const int in = (passes - 1) & 1;
+    M.sorted_in = in;
+    s->prof_begin(std::string("pbm:") + M.d->name);
+    const int g = (n + 255) / 256;
+    switch (M.d->rec_quads) {
+#define GATHER_CASE(Q)                                                                                                   \
+    case Q:                                                                                                              \
+        k_gather_pbm<Q><<<g, 256, 0, s->stream>>>(M.keys[in], M.vals[in], M.unsorted, M.sorted, n, M.cell_start,          \
+                                                  (unsigned int)M.d->grid_size, M.gap_queue, gap_count);                 \
+        break;
+        GATHER_CASE(1)
+        GATHER_CASE(2)
+        GATHER_CASE(3)
+        GATHER_CASE(4)
+        GATHER_CASE(5)
+        GATHER_CASE(6)
+        GATHER_CASE(7)
+        GATHER_CASE(8)
+#undef GATHER_CASE
+        default:
+            return set_err(FGPU_ERR_MODEL, "message %s: record of %d quads is not supported", M.d->name, M.d->rec_quads);
+    }
+    LAUNCH_CHECK();
+    k_fill_gaps<<<148, 256, 0, s->stream>>>(M.cell_start, M.gap_queue, gap_count);
+    LAUNCH_CHECK();
+    s->prof_end();
+    return FGPU_OK;
+}
+
+/* ------------------------------------------------------------------------- */
+/* one agent function: <Agent>_<func>(stream), simulation.xslt:1402-1974      */
+/* ------------------------------------------------------------------------- */
+static int run_function(fgpu_sim *s, int fi) {
+    const fgpu_model *m = s->model;
+    const fgpu_function &F = m->functions[fi];
+    AgentRT &A = s->agents[F.agent];
+    const int cur = F.current_state, nxt = F.next_state;
+
+    if (A.h_state_count[cur] == 0) return FGPU_OK; /* sim:1417-1420 */
+    const int state_list_size = A.h_state_count[cur];
+
+    if (F.xagent_output >= 0) {
+        /* reset_<B>_scan_input(d_<B>s_new), sim:1427-1435 */
+        AgentRT &B = s->agents[F.xagent_output];
+        const int nz = std::min(state_list_size, B.d->buffer_size);
+        CU(cudaMemsetAsync(B.newl + B.d->scan_offset, 0, sizeof(int) * (size_t)nz, s->stream));
+    }
+
+    if (F.condition == FGPU_COND_FUNCTION) {
+        /* sim:1439-1528 */
+        A.h_count = A.h_state_count[cur];
+        fgpu_filter fa;
+        fa.current = A.state[cur];
+        fa.working = A.work;
+        fa.n = A.h_count;
+        fa.flags_current = (int *)(A.state[cur] + A.d->scan_offset);
+        fa.flags_working = (int *)(A.work + A.d->scan_offset);
+        s->prof_begin(std::string("cond:") + F.name);
+        F.filter(&fa, s->stream);
+        LAUNCH_CHECK();
+        int kept = 0, working = 0;
+        int rc = compact(s, A, A.state[cur], A.swap, 0, A.h_count, (const int *)(A.state[cur] + A.d->scan_offset), true, &kept);
+        if (rc) return rc;
+        A.h_state_count[cur] = kept;
+        std::swap(A.state[cur], A.swap);
+        rc = compact(s, A, A.work, A.swap, 0, A.h_count, (const int *)(A.work + A.d->scan_offset), true, &working);
+        if (rc) return rc;
+        A.h_count = working;
+        std::swap(A.work, A.swap);
+        s->prof_end();
+        if (A.h_count == 0) return FGPU_OK;
+    } else if (F.condition == FGPU_COND_GLOBAL) {
+        /* sim:1530-1588 */
+        A.h_count = A.h_state_count[cur];
+        fgpu_filter fa;
+        fa.current = A.state[cur];
+        fa.working = nullptr;
+        fa.n = A.h_count;
+        fa.flags_current = (int *)(A.state[cur] + A.d->scan_offset);
+        fa.flags_working = nullptr;
+        F.filter(&fa, s->stream);
+        LAUNCH_CHECK();
+        int ntrue = 0;
+        int rc = compact(s, A, nullptr, nullptr, 0, A.h_count, (const int *)(A.state[cur] + A.d->scan_offset), false, &ntrue);
+        if (rc) return rc;
+        const bool mismatch = F.gc_must_evaluate_to ? (ntrue != A.h_count) : (ntrue == A.h_count);
+        if (mismatch && s->gc_count[fi] < F.gc_max_iterations) {
+            s->gc_count[fi]++;
+            return FGPU_OK;
+        }
+        if (s->gc_count[fi] == F.gc_max_iterations)
+            printf("Global agent condition for %s function reached the maximum number of %d conditions\n", F.name,
+                   F.gc_max_iterations);
+        s->gc_count[fi] = 0;
+        std::swap(A.work, A.state[cur]);
+        A.h_state_count[cur] = 0;
+    } else {
+        /* sim:1590-1601: currentState maps to working list */
+        std::swap(A.work, A.state[cur]);
+        A.h_count = A.h_state_count[cur];
+        A.h_state_count[cur] = 0;
+    }
+
+    MsgRT *Mout = F.output_message >= 0 ? &s->msgs[F.output_message] : nullptr;
+    MsgRT *Min = F.input_message >= 0 ? &s->msgs[F.input_message] : nullptr;
+    if (Mout && Mout->h_count + A.h_count > Mout->d->buffer_size) /* sim:1607-1613 */
+        return set_err(FGPU_ERR_OVERFLOW, "Error: Buffer size of %s message will be exceeded in function %s", Mout->d->name, F.name);
+    if (Mout && F.output_type != FGPU_OUT_SINGLE)
+        return set_err(FGPU_ERR_MODEL, "function %s: optional_message output is not implemented yet", F.name);
+
+    fgpu_launch L;
+    memset(&L, 0, sizeof(L));
+    L.agents = A.work;
+    L.n = A.h_count;
+    L.order = nullptr;
+    if (F.xagent_output >= 0) L.new_agents = s->agents[F.xagent_output].newl;
+    if (Min) {
+        L.in_recs = (Min->d->partitioning == FGPU_PART_SPATIAL) ? (const void *)Min->sorted : (const void *)Min->unsorted;
+        L.in_cell_start = Min->cell_start;
+        L.in_count = Min->h_count;
+        /* cell-coherent processing order: only when this very list produced the
+         * messages (message k <-> list index k) and has not been restructured since */
+        if (s->opt_order && Min->d->partitioning == FGPU_PART_SPATIAL && Min->producers == 1 &&
+            Min->producer_buf == A.work && Min->producer_epoch == s->epoch_of(A.work) && Min->h_count == A.h_count &&
+            Min->built)
+            L.order = Min->vals[Min->sorted_in];
+    }
+    if (Mout) {
+        L.out_recs = Mout->unsorted;
+        L.out_keys = Mout->keys_in;
+        L.out_base = Mout->h_count; /* a second producer appends; the whole list is re-binned (sim:1836-1837) */
+    }
+    if (F.rng) {
+        L.seeds = s->seeds;
+        L.Ax = s->Ax;
+        L.Ay = s->Ay;
+        L.Cx = s->Cx;
+        L.Cy = s->Cy;
+    }
+    s->prof_begin(std::string("func:") + F.name);
+    F.launch(&L, s->stream);
+    LAUNCH_CHECK();
+    s->prof_end();
+
+    if (Mout) {
+        /* sim:1734-1754 */
+        if (Mout->h_count == 0) {
+            Mout->producers = 1;
+            Mout->producer_buf = A.work;
+            Mout->producer_epoch = s->epoch_of(A.work);
+        } else {
+            Mout->producers++;
+        }
+        Mout->h_count += A.h_count;
+    }
+
+    const int pre_death_count = A.h_count;
+    if (F.reallocate) {
+        /* sim:1763-1792 */
+        s->prof_begin(std::string("death:") + F.name);
+        int alive = 0;
+        int rc = compact(s, A, A.work, A.swap, 0, A.h_count, (const int *)(A.work + A.d->scan_offset), true, &alive);
+        if (rc) return rc;
+        std::swap(A.work, A.swap);
+        A.h_count = alive;
+        s->prof_end();
+    }
+    if (F.xagent_output >= 0) {
+        /* sim:1794-1829 */
+        AgentRT &B = s->agents[F.xagent_output];
+        const int st = F.xagent_output_state;
+        s->prof_begin(std::string("birth:") + F.name);
+        int born = 0;
+        int rc = compact(s, B, nullptr, nullptr, 0, pre_death_count, (const int *)(B.newl + B.d->scan_offset), false, &born);
+        if (rc) return rc;
+        if (B.h_state_count[st] + born > B.d->buffer_size)
+            return set_err(FGPU_ERR_OVERFLOW, "Error: Buffer size of %s agents in state %s will be exceeded writing new agents in function %s",
+                           B.d->name, B.d->states[st], F.name);
+        const int nb = (pre_death_count + COMPACT_THREADS - 1) / COMPACT_THREADS;
+        k_compact_scatter<<<nb, COMPACT_THREADS, 0, s->stream>>>(B.newl, B.state[st], B.cols,
+                                                                 (const int *)(B.newl + B.d->scan_offset), B.block_sums,
+                                                                 B.h_state_count[st], pre_death_count);
+        LAUNCH_CHECK();
+        s->touch(B.state[st]);
+        B.h_state_count[st] += born;
+        s->prof_end();
+    }
+    if (Mout && Mout->d->partitioning == FGPU_PART_SPATIAL) {
+        int rc = build_spatial(s, *Mout);
+        if (rc) return rc;
+    }
+    /* move agents to next state, sim:1936-1972 */
+    if (A.h_state_count[nxt] + A.h_count > A.d->buffer_size)
+        return set_err(FGPU_ERR_OVERFLOW, "Error: Buffer size of %s agents in state %s will be exceeded moving working agents to next state in function %s",
+                       F.name, A.d->states[nxt], F.name);
+    if (F.swappable) {
+        std::swap(A.work, A.state[cur]);
+    } else if (A.h_count > 0) {
+        s->prof_begin(std::string("append:") + F.name);
+        k_append<<<(A.h_count + 255) / 256, 256, 0, s->stream>>>(A.work, A.state[nxt], A.cols, A.h_state_count[nxt], A.h_count);
+        LAUNCH_CHECK();
+        s->touch(A.state[nxt]);
+        s->prof_end();
+    }
+    A.h_state_count[nxt] += A.h_count;
+    return FGPU_OK;
+}
+
+static int begin_iteration(fgpu_sim *s) {
+    s->iteration++;
+    for (MsgRT &M : s->msgs) { /* sim:888-892 */
+        M.h_count = 0;
+        M.producers = 0;
+        M.producer_buf = nullptr;
+        M.built = false;
+    }
+    return FGPU_OK;
+}
+
+static int single_iteration(fgpu_sim *s) {
+    const fgpu_model *m = s->model;
+    begin_iteration(s);
+    for (int l = 0; l < m->nlayers; ++l)
+        for (int k = 0; k < m->layers[l].nfunctions; ++k) {
+            int rc = run_function(s, m->layers[l].functions[k]);
+            if (rc) return rc;
+        }
+    if (!s->capturing)
+        for (int k = 0; k < m->nstep_functions; ++k) {
+            CU(cudaStreamSynchronize(s->stream));
+            m->step_functions[k]();
+        }
+    return FGPU_OK;
+}
+
+static std::vector<int> current_counts(fgpu_sim *s) {
+    std::vector<int> c;
+    for (AgentRT &A : s->agents)
+        for (int v : A.h_state_count) c.push_back(v);
+    c.push_back(s->opt_order);
+    c.push_back(s->opt_radix_bits);
+    return c;
+}
+
+static int step_async(fgpu_sim *s, int n) {
+    if (n <= 0) return FGPU_OK;
+    CU(cudaSetDevice(s->device));
+    const bool use_graph = s->is_static && s->opt_graph && !s->profiling;
+    CU(cudaEventRecord(s->ev0, s->stream));
+    if (use_graph) {
+        if (!s->graph || s->graph_counts != current_counts(s)) {
+            invalidate_graph(s);
+            cudaGraph_t g = nullptr;
+            const long long before = s->launches;
+            const unsigned int it = s->iteration;
+            CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+            s->capturing = true;
+            int rc = single_iteration(s);
+            s->capturing = false;
+            cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+            s->iteration = it;
+            s->graph_launches = s->launches - before;
+            s->launches = before;
+            if (rc) {
+                if (g) cudaGraphDestroy(g);
+                return rc;
+            }
+            if (e != cudaSuccess) return set_err(FGPU_ERR_CUDA, "cudaStreamEndCapture -> %s", cudaGetErrorString(e));
+            CU(cudaGraphInstantiate(&s->graph, g, 0));
+            CU(cudaGraphDestroy(g));
+            s->graph_counts = current_counts(s);
+            /* the event recorded before the capture is still valid */
+        }
+        for (int i = 0; i < n; ++i) {
+            CU(cudaGraphLaunch(s->graph, s->stream));
+            s->launches += s->graph_launches;
+        }
+        /* host-side bookkeeping of one iteration is idempotent for static models */
+        s->iteration += (unsigned int)n;
+    } else {
+        for (int i = 0; i < n; ++i) {
+            int rc = single_iteration(s);
+            if (rc) return rc;
+        }
+    }
+    CU(cudaEventRecord(s->ev1, s->stream));
+    return FGPU_OK;
+}
+
+extern "C" int fgpu_sim_step_async(fgpu_sim *s, int n) {
+    if (!s) return set_err(FGPU_ERR_ARG, "null sim");
+    return step_async(s, n);
+}
+
+extern "C" int fgpu_sim_sync(fgpu_sim *s) {
+    if (!s) return set_err(FGPU_ERR_ARG, "null sim");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    return FGPU_OK;
+}
+
+extern "C" int fgpu_sim_step(fgpu_sim *s, int n) {
+    if (!s) return set_err(FGPU_ERR_ARG, "null sim");
+    int rc = step_async(s, n);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    if (n > 0) CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+    return FGPU_OK;
+}
+
+extern "C" int fgpu_sim_begin_iteration(fgpu_sim *s) {
+    if (!s) return set_err(FGPU_ERR_ARG, "null sim");
+    return begin_iteration(s);
+}
+
+extern "C" int fgpu_sim_run_function(fgpu_sim *s, int function) {
+    if (!s || function < 0 || function >= s->model->nfunctions) return set_err(FGPU_ERR_ARG, "bad function index");
+    CU(cudaSetDevice(s->device));
+    int rc = run_function(s, function);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    return FGPU_OK;
+}
+
+extern "C" unsigned int fgpu_sim_iteration(const fgpu_sim *s) { return s ? s->iteration : 0u; }
+extern "C" long long fgpu_sim_launch_count(const fgpu_sim *s) { return s ? s->launches : 0; }
+extern "C" float fgpu_sim_last_step_ms(const fgpu_sim *s) { return s ? s->last_ms : 0.f; }
+
+extern "C" int fgpu_sim_run_init_functions(fgpu_sim *s) {
+    if (!s) return set_err(FGPU_ERR_ARG, "null sim");
+    CU(cudaSetDevice(s->device));
+    for (int k = 0; k < s->model->ninit_functions; ++k) s->model->init_functions[k]();
+    CU(cudaDeviceSynchronize());
+    return FGPU_OK;
+}
+
+extern "C" int fgpu_sim_run_exit_functions(fgpu_sim *s) {
+    if (!s) return set_err(FGPU_ERR_ARG, "null sim");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    for (int k = 0; k < s->model->nexit_functions; ++k) s->model->exit_functions[k]();
+    return FGPU_OK;
+}
+
+extern "C" int fgpu_sim_set_option(fgpu_sim *s, const char *key, int value) {
+    if (!s || !key) return set_err(FGPU_ERR_ARG, "bad argument");
+    if (!strcmp(key, "order")) s->opt_order = value ? 1 : 0;
+    else if (!strcmp(key, "graph")) s->opt_graph = value ? 1 : 0;
+    else if (!strcmp(key, "radix_bits")) {
+        if (value < 4 || value > SORT_MAXBITS) return set_err(FGPU_ERR_ARG, "radix_bits must be in [4,%d]", SORT_MAXBITS);
+        s->opt_radix_bits = value;
+    } else
+        return set_err(FGPU_ERR_ARG, "unknown option '%s'", key);
+    invalidate_graph(s);
+    return FGPU_OK;
+}
+
+/* One iteration in stream mode with a cudaEvent pair around every stage
+ * (INSTRUMENT_AGENT_FUNCTIONS, simulation.xslt:898-914, at stage granularity). */
+extern "C" int fgpu_sim_profile_iteration(fgpu_sim *s, const char **names, float *ms, int cap) {
+    if (!s) return set_err(FGPU_ERR_ARG, "null sim");
+    CU(cudaSetDevice(s->device));
+    for (ProfEntry &e : s->prof) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    s->prof.clear();
+    s->profiling = true;
+    int rc = single_iteration(s);
+    s->profiling = false;
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(s->stream));
+    s->prof_names.clear();
+    s->prof_ms.clear();
+    for (ProfEntry &e : s->prof) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e.a, e.b);
+        s->prof_names.push_back(e.name);
+        s->prof_ms.push_back(t);
+    }
+    const int n = std::min(cap, (int)s->prof_names.size());
+    for (int i = 0; i < n; ++i) {
+        if (names) names[i] = s->prof_names[i].c_str();
+        if (ms) ms[i] = s->prof_ms[i];
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------------------- */
+/* kernel-level entry points used by the parity tests                         */
+/* ------------------------------------------------------------------------- */
+extern "C" int fgpu_debug_sort_pairs(const unsigned int *keys, int n, int key_bits, int max_digit_bits,
+                                     unsigned int *keys_out, unsigned int *vals_out) {
+    if (n < 0 || key_bits < 1 || key_bits > 32) return set_err(FGPU_ERR_ARG, "bad argument");
+    if (n == 0) return FGPU_OK;
+    int passes = 1;
+    const int max_bits = std::min(std::max(max_digit_bits, 1), SORT_MAXBITS);
+    const int digit_bits = choose_digit_bits(key_bits, max_bits, &passes);
+    if (passes > SORT_MAX_PASSES) return set_err(FGPU_ERR_ARG, "too many passes");
+    unsigned int *k[2], *v[2], *scratch;
+    const int tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    const size_t sb = sizeof(unsigned int) * ((size_t)SORT_MAX_PASSES * SORT_BINS + 8 + (size_t)passes * tiles * SORT_BINS);
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaMalloc(&k[i], sizeof(unsigned int) * (size_t)n));
+        CU(cudaMalloc(&v[i], sizeof(unsigned int) * (size_t)n));
+    }
+    CU(cudaMalloc(&scratch, sb));
+    CU(cudaMemcpy(k[0], keys, sizeof(unsigned int) * (size_t)n, cudaMemcpyHostToDevice));
+    CU(cudaMemset(scratch, 0, sb));
+    unsigned int *hist = scratch, *tickets = scratch + SORT_MAX_PASSES * SORT_BINS, *status = scratch + SORT_MAX_PASSES * SORT_BINS + 8;
+    k_radix_hist<<<std::min((n + 255) / 256, 148 * 8), 256>>>(k[0], n, hist, passes, digit_bits);
+    int in = 0;
+    for (int p = 0; p < passes; ++p) {
+        k_radix_pass<<<tiles, SORT_THREADS>>>(k[in], p == 0 ? nullptr : v[in], k[in ^ 1], v[in ^ 1], n, p * digit_bits,
+                                              digit_bits, hist + p * SORT_BINS, status + (size_t)p * tiles * SORT_BINS, tickets + p);
+        in ^= 1;
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(keys_out, k[in], sizeof(unsigned int) * (size_t)n, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(vals_out, v[in], sizeof(unsigned int) * (size_t)n, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(k[i]);
+        cudaFree(v[i]);
+    }
+    cudaFree(scratch);
+    return FGPU_OK;
+}
+
+/* flags -> (positions of survivors, count); columns = one 4-byte payload column */
+extern "C" int fgpu_debug_compact(const int *flags, const unsigned int *payload, int n, unsigned int *out, int *count_out) {
+    if (n < 0 || !count_out) return set_err(FGPU_ERR_ARG, "bad argument");
+    *count_out = 0;
+    if (n == 0) return FGPU_OK;
+    int *d_flags, *d_total;
+    unsigned int *d_in, *d_out, *d_bs;
+    const int nb = (n + COMPACT_THREADS - 1) / COMPACT_THREADS;
+    CU(cudaMalloc(&d_flags, sizeof(int) * (size_t)n));
+    CU(cudaMalloc(&d_in, sizeof(unsigned int) * (size_t)n));
+    CU(cudaMalloc(&d_out, sizeof(unsigned int) * (size_t)n));
+    CU(cudaMalloc(&d_bs, sizeof(unsigned int) * (size_t)(nb + 1)));
+    CU(cudaMalloc(&d_total, sizeof(int)));
+    CU(cudaMemcpy(d_flags, flags, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_in, payload, sizeof(unsigned int) * (size_t)n, cudaMemcpyHostToDevice));
+    ColSet cols;
+    cols.ncols = 1;
+    cols.size[0] = 4;
+    cols.off[0] = 0;
+    k_flag_blocksum<<<nb, COMPACT_THREADS>>>(d_flags, n, d_bs);
+    k_scan_blocksums<<<1, 1024>>>(d_bs, nb, d_total);
+    k_compact_scatter<<<nb, COMPACT_THREADS>>>((const char *)d_in, (char *)d_out, cols, d_flags, d_bs, 0, n);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(count_out, d_total, sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out, d_out, sizeof(unsigned int) * (size_t)(*count_out), cudaMemcpyDeviceToHost));
+    cudaFree(d_flags);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    cudaFree(d_bs);
+    cudaFree(d_total);
+    return FGPU_OK;
+}

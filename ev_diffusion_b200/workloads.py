@@ -1,0 +1,122 @@
+"""Synthetic workloads of BASELINE.md / SURVEY.md 8(d): model variants (XML-only
+scaling of the authored models) and their seeded initial states.
+
+Initial positions come from splitmix64 (top 24 bits / 2^24), as specified for
+config C2: ``positions = extent * u``, seed 42 for C2, 46 for C2-16M.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Dict, Tuple
+
+import numpy as np
+
+from . import build
+
+MASK64 = (1 << 64) - 1
+
+
+def splitmix64(seed: int, n: int) -> np.ndarray:
+    """n outputs of splitmix64 started at `seed` (vectorised: the state is seed + (i+1)*gamma)."""
+    gamma = np.uint64(0x9E3779B97F4A7C15)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed & MASK64) + gamma * (np.arange(n, dtype=np.uint64) + np.uint64(1))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return z
+
+
+def uniform24(seed: int, n: int) -> np.ndarray:
+    """float32 uniforms in [0,1) with 24-bit resolution (exact in binary32)."""
+    return ((splitmix64(seed, n) >> np.uint64(40)).astype(np.float32) / np.float32(16777216.0)).astype(np.float32)
+
+
+@dataclass
+class BrownianConfig:
+    name: str
+    n: int
+    dims: Tuple[int, int, int]
+    seed: int
+    sigma: float = 0.25
+
+    @property
+    def cells(self) -> int:
+        return self.dims[0] * self.dims[1] * self.dims[2]
+
+
+BROWNIAN = {
+    # BASELINE config C2: 1M agents, 64^3 cells, 4 agents / cell
+    "c2": BrownianConfig("Brownian", 1 << 20, (64, 64, 64), 42),
+    # north-star target: 16M agents, 128 x 128 x 256 cells
+    "c2_16m": BrownianConfig("Brownian_16M", 1 << 24, (128, 128, 256), 46),
+    # small parity case (the oracle finishes in well under a second)
+    "c2_small": BrownianConfig("Brownian_small", 1 << 14, (16, 16, 16), 7),
+    # tiny ragged case: count < bufferSize, few agents per tile, some empty cells
+    "c2_tiny": BrownianConfig("Brownian_tiny", 4096, (16, 16, 16), 11),
+}
+
+BROWNIAN_XML = os.path.join(build.MODELS, "Brownian", "src", "model", "XMLModelFile.xml")
+
+
+def brownian_xml(cfg: BrownianConfig) -> str:
+    """XML-only scaling of models/Brownian: bufferSize, bounds, DOMAIN_* (functions.c untouched)."""
+    if cfg.name == "Brownian":
+        return BROWNIAN_XML
+    dx, dy, dz = cfg.dims
+    rep = {
+        "<gpu:bufferSize>1048576</gpu:bufferSize>": f"<gpu:bufferSize>{cfg.n}</gpu:bufferSize>",
+        "<gpu:xmax>64</gpu:xmax>": f"<gpu:xmax>{dx}</gpu:xmax>",
+        "<gpu:ymax>64</gpu:ymax>": f"<gpu:ymax>{dy}</gpu:ymax>",
+        "<gpu:zmax>64</gpu:zmax>": f"<gpu:zmax>{dz}</gpu:zmax>",
+        "<name>DOMAIN_X</name>\n        <defaultValue>64.0</defaultValue>": f"<name>DOMAIN_X</name>\n        <defaultValue>{dx}.0</defaultValue>",
+        "<name>DOMAIN_Y</name>\n        <defaultValue>64.0</defaultValue>": f"<name>DOMAIN_Y</name>\n        <defaultValue>{dy}.0</defaultValue>",
+        "<name>DOMAIN_Z</name>\n        <defaultValue>64.0</defaultValue>": f"<name>DOMAIN_Z</name>\n        <defaultValue>{dz}.0</defaultValue>",
+        "<name>Brownian</name>": f"<name>{cfg.name}</name>",
+    }
+    dst = os.path.join(build.GEN, cfg.name, "src", "model", "XMLModelFile.xml")
+    build.write_scaled_xml(BROWNIAN_XML, dst, rep)
+    # the scripts are shared, not copied: the build is pointed at the original functions.c
+    return dst
+
+
+def brownian_function_files():
+    return [os.path.join(build.MODELS, "Brownian", "src", "model", "functions.c")]
+
+
+def brownian_state(cfg: BrownianConfig, count: int = None) -> Dict[str, np.ndarray]:
+    n = cfg.n if count is None else count
+    u = uniform24(cfg.seed, 3 * n)
+    ext = np.array(cfg.dims, dtype=np.float32)
+    return {
+        "id": np.arange(n, dtype=np.int32),
+        "x": (u[0::3] * ext[0]).astype(np.float32),
+        "y": (u[1::3] * ext[1]).astype(np.float32),
+        "z": (u[2::3] * ext[2]).astype(np.float32),
+        "nbr": np.zeros(n, dtype=np.int32),
+    }
+
+
+def write_states_xml(path: str, agent_name: str, columns: Dict[str, np.ndarray], env: Dict[str, float] = None) -> str:
+    """0.xml in the reference's layout (io.xslt:124-200) with round-trippable `%.9g` floats."""
+    names = list(columns.keys())
+    n = len(columns[names[0]])
+    with open(path, "w") as fh:
+        fh.write("<states>\n<itno>0</itno>\n")
+        if env:
+            fh.write("<environment>\n")
+            for k, v in env.items():
+                fh.write(f"<{k}>{v!r}</{k}>\n")
+            fh.write("</environment>\n")
+        for i in range(n):
+            fh.write(f"<xagent>\n<name>{agent_name}</name>\n")
+            for k in names:
+                v = columns[k][i]
+                if np.issubdtype(columns[k].dtype, np.floating):
+                    fh.write(f"<{k}>{float(v):.9g}</{k}>\n")
+                else:
+                    fh.write(f"<{k}>{int(v)}</{k}>\n")
+            fh.write("</xagent>\n")
+        fh.write("</states>\n")
+    return path

@@ -1,0 +1,145 @@
+/*
+ * fgpu.h -- C ABI of the B200-native FLAME GPU 1.5 simulation-step runtime
+ * (libfgpu_rt.so).
+ *
+ * The reference has no FFI: its seam is source level.  Each
+ * entry point below names the generated reference function it replaces
+ * (line numbers are lines of the .xslt templates under
+ * /root/reference/FLAMEGPU/templates/).  All functions return 0 on success
+ * and a negative code on failure (the reference prints and calls exit(),
+ * simulation.xslt:198-206); `fgpu_last_error()` returns the message.
+ *
+ * Threading: one fgpu_sim = one host thread + its CUDA stream.  Objects are
+ * independent; the core has no global state.
+ * Ownership: every pointer passed in is borrowed for the call.  Host buffers
+ * handed to read/write calls must hold `count` elements of the variable type.
+ */
+#ifndef FGPU_H
+#define FGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "fgpu_model.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fgpu_sim fgpu_sim;
+
+enum {
+    FGPU_OK = 0,
+    FGPU_ERR_ARG = -1,        /* bad index / null pointer */
+    FGPU_ERR_CUDA = -2,       /* a CUDA call failed (gpuErrchk, simulation.xslt:198) */
+    FGPU_ERR_OVERFLOW = -3,   /* a buffer-size guard fired (simulation.xslt:1609,1816,1940; io.xslt:406) */
+    FGPU_ERR_IO = -4,         /* file could not be read */
+    FGPU_ERR_MODEL = -5,      /* plugin missing / ABI mismatch */
+    FGPU_ERR_COMM = -6        /* slab exchange failed */
+};
+
+const char *fgpu_last_error(void);
+
+/* ---- model plugins ------------------------------------------------------ */
+/* dlopen()s a model plugin built from XMLModelFile.xml + functions.c and
+ * returns its descriptor (replaces the xsltproc + nvcc step, tools/common.mk:347-451). */
+const fgpu_model *fgpu_model_load(const char *plugin_path);
+
+/* ---- lifecycle ----------------------------------------------------------- */
+/* initialise() without the XML read: allocation, partition constants, rand48
+ * seeding (simulation.xslt:472-747).  `device` is the CUDA ordinal (main.xslt:311). */
+fgpu_sim *fgpu_sim_create(const fgpu_model *model, int device);
+/* cleanup() (simulation.xslt:779-876). */
+void fgpu_sim_destroy(fgpu_sim *sim);
+
+/* readInitialStates() (io.xslt:211-621): parse a 0.xml into the initial state
+ * lists, apply <environment> constants, upload. */
+int fgpu_sim_load_states(fgpu_sim *sim, const char *xml_path);
+
+/* Direct upload of one state list from host SoA columns (one pointer per
+ * agent variable, XML order; NULL = defaultValue).  Replaces the malloc +
+ * cudaMemcpy H2D of the whole list struct (simulation.xslt:568-581). */
+int fgpu_sim_set_agents(fgpu_sim *sim, int agent, int state, int count, const void *const *columns);
+
+/* Host-side mirror of h_add_agents_<A>_<S> (simulation.xslt:1275-1320): append. */
+int fgpu_sim_add_agents(fgpu_sim *sim, int agent, int state, int count, const void *const *columns);
+
+/* Init / step / exit functions of the model are run by fgpu_sim_run_init_functions
+ * (simulation.xslt:703-716) and inside fgpu_sim_step (simulation.xslt:933-946). */
+int fgpu_sim_run_init_functions(fgpu_sim *sim);
+int fgpu_sim_run_exit_functions(fgpu_sim *sim);
+
+/* ---- stepping ------------------------------------------------------------ */
+/* n x singleIteration() (simulation.xslt:878-975).  Models whose functions have
+ * no condition / death / birth run as a captured CUDA graph with no host
+ * round trips; the call returns after the work is enqueued AND complete. */
+int fgpu_sim_step(fgpu_sim *sim, int n);
+/* Same, but returns as soon as the work is enqueued on the simulation stream. */
+int fgpu_sim_step_async(fgpu_sim *sim, int n);
+int fgpu_sim_sync(fgpu_sim *sim);
+
+/* Fine-grained stepping used by parity tests: the prologue of singleIteration
+ * (message counts := 0, simulation.xslt:885-892) and one <A>_<f>(stream)
+ * wrapper (simulation.xslt:1402-1974). */
+int fgpu_sim_begin_iteration(fgpu_sim *sim);
+int fgpu_sim_run_function(fgpu_sim *sim, int function);
+unsigned int fgpu_sim_iteration(const fgpu_sim *sim);      /* getIterationNumber() */
+
+/* ---- queries (get_agent_<A>_<S>_count etc., header.xslt:588-645) --------- */
+int fgpu_sim_agent_count(fgpu_sim *sim, int agent, int state);
+/* Copies variable `var` of the first `count` agents of a state list to `dst`. */
+int fgpu_sim_read_agent_var(fgpu_sim *sim, int agent, int state, int var, void *dst, int count);
+/* get_device_<A>_<S>_agents(): borrowed device pointer to a list in the
+ * reference's xmachine_memory_<A>_list layout; invalidated by the next step. */
+void *fgpu_sim_device_agents(fgpu_sim *sim, int agent, int state);
+
+int fgpu_sim_message_count(fgpu_sim *sim, int message);
+/* Sorted message list, variable `var`, unpacked to a dense host array. */
+int fgpu_sim_read_message_var(fgpu_sim *sim, int message, int var, void *dst, int count);
+/* Partition boundary matrix in normalised form: for each cell,
+ * count[c] and start[c] (start is only meaningful where count > 0). */
+int fgpu_sim_read_pbm(fgpu_sim *sim, int message, int *start, int *count);
+/* Cell key of each *unsorted* message (message_<M>_hash, kernals.xslt:877-889)
+ * and the sorted permutation (value array of the radix sort, sim:1867). */
+int fgpu_sim_read_message_keys(fgpu_sim *sim, int message, unsigned int *keys, int count);
+int fgpu_sim_read_message_order(fgpu_sim *sim, int message, unsigned int *order, int count);
+/* rand48 seeds, 2 x uint32 per slot (simulation.xslt:681-686). */
+int fgpu_sim_read_seeds(fgpu_sim *sim, unsigned int *dst_xy, int count);
+int fgpu_sim_rand48_constants(fgpu_sim *sim, unsigned int *AxAyCxCy);
+
+/* set_<constant>() by name (header.xslt:771). */
+int fgpu_sim_set_constant(fgpu_sim *sim, const char *name, const void *value);
+int fgpu_sim_get_constant(fgpu_sim *sim, const char *name, void *value);
+
+/* ---- instrumentation (INSTRUMENT_ITERATIONS, simulation.xslt:370-377) ---- */
+/* Kernel launches issued by the simulation stream since creation. */
+long long fgpu_sim_launch_count(const fgpu_sim *sim);
+/* Device milliseconds of the last fgpu_sim_step call (cudaEvent pair on the
+ * simulation stream, like main.xslt:405-436). */
+float fgpu_sim_last_step_ms(const fgpu_sim *sim);
+/* Tuning knobs: "order" (0/1 cell-coherent processing of message consumers),
+ * "graph" (0/1 CUDA-graph replay), "radix_bits" (4..11), "stage" (0/1). */
+int fgpu_sim_set_option(fgpu_sim *sim, const char *key, int value);
+/* Per-kernel-class device time of the most recent profiled iteration.
+ * Writes up to `cap` (name,ms) pairs; returns the number written. */
+int fgpu_sim_profile_iteration(fgpu_sim *sim, const char **names, float *ms, int cap);
+
+/* ---- kernel-level entry points for the parity tests ---------------------- */
+/* The hand-written LSD radix sort (replaces cub::DeviceRadixSort::SortPairs,
+ * simulation.xslt:1867): sorts (keys[i], i) on the low `key_bits` bits with
+ * digits of at most `max_digit_bits` bits; host in, host out. */
+int fgpu_debug_sort_pairs(const unsigned int *keys, int n, int key_bits, int max_digit_bits,
+                          unsigned int *keys_out, unsigned int *vals_out);
+/* Stable compaction of payload[i] where flags[i] == 1 (scatter_<A>_Agents, kernals.xslt:239-257). */
+int fgpu_debug_compact(const int *flags, const unsigned int *payload, int n, unsigned int *out, int *count_out);
+
+/* ---- 1-D slab decomposition over the GPUs of one node ------ */
+/* `nccl_unique_id` is the 128-byte ncclUniqueId produced by rank 0 and
+ * broadcast by the host program (torch.distributed in bench.py).  The slab
+ * axis is the slowest hash axis (z; y for 2-D grids, kernals.xslt:888). */
+int fgpu_sim_slab_init(fgpu_sim *sim, int rank, int world, const void *nccl_unique_id);
+int fgpu_nccl_unique_id(void *out128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FGPU_H */
