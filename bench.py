@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/s of the FLAME GPU 1.5 simulation step (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2_16m] [--impl ours|reference]
+
+One "step" = one simulation iteration (singleIteration(), simulation.xslt:878-975) of
+the Brownian random-walk model over its whole population.  The default workload is
+BASELINE config C2 (1 048 576 float agents, 64^3 spatially partitioned cells,
+rand48, wall reflection).  Prints ONE JSON line (rank 0).
+
+ value      whole-job agent-steps/s, inputs resident in HBM, device time from CUDA
+            events on the simulation stream, max over ranks; every timed iteration
+            starts from a flushed L2 (a 256 MiB scratch buffer is rewritten between
+            iterations, outside the timed span)
+ e2e        the same metric through the public API with HOST buffers: per step the
+            population is uploaded from pinned host memory, one iteration runs, and
+            the resulting x,y,z,nbr columns are read back
+ roofline   dominant kernel, algorithmic bytes / CUDA-event time
+ cpu_baseline  the CPU oracle (host-C execution of the same functions.c, OpenMP) on a
+            bounded sample of the same workload
+ --impl reference  the reference has no CPU path and its CUDA cannot be generated or
+            compiled in this image (no xsltproc; texture references); the arm times
+            the host-C oracle on all host cores, as the task statement prescribes.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from ev_diffusion_b200 import build as B, workloads as W  # noqa: E402
+
+METRIC = "agent-steps/sec"
+FLUSH_BYTES = 256 << 20
+
+# algorithmic bytes per agent-step, SURVEY.md 8(d) row C2 (the rule is applied per function)
+B_ALG = {
+    "func:output_location": 32.0,   # 16 r (id,x,y,z) + 16 w (message)
+    "build:location": 94.0,         # 12 (key source) + 3 passes x 16 + 16 r + 16 w (payload) + p=2
+    "func:count_neighbours": 38.0,  # 16 r + 16 (messages, perfect reuse) + 4 w + p=2
+    "func:move": 40.0,              # 12 r + 8 + 8 (seed) + 12 w
+}
+B_ALG_ITERATION = 204.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """SM clock / throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index=0, period=0.05):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.period, self.index, self._stop = period, index, threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake": 0x80, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        if self.ok:
+            self.join(timeout=1.0)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def run_reference(args, cfg):
+    """CPU arm: the host-C oracle (OpenMP, all host cores) on the same workload."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from oracle import gen_oracle
+    from oracle.oracle import OracleSimulation
+    cores = os.cpu_count() or 1
+    so = gen_oracle.oracle_path(cfg.name)
+    if not os.path.exists(so):
+        so = gen_oracle.build_oracle(W.brownian_xml(cfg), cfg.name, function_files=W.brownian_function_files())
+    sim = OracleSimulation(so, threads=cores)
+    st = W.brownian_state(cfg)
+    sim.set_agents("Particle", "default", st)
+    sim.step(args.warmup)
+    t0 = time.perf_counter()
+    sim.step(args.steps)
+    dt = time.perf_counter() - t0
+    value = cfg.n * args.steps / dt
+    line = {
+        "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": workload_name(args, cfg), "agents": cfg.n, "cells": list(cfg.dims)},
+        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full iterations of the {cfg.n}-agent workload, OpenMP {cores} threads"},
+        "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference has no CPU path and its CUDA cannot be built here (no xsltproc; texture references "
+                "rejected by CUDA 12.9): this arm is the host-C oracle executing the same functions.c",
+    }
+    print(json.dumps(line))
+
+
+def workload_name(args, cfg):
+    return {"c2": "C2 Brownian random walk, 1M float agents, 64^3 spatially partitioned cells, rand48, wall reflection",
+            "c2_16m": "C2-16M Brownian random walk, 16M float agents, 128x128x256 cells"}.get(args.workload, cfg.name)
+
+
+def cpu_baseline(cfg, budget_s=12.0):
+    from oracle import gen_oracle
+    from oracle.oracle import OracleSimulation
+    cores = os.cpu_count() or 1
+    sim = OracleSimulation(gen_oracle.oracle_path(cfg.name), threads=cores)
+    sim.set_agents("Particle", "default", W.brownian_state(cfg))
+    sim.step(1)
+    t0 = time.perf_counter()
+    iters = 0
+    while iters < 3 or (time.perf_counter() - t0 < budget_s and iters < 20):
+        sim.step(1)
+        iters += 1
+        if time.perf_counter() - t0 > 3 * budget_s:
+            break
+    dt = time.perf_counter() - t0
+    sim.close()
+    return {"value": cfg.n * iters / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{iters} full iterations of the {cfg.n}-agent workload ({dt:.1f} s), OpenMP {cores} threads"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2", choices=sorted(W.BROWNIAN.keys()))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--option", action="append", default=[], help="runtime option key=value")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    cfg = W.BROWNIAN[args.workload]
+
+    if args.impl == "reference":
+        run_reference(args, cfg)
+        return
+
+    rank, world, local = dist_env()
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+
+    from ev_diffusion_b200.runtime import Simulation
+    plugin = B.model_path(cfg.name)
+    if not os.path.exists(plugin):
+        raise SystemExit(f"{plugin} missing: run `python -c 'import __graft_entry__ as g; g.build()'` first")
+    sim = Simulation(plugin, device=local)
+    for kv in args.option:
+        k, v = kv.split("=")
+        sim.set_option(k, int(v))
+    state = W.brownian_state(cfg)
+    sim.set_agents("Particle", "default", state)
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+        sim.sync()
+
+    # ---- device-resident metric ------------------------------------------------
+    sim.step(args.warmup)
+    barrier()
+    launches0 = sim.launch_count
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_each = sim.step_timed(args.steps, FLUSH_BYTES)
+    barrier()
+    clocks = sampler.stop()
+    launches = sim.launch_count - launches0
+    total_ms = float(ms_each.sum())
+    if dist is not None:
+        import torch
+        t = torch.tensor([total_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = cfg.n * world * args.steps / (total_ms * 1e-3)
+
+    # warm-L2 variant: K back-to-back graph replays, one event pair
+    sim.step(args.steps)
+    warm_ms = sim.last_step_ms
+
+    # ---- per-stage times (stream mode, one cudaEvent pair per stage) ------------
+    stage = {}
+    reps = min(args.steps, 20)
+    for _ in range(reps):
+        for name, ms in sim.profile_iteration():
+            stage[name] = stage.get(name, 0.0) + ms / reps
+    classes = {"func:output_location": stage.get("func:output_location", 0.0),
+               "build:location": stage.get("sort:location", 0.0) + stage.get("pbm:location", 0.0),
+               "func:count_neighbours": stage.get("func:count_neighbours", 0.0),
+               "func:move": stage.get("func:move", 0.0)}
+    dom = max(classes, key=lambda k: classes[k])
+    peak, peak_src = peaks()
+    dom_ms = classes[dom]
+    achieved = B_ALG[dom] * cfg.n / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_agent": B_ALG[dom], "kernel_ms": dom_ms,
+                "stage_ms": {k: round(v, 5) for k, v in stage.items()},
+                "iteration": {"alg_bytes_per_agent_step": B_ALG_ITERATION,
+                              "achieved": B_ALG_ITERATION * cfg.n * args.steps / (total_ms * 1e-3) / 1e9,
+                              "frac": B_ALG_ITERATION * cfg.n * args.steps / (total_ms * 1e-3) / 1e9 / peak}}
+
+    # ---- end to end through the public API with host buffers --------------------
+    e2e_steps = min(args.steps, 20)
+    try:
+        import torch
+        pin = {k: torch.from_numpy(v.copy()).pin_memory().numpy() for k, v in state.items()}
+    except Exception:
+        pin = {k: v.copy() for k, v in state.items()}
+    h2d = sum(v.nbytes for v in pin.values())
+    d2h = 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sim.set_agents("Particle", "default", pin)
+        sim.step(1)
+        out = [sim.agent_var("Particle", "default", k) for k in ("x", "y", "z", "nbr")]
+    barrier()
+    e2e_dt = time.perf_counter() - t0
+    d2h = sum(o.nbytes for o in out)
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_dt], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e = {"value": cfg.n * world * e2e_steps / e2e_dt, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "steps": e2e_steps}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, cfg), "agents_per_gpu": cfg.n, "cells": list(cfg.dims),
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (slab exchange: see DESIGN.md)",
+                   "l2": "flushed between timed iterations (256 MiB scratch rewrite, untimed)",
+                   "options": args.option},
+        "ms_per_step_warm_l2": warm_ms / args.steps,
+        "value_warm_l2": cfg.n * world * args.steps / (warm_ms * 1e-3),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(cfg)
+    if rank == 0:
+        print(json.dumps(line))
+    sim.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -133,6 +133,8 @@ struct fgpu_sim {
     std::vector<float> prof_ms;
     unsigned int *unpack_tmp = nullptr;
     size_t unpack_tmp_n = 0;
+    void *flush_buf = nullptr;
+    size_t flush_bytes = 0;
 
     void touch(const char *buf) { epoch[buf] = ++epoch_counter; }
     unsigned long long epoch_of(const char *buf) {
@@ -333,6 +335,7 @@ extern "C" void fgpu_sim_destroy(fgpu_sim *s) {
     }
     cudaFree(s->seeds);
     cudaFree(s->unpack_tmp);
+    cudaFree(s->flush_buf);
     for (ProfEntry &e : s->prof) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
@@ -1093,6 +1096,41 @@ extern "C" int fgpu_sim_step(fgpu_sim *s, int n) {
     CU(cudaStreamSynchronize(s->stream));
     if (n > 0) CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
     return FGPU_OK;
+}
+
+/* n iterations, each timed separately with a cudaEvent pair on the simulation
+ * stream; `flush_bytes` > 0 writes a scratch buffer of that size before every
+ * iteration (outside the timed span) so that each iteration starts with a cold L2. */
+extern "C" int fgpu_sim_step_timed(fgpu_sim *s, int n, size_t flush_bytes, float *ms_each) {
+    if (!s || n < 0) return set_err(FGPU_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(s->device));
+    if (flush_bytes > s->flush_bytes) {
+        if (s->flush_buf) cudaFree(s->flush_buf);
+        s->flush_buf = nullptr;
+        s->flush_bytes = 0;
+        CU(cudaMalloc(&s->flush_buf, flush_bytes));
+        s->flush_bytes = flush_bytes;
+    }
+    std::vector<cudaEvent_t> ev(2 * (size_t)n);
+    for (auto &e : ev) CU(cudaEventCreate(&e));
+    int rc = FGPU_OK;
+    for (int i = 0; i < n && rc == FGPU_OK; ++i) {
+        if (flush_bytes) CU(cudaMemsetAsync(s->flush_buf, i & 0xff, flush_bytes, s->stream));
+        CU(cudaEventRecord(ev[2 * i], s->stream));
+        rc = step_async(s, 1);
+        CU(cudaEventRecord(ev[2 * i + 1], s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    float total = 0.f;
+    for (int i = 0; i < n; ++i) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]);
+        if (ms_each) ms_each[i] = t;
+        total += t;
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    s->last_ms = total;
+    return rc;
 }
 
 extern "C" int fgpu_sim_begin_iteration(fgpu_sim *s) {

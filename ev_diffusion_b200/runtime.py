@@ -398,6 +398,8 @@ def load_runtime() -> C.CDLL:
     lib.fgpu_sim_step_async.argtypes = [C.c_void_p, C.c_int]
     lib.fgpu_sim_sync.restype = C.c_int
     lib.fgpu_sim_sync.argtypes = [C.c_void_p]
+    lib.fgpu_sim_step_timed.restype = C.c_int
+    lib.fgpu_sim_step_timed.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]
     lib.fgpu_sim_launch_count.restype = C.c_longlong
     lib.fgpu_sim_launch_count.argtypes = [C.c_void_p]
     lib.fgpu_sim_last_step_ms.restype = C.c_float
@@ -446,6 +448,12 @@ class Simulation(SimBase):
 
     def sync(self) -> None:
         self._check(self._lib.fgpu_sim_sync(self._h))
+
+    def step_timed(self, n: int, flush_bytes: int = 0) -> np.ndarray:
+        """n iterations, device milliseconds of each (cold L2 when flush_bytes > 0)."""
+        ms = np.zeros(n, dtype=np.float32)
+        self._check(self._lib.fgpu_sim_step_timed(self._h, int(n), int(flush_bytes), ms.ctypes.data))
+        return ms
 
     @property
     def launch_count(self) -> int:

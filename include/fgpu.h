@@ -76,6 +76,11 @@ int fgpu_sim_step(fgpu_sim *sim, int n);
 /* Same, but returns as soon as the work is enqueued on the simulation stream. */
 int fgpu_sim_step_async(fgpu_sim *sim, int n);
 int fgpu_sim_sync(fgpu_sim *sim);
+/* n iterations timed one by one with cudaEvent pairs on the simulation stream
+ * (INSTRUMENT_ITERATIONS, simulation.xslt:881-883,969-974).  flush_bytes > 0
+ * rewrites a scratch buffer of that size before each iteration, outside the
+ * timed span, so every iteration starts from a cold L2. */
+int fgpu_sim_step_timed(fgpu_sim *sim, int n, size_t flush_bytes, float *ms_each);
 
 /* Fine-grained stepping used by parity tests: the prologue of singleIteration
  * (message counts := 0, simulation.xslt:885-892) and one <A>_<f>(stream)
