@@ -64,7 +64,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index=0, period=0.05):
         super().__init__(daemon=True)
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self.period, self.index, self._stop = period, index, threading.Event()
+        self.period, self.index, self._halt = period, index, threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -82,7 +82,7 @@ class ClockSampler(threading.Thread):
         nv = self.nv
         names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
                  "hw_power_brake": 0x80, "sw_power_cap": 0x4}
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
@@ -95,7 +95,7 @@ class ClockSampler(threading.Thread):
             time.sleep(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         if self.ok:
             self.join(timeout=1.0)
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,

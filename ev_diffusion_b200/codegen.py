@@ -281,25 +281,27 @@ def _cuda_message_api(m: Message) -> str:
         out.append(f"""FGPU_DEV {S}* get_first_{name}_message({S}_list* messages, {S}_PBM* partition_matrix, float x, float y, float z){{
     (void)partition_matrix;
     if (messages->in_count == 0) return nullptr;   /* krn:1117 */
-    fgpu::grid_position<{T}>(x, y, z, messages->cx, messages->cy, messages->cz);
-    messages->step = 0;
-    return const_cast<{S}*>(fgpu::open_next_range<{S}, {T}>(messages));
+    fgpu::begin_walk<{S}, {T}>(messages, x, y, z);
+    if (!fgpu::open_next_range<{S}, {T}>(messages)) return nullptr;
+    return fgpu::current_message<{S}, {T}>(messages);
 }}
 FGPU_DEV {S}* get_next_{name}_message({S}* current, {S}_list* messages, {S}_PBM* partition_matrix){{
-    (void)partition_matrix;
-    const {S}* nxt = current + 1;
-    if (nxt >= messages->end) nxt = fgpu::open_next_range<{S}, {T}>(messages);
-    return const_cast<{S}*>(nxt);
+    (void)current; (void)partition_matrix;
+    if (++messages->cur >= messages->end) {{
+        if (!fgpu::open_next_range<{S}, {T}>(messages)) return nullptr;
+    }}
+    return fgpu::current_message<{S}, {T}>(messages);
 }}""")
     else:
         out.append(f"""FGPU_DEV {S}* get_first_{name}_message({S}_list* messages){{
     if (messages->in_count == 0) return nullptr;
-    messages->end = messages->in_recs + messages->in_count;
-    return const_cast<{S}*>(messages->in_recs);
+    messages->base = messages->in_recs; messages->cur = 0; messages->end = messages->in_count;
+    return fgpu::current_message<{S}, {T}>(messages);
 }}
 FGPU_DEV {S}* get_next_{name}_message({S}* current, {S}_list* messages){{
-    const {S}* nxt = current + 1;
-    return (nxt >= messages->end) ? nullptr : const_cast<{S}*>(nxt);
+    (void)current;
+    if (++messages->cur >= messages->end) return nullptr;
+    return fgpu::current_message<{S}, {T}>(messages);
 }}""")
     return "\n".join(out) + "\n"
 
@@ -389,13 +391,25 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
     a = model.agent(f.agent)
     A = a.name
     bs = 128 if f.input_message else 256
+    spatial_in = bool(f.input_message) and model.message(f.input_message).partitioning == "spatial"
     out = [f"/* GPUFLAME_{f.name} (krn:1320-1387) */",
            f"__global__ void __launch_bounds__({bs}) fgpu_k_{f.name}(const fgpu_launch L)\n{{",
-           "    const int t = blockIdx.x * blockDim.x + threadIdx.x;",
-           "    if (t >= L.n) return;",
-           "    const int index = L.order ? (int)__ldg(L.order + t) : t;",
-           f"    xmachine_memory_{A}_list* __restrict__ agents = (xmachine_memory_{A}_list*)L.agents;",
-           f"    xmachine_memory_{A} agent;"]
+           "    const int t = blockIdx.x * blockDim.x + threadIdx.x;"]
+    if spatial_in:
+        M = f.input_message
+        out += [
+            "    /* neighbourhood staging: header | 9 PBM row windows | message windows */",
+            "    extern __shared__ uint4 fgpu_dsm[];",
+            "    fgpu::StageShared* fgpu_sh = (fgpu::StageShared*)fgpu_dsm;",
+            "    int* fgpu_s_cs = (int*)(fgpu_dsm + fgpu::STAGE_HDR_QUADS);",
+            f"    xmachine_message_{M}* fgpu_s_msgs = (xmachine_message_{M}*)(fgpu_s_cs + 9 * fgpu::STAGE_CSW);",
+            f"    fgpu::stage_block<xmachine_message_{M}, fgpu_traits_{M}>(fgpu_sh, fgpu_s_cs, fgpu_s_msgs, L.stage_msgs,",
+            f"        (const xmachine_message_{M}*)L.in_recs, L.in_cell_start, L.in_sorted_keys, L.order != nullptr, L.n, L.in_count);",
+        ]
+    out += ["    if (t >= L.n) return;",
+            "    const int index = L.order ? (int)__ldg(L.order + t) : t;",
+            f"    xmachine_memory_{A}_list* __restrict__ agents = (xmachine_memory_{A}_list*)L.agents;",
+            f"    xmachine_memory_{A} agent;"]
     for v in a.variables:
         if v.array_length:
             out.append(f"    agent.{v.name} = &(agents->{v.name}[index]);")
@@ -409,7 +423,12 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
         M = f.input_message
         out.append(f"    xmachine_message_{M}_list inp;")
         out.append(f"    inp.in_recs = (const xmachine_message_{M}*)L.in_recs; inp.cell_start = L.in_cell_start; inp.in_count = L.in_count;")
-        out.append("    inp.out_recs = nullptr; inp.out_keys = nullptr; inp.out_index = 0; inp.end = nullptr; inp.step = 0;")
+        out.append("    inp.out_recs = nullptr; inp.out_keys = nullptr; inp.out_index = 0; inp.cur = 0; inp.end = 0;")
+        out.append("    inp.base = inp.in_recs; inp.step = 0; inp.cx = 0; inp.cy = 0; inp.cz = 0; inp.fast = 0;")
+        if spatial_in:
+            out.append("    inp.sh = fgpu_sh; inp.s_cs = fgpu_s_cs; inp.s_msgs = fgpu_s_msgs;")
+        else:
+            out.append("    inp.sh = nullptr; inp.s_cs = nullptr; inp.s_msgs = nullptr;")
         call.append("&inp")
         if model.message(M).partitioning == "spatial":
             call.append(f"(xmachine_message_{M}_PBM*)nullptr")
@@ -418,7 +437,9 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
         if f.input_message == M:
             raise ModelError(f"function '{f.name}' reads and writes message '{M}'")
         out.append(f"    xmachine_message_{M}_list outp;")
-        out.append("    outp.in_recs = nullptr; outp.cell_start = nullptr; outp.in_count = 0; outp.end = nullptr; outp.step = 0;")
+        out.append("    outp.in_recs = nullptr; outp.cell_start = nullptr; outp.in_count = 0; outp.cur = 0; outp.end = 0;")
+        out.append("    outp.base = nullptr; outp.step = 0; outp.cx = 0; outp.cy = 0; outp.cz = 0; outp.fast = 0;")
+        out.append("    outp.sh = nullptr; outp.s_cs = nullptr; outp.s_msgs = nullptr;")
         out.append(f"    outp.out_recs = (xmachine_message_{M}*)L.out_recs; outp.out_keys = L.out_keys; outp.out_index = L.out_base + index;")
         call.append("&outp")
     if f.rng:
@@ -436,7 +457,22 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
     if f.rng:
         out.append("    ((uint2*)L.seeds)[index] = make_uint2(rng.sx, rng.sy);")
     out.append("}")
-    out.append(f"""static void fgpu_launch_{f.name}(const fgpu_launch* a, void* stream){{
+    if spatial_in:
+        M = f.input_message
+        out.append(f"""static void fgpu_launch_{f.name}(const fgpu_launch* a, void* stream){{
+    if (a->n <= 0) return;
+    const int grid = (a->n + {bs} - 1) / {bs};
+    const size_t smem = (size_t)fgpu::STAGE_HDR_QUADS * 16 + 9 * fgpu::STAGE_CSW * sizeof(int)
+                      + (size_t)(a->stage_msgs > 0 ? a->stage_msgs : 0) * sizeof(xmachine_message_{M});
+    static size_t configured = 0;
+    if (smem > configured) {{
+        cudaFuncSetAttribute(fgpu_k_{f.name}, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }}
+    fgpu_k_{f.name}<<<grid, {bs}, smem, (cudaStream_t)stream>>>(*a);
+}}""")
+    else:
+        out.append(f"""static void fgpu_launch_{f.name}(const fgpu_launch* a, void* stream){{
     if (a->n <= 0) return;
     const int grid = (a->n + {bs} - 1) / {bs};
     fgpu_k_{f.name}<<<grid, {bs}, 0, (cudaStream_t)stream>>>(*a);

@@ -15,7 +15,9 @@
  *    through a shared-memory slot (krn:1100-1103);
  *  - the partition boundary matrix is a CSR array cell_start[cells+1]; the
  *    three x-neighbours of a row are one contiguous range, so a 27-cell walk
- *    costs 18 index loads instead of 54 (krn:1061-1062);
+ *    costs 18 index loads instead of 54 (krn:1061-1062); blocks that process
+ *    agents in cell order stage their PBM slices and message slices in shared
+ *    memory once and walk them from there;
  *  - the cursor lives in a per-thread proxy that the compiler keeps in
  *    registers;
  *  - the rand48 state is loaded once per agent function, iterated in
@@ -62,13 +64,99 @@ FGPU_DEV unsigned int cell_hash(int cx, int cy, int cz) {
     return (unsigned int)(((cz * T::DIMY) * T::DIMX) + (cy * T::DIMX) + cx);
 }
 
+/* ---- block-level staging of the neighbourhood ---------------------------------- */
+/* When a message consumer processes its agents in cell order (fgpu_launch.order),
+ * the agents of one block occupy a short run of consecutive cells [c_lo, c_hi].
+ * Their 27-cell neighbourhoods are then 9 windows of consecutive cells (one per
+ * (dy,dz) row offset), i.e. 9 contiguous slices of the partition boundary
+ * matrix and 9 contiguous slices of the sorted message list.  The block copies
+ * those slices into shared memory once (coalesced 16-byte loads) and every
+ * thread walks its neighbourhood out of shared memory: no L1/L2 misses inside
+ * the divergent message loop, where one missing lane stalls the whole warp.
+ * Threads whose cell is not fully interior (any wrap), lies outside the
+ * block's span, or whose block does not fit the staging capacity use the
+ * on-demand global walk below instead -- same visiting order, same results. */
+constexpr int STAGE_CSW = 128;            /* staged PBM row window: span + 3 cell boundaries */
+constexpr int STAGE_HDR_QUADS = 8;        /* StageShared fits in 128 bytes */
+
+struct StageShared {
+    int ok;         /* 1 = windows staged */
+    int c_lo, c_hi; /* cell span of the block's agents (hash space) */
+    int adj[9];     /* shared-memory message index = sorted message index + adj[row] */
+    int cnt[9];     /* messages in the window of each row (scratch) */
+};
+static_assert(sizeof(StageShared) <= STAGE_HDR_QUADS * 16, "staging header overflows its slot");
+
+template <class T>
+FGPU_DEV int row_offset(int k) {
+    /* rows are enumerated z-major, y-minor like next_cell3D; in 2-D mode z does not move */
+    if (T::IS2D) return (k - 1) * T::DIMX;
+    return ((k % 3) - 1) * T::DIMX + ((k / 3) - 1) * T::DIMX * T::DIMY;
+}
+
+template <class Msg, class T>
+FGPU_DEV void stage_block(StageShared *sh, int *s_cs, Msg *s_msgs, int stage_msgs, const Msg *recs,
+                          const unsigned int *cell_start, const unsigned int *sorted_keys, bool ordered, int n,
+                          int count) {
+    constexpr int NROWS = T::IS2D ? 3 : 9;
+    constexpr int CELLS = T::DIMX * T::DIMY * T::DIMZ;
+    constexpr int NQ = (int)(sizeof(Msg) / 16);
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    if (tid == 0) {
+        int ok = (stage_msgs > 0) && ordered && (sorted_keys != nullptr) && (count == n) && (n > 0);
+        int c_lo = 0, c_hi = -1;
+        if (ok) {
+            const int t0 = blockIdx.x * nthreads;
+            const int t1 = min(t0 + nthreads, n) - 1;
+            c_lo = (int)sorted_keys[t0];
+            c_hi = (int)sorted_keys[t1];
+            const int reach = T::IS2D ? (T::DIMX + 1) : (T::DIMX * T::DIMY + T::DIMX + 1);
+            ok = (c_hi - c_lo + 4 <= STAGE_CSW) && (c_lo - reach >= 0) && (c_hi + reach <= CELLS - 1);
+        }
+        sh->ok = ok;
+        sh->c_lo = c_lo;
+        sh->c_hi = c_hi;
+    }
+    __syncthreads();
+    if (!sh->ok) return;
+    const int c_lo = sh->c_lo;
+    const int w = sh->c_hi - c_lo + 4; /* boundaries needed per row: cells c_lo-1 .. c_hi+1, plus one */
+#pragma unroll
+    for (int k = 0; k < NROWS; ++k) {
+        const int first = c_lo + row_offset<T>(k) - 1;
+        for (int i = tid; i < w; i += nthreads) s_cs[k * STAGE_CSW + i] = (int)__ldg(cell_start + first + i);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int total = 0;
+        for (int k = 0; k < NROWS; ++k) {
+            const int wlo = s_cs[k * STAGE_CSW], whi = s_cs[k * STAGE_CSW + w - 1];
+            sh->adj[k] = total - wlo;
+            sh->cnt[k] = whi - wlo;
+            total += whi - wlo;
+        }
+        if (total > stage_msgs) sh->ok = 0;
+    }
+    __syncthreads();
+    if (!sh->ok) return;
+#pragma unroll
+    for (int k = 0; k < NROWS; ++k) {
+        const int wlo = s_cs[k * STAGE_CSW];
+        const uint4 *src = reinterpret_cast<const uint4 *>(recs + wlo);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_msgs + (wlo + sh->adj[k]));
+        const int quads = sh->cnt[k] * NQ;
+        for (int i = tid; i < quads; i += nthreads) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+}
+
 /* ---- per-thread message proxy -------------------------------------------- */
 /* `Msg` is the user-visible struct xmachine_message_<M> (16-byte aligned, payload
  * only); the sorted message list in HBM is an array of exactly that struct, so
- * get_first/next hand user code a pointer straight into the list (no staging
- * copy; the reference copies every message through a shared-memory slot,
- * krn:1084-1103).  `T` holds the partition constants.  The generated header
- * derives xmachine_message_<M>_list from this. */
+ * get_first/next hand user code a pointer straight into the list -- or into the
+ * block's staged copy of it (the reference copies every message through a
+ * per-thread shared-memory slot, krn:1084-1103).  `T` holds the partition
+ * constants.  The generated header derives xmachine_message_<M>_list from this. */
 template <class Msg, class T>
 struct MessageProxy {
     /* input side */
@@ -80,18 +168,39 @@ struct MessageProxy {
     unsigned int *out_keys;
     int out_index;
     /* cursor (replaces _relative_cell/_cell_index/_cell_index_max/_agent_grid_cell, hdr:170-173) */
-    const Msg *end;   /* one past the last message of the open range */
-    int step;         /* next relative cell to open: 0..26 (3-D) or 0..8 (2-D) */
-    int cx, cy, cz;   /* agent grid cell */
+    const Msg *base;  /* list the open range indexes: in_recs or the staged copy */
+    int cur, end;     /* current message index, end of the open range */
+    int step;         /* fast: next row (0..8); slow: next relative cell (0..26) */
+    int cx, cy, cz;   /* slow: agent grid cell; fast: cx = cell index relative to the block's span */
+    int fast;
+    /* block-shared staging area */
+    const StageShared *sh;
+    const int *s_cs;
+    const Msg *s_msgs;
 };
 
-/* Opens the next non-empty cell range and returns its first message (nullptr
- * when the neighbourhood is exhausted).  Cells are visited x-fastest from
- * (-1,-1,-1) to (1,1,1) exactly like next_cell3D/next_cell2D (krn:105-154);
- * when the three x cells of a row do not wrap they are adjacent hashes and
- * are opened as one range (same visiting order). */
+/* Opens the next non-empty range of the neighbourhood; false when exhausted.
+ * Cells are visited x-fastest from (-1,-1,-1) to (1,1,1) exactly like
+ * next_cell3D/next_cell2D (krn:105-154).  The three x cells of a row are
+ * adjacent hashes unless x wraps, and are then opened as one range (same
+ * visiting order). */
 template <class Msg, class T>
-FGPU_DEV const Msg *open_next_range(MessageProxy<Msg, T> *p) {
+FGPU_DEV bool open_next_range(MessageProxy<Msg, T> *p) {
+    if (p->fast) {
+        constexpr int NROWS = T::IS2D ? 3 : 9;
+        while (p->step < NROWS) {
+            const int k = p->step++;
+            const int lo = p->s_cs[k * STAGE_CSW + p->cx];
+            const int hi = p->s_cs[k * STAGE_CSW + p->cx + 3];
+            if (lo < hi) {
+                const int a = p->sh->adj[k];
+                p->cur = lo + a;
+                p->end = hi + a;
+                return true;
+            }
+        }
+        return false;
+    }
     constexpr int NSTEPS = T::IS2D ? 9 : 27;
     while (p->step < NSTEPS) {
         const int s = p->step;
@@ -100,7 +209,6 @@ FGPU_DEV const Msg *open_next_range(MessageProxy<Msg, T> *p) {
         const int rz = T::IS2D ? -1 : (s / 9) - 1;   /* 2-D: relative z stays -1 (krn:137-154) */
         int lo, hi;
         if (rx == -1 && p->cx >= 1 && p->cx + 1 < T::DIMX) {
-            /* whole row x-1..x+1 without wrap: one contiguous hash range */
             const unsigned int h = cell_hash<T>(p->cx - 1, p->cy + ry, p->cz + rz);
             lo = (int)__ldg(p->cell_start + h);
             hi = (int)__ldg(p->cell_start + h + 3);
@@ -112,11 +220,41 @@ FGPU_DEV const Msg *open_next_range(MessageProxy<Msg, T> *p) {
             p->step = s + 1;
         }
         if (lo < hi) {
-            p->end = p->in_recs + hi;
-            return p->in_recs + lo;
+            p->cur = lo;
+            p->end = hi;
+            return true;
         }
     }
-    return nullptr;
+    return false;
+}
+
+/* get_first: locate the agent's cell and choose the staged or the global walk. */
+template <class Msg, class T>
+FGPU_DEV void begin_walk(MessageProxy<Msg, T> *p, float x, float y, float z) {
+    int cx, cy, cz;
+    grid_position<T>(x, y, z, cx, cy, cz);
+    p->step = 0;
+    p->fast = 0;
+    p->base = p->in_recs;
+    p->cx = cx;
+    p->cy = cy;
+    p->cz = cz;
+    if (p->sh != nullptr && p->sh->ok) {
+        const bool interior = (cx >= 1) && (cx + 1 < T::DIMX) && (cy >= 1) && (cy + 1 < T::DIMY) &&
+                              (T::IS2D || ((cz >= 1) && (cz + 1 < T::DIMZ)));
+        const int c = (int)cell_hash<T>(cx, cy, cz);
+        if (interior && c >= p->sh->c_lo && c <= p->sh->c_hi) {
+            p->fast = 1;
+            p->cx = c - p->sh->c_lo;
+            p->base = p->s_msgs;
+        }
+    }
+}
+
+/* Hands the current message to user code: a pointer straight into the list. */
+template <class Msg, class T>
+FGPU_DEV Msg *current_message(MessageProxy<Msg, T> *p) {
+    return const_cast<Msg *>(p->base + p->cur);
 }
 
 /* ---- rand48 ---------------------------------------------------------------- */

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FGPU_MODEL_ABI_VERSION 3
+#define FGPU_MODEL_ABI_VERSION 4
 
 /* One agent or message variable.  Agent lists keep the reference's SoA struct
  * layout (header.xslt:187-194): int _position[MAX]; int _scan_input[MAX];
@@ -80,6 +80,8 @@ typedef struct fgpu_launch {
     const void *in_recs;          /* xmachine_message_<M>[count], cell-sorted */
     const unsigned int *in_cell_start;  /* CSR: grid_size+1 entries */
     int in_count;                 /* h_message_<M>_count */
+    const unsigned int *in_sorted_keys; /* cell key of each sorted message (block staging), may be NULL */
+    int stage_msgs;               /* shared-memory staging capacity in messages; 0 = no staging */
     /* output message (unsorted staging + cell keys) */
     void *out_recs;
     unsigned int *out_keys;
