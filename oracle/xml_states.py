@@ -1,0 +1,113 @@
+"""ORACLE: Python restatement of the reference's 0.xml reader.  TEST INFRASTRUCTURE ONLY.
+
+Follows ``readInitialStates`` (FLAMEGPU/templates/io.xslt:211-621) character by
+character: tags are matched by exact name, variable tags by *bare name across
+all agent types* (io:458-459), values are parsed when the next ``<`` arrives
+with C semantics (``(float)atof``, ``strtol(..., 0)``; cmn:168-221), an agent
+is committed on ``</xagent>`` under the last ``<name>`` seen, unspecified
+variables take ``defaultValue`` or 0, unknown tags are ignored, ``<!-- -->``
+comments are skipped, reading stops at ``</states>``.
+"""
+from __future__ import annotations
+
+import ctypes
+import re
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+_libc = ctypes.CDLL("libc.so.6")
+_libc.atof.restype = ctypes.c_double
+_libc.atof.argtypes = [ctypes.c_char_p]
+_libc.strtol.restype = ctypes.c_long
+_libc.strtol.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int]
+_libc.strtoul.restype = ctypes.c_ulong
+_libc.strtoul.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int]
+
+
+def _parse(ctype: str, text: str):
+    b = text.encode("latin-1", "replace")
+    if ctype == "float":
+        return np.float32(_libc.atof(b))
+    if ctype == "double":
+        return np.float64(_libc.atof(b))
+    if ctype == "int":
+        return np.int32(np.int64(_libc.strtol(b, None, 0)).astype(np.int32))
+    if ctype == "unsigned int":
+        return np.uint32(np.uint64(_libc.strtoul(b, None, 0)).astype(np.uint32))
+    raise ValueError(ctype)
+
+
+def read_states(path: str, agents: List[Tuple[str, List[Tuple[str, str, float]]]], constants: List[Tuple[str, str]] = ()):
+    """agents: [(agent name, [(var name, ctype, default)])].  Returns
+    ({agent: {var: array}}, {constant: value})."""
+    data = open(path, "rb").read().decode("latin-1")
+    out = {a: {v: [] for v, _, _ in vs} for a, vs in agents}
+    defaults = {a: {v: _parse(t, repr(d) if t in ("float", "double") else str(int(d))) for v, t, d in vs} for a, vs in agents}
+    types = {a: {v: t for v, t, _ in vs} for a, vs in agents}
+    cur = {a: dict(defaults[a]) for a, _ in agents}
+    env: Dict[str, object] = {}
+    ctypes_env = dict(constants)
+    buf: List[str] = []
+    in_tag = in_comment = in_env = in_xagent = in_name = False
+    open_var = ""
+    agentname = ""
+    for c in data:
+        if in_comment:
+            if c == "-":
+                buf.append(c)
+            elif c == ">" and len(buf) >= 2:
+                in_comment = False
+                buf = []
+            else:
+                buf = []
+        elif c == ">":
+            tag = "".join(buf)
+            if tag == "/states":
+                break
+            if tag == "environment":
+                in_env = True
+            if tag == "/environment":
+                in_env = False
+            if tag == "name":
+                in_name = True
+            if tag == "/name":
+                in_name = False
+            if tag == "xagent":
+                in_xagent = True
+            if tag == "/xagent":
+                if agentname in out:
+                    for v in out[agentname]:
+                        out[agentname][v].append(cur[agentname][v])
+                cur = {a: dict(defaults[a]) for a, _ in agents}
+                in_xagent = False
+            if tag.startswith("/"):
+                if open_var == tag[1:]:
+                    open_var = ""
+            else:
+                open_var = tag
+            in_tag = False
+            buf = []
+        elif c == "<":
+            text = "".join(buf)
+            in_tag = True
+            if in_name:
+                agentname = text
+            elif in_xagent:
+                for a, vs in agents:
+                    if open_var in types[a]:
+                        cur[a][open_var] = _parse(types[a][open_var], text)
+            elif in_env:
+                if open_var in ctypes_env:
+                    env[open_var] = _parse(ctypes_env[open_var], text)
+            buf = []
+        elif in_tag:
+            if len(buf) == 2 and c == "-" and buf[1] == "-" and buf[0] == "!":
+                in_comment = True
+                buf = []
+            buf.append(c)
+        else:
+            buf.append(c)
+    np_types = {"float": np.float32, "double": np.float64, "int": np.int32, "unsigned int": np.uint32}
+    res = {a: {v: np.array(out[a][v], dtype=np_types[types[a][v]]) for v in out[a]} for a in out}
+    return res, env
