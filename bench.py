@@ -194,7 +194,14 @@ def main():
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
 
-    from ev_diffusion_b200.runtime import Simulation
+    from ev_diffusion_b200 import slabs
+    from ev_diffusion_b200.runtime import Simulation, nccl_unique_id
+    if world > 1:
+        # weak scaling over z-slabs: 1M agents and 64 cell planes per GPU, halo + migration over NCCL
+        key = f"{args.workload}_w{world}"
+        if key not in W.BROWNIAN:
+            raise SystemExit(f"no slab variant {key} of workload {args.workload}")
+        cfg = W.BROWNIAN[key]
     plugin = B.model_path(cfg.name)
     if not os.path.exists(plugin):
         raise SystemExit(f"{plugin} missing: run `python -c 'import __graft_entry__ as g; g.build()'` first")
@@ -203,7 +210,18 @@ def main():
         k, v = kv.split("=")
         sim.set_option(k, int(v))
     state = W.brownian_state(cfg)
+    if world > 1:
+        import torch
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(uid, 0)
+        sim.slab_init(rank, world, uid.cpu().numpy().tobytes())
+        m = sim.model.messages[0]
+        plan = slabs.make_plan(m.dims, m.min_bounds, m.max_bounds, m.is_2d, rank, world)
+        state = slabs.partition_state(state, plan)
     sim.set_agents("Particle", "default", state)
+    n_local0 = len(state["id"])
 
     def barrier():
         if dist is not None:
@@ -228,11 +246,17 @@ def main():
         t = torch.tensor([total_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-    value = cfg.n * world * args.steps / (total_ms * 1e-3)
+    n_global = cfg.n if world > 1 else cfg.n   # cfg.n is the whole-job population in both cases
+    value = n_global * args.steps / (total_ms * 1e-3)
 
-    # warm-L2 variant: K back-to-back graph replays, one event pair
+    # warm-L2 variant: K back-to-back iterations (graph replays on one GPU), one event pair
     sim.step(args.steps)
     warm_ms = sim.last_step_ms
+    if dist is not None:
+        import torch
+        t = torch.tensor([warm_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        warm_ms = float(t.item())
 
     # ---- per-stage times (stream mode, one cudaEvent pair per stage) ------------
     stage = {}
@@ -247,14 +271,15 @@ def main():
     dom = max(classes, key=lambda k: classes[k])
     peak, peak_src = peaks()
     dom_ms = classes[dom]
-    achieved = B_ALG[dom] * cfg.n / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    n_kernel = sim.agent_count("Particle", "default")   # units one launch of the dominant kernel processes
+    achieved = B_ALG[dom] * n_kernel / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "alg_bytes_per_agent": B_ALG[dom], "kernel_ms": dom_ms,
                 "stage_ms": {k: round(v, 5) for k, v in stage.items()},
                 "iteration": {"alg_bytes_per_agent_step": B_ALG_ITERATION,
-                              "achieved": B_ALG_ITERATION * cfg.n * args.steps / (total_ms * 1e-3) / 1e9,
-                              "frac": B_ALG_ITERATION * cfg.n * args.steps / (total_ms * 1e-3) / 1e9 / peak}}
+                              "achieved_per_gpu": B_ALG_ITERATION * n_global / world * args.steps / (total_ms * 1e-3) / 1e9,
+                              "frac": B_ALG_ITERATION * n_global / world * args.steps / (total_ms * 1e-3) / 1e9 / peak}}
 
     # ---- end to end through the public API with host buffers --------------------
     e2e_steps = min(args.steps, 20)
@@ -279,19 +304,21 @@ def main():
         t = torch.tensor([e2e_dt], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
-    e2e = {"value": cfg.n * world * e2e_steps / e2e_dt, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+    e2e = {"value": n_global * e2e_steps / e2e_dt, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": e2e_steps}
 
     line = {
         "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args, cfg), "agents_per_gpu": cfg.n, "cells": list(cfg.dims),
-                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (slab exchange: see DESIGN.md)",
+        "config": {"workload": workload_name(args, cfg), "agents": n_global, "agents_per_gpu": n_global // world,
+                   "cells": list(cfg.dims),
+                   "parallelism": "single GPU" if world == 1 else
+                   f"{world} z-slabs of {cfg.dims[2] // world} cell planes, halo planes + migrating agents over NCCL send/recv",
                    "l2": "flushed between timed iterations (256 MiB scratch rewrite, untimed)",
                    "options": args.option},
         "ms_per_step_warm_l2": warm_ms / args.steps,
-        "value_warm_l2": cfg.n * world * args.steps / (warm_ms * 1e-3),
+        "value_warm_l2": n_global * args.steps / (warm_ms * 1e-3),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -533,7 +533,7 @@ static void fgpu_launch_filter_{f.name}(const fgpu_filter* a, void* stream){{
 """
 
 
-def _descriptor_tables(model: Model, mode: str, launch_prefix: str) -> str:
+def _descriptor_tables(model: Model, mode: str, launch_prefix: str, sources: Optional[List[str]] = None) -> str:
     """The fgpu_model tables (shared by both back ends; the oracle passes its
     own thunks in place of kernel launchers)."""
     out = []
@@ -595,7 +595,8 @@ def _descriptor_tables(model: Model, mode: str, launch_prefix: str) -> str:
             f'{aidx[f.xagent_output] if f.xagent_output else -1}, '
             f'{model.agent(f.xagent_output).states.index(f.xagent_output_state) if f.xagent_output else -1}, '
             f'{int(f.reallocate)}, {swappable}, {int(f.rng)}, {cond}, {f.gc_max_iterations}, {int(f.gc_must_evaluate_to)}, '
-            f'{launch_prefix}{f.name}, {filt}, {128 if f.input_message else 256}}},')
+            f'{launch_prefix}{f.name}, {filt}, {128 if f.input_message else 256}, '
+            f'{int(bool(written_variables(f, a, sources or []) & {"x", "y", "z"}))}}},')
     out.append("static const fgpu_function fgpu_functions[] = {\n" + "\n".join(rows) + "\n};")
     lrows = []
     for i, layer in enumerate(model.layers):
@@ -677,7 +678,7 @@ def emit_cuda_glue(model: Model, function_files: List[str]) -> str:
         if f.condition is not None or f.global_condition is not None:
             out.append(_cuda_filter(model, f))
     out.append(_constants_code(model, cuda=True))
-    out.append(_descriptor_tables(model, "cuda", "fgpu_launch_"))
+    out.append(_descriptor_tables(model, "cuda", "fgpu_launch_", sources))
     out.append(_model_struct(model))
     return "\n".join(out) + "\n"
 

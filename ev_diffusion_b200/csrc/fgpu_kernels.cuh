@@ -280,9 +280,9 @@ constexpr int COMPACT_THREADS = 1024;
 
 /* number of flagged (== 1) elements per block */
 __global__ void __launch_bounds__(COMPACT_THREADS)
-k_flag_blocksum(const int *__restrict__ flags, int n, unsigned int *__restrict__ block_sums) {
+k_flag_blocksum(const int *__restrict__ flags, int n, unsigned int *__restrict__ block_sums, int match) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int f = (i < n) && (flags[i] == 1);
+    const int f = (i < n) && (flags[i] == match);
     const int c = __syncthreads_count(f);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = (unsigned int)c;
 }
@@ -327,12 +327,13 @@ __global__ void __launch_bounds__(1024) k_scan_blocksums(unsigned int *block_sum
 
 /* stable scatter of flagged agents: dst[dst_offset + rank] = src[i] for every column */
 __global__ void __launch_bounds__(COMPACT_THREADS)
-k_compact_scatter(const char *__restrict__ src, char *__restrict__ dst, const ColSet cols,
-                  const int *__restrict__ flags, const unsigned int *__restrict__ block_offsets, int dst_offset, int n) {
+k_compact_scatter(const char *__restrict__ src, char *__restrict__ dst, const ColSet cols, const ColSet dcols,
+                  const int *__restrict__ flags, const unsigned int *__restrict__ block_offsets, int dst_offset, int n,
+                  int match, int dst_cap, int *overflow) {
     __shared__ unsigned int s_warp[32];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool f = (i < n) && (flags[i] == 1);
+    const bool f = (i < n) && (flags[i] == match);
     const unsigned int ballot = __ballot_sync(0xffffffffu, f);
     if (lane == 0) s_warp[warp] = __popc(ballot);
     __syncthreads();
@@ -349,11 +350,15 @@ k_compact_scatter(const char *__restrict__ src, char *__restrict__ dst, const Co
     __syncthreads();
     if (!f) return;
     const size_t out = (size_t)dst_offset + block_offsets[blockIdx.x] + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u));
+    if (out >= (size_t)dst_cap) { /* fixed-capacity exchange buffers (slab mode): report, never write out of bounds */
+        if (overflow) atomicExch(overflow, 1);
+        return;
+    }
     for (int c = 0; c < cols.ncols; ++c) {
         if (cols.size[c] == 4)
-            ((unsigned int *)(dst + cols.off[c]))[out] = ((const unsigned int *)(src + cols.off[c]))[i];
+            ((unsigned int *)(dst + dcols.off[c]))[out] = ((const unsigned int *)(src + cols.off[c]))[i];
         else
-            ((unsigned long long *)(dst + cols.off[c]))[out] = ((const unsigned long long *)(src + cols.off[c]))[i];
+            ((unsigned long long *)(dst + dcols.off[c]))[out] = ((const unsigned long long *)(src + cols.off[c]))[i];
     }
 }
 
@@ -369,6 +374,122 @@ k_append(const char *__restrict__ src, char *__restrict__ dst, const ColSet cols
         else
             ((unsigned long long *)(dst + cols.off[c]))[out] = ((const unsigned long long *)(src + cols.off[c]))[i];
     }
+}
+
+/* ------------------------------------------------------------------------- */
+/* 1-D slab decomposition: halo planes of the sorted message list, migrants    */
+/* ------------------------------------------------------------------------- */
+/* Exchange buffers have a fixed capacity so that the NCCL message sizes are
+ * known on the host without a device round trip; the true counts travel in a
+ * 4-int header: {count, overflow, 0, 0}. */
+constexpr int XHDR = 4;
+
+/* plane -> send buffer: header | (plane_cells + 1) cell_start entries rebased to 0 | records */
+template <int NQ>
+__global__ void __launch_bounds__(256)
+k_pack_plane(const uint4 *__restrict__ sorted_local, const unsigned int *__restrict__ cell_start, int first_cell,
+             int plane_cells, int cap, int *__restrict__ out) {
+    const int lo = (int)cell_start[first_cell], hi = (int)cell_start[first_cell + plane_cells];
+    const int cnt = hi - lo;
+    const int stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid == 0) {
+        out[0] = min(cnt, cap);
+        out[1] = cnt > cap;
+        out[2] = 0;
+        out[3] = 0;
+    }
+    int *cs = out + XHDR;
+    for (int i = tid; i <= plane_cells; i += stride) cs[i] = min((int)cell_start[first_cell + i] - lo, cap);
+    uint4 *recs = reinterpret_cast<uint4 *>(out + XHDR + ((plane_cells + 1 + 3) & ~3));
+    const int quads = min(cnt, cap) * NQ;
+    for (int i = tid; i < quads; i += stride) recs[i] = sorted_local[(size_t)lo * NQ + i];
+}
+
+/* Merge: shift the owned planes' cell_start by the position of the local block
+ * inside the combined buffer, splice in the two received halo planes.
+ *   combined buffer: [ ... low halo | local block (n records at `local_at`) | high halo ... ] */
+template <int NQ>
+__global__ void __launch_bounds__(256)
+k_merge_halo(uint4 *__restrict__ combined, unsigned int *__restrict__ cell_start, int local_at, int n,
+             int own_first_cell, int own_cells, const int *__restrict__ lo_buf, int lo_first_cell,
+             const int *__restrict__ hi_buf, int hi_first_cell, int plane_cells, int *status) {
+    const int stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lo_cnt = lo_buf[0], hi_cnt = hi_buf[0];
+    if (tid == 0 && (lo_buf[1] || hi_buf[1])) atomicExch(status, 1);
+    const int pad = (plane_cells + 1 + 3) & ~3;
+    /* owned planes (including the closing boundary) */
+    for (int i = tid; i <= own_cells; i += stride) cell_start[own_first_cell + i] += (unsigned int)local_at;
+    __threadfence();
+    /* low halo sits immediately below the local block, high halo immediately above */
+    const int lo_at = local_at - lo_cnt, hi_at = local_at + n;
+    /* a halo plane adjacent in hash order shares its boundary entry with the owned block; that entry already
+     * holds the right value (local_at or local_at + n), so the shared entry is skipped */
+    for (int i = tid; i <= plane_cells; i += stride) {
+        const int c_lo = lo_first_cell + i;
+        if (!(c_lo >= own_first_cell && c_lo <= own_first_cell + own_cells)) cell_start[c_lo] = (unsigned int)(lo_at + lo_buf[XHDR + i]);
+        const int c_hi = hi_first_cell + i;
+        if (!(c_hi >= own_first_cell && c_hi <= own_first_cell + own_cells)) cell_start[c_hi] = (unsigned int)(hi_at + hi_buf[XHDR + i]);
+    }
+    const uint4 *lo_recs = reinterpret_cast<const uint4 *>(lo_buf + XHDR + pad);
+    const uint4 *hi_recs = reinterpret_cast<const uint4 *>(hi_buf + XHDR + pad);
+    for (int i = tid; i < lo_cnt * NQ; i += stride) combined[(size_t)lo_at * NQ + i] = lo_recs[i];
+    for (int i = tid; i < hi_cnt * NQ; i += stride) combined[(size_t)hi_at * NQ + i] = hi_recs[i];
+}
+
+/* Owner of each agent along the slab axis: 1 = stays, 2 = lower neighbour, 3 = upper neighbour,
+ * 4 = further than one slab away (reported).  The plane is the cell coordinate of
+ * message_<M>_grid_position + the wrap rule of message_<M>_hash (krn:860-889). */
+__global__ void __launch_bounds__(256)
+k_owner_flags(const float *__restrict__ coord, int n, float minb, float maxb, int nplanes, int planes_per_rank, int rank,
+              int world, int *__restrict__ flags, int *status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int p = (int)floorf(__fdiv_rn(__fmul_rn(__fsub_rn(coord[i], minb), (float)nplanes), __fsub_rn(maxb, minb)));
+    p = (p < 0) ? nplanes - 1 : p;
+    p = (p >= nplanes) ? 0 : p;
+    const int owner = min(p / planes_per_rank, world - 1);
+    int f = 4;
+    if (owner == rank) f = 1;
+    else if (owner == (rank + world - 1) % world && owner == (rank + 1) % world) f = (p < rank * planes_per_rank) ? 2 : 3; /* world == 2 */
+    else if (owner == (rank + world - 1) % world) f = 2;
+    else if (owner == (rank + 1) % world) f = 3;
+    flags[i] = f;
+    if (f == 4) atomicExch(status, 2);
+}
+
+/* header of a migrant buffer := {count (clamped), overflow} from the compaction total */
+__global__ void k_set_header(int *hdr, const int *total, int cap) {
+    const int t = *total;
+    hdr[0] = min(t, cap);
+    hdr[1] = t > cap;
+    hdr[2] = 0;
+    hdr[3] = 0;
+}
+
+/* append received migrants: dst[dst_base + *off_a + *off_b + i] = src[i] for i < src_hdr[0] */
+__global__ void __launch_bounds__(256)
+k_append_received(const char *__restrict__ src, const int *__restrict__ src_hdr, char *__restrict__ dst, const ColSet scols,
+                  const ColSet dcols, const int *off_a, const int *off_b, int dst_cap, int *status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cnt = src_hdr[0];
+    if (i == 0 && src_hdr[1]) atomicExch(status, 3);
+    if (i >= cnt) return;
+    const size_t out = (size_t)(off_a ? *off_a : 0) + (size_t)(off_b ? *off_b : 0) + i;
+    if (out >= (size_t)dst_cap) {
+        atomicExch(status, 4);
+        return;
+    }
+    for (int c = 0; c < scols.ncols; ++c) {
+        if (scols.size[c] == 4)
+            ((unsigned int *)(dst + dcols.off[c]))[out] = ((const unsigned int *)(src + scols.off[c]))[i];
+        else
+            ((unsigned long long *)(dst + dcols.off[c]))[out] = ((const unsigned long long *)(src + scols.off[c]))[i];
+    }
+}
+
+/* result[0] = *a + hdr_b[0] + hdr_c[0] (new local population) */
+__global__ void k_sum_counts(int *result, const int *a, const int *hdr_b, const int *hdr_c) {
+    result[0] = *a + hdr_b[0] + hdr_c[0];
 }
 
 }  // namespace fgpu

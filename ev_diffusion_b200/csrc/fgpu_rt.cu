@@ -94,6 +94,36 @@ struct MsgRT {
     int producers = 0;
     int sorted_in = 0; /* index of keys/vals buffer holding the final sorted pairs */
     bool built = false;
+    int local_at = 0;  /* record index of the local block inside `sorted` (slab mode: halo_cap) */
+};
+
+/* ---- 1-D slab decomposition state ---- */
+struct SlabMsg {
+    int *send_lo = nullptr, *send_hi = nullptr, *recv_lo = nullptr, *recv_hi = nullptr;
+    size_t bytes = 0;
+};
+struct SlabAgent {
+    char *send_dn = nullptr, *send_up = nullptr, *recv_lo = nullptr, *recv_hi = nullptr;
+    size_t bytes = 0;
+    ColSet bufcols; /* column offsets inside a migrant buffer (after the 16-byte header) */
+    int axis_var = -1;
+    int *d_counts = nullptr; /* per state: {n_stay, n_new} */
+};
+struct SlabRT {
+    bool on = false;
+    int rank = 0, world = 1;
+    void *comm = nullptr;
+    int axis = 2;          /* 2 = z, 1 = y (2-D grids) */
+    int nplanes = 1, plane_cells = 1, ppr = 1, p0 = 0, p1 = 1;
+    int lo_rank = 0, hi_rank = 0;
+    int halo_cap = 0, mig_cap = 0;
+    float axis_min = 0.f, axis_max = 1.f;
+    std::vector<SlabMsg> msgs;
+    std::vector<SlabAgent> agents;
+    int *d_status = nullptr;
+    int *h_pinned = nullptr; /* pinned mirror: status + counts */
+    bool dirty = false;
+    long long halo_bytes = 0, mig_bytes = 0; /* NCCL bytes sent per iteration (instrumentation) */
 };
 
 struct ProfEntry {
@@ -137,6 +167,7 @@ struct fgpu_sim {
     size_t unpack_tmp_n = 0;
     void *flush_buf = nullptr;
     size_t flush_bytes = 0;
+    SlabRT slab;
 
     void touch(const char *buf) { epoch[buf] = ++epoch_counter; }
     unsigned long long epoch_of(const char *buf) {
@@ -158,6 +189,7 @@ struct fgpu_sim {
     }
 };
 
+static void slab_release(fgpu_sim *s);
 static size_t msg_plane_bytes(const fgpu_message *m) { return (size_t)m->rec_quads * m->buffer_size * sizeof(uint4); }
 
 /* ------------------------------------------------------------------------- */
@@ -335,6 +367,22 @@ extern "C" void fgpu_sim_destroy(fgpu_sim *s) {
         cudaFree(M.scratch);
         cudaFree(M.gap_queue);
     }
+    for (SlabMsg &X : s->slab.msgs) {
+        cudaFree(X.send_lo);
+        cudaFree(X.send_hi);
+        cudaFree(X.recv_lo);
+        cudaFree(X.recv_hi);
+    }
+    for (SlabAgent &X : s->slab.agents) {
+        cudaFree(X.send_dn);
+        cudaFree(X.send_up);
+        cudaFree(X.recv_lo);
+        cudaFree(X.recv_hi);
+        cudaFree(X.d_counts);
+    }
+    if (s->slab.d_status) cudaFree(s->slab.d_status);
+    if (s->slab.h_pinned) cudaFreeHost(s->slab.h_pinned);
+    slab_release(s);
     cudaFree(s->seeds);
     cudaFree(s->unpack_tmp);
     cudaFree(s->flush_buf);
@@ -456,7 +504,7 @@ extern "C" int fgpu_sim_read_message_var(fgpu_sim *s, int message, int var, void
     if (count == 0) return FGPU_OK;
     CU(cudaSetDevice(s->device));
     const fgpu_var &V = M.d->vars[var];
-    const uint4 *src = (M.d->partitioning == FGPU_PART_SPATIAL) ? M.sorted : M.unsorted;
+    const uint4 *src = (M.d->partitioning == FGPU_PART_SPATIAL) ? M.sorted + (size_t)M.local_at * M.d->rec_quads : M.unsorted;
     int rc = ensure_tmp(s, (size_t)count);
     if (rc) return rc;
     const int words = V.size / 4;
@@ -730,13 +778,15 @@ extern "C" int fgpu_sim_load_states(fgpu_sim *s, const char *xml_path) {
  * With count_out != nullptr the survivor count is read back (blocking, like
  * the two 4-byte D2H copies after every cub scan, e.g. simulation.xslt:1476). */
 static int compact(fgpu_sim *s, AgentRT &A, const char *src, char *dst, int dst_offset, int n, const int *flags,
-                   bool scatter, int *count_out) {
+                   bool scatter, int *count_out, int match = 1, const ColSet *dcols = nullptr, int dst_cap = 0x7fffffff,
+                   int *overflow = nullptr) {
     if (n <= 0) {
         if (count_out) *count_out = 0;
+        CU(cudaMemsetAsync(A.d_total, 0, sizeof(int), s->stream));
         return FGPU_OK;
     }
     const int nb = (n + COMPACT_THREADS - 1) / COMPACT_THREADS;
-    k_flag_blocksum<<<nb, COMPACT_THREADS, 0, s->stream>>>(flags, n, A.block_sums);
+    k_flag_blocksum<<<nb, COMPACT_THREADS, 0, s->stream>>>(flags, n, A.block_sums, match);
     LAUNCH_CHECK();
     k_scan_blocksums<<<1, 1024, 0, s->stream>>>(A.block_sums, nb, A.d_total);
     LAUNCH_CHECK();
@@ -745,7 +795,8 @@ static int compact(fgpu_sim *s, AgentRT &A, const char *src, char *dst, int dst_
         CU(cudaStreamSynchronize(s->stream));
     }
     if (scatter) {
-        k_compact_scatter<<<nb, COMPACT_THREADS, 0, s->stream>>>(src, dst, A.cols, flags, A.block_sums, dst_offset, n);
+        k_compact_scatter<<<nb, COMPACT_THREADS, 0, s->stream>>>(src, dst, A.cols, dcols ? *dcols : A.cols, flags, A.block_sums,
+                                                                 dst_offset, n, match, dst_cap, overflow);
         LAUNCH_CHECK();
         s->touch(dst);
     }
@@ -797,7 +848,7 @@ static int build_spatial(fgpu_sim *s, MsgRT &M) {
     switch (M.d->rec_quads) {
 #define GATHER_CASE(Q)                                                                                                   \
     case Q:                                                                                                              \
-        k_gather_pbm<Q><<<g, 256, 0, s->stream>>>(M.keys[in], M.vals[in], M.unsorted, M.sorted, n, M.cell_start,          \
+        k_gather_pbm<Q><<<g, 256, 0, s->stream>>>(M.keys[in], M.vals[in], M.unsorted, M.sorted + (size_t)M.local_at * Q, n, M.cell_start, \
                                                   (unsigned int)M.d->grid_size, M.gap_queue, gap_count);                 \
         break;
         GATHER_CASE(1)
@@ -819,6 +870,337 @@ static int build_spatial(fgpu_sim *s, MsgRT &M) {
     return FGPU_OK;
 }
 
+
+/* ------------------------------------------------------------------------- */
+/* 1-D slab decomposition over the GPUs of one node            */
+/* ------------------------------------------------------------------------- */
+/* NCCL is bound at run time (dlopen) so that the runtime has no link-time
+ * dependency on it and shares the copy torch already loaded, if any. */
+namespace {
+struct NcclUid { char internal[128]; };
+typedef int (*nccl_get_uid_fn)(NcclUid *);
+typedef int (*nccl_init_rank_fn)(void **, int, NcclUid, int);
+typedef int (*nccl_sendrecv_fn)(const void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*nccl_recv_fn)(void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*nccl_void_fn)(void);
+typedef int (*nccl_destroy_fn)(void *);
+typedef const char *(*nccl_errstr_fn)(int);
+struct NcclApi {
+    void *lib = nullptr;
+    nccl_get_uid_fn GetUniqueId = nullptr;
+    nccl_init_rank_fn CommInitRank = nullptr;
+    nccl_sendrecv_fn Send = nullptr;
+    nccl_recv_fn Recv = nullptr;
+    nccl_void_fn GroupStart = nullptr, GroupEnd = nullptr;
+    nccl_destroy_fn CommDestroy = nullptr;
+    nccl_errstr_fn GetErrorString = nullptr;
+} g_nccl;
+const int NCCL_INT8 = 0; /* ncclInt8 / ncclChar */
+
+int load_nccl() {
+    if (g_nccl.lib) return FGPU_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return set_err(FGPU_ERR_COMM, "cannot load libnccl.so.2: %s", dlerror());
+    g_nccl.GetUniqueId = (nccl_get_uid_fn)dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (nccl_init_rank_fn)dlsym(h, "ncclCommInitRank");
+    g_nccl.Send = (nccl_sendrecv_fn)dlsym(h, "ncclSend");
+    g_nccl.Recv = (nccl_recv_fn)dlsym(h, "ncclRecv");
+    g_nccl.GroupStart = (nccl_void_fn)dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (nccl_void_fn)dlsym(h, "ncclGroupEnd");
+    g_nccl.CommDestroy = (nccl_destroy_fn)dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (nccl_errstr_fn)dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart || !g_nccl.GroupEnd)
+        return set_err(FGPU_ERR_COMM, "libnccl.so.2 lacks a required symbol");
+    g_nccl.lib = h;
+    return FGPU_OK;
+}
+}  // namespace
+
+#define NC(call)                                                                                          \
+    do {                                                                                                  \
+        int r_ = (call);                                                                                  \
+        if (r_ != 0)                                                                                      \
+            return set_err(FGPU_ERR_COMM, "%s:%d: %s -> %s", __FILE__, __LINE__, #call,                   \
+                           g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error");            \
+    } while (0)
+
+static void slab_release(fgpu_sim *s) {
+    if (s->slab.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->slab.comm);
+    s->slab.comm = nullptr;
+}
+
+extern "C" int fgpu_nccl_unique_id(void *out128) {
+    if (!out128) return set_err(FGPU_ERR_ARG, "null pointer");
+    int rc = load_nccl();
+    if (rc) return rc;
+    NC(g_nccl.GetUniqueId((NcclUid *)out128));
+    return FGPU_OK;
+}
+
+/* rand48 seeds of a slab: slot i of rank r continues the reference stream at position r*N + i, and the
+ * stride constants leap over world*N slots, so that the ranks' streams never overlap. */
+static int seed_rand48(fgpu_sim *s, unsigned long long skip, unsigned long long stride_slots) {
+    static const unsigned long long a = 0x5DEECE66DULL, c = 0xB;
+    const unsigned int N = (unsigned int)s->model->buffer_size_max;
+    unsigned long long A = 1ULL, C = 0ULL;
+    for (unsigned long long i = 0; i < stride_slots; ++i) {
+        C += A * c;
+        A *= a;
+    }
+    s->Ax = (unsigned int)(A & 0xFFFFFFULL);
+    s->Ay = (unsigned int)((A >> 24) & 0xFFFFFFULL);
+    s->Cx = (unsigned int)(C & 0xFFFFFFULL);
+    s->Cy = (unsigned int)((C >> 24) & 0xFFFFFFULL);
+    std::vector<uint2> h(N);
+    unsigned long long x = (((unsigned long long)123) << 16) | 0x330E;
+    for (unsigned long long i = 0; i < skip; ++i) x = a * x + c;
+    for (unsigned int i = 0; i < N; ++i) {
+        x = a * x + c;
+        h[i].x = (unsigned int)(x & 0xFFFFFFULL);
+        h[i].y = (unsigned int)((x >> 24) & 0xFFFFFFULL);
+    }
+    CU(cudaMemcpyAsync(s->seeds, h.data(), sizeof(uint2) * (size_t)N, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FGPU_OK;
+}
+
+extern "C" int fgpu_sim_slab_init(fgpu_sim *s, int rank, int world, const void *nccl_unique_id, int halo_cap, int mig_cap) {
+    if (!s || world < 2 || rank < 0 || rank >= world || !nccl_unique_id) return set_err(FGPU_ERR_ARG, "bad slab arguments");
+    const fgpu_model *m = s->model;
+    CU(cudaSetDevice(s->device));
+    int rc = load_nccl();
+    if (rc) return rc;
+    SlabRT &S = s->slab;
+    /* every spatially partitioned message must live on the same grid */
+    const fgpu_message *g = nullptr;
+    for (int i = 0; i < m->nmessages; ++i) {
+        const fgpu_message *M = &m->messages[i];
+        if (M->partitioning != FGPU_PART_SPATIAL) continue;
+        if (!g) g = M;
+        else if (memcmp(g->dims, M->dims, sizeof(g->dims)) || memcmp(g->min_bounds, M->min_bounds, sizeof(g->min_bounds)) ||
+                 memcmp(g->max_bounds, M->max_bounds, sizeof(g->max_bounds)))
+            return set_err(FGPU_ERR_MODEL, "slab mode needs all spatial messages on one partition grid (%s differs from %s)", M->name, g->name);
+    }
+    if (!g) return set_err(FGPU_ERR_MODEL, "slab mode needs a spatially partitioned message");
+    S.axis = g->is_2d ? 1 : 2;
+    S.nplanes = g->dims[S.axis];
+    S.plane_cells = (S.axis == 2) ? g->dims[0] * g->dims[1] : g->dims[0];
+    if (S.nplanes % world != 0 || S.nplanes / world < 2)
+        return set_err(FGPU_ERR_MODEL, "%d cell planes cannot be cut into %d slabs of >= 2 whole planes", S.nplanes, world);
+    S.rank = rank;
+    S.world = world;
+    S.ppr = S.nplanes / world;
+    S.p0 = rank * S.ppr;
+    S.p1 = S.p0 + S.ppr;
+    S.lo_rank = (rank + world - 1) % world;
+    S.hi_rank = (rank + 1) % world;
+    S.axis_min = g->min_bounds[S.axis];
+    S.axis_max = g->max_bounds[S.axis];
+    int maxbuf = 0;
+    for (int a = 0; a < m->nagents; ++a) maxbuf = std::max(maxbuf, m->agents[a].buffer_size);
+    S.halo_cap = halo_cap > 0 ? halo_cap : std::max(4096, (int)std::min<long long>(maxbuf, 4LL * maxbuf / S.ppr));
+    S.mig_cap = mig_cap > 0 ? mig_cap : S.halo_cap;
+    NcclUid uid;
+    memcpy(&uid, nccl_unique_id, sizeof(uid));
+    NC(g_nccl.CommInitRank(&S.comm, world, uid, rank));
+    CU(cudaMalloc(&S.d_status, sizeof(int) * 8));
+    CU(cudaMemset(S.d_status, 0, sizeof(int) * 8));
+    CU(cudaMallocHost(&S.h_pinned, sizeof(int) * 256));
+    /* messages: the sorted buffer gains room for one halo plane on each side of the local block */
+    S.msgs.resize(m->nmessages);
+    const int pad = (S.plane_cells + 1 + 3) & ~3;
+    for (int i = 0; i < m->nmessages; ++i) {
+        MsgRT &M = s->msgs[i];
+        if (M.d->partitioning != FGPU_PART_SPATIAL) continue;
+        cudaFree(M.sorted);
+        M.sorted = nullptr;
+        CU(cudaMalloc(&M.sorted, (size_t)M.d->rec_quads * 16 * ((size_t)M.d->buffer_size + 2 * (size_t)S.halo_cap)));
+        M.local_at = S.halo_cap;
+        SlabMsg &X = S.msgs[i];
+        X.bytes = sizeof(int) * (size_t)(XHDR + pad) + (size_t)S.halo_cap * M.d->rec_quads * 16;
+        CU(cudaMalloc(&X.send_lo, X.bytes));
+        CU(cudaMalloc(&X.send_hi, X.bytes));
+        CU(cudaMalloc(&X.recv_lo, X.bytes));
+        CU(cudaMalloc(&X.recv_hi, X.bytes));
+        CU(cudaMemset(X.recv_lo, 0, X.bytes));
+        CU(cudaMemset(X.recv_hi, 0, X.bytes));
+    }
+    /* agents: fixed-capacity migrant buffers, one column block per variable */
+    S.agents.resize(m->nagents);
+    const char *axis_name = (S.axis == 2) ? "z" : "y";
+    for (int a = 0; a < m->nagents; ++a) {
+        AgentRT &A = s->agents[a];
+        SlabAgent &X = S.agents[a];
+        X.axis_var = -1;
+        for (int v = 0; v < A.d->nvars; ++v)
+            if (!strcmp(A.d->vars[v].name, axis_name) && A.d->vars[v].is_float && A.d->vars[v].size == 4) X.axis_var = v;
+        if (X.axis_var < 0) continue; /* agents without a position never migrate */
+        size_t off = 16;
+        X.bufcols.ncols = A.d->nvars;
+        for (int v = 0; v < A.d->nvars; ++v) {
+            off = (off + 15) & ~(size_t)15;
+            X.bufcols.size[v] = A.d->vars[v].size;
+            X.bufcols.off[v] = off;
+            off += (size_t)A.d->vars[v].size * S.mig_cap;
+        }
+        X.bytes = (off + 15) & ~(size_t)15;
+        CU(cudaMalloc(&X.send_dn, X.bytes));
+        CU(cudaMalloc(&X.send_up, X.bytes));
+        CU(cudaMalloc(&X.recv_lo, X.bytes));
+        CU(cudaMalloc(&X.recv_hi, X.bytes));
+        CU(cudaMalloc(&X.d_counts, sizeof(int) * 2 * (size_t)A.d->nstates));
+        CU(cudaMemset(X.d_counts, 0, sizeof(int) * 2 * (size_t)A.d->nstates));
+    }
+    rc = seed_rand48(s, (unsigned long long)rank * (unsigned long long)m->buffer_size_max,
+                     (unsigned long long)world * (unsigned long long)m->buffer_size_max);
+    if (rc) return rc;
+    S.on = true;
+    s->is_static = false; /* populations change every iteration: no graph replay in slab mode */
+    invalidate_graph(s);
+    return FGPU_OK;
+}
+
+extern "C" int fgpu_sim_slab_info(fgpu_sim *s, int *out8) {
+    if (!s || !out8) return set_err(FGPU_ERR_ARG, "bad argument");
+    const SlabRT &S = s->slab;
+    out8[0] = S.on;
+    out8[1] = S.axis;
+    out8[2] = S.nplanes;
+    out8[3] = S.p0;
+    out8[4] = S.p1;
+    out8[5] = S.halo_cap;
+    out8[6] = S.mig_cap;
+    out8[7] = S.plane_cells;
+    return FGPU_OK;
+}
+
+/* Halo exchange after a spatial message build: my two boundary planes go to the neighbours, theirs are
+ * spliced around my local block (contiguous ranges of the SORTED list, so within-cell order is the owner's). */
+static int slab_exchange_halo(fgpu_sim *s, int mi) {
+    SlabRT &S = s->slab;
+    MsgRT &M = s->msgs[mi];
+    SlabMsg &X = S.msgs[mi];
+    const int n = M.h_count, PL = S.plane_cells, Q = M.d->rec_quads;
+    if (n == 0) CU(cudaMemsetAsync(M.cell_start, 0, sizeof(unsigned int) * ((size_t)M.d->grid_size + 1), s->stream));
+    const uint4 *local = M.sorted + (size_t)M.local_at * Q;
+    s->prof_begin(std::string("halo:") + M.d->name);
+    const int g = std::min(148 * 4, (std::max(S.halo_cap * Q, PL) + 255) / 256);
+    switch (Q) {
+#define PACK_CASE(QQ)                                                                                                       \
+    case QQ:                                                                                                                \
+        k_pack_plane<QQ><<<g, 256, 0, s->stream>>>(local, M.cell_start, S.p0 * PL, PL, S.halo_cap, X.send_lo);              \
+        k_pack_plane<QQ><<<g, 256, 0, s->stream>>>(local, M.cell_start, (S.p1 - 1) * PL, PL, S.halo_cap, X.send_hi);        \
+        break;
+        PACK_CASE(1) PACK_CASE(2) PACK_CASE(3) PACK_CASE(4) PACK_CASE(5) PACK_CASE(6) PACK_CASE(7) PACK_CASE(8)
+#undef PACK_CASE
+        default:
+            return set_err(FGPU_ERR_MODEL, "record of %d quads unsupported", Q);
+    }
+    s->launches += 2;
+    CU(cudaGetLastError());
+    NC(g_nccl.GroupStart());
+    NC(g_nccl.Send(X.send_lo, X.bytes, NCCL_INT8, S.lo_rank, S.comm, s->stream));
+    NC(g_nccl.Send(X.send_hi, X.bytes, NCCL_INT8, S.hi_rank, S.comm, s->stream));
+    NC(g_nccl.Recv(X.recv_hi, X.bytes, NCCL_INT8, S.hi_rank, S.comm, s->stream));
+    NC(g_nccl.Recv(X.recv_lo, X.bytes, NCCL_INT8, S.lo_rank, S.comm, s->stream));
+    NC(g_nccl.GroupEnd());
+    S.halo_bytes += 2 * (long long)X.bytes;
+    const int lo_first = ((S.p0 - 1 + S.nplanes) % S.nplanes) * PL, hi_first = (S.p1 % S.nplanes) * PL;
+    switch (Q) {
+#define MERGE_CASE(QQ)                                                                                                      \
+    case QQ:                                                                                                                \
+        k_merge_halo<QQ><<<g, 256, 0, s->stream>>>(M.sorted, M.cell_start, M.local_at, n, S.p0 * PL, S.ppr * PL, X.recv_lo, \
+                                                   lo_first, X.recv_hi, hi_first, PL, S.d_status);                         \
+        break;
+        MERGE_CASE(1) MERGE_CASE(2) MERGE_CASE(3) MERGE_CASE(4) MERGE_CASE(5) MERGE_CASE(6) MERGE_CASE(7) MERGE_CASE(8)
+#undef MERGE_CASE
+    }
+    LAUNCH_CHECK();
+    s->prof_end();
+    return FGPU_OK;
+}
+
+/* Migration: agents whose plane left the slab are compacted out and sent to the owning neighbour; arrivals
+ * are appended after the stayers (lower neighbour's first).  One host round trip at the end learns the new
+ * populations (the reference pays two blocking D2H copies after every scan, e.g. sim:1476-1477). */
+static int slab_migrate(fgpu_sim *s) {
+    SlabRT &S = s->slab;
+    const fgpu_model *m = s->model;
+    s->prof_begin("migrate");
+    int slot = 0;
+    for (int a = 0; a < m->nagents; ++a) {
+        AgentRT &A = s->agents[a];
+        SlabAgent &X = S.agents[a];
+        if (X.axis_var < 0) continue;
+        for (int st = 0; st < A.d->nstates; ++st, ++slot) {
+            const int n = A.h_state_count[st];
+            char *list = A.state[st];
+            int *flags = (int *)(list + A.d->scan_offset);
+            int *cnt = X.d_counts + 2 * st;
+            if (n > 0) {
+                k_owner_flags<<<(n + 255) / 256, 256, 0, s->stream>>>((const float *)(list + A.d->vars[X.axis_var].list_offset), n,
+                                                                   S.axis_min, S.axis_max, S.nplanes, S.ppr, S.rank, S.world, flags,
+                                                                   S.d_status);
+                LAUNCH_CHECK();
+            }
+            int rc = compact(s, A, list, A.swap, 0, n, flags, true, nullptr, 1);
+            if (rc) return rc;
+            CU(cudaMemcpyAsync(cnt, A.d_total, sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
+            rc = compact(s, A, list, X.send_dn, 0, n, flags, true, nullptr, 2, &X.bufcols, S.mig_cap, S.d_status + 1);
+            if (rc) return rc;
+            k_set_header<<<1, 1, 0, s->stream>>>((int *)X.send_dn, A.d_total, S.mig_cap);
+            LAUNCH_CHECK();
+            rc = compact(s, A, list, X.send_up, 0, n, flags, true, nullptr, 3, &X.bufcols, S.mig_cap, S.d_status + 1);
+            if (rc) return rc;
+            k_set_header<<<1, 1, 0, s->stream>>>((int *)X.send_up, A.d_total, S.mig_cap);
+            LAUNCH_CHECK();
+            NC(g_nccl.GroupStart());
+            NC(g_nccl.Send(X.send_dn, X.bytes, NCCL_INT8, S.lo_rank, S.comm, s->stream));
+            NC(g_nccl.Send(X.send_up, X.bytes, NCCL_INT8, S.hi_rank, S.comm, s->stream));
+            NC(g_nccl.Recv(X.recv_hi, X.bytes, NCCL_INT8, S.hi_rank, S.comm, s->stream));
+            NC(g_nccl.Recv(X.recv_lo, X.bytes, NCCL_INT8, S.lo_rank, S.comm, s->stream));
+            NC(g_nccl.GroupEnd());
+            S.mig_bytes += 2 * (long long)X.bytes;
+            const int gb = (S.mig_cap + 255) / 256;
+            k_append_received<<<gb, 256, 0, s->stream>>>(X.recv_lo, (const int *)X.recv_lo, A.swap, X.bufcols, A.cols, cnt, nullptr,
+                                                         A.d->buffer_size, S.d_status + 2);
+            LAUNCH_CHECK();
+            k_append_received<<<gb, 256, 0, s->stream>>>(X.recv_hi, (const int *)X.recv_hi, A.swap, X.bufcols, A.cols, cnt,
+                                                         (const int *)X.recv_lo, A.d->buffer_size, S.d_status + 2);
+            LAUNCH_CHECK();
+            k_sum_counts<<<1, 1, 0, s->stream>>>(cnt + 1, cnt, (const int *)X.recv_lo, (const int *)X.recv_hi);
+            LAUNCH_CHECK();
+            CU(cudaMemcpyAsync(S.h_pinned + 8 + slot, cnt + 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+            std::swap(A.state[st], A.swap);
+            s->touch(A.state[st]);
+        }
+    }
+    CU(cudaMemcpyAsync(S.h_pinned, S.d_status, sizeof(int) * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->prof_end();
+    if (S.h_pinned[0] == 1 || S.h_pinned[1] || S.h_pinned[2])
+        return set_err(FGPU_ERR_OVERFLOW, "slab exchange: fixed-capacity buffer overflow (halo %d, migrants %d, status %d/%d/%d)",
+                       S.halo_cap, S.mig_cap, S.h_pinned[0], S.h_pinned[1], S.h_pinned[2]);
+    if (S.h_pinned[0] == 2) return set_err(FGPU_ERR_COMM, "slab exchange: an agent moved further than one slab in one step");
+    slot = 0;
+    for (int a = 0; a < m->nagents; ++a) {
+        if (S.agents[a].axis_var < 0) continue;
+        for (int st = 0; st < s->agents[a].d->nstates; ++st, ++slot) {
+            const int nn = S.h_pinned[8 + slot];
+            if (nn > s->agents[a].d->buffer_size)
+                return set_err(FGPU_ERR_OVERFLOW, "slab migration: %d agents exceed the buffer of %s", nn, s->agents[a].d->name);
+            s->agents[a].h_state_count[st] = nn;
+        }
+    }
+    S.dirty = false;
+    return FGPU_OK;
+}
+
 /* ------------------------------------------------------------------------- */
 /* one agent function: <Agent>_<func>(stream), simulation.xslt:1402-1974      */
 /* ------------------------------------------------------------------------- */
@@ -828,7 +1210,14 @@ static int run_function(fgpu_sim *s, int fi) {
     AgentRT &A = s->agents[F.agent];
     const int cur = F.current_state, nxt = F.next_state;
 
-    if (A.h_state_count[cur] == 0) return FGPU_OK; /* sim:1417-1420 */
+    if (s->slab.on) {
+        /* every rank must take part in every exchange: empty lists still run their (empty) functions */
+        if (s->slab.dirty && F.output_message >= 0 && s->msgs[F.output_message].d->partitioning == FGPU_PART_SPATIAL) {
+            int rc = slab_migrate(s);
+            if (rc) return rc;
+        }
+    } else if (A.h_state_count[cur] == 0)
+        return FGPU_OK; /* sim:1417-1420 */
     const int state_list_size = A.h_state_count[cur];
 
     if (F.xagent_output >= 0) {
@@ -974,9 +1363,9 @@ static int run_function(fgpu_sim *s, int fi) {
             return set_err(FGPU_ERR_OVERFLOW, "Error: Buffer size of %s agents in state %s will be exceeded writing new agents in function %s",
                            B.d->name, B.d->states[st], F.name);
         const int nb = (pre_death_count + COMPACT_THREADS - 1) / COMPACT_THREADS;
-        k_compact_scatter<<<nb, COMPACT_THREADS, 0, s->stream>>>(B.newl, B.state[st], B.cols,
+        k_compact_scatter<<<nb, COMPACT_THREADS, 0, s->stream>>>(B.newl, B.state[st], B.cols, B.cols,
                                                                  (const int *)(B.newl + B.d->scan_offset), B.block_sums,
-                                                                 B.h_state_count[st], pre_death_count);
+                                                                 B.h_state_count[st], pre_death_count, 1, 0x7fffffff, nullptr);
         LAUNCH_CHECK();
         s->touch(B.state[st]);
         B.h_state_count[st] += born;
@@ -985,7 +1374,12 @@ static int run_function(fgpu_sim *s, int fi) {
     if (Mout && Mout->d->partitioning == FGPU_PART_SPATIAL) {
         int rc = build_spatial(s, *Mout);
         if (rc) return rc;
+        if (s->slab.on) {
+            rc = slab_exchange_halo(s, F.output_message);
+            if (rc) return rc;
+        }
     }
+    if (s->slab.on && (F.writes_position || F.xagent_output >= 0)) s->slab.dirty = true;
     /* move agents to next state, sim:1936-1972 */
     if (A.h_state_count[nxt] + A.h_count > A.d->buffer_size)
         return set_err(FGPU_ERR_OVERFLOW, "Error: Buffer size of %s agents in state %s will be exceeded moving working agents to next state in function %s",
@@ -1022,6 +1416,10 @@ static int single_iteration(fgpu_sim *s) {
             int rc = run_function(s, m->layers[l].functions[k]);
             if (rc) return rc;
         }
+    if (s->slab.on && s->slab.dirty) {
+        int rc = slab_migrate(s);
+        if (rc) return rc;
+    }
     if (!s->capturing)
         for (int k = 0; k < m->nstep_functions; ++k) {
             CU(cudaStreamSynchronize(s->stream));
@@ -1283,9 +1681,9 @@ extern "C" int fgpu_debug_compact(const int *flags, const unsigned int *payload,
     cols.ncols = 1;
     cols.size[0] = 4;
     cols.off[0] = 0;
-    k_flag_blocksum<<<nb, COMPACT_THREADS>>>(d_flags, n, d_bs);
+    k_flag_blocksum<<<nb, COMPACT_THREADS>>>(d_flags, n, d_bs, 1);
     k_scan_blocksums<<<1, 1024>>>(d_bs, nb, d_total);
-    k_compact_scatter<<<nb, COMPACT_THREADS>>>((const char *)d_in, (char *)d_out, cols, d_flags, d_bs, 0, n);
+    k_compact_scatter<<<nb, COMPACT_THREADS>>>((const char *)d_in, (char *)d_out, cols, cols, d_flags, d_bs, 0, n, 1, 0x7fffffff, nullptr);
     CU(cudaGetLastError());
     CU(cudaMemcpy(count_out, d_total, sizeof(int), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(out, d_out, sizeof(unsigned int) * (size_t)(*count_out), cudaMemcpyDeviceToHost));

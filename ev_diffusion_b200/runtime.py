@@ -56,7 +56,7 @@ class _Function(C.Structure):
                 ("xagent_output", C.c_int), ("xagent_output_state", C.c_int), ("reallocate", C.c_int),
                 ("swappable", C.c_int), ("rng", C.c_int), ("condition", C.c_int), ("gc_max_iterations", C.c_int),
                 ("gc_must_evaluate_to", C.c_int), ("launch", C.c_void_p), ("filter", C.c_void_p),
-                ("block_size", C.c_int)]
+                ("block_size", C.c_int), ("writes_position", C.c_int)]
 
 
 class _Layer(C.Structure):
@@ -410,6 +410,12 @@ def load_runtime() -> C.CDLL:
     lib.fgpu_sim_profile_iteration.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     lib.fgpu_sim_device_agents.restype = C.c_void_p
     lib.fgpu_sim_device_agents.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.fgpu_nccl_unique_id.restype = C.c_int
+    lib.fgpu_nccl_unique_id.argtypes = [C.c_void_p]
+    lib.fgpu_sim_slab_init.restype = C.c_int
+    lib.fgpu_sim_slab_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    lib.fgpu_sim_slab_info.restype = C.c_int
+    lib.fgpu_sim_slab_info.argtypes = [C.c_void_p, C.c_void_p]
     lib.fgpu_debug_sort_pairs.restype = C.c_int
     lib.fgpu_debug_sort_pairs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.fgpu_debug_compact.restype = C.c_int
@@ -466,12 +472,32 @@ class Simulation(SimBase):
     def set_option(self, key: str, value: int) -> None:
         self._check(self._lib.fgpu_sim_set_option(self._h, key.encode(), int(value)))
 
+    # -- 1-D slab decomposition (one process per GPU)
+    def slab_init(self, rank: int, world: int, unique_id: bytes, halo_cap: int = 0, mig_cap: int = 0) -> None:
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.fgpu_sim_slab_init(self._h, int(rank), int(world), buf, int(halo_cap), int(mig_cap)))
+
+    def slab_info(self) -> dict:
+        out = np.zeros(8, dtype=np.int32)
+        self._check(self._lib.fgpu_sim_slab_info(self._h, out.ctypes.data))
+        keys = ("enabled", "axis", "nplanes", "p0", "p1", "halo_cap", "mig_cap", "plane_cells")
+        return dict(zip(keys, (int(v) for v in out)))
+
     def profile_iteration(self):
         cap = 256
         names = (C.c_char_p * cap)()
         ms = (C.c_float * cap)()
         n = self._check(self._lib.fgpu_sim_profile_iteration(self._h, names, ms, cap))
         return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
+
+def nccl_unique_id() -> bytes:
+    """ncclGetUniqueId() through the runtime (rank 0 calls this; the host program broadcasts it)."""
+    lib = load_runtime()
+    buf = C.create_string_buffer(128)
+    if lib.fgpu_nccl_unique_id(buf) < 0:
+        raise FgpuError(lib.fgpu_last_error().decode())
+    return buf.raw
 
 
 def debug_sort_pairs(keys: np.ndarray, key_bits: int, max_digit_bits: int = 8):

@@ -40,6 +40,12 @@ class BrownianConfig:
     dims: Tuple[int, int, int]
     seed: int
     sigma: float = 0.25
+    buffer: int = 0      # bufferSize of the model (per rank); 0 = n
+    world: int = 1       # number of slabs the global population is cut into
+
+    @property
+    def buffer_size(self) -> int:
+        return self.buffer or self.n
 
     @property
     def cells(self) -> int:
@@ -55,6 +61,12 @@ BROWNIAN = {
     "c2_small": BrownianConfig("Brownian_small", 1 << 14, (16, 16, 16), 7),
     # tiny ragged case: count < bufferSize, few agents per tile, some empty cells
     "c2_tiny": BrownianConfig("Brownian_tiny", 4096, (16, 16, 16), 11),
+    # weak scaling over z-slabs: 1M agents and 64 cell planes per GPU
+    "c2_w2": BrownianConfig("Brownian_w2", 2 << 20, (64, 64, 128), 42, buffer=1310720, world=2),
+    "c2_w4": BrownianConfig("Brownian_w4", 4 << 20, (64, 64, 256), 42, buffer=1310720, world=4),
+    "c2_w8": BrownianConfig("Brownian_w8", 8 << 20, (64, 64, 512), 42, buffer=1310720, world=8),
+    # small 2-slab parity case
+    "c2_s2": BrownianConfig("Brownian_s2", 1 << 15, (16, 16, 32), 13, buffer=24576, world=2),
 }
 
 BROWNIAN_XML = os.path.join(build.MODELS, "Brownian", "src", "model", "XMLModelFile.xml")
@@ -66,7 +78,7 @@ def brownian_xml(cfg: BrownianConfig) -> str:
         return BROWNIAN_XML
     dx, dy, dz = cfg.dims
     rep = {
-        "<gpu:bufferSize>1048576</gpu:bufferSize>": f"<gpu:bufferSize>{cfg.n}</gpu:bufferSize>",
+        "<gpu:bufferSize>1048576</gpu:bufferSize>": f"<gpu:bufferSize>{cfg.buffer_size}</gpu:bufferSize>",
         "<gpu:xmax>64</gpu:xmax>": f"<gpu:xmax>{dx}</gpu:xmax>",
         "<gpu:ymax>64</gpu:ymax>": f"<gpu:ymax>{dy}</gpu:ymax>",
         "<gpu:zmax>64</gpu:zmax>": f"<gpu:zmax>{dz}</gpu:zmax>",

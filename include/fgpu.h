@@ -138,11 +138,23 @@ int fgpu_debug_sort_pairs(const unsigned int *keys, int n, int key_bits, int max
 int fgpu_debug_compact(const int *flags, const unsigned int *payload, int n, unsigned int *out, int *count_out);
 
 /* ---- 1-D slab decomposition over the GPUs of one node ------ */
-/* `nccl_unique_id` is the 128-byte ncclUniqueId produced by rank 0 and
- * broadcast by the host program (torch.distributed in bench.py).  The slab
- * axis is the slowest hash axis (z; y for 2-D grids, kernals.xslt:888). */
-int fgpu_sim_slab_init(fgpu_sim *sim, int rank, int world, const void *nccl_unique_id);
+/* The reference is single-GPU (one cudaSetDevice, main.xslt:311); this is the one
+ * parallelism strategy the B200 runtime adds.  The partition grid is cut into
+ * `world` slabs of whole cell planes along the slowest hash axis (z; y for 2-D
+ * grids, kernals.xslt:888).  After every spatial message build the two boundary
+ * planes of the sorted message list travel to the neighbouring ranks (including
+ * the wrap pair 0 <-> world-1, because message_<M>_hash sends out-of-range
+ * neighbour cells to the opposite face, kernals.xslt:880-885); after every
+ * function that moves agents, agents whose plane left the slab migrate to the
+ * owning neighbour.  Transport: NCCL send/recv over NVLink on the simulation
+ * stream, fixed-capacity buffers (halo_cap messages / mig_cap agents per
+ * direction; 0 = automatic), true counts in a device-side header.
+ * `nccl_unique_id` is the 128-byte ncclUniqueId made by rank 0
+ * (fgpu_nccl_unique_id) and broadcast by the host program. */
 int fgpu_nccl_unique_id(void *out128);
+int fgpu_sim_slab_init(fgpu_sim *sim, int rank, int world, const void *nccl_unique_id, int halo_cap, int mig_cap);
+/* {enabled, axis, nplanes, first owned plane, one past last owned plane, halo_cap, mig_cap, cells per plane} */
+int fgpu_sim_slab_info(fgpu_sim *sim, int *out8);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FGPU_MODEL_ABI_VERSION 4
+#define FGPU_MODEL_ABI_VERSION 5
 
 /* One agent or message variable.  Agent lists keep the reference's SoA struct
  * layout (header.xslt:187-194): int _position[MAX]; int _scan_input[MAX];
@@ -124,6 +124,7 @@ typedef struct fgpu_function {
     fgpu_launch_fn launch;
     fgpu_filter_fn filter;        /* NULL unless condition != NONE */
     int block_size;               /* threads per block the launcher uses */
+    int writes_position;          /* the script may modify x, y or z (slab mode: agents may change owner) */
 } fgpu_function;
 
 typedef struct fgpu_layer {
