@@ -101,6 +101,7 @@ def build_model(xml_path: str, name: str, fmad: bool = True, force: bool = False
     float results are bit-comparable with the host oracle compiled with
     ``-ffp-contract=off``.
     """
+    build_runtime()   # the plugin's Face-2 shim links against libfgpu_rt.so
     model = xmml.parse_model(xml_path)
     mdir = os.path.dirname(os.path.abspath(xml_path))
     if function_files is None:
@@ -114,15 +115,35 @@ def build_model(xml_path: str, name: str, fmad: bool = True, force: bool = False
     out = model_path(name)
     cmd = [NVCC] + ARCH_FLAGS + COMMON + ["-Xptxas", "-v", "-fmad=" + ("true" if fmad else "false"),
                                           "-I", gen, "-I", INCLUDE, "-I", CSRC, "-I", mdir,
-                                          files["model_glue.cu"], "-o", out]
+                                          files["model_glue.cu"], "-o", out,
+                                          "-L", LIB, "-lfgpu_rt", "-Xlinker", "-rpath=$ORIGIN/.."]
     deps = [files["header.h"], files["model_glue.cu"], os.path.join(CSRC, "fgpu_device.cuh"),
-            os.path.join(CSRC, "fgpu_glm.h"), os.path.join(INCLUDE, "fgpu_model.h")] + list(function_files)
+            os.path.join(CSRC, "fgpu_glm.h"), os.path.join(INCLUDE, "fgpu_model.h"), os.path.join(INCLUDE, "fgpu.h")] + list(function_files)
     stamp = _stamp(deps, " ".join(cmd))
     if not force and _fresh(out, stamp):
         return out
     text = _run(cmd, log=out + ".log")
     if verbose:
         print(text)
+    _mark(out, stamp)
+    return out
+
+
+def build_driver(source: str, model_name: str, out_name: str, force: bool = False) -> str:
+    """Compile a host driver written against the reference's Face-2 names (initialise,
+    singleIteration, ...) and link it to a model plugin + libfgpu_rt.so."""
+    gen = os.path.join(GEN, model_name)
+    out = os.path.join(LIB, "drivers", out_name)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [NVCC] + ARCH_FLAGS + ["-std=c++17", "-O2", "-cudart", "shared", "-diag-suppress", "20012,177,550",
+                                 "-I", gen, "-I", INCLUDE, "-I", CSRC, source, "-o", out,
+                                 "-L", os.path.join(LIB, "models"), f"-l:{model_name}.so", "-L", LIB, "-lfgpu_rt",
+                                 "-Xlinker", "-rpath=$ORIGIN/../models:$ORIGIN/..:/usr/local/cuda/lib64"]
+    deps = [source, model_path(model_name), runtime_path()]
+    stamp = _stamp(deps, " ".join(cmd))
+    if not force and _fresh(out, stamp):
+        return out
+    _run(cmd, log=out + ".log")
     _mark(out, stamp)
     return out
 

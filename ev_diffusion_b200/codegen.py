@@ -640,6 +640,43 @@ def _constants_code(model: Model, cuda: bool) -> str:
     return "\n".join(out) + "\n"
 
 
+def _face2_shim(model: Model, cuda: bool) -> str:
+    """Face-2 names of the reference (header.xslt:531-645) on top of the C ABI, preserving
+    the reference's error behaviour (message + exit(), simulation.xslt:198-206).  The oracle
+    build gets no-op bind only (its driver is the test harness)."""
+    if not cuda:
+        return "static void fgpu_plugin_bind(void*){}\n"
+    out = ['#include "fgpu.h"',
+           "static fgpu_sim* fgpu_cur = nullptr;",
+           "static bool fgpu_exit_early = false;",
+           "static void fgpu_plugin_bind(void* sim){ fgpu_cur = (fgpu_sim*)sim; }",
+           'static void fgpu_die(){ fprintf(stderr, "%s\\n", fgpu_last_error()); fflush(stderr); exit(EXIT_FAILURE); }',
+           "unsigned int getIterationNumber(){ return fgpu_sim_iteration(fgpu_cur); }",
+           "void set_exit_early(){ fgpu_exit_early = true; }",
+           "bool get_exit_early(){ return fgpu_exit_early; }",
+           """void initialise(char * inputfile){
+    /* simulation.xslt:472-747: allocate, read the initial states, seed rand48, run init functions */
+    const char* dev = getenv("FGPU_DEVICE");
+    fgpu_cur = fgpu_sim_create(fgpu_model_get(), dev ? atoi(dev) : 0);
+    if (!fgpu_cur) fgpu_die();
+    if (fgpu_sim_load_states(fgpu_cur, inputfile) != FGPU_OK) fgpu_die();
+    if (fgpu_sim_run_init_functions(fgpu_cur) != FGPU_OK) fgpu_die();
+}
+void singleIteration(){ if (fgpu_sim_step(fgpu_cur, 1) != FGPU_OK) fgpu_die(); }
+void cleanup(){ fgpu_sim_run_exit_functions(fgpu_cur); fgpu_sim_destroy(fgpu_cur); fgpu_cur = nullptr; }"""]
+    for ai, a in enumerate(model.agents):
+        out.append(f"int get_agent_{a.name}_MAX_count(){{ return xmachine_memory_{a.name}_MAX; }}")
+        for si, st in enumerate(a.states):
+            out.append(f"int get_agent_{a.name}_{st}_count(){{ return fgpu_sim_agent_count(fgpu_cur, {ai}, {si}); }}")
+            out.append(f"void reset_{a.name}_{st}_count(){{ fgpu_sim_set_agents(fgpu_cur, {ai}, {si}, 0, nullptr); }}")
+            out.append(f"xmachine_memory_{a.name}_list* get_device_{a.name}_{st}_agents(){{ return (xmachine_memory_{a.name}_list*)fgpu_sim_device_agents(fgpu_cur, {ai}, {si}); }}")
+            for vi, v in enumerate(a.variables):
+                if not v.array_length:
+                    out.append(f"{v.type} get_{a.name}_{st}_variable_{v.name}(unsigned int index){{ {v.type} t = 0; "
+                               f"if (fgpu_sim_read_agent_value(fgpu_cur, {ai}, {si}, {vi}, index, &t) != FGPU_OK) fgpu_die(); return t; }}")
+    return "\n".join(out) + "\n"
+
+
 def _model_struct(model: Model) -> str:
     def fnlist(kind, names):
         if not names:
@@ -657,7 +694,8 @@ def _model_struct(model: Model) -> str:
     fgpu_init_constants,
     {len(model.init_functions)}, fgpu_init_functions,
     {len(model.step_functions)}, fgpu_step_functions,
-    {len(model.exit_functions)}, fgpu_exit_functions
+    {len(model.exit_functions)}, fgpu_exit_functions,
+    fgpu_plugin_bind
 }};
 extern "C" const fgpu_model* fgpu_model_get(void){{ return &fgpu_the_model; }}
 """)
@@ -679,6 +717,8 @@ def emit_cuda_glue(model: Model, function_files: List[str]) -> str:
             out.append(_cuda_filter(model, f))
     out.append(_constants_code(model, cuda=True))
     out.append(_descriptor_tables(model, "cuda", "fgpu_launch_", sources))
+    out.append('extern "C" const fgpu_model* fgpu_model_get(void);')
+    out.append(_face2_shim(model, cuda=True))
     out.append(_model_struct(model))
     return "\n".join(out) + "\n"
 

@@ -475,6 +475,18 @@ extern "C" int fgpu_sim_read_agent_var(fgpu_sim *s, int agent, int state, int va
     return FGPU_OK;
 }
 
+extern "C" int fgpu_sim_read_agent_value(fgpu_sim *s, int agent, int state, int var, unsigned int index, void *dst) {
+    if (!s || !dst || agent < 0 || agent >= (int)s->agents.size()) return set_err(FGPU_ERR_ARG, "bad argument");
+    AgentRT &A = s->agents[agent];
+    if (state < 0 || state >= A.d->nstates || var < 0 || var >= A.d->nvars) return set_err(FGPU_ERR_ARG, "bad index");
+    if (index >= (unsigned int)A.h_state_count[state]) return set_err(FGPU_ERR_ARG, "agent index %u out of range", index);
+    CU(cudaSetDevice(s->device));
+    const fgpu_var &V = A.d->vars[var];
+    CU(cudaMemcpyAsync(dst, A.state[state] + V.list_offset + (size_t)index * V.size, V.size, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FGPU_OK;
+}
+
 extern "C" void *fgpu_sim_device_agents(fgpu_sim *s, int agent, int state) {
     if (!s || agent < 0 || agent >= (int)s->agents.size()) return nullptr;
     AgentRT &A = s->agents[agent];
@@ -1423,6 +1435,7 @@ static int single_iteration(fgpu_sim *s) {
     if (!s->capturing)
         for (int k = 0; k < m->nstep_functions; ++k) {
             CU(cudaStreamSynchronize(s->stream));
+            if (m->bind) m->bind(s);
             m->step_functions[k]();
         }
     return FGPU_OK;
@@ -1561,6 +1574,7 @@ extern "C" float fgpu_sim_last_step_ms(const fgpu_sim *s) { return s ? s->last_m
 extern "C" int fgpu_sim_run_init_functions(fgpu_sim *s) {
     if (!s) return set_err(FGPU_ERR_ARG, "null sim");
     CU(cudaSetDevice(s->device));
+    if (s->model->bind) s->model->bind(s);
     for (int k = 0; k < s->model->ninit_functions; ++k) s->model->init_functions[k]();
     CU(cudaDeviceSynchronize());
     return FGPU_OK;
@@ -1570,6 +1584,7 @@ extern "C" int fgpu_sim_run_exit_functions(fgpu_sim *s) {
     if (!s) return set_err(FGPU_ERR_ARG, "null sim");
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->stream));
+    if (s->model->bind) s->model->bind(s);
     for (int k = 0; k < s->model->nexit_functions; ++k) s->model->exit_functions[k]();
     return FGPU_OK;
 }

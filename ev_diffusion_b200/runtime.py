@@ -78,7 +78,7 @@ class _Model(C.Structure):
                 ("init_constants", C.c_void_p),
                 ("ninit_functions", C.c_int), ("init_functions", C.c_void_p),
                 ("nstep_functions", C.c_int), ("step_functions", C.c_void_p),
-                ("nexit_functions", C.c_int), ("exit_functions", C.c_void_p)]
+                ("nexit_functions", C.c_int), ("exit_functions", C.c_void_p), ("bind", C.c_void_p)]
 
 
 # ---- description objects ----------------------------------------------------

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FGPU_MODEL_ABI_VERSION 5
+#define FGPU_MODEL_ABI_VERSION 6
 
 /* One agent or message variable.  Agent lists keep the reference's SoA struct
  * layout (header.xslt:187-194): int _position[MAX]; int _scan_input[MAX];
@@ -162,6 +162,9 @@ typedef struct fgpu_model {
     void (*const *step_functions)(void);
     int nexit_functions;
     void (*const *exit_functions)(void);
+    /* Makes `sim` the simulation the plugin's Face-2 shim (initialise, singleIteration,
+     * get_agent_<A>_<S>_count ... header.xslt:531-645) and its init/step/exit functions act on. */
+    void (*bind)(void *sim);
 } fgpu_model;
 
 /* The single symbol a model plugin exports. */

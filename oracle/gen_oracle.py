@@ -374,6 +374,7 @@ template <int AGENT_TYPE> void add_{a.name}_agent(xmachine_memory_{a.name}_list*
             out.append(_filter(model, f))
     out.append(codegen._constants_code(model, cuda=False))
     out.append(codegen._descriptor_tables(model, "oracle", "orc_thunk_").replace("orc_thunk_filter_", "orc_filter_"))
+    out.append(codegen._face2_shim(model, cuda=False))
     out.append(codegen._model_struct(model))
     rows = []
     for m in model.messages:

@@ -1,0 +1,43 @@
+"""Drop-in boundary, host face: a console driver written only against the reference's
+generated host API names (initialise, singleIteration, cleanup, get_agent_<A>_<S>_count,
+get_<A>_<S>_variable_<v>; header.xslt:531-645) links against a model plugin +
+libfgpu_rt.so and reproduces the run driven through the C ABI."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from common import W, brownian_plugin, build
+from ev_diffusion_b200.runtime import Simulation
+
+pytestmark = pytest.mark.gpu
+
+
+def test_console_driver_matches_c_abi(tmp_path):
+    exe = os.path.join(build.LIB, "drivers", "console_Brownian_tiny")
+    if not os.path.exists(exe):
+        pytest.skip("driver not prebuilt")
+    cfg = W.BROWNIAN["c2_tiny"]
+    st = W.brownian_state(cfg, 3000)
+    xml = W.write_states_xml(str(tmp_path / "0.xml"), "Particle", st)
+    out = subprocess.run([exe, xml, "7"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout
+    assert "Total Processing time:" in out.stdout
+    m = re.search(r"iteration (\d+) count (\d+) max (\d+)", out.stdout)
+    assert m and (int(m.group(1)), int(m.group(2)), int(m.group(3))) == (7, 3000, cfg.n)
+    sim = Simulation(brownian_plugin("c2_tiny", exact=True))
+    sim.load_states(xml)
+    sim.step(7)
+    a = sim.agents("Particle")
+    rows = re.findall(r"agent (\d+) id (-?\d+) x (\S+) y (\S+) z (\S+) nbr (-?\d+)", out.stdout)
+    assert len(rows) == 8
+    for i, idv, x, y, z, nbr in rows:
+        i = int(i)
+        assert int(idv) == a["id"][i] and int(nbr) == a["nbr"][i]
+        assert np.float32(x) == a["x"][i] and np.float32(y) == a["y"][i] and np.float32(z) == a["z"][i]
+    sim.close()
+    # error behaviour of the reference: message + exit(EXIT_FAILURE) (simulation.xslt:198-206)
+    bad = subprocess.run([exe, str(tmp_path / "missing.xml"), "1"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert bad.returncode != 0 and "Could not open" in bad.stdout
