@@ -1,10 +1,10 @@
 /*
  * fgpu_kernels.cuh -- model-agnostic sm_100a kernels of the simulation step.
  *
- *   (1) spatial message build: LSD radix sort of (cell key, message index) with
- *       one global histogram pass + one "onesweep" scatter pass per digit
- *       (decoupled look-back between tiles), then a fused gather of the packed
- *       message records + partition-boundary (CSR cell_start) construction.
+ *   (1) spatial message build: LSD radix sort of (cell key, message index)
+ *       (per pass: tile histograms, per-digit scan over tiles, stable scatter),
+ *       then a fused gather of the packed message records + partition-boundary
+ *       (CSR cell_start) construction.
  *       Replaces hist/reorder (krn:899-934) and hash + cub::DeviceRadixSort +
  *       reorder (krn:944-1021, sim:1860-1885); the order produced is the
  *       deterministic one: stable by cell, ties by message index.
@@ -27,45 +27,49 @@ namespace fgpu {
 /* ------------------------------------------------------------------------- */
 /* radix sort                                                                 */
 /* ------------------------------------------------------------------------- */
-constexpr int SORT_MAXBITS = 8;
-constexpr int SORT_BINS = 1 << SORT_MAXBITS;
+/* LSD radix sort of (cell key, message index).  One pass = three launches over
+ * tiles of 4096 keys, with no inter-block waiting of any kind:
+ *   k_tile_hist     digit counts of every tile            -> tile_hist[bin][tile]
+ *   k_row_scan      per digit: exclusive scan over tiles  -> tile_hist (in place), totals[bin]
+ *   k_radix_scatter re-reads the tile, ranks it in shared memory (warp match.any
+ *                   + per-warp 16-bit counters, stable), stages it in digit order
+ *                   and writes contiguous runs per digit.
+ * (Round 1 first used a single-sweep pass with decoupled look-back; on B200 a
+ * 4096-key tile takes ~5 us while the look-back chain across the ~450 co-resident
+ * tiles took ~20 us per wave -- profiles/r01_notes.md -- so the chain-free form is
+ * both faster and free of spin-waits.)
+ * Digits are up to 11 bits wide; the digit width is balanced over the passes. */
+constexpr int SORT_MAXBITS = 11;
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; /* 4096 keys per tile */
-constexpr int SORT_MAX_PASSES = 4;
+constexpr int SORT_MAX_PASSES = 8;
+constexpr int SORT_MAX_BINS = 1 << SORT_MAXBITS;
 
-constexpr unsigned int ST_PREFIX = 0x80000000u; /* inclusive prefix published */
-constexpr unsigned int ST_AGG = 0x40000000u;    /* tile aggregate published */
-constexpr unsigned int ST_VAL = 0x3fffffffu;
-
-__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p) {
-    unsigned int v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void st_volatile_u32(unsigned int *p, unsigned int v) {
-    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-/* Digit histograms of every pass in one read of the keys.
- * hist layout: [pass][SORT_BINS]. */
-__global__ void __launch_bounds__(256) k_radix_hist(const unsigned int *__restrict__ keys, int n,
-                                                    unsigned int *__restrict__ hist, int passes, int digit_bits) {
-    __shared__ unsigned int sh[SORT_MAX_PASSES * SORT_BINS];
-    for (int i = threadIdx.x; i < passes * SORT_BINS; i += blockDim.x) sh[i] = 0;
+/* digit counts of one tile; tile_hist is bin-major so that k_row_scan reads rows contiguously */
+__global__ void __launch_bounds__(SORT_THREADS)
+k_tile_hist(const unsigned int *__restrict__ keys, int n, int shift, int digit_bits, unsigned int *__restrict__ tile_hist,
+            int tiles) {
+    extern __shared__ unsigned int sh[]; /* 1 << digit_bits */
+    const int nbins = 1 << digit_bits;
+    for (int i = threadIdx.x; i < nbins; i += SORT_THREADS) sh[i] = 0;
     __syncthreads();
-    const unsigned int mask = (1u << digit_bits) - 1u;
-    const int stride = gridDim.x * blockDim.x;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const unsigned int k = keys[i];
-        for (int p = 0; p < passes; ++p) atomicAdd(&sh[p * SORT_BINS + ((k >> (p * digit_bits)) & mask)], 1u);
+    const unsigned int mask = (unsigned int)nbins - 1u;
+    const int base = blockIdx.x * SORT_TILE;
+    unsigned int k[SORT_ITEMS];
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; ++r) { /* all loads in flight before the first shared atomic */
+        const int idx = base + r * SORT_THREADS + threadIdx.x;
+        k[r] = (idx < n) ? keys[idx] : 0xffffffffu;
+    }
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; ++r) {
+        const int idx = base + r * SORT_THREADS + threadIdx.x;
+        if (idx < n) atomicAdd(&sh[(k[r] >> shift) & mask], 1u);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < passes * SORT_BINS; i += blockDim.x) {
-        const unsigned int v = sh[i];
-        if (v) atomicAdd(&hist[i], v);
-    }
+    for (int i = threadIdx.x; i < nbins; i += SORT_THREADS) tile_hist[(size_t)i * tiles + blockIdx.x] = sh[i];
 }
 
 /* Block-wide exclusive scan of one value per thread (256 threads). */
@@ -87,29 +91,59 @@ __device__ __forceinline__ unsigned int block_exclusive_scan_256(unsigned int v,
     return base + inc - v;
 }
 
-/* One LSD pass.  Tiles take tickets so that a tile only ever waits on tiles
- * that are already running (forward progress of the look-back).
- *   vals_in == nullptr : values are the identity (first pass)
- * Stability: within a tile items are ranked in (warp, round, lane) order, which
- * is ascending input index; tiles are ordered by ticket == input order. */
+/* one block per digit: exclusive scan of that digit's counts over the tiles, in place */
 __global__ void __launch_bounds__(SORT_THREADS)
-k_radix_pass(const unsigned int *__restrict__ keys_in, const unsigned int *__restrict__ vals_in,
-             unsigned int *__restrict__ keys_out, unsigned int *__restrict__ vals_out, int n, int shift,
-             int digit_bits, const unsigned int *__restrict__ hist, unsigned int *status, unsigned int *ticket) {
-    __shared__ unsigned int s_warp_hist[SORT_WARPS][SORT_BINS];
-    __shared__ unsigned int s_tile_excl[SORT_BINS];
-    __shared__ int s_goff[SORT_BINS];
-    __shared__ unsigned int s_keys[SORT_TILE];
-    __shared__ unsigned int s_vals[SORT_TILE];
+k_row_scan(unsigned int *__restrict__ tile_hist, int tiles, unsigned int *__restrict__ totals) {
     __shared__ unsigned int s_scan[SORT_WARPS];
-    __shared__ unsigned int s_tile;
+    unsigned int *row = tile_hist + (size_t)blockIdx.x * tiles;
+    const int per = (tiles + SORT_THREADS - 1) / SORT_THREADS;
+    const int lo = threadIdx.x * per, hi = min(lo + per, tiles);
+    unsigned int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += row[i];
+    unsigned int run = block_exclusive_scan_256(sum, s_scan);
+    for (int i = lo; i < hi; ++i) {
+        const unsigned int t = row[i];
+        row[i] = run;
+        run += t;
+    }
+    if (threadIdx.x == SORT_THREADS - 1) totals[blockIdx.x] = run;
+}
+
+/* shared memory of one scatter pass with digits of BITS bits */
+template <int BITS>
+struct SortSmem {
+    static constexpr int BINS = 1 << BITS;
+    unsigned short warp_hist[SORT_WARPS][BINS];
+    unsigned int tile_excl[BINS];
+    int goff[BINS];
+    unsigned int keys[SORT_TILE];
+    unsigned int vals[SORT_TILE];
+    unsigned int scan[SORT_WARPS];
+};
+
+/*   vals_in == nullptr : values are the identity (first pass)
+ * Stability: within a tile items are ranked in (warp, round, lane) order, which is
+ * ascending input index; tiles are in input order.  BITS is the compile-time digit
+ * capacity (bins per thread = 2^BITS / 256); digit_bits <= BITS is the width in use. */
+template <int BITS>
+__global__ void __launch_bounds__(SORT_THREADS)
+k_radix_scatter(const unsigned int *__restrict__ keys_in, const unsigned int *__restrict__ vals_in,
+                unsigned int *__restrict__ keys_out, unsigned int *__restrict__ vals_out, int n, int shift,
+                int digit_bits, const unsigned int *__restrict__ tile_hist, const unsigned int *__restrict__ totals,
+                int tiles) {
+    constexpr int BINS = 1 << BITS;
+    constexpr int BPT = BINS / SORT_THREADS; /* bins per thread: 1, 2, 4 or 8 */
+    extern __shared__ __align__(16) unsigned char sort_smem_raw[];
+    SortSmem<BITS> &sm = *reinterpret_cast<SortSmem<BITS> *>(sort_smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = tid; i < SORT_WARPS * SORT_BINS; i += SORT_THREADS) (&s_warp_hist[0][0])[i] = 0;
+    {
+        unsigned int *z = reinterpret_cast<unsigned int *>(&sm.warp_hist[0][0]);
+        for (int i = tid; i < SORT_WARPS * BINS / 2; i += SORT_THREADS) z[i] = 0;
+    }
     __syncthreads();
-    const unsigned int tile = s_tile;
-    const int base = (int)tile * SORT_TILE;
+    const int tile = blockIdx.x;
+    const int base = tile * SORT_TILE;
     const int nbins = 1 << digit_bits;
     const unsigned int mask = (unsigned int)nbins - 1u;
     const unsigned int lt = (1u << lane) - 1u;
@@ -123,82 +157,89 @@ k_radix_pass(const unsigned int *__restrict__ keys_in, const unsigned int *__res
         key[r] = valid ? keys_in[idx] : 0u;
         val[r] = valid ? (vals_in ? vals_in[idx] : (unsigned int)idx) : 0xffffffffu;
     }
+    /* Stable ranking inside the warp.  The lanes holding the same digit are found with one
+     * ballot per digit bit (BITS cheap VOTEs) instead of match.any: ncu showed match.any on
+     * ~30 distinct digits per warp costing ~200 cycles of the ADU pipe per call, 58 % pipe
+     * utilisation and the top stall of the pass (profiles/r01_notes.md). */
 #pragma unroll
     for (int r = 0; r < SORT_ITEMS; ++r) {
         const int idx = base + warp * (SORT_ITEMS * 32) + r * 32 + lane;
         const bool valid = idx < n;
-        const unsigned int d = valid ? ((key[r] >> shift) & mask) : 0xffffffffu;
-        const unsigned int peers = __match_any_sync(0xffffffffu, d);
-        const int leader = __ffs(peers) - 1;
-        unsigned int prev = 0;
-        if (lane == leader && valid) {
-            prev = s_warp_hist[warp][d];
-            s_warp_hist[warp][d] = prev + __popc(peers);
+        const unsigned int d = (key[r] >> shift) & mask;
+        unsigned int peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+        for (int b = 0; b < BITS; ++b) {
+            /* m = all ones if bit b of the digit is set; lanes agreeing with me on this bit are ~(bal ^ m) */
+            const int m = ((int)(d << (31 - b))) >> 31;
+            const unsigned int bal = __ballot_sync(0xffffffffu, m != 0);
+            peers &= ~(bal ^ (unsigned int)m);
         }
-        prev = __shfl_sync(0xffffffffu, prev, leader);
-        rank[r] = (unsigned short)(prev + __popc(peers & lt));
+        /* every lane of a group reads the group's counter (same address: broadcast), the first
+         * lane of the group then adds the group size; same-warp shared accesses stay in order */
+        const unsigned int before = __popc(peers & lt);
+        unsigned int prev = 0;
+        if (valid) prev = sm.warp_hist[warp][d];
+        if (valid && before == 0) sm.warp_hist[warp][d] = (unsigned short)(prev + __popc(peers));
+        rank[r] = (unsigned short)(prev + before);
         __syncwarp();
     }
     __syncthreads();
 
-    /* per digit: exclusive offsets across warps, tile count */
-    unsigned int count = 0;
-    if (tid < nbins) {
-        unsigned int run = 0;
+    /* per digit: exclusive offsets across warps and the tile count.  Thread t owns the BPT
+     * consecutive bins [t*BPT, (t+1)*BPT), so one block scan of the per-thread sums yields the
+     * exclusive prefix over all bins (inside the tile, and of the global digit totals). */
+    unsigned int count[BPT], gcount[BPT];
+    unsigned int csum = 0, gsum = 0;
 #pragma unroll
-        for (int w = 0; w < SORT_WARPS; ++w) {
-            const unsigned int t = s_warp_hist[w][tid];
-            s_warp_hist[w][tid] = run;
-            run += t;
-        }
-        count = run;
-    }
-    const unsigned int tile_excl = block_exclusive_scan_256(count, s_scan);
-    const unsigned int gcount = (tid < nbins) ? hist[tid] : 0u;
-    const unsigned int digit_base = block_exclusive_scan_256(gcount, s_scan);
-
-    if (tid < nbins) {
-        unsigned int *st = status + (size_t)tile * SORT_BINS;
-        unsigned int excl = 0;
-        if (tile == 0) {
-            st_volatile_u32(st + tid, ST_PREFIX | count);
-        } else {
-            st_volatile_u32(st + tid, ST_AGG | count);
-            for (int t = (int)tile - 1;; --t) {
-                const unsigned int *p = status + (size_t)t * SORT_BINS + tid;
-                unsigned int v;
-                do {
-                    v = ld_volatile_u32(p);
-                } while ((v & (ST_PREFIX | ST_AGG)) == 0u);
-                excl += v & ST_VAL;
-                if (v & ST_PREFIX) break;
+    for (int k = 0; k < BPT; ++k) {
+        const int d = tid * BPT + k;
+        unsigned int run = 0;
+        if (d < nbins) {
+#pragma unroll
+            for (int w = 0; w < SORT_WARPS; ++w) {
+                const unsigned int t = sm.warp_hist[w][d];
+                sm.warp_hist[w][d] = (unsigned short)run;
+                run += t;
             }
-            st_volatile_u32(st + tid, ST_PREFIX | (excl + count));
         }
-        s_tile_excl[tid] = tile_excl;
-        s_goff[tid] = (int)(digit_base + excl) - (int)tile_excl;
+        count[k] = run;
+        gcount[k] = (d < nbins) ? totals[d] : 0u;
+        csum += run;
+        gsum += gcount[k];
+    }
+    unsigned int tile_excl = block_exclusive_scan_256(csum, sm.scan);
+    unsigned int digit_base = block_exclusive_scan_256(gsum, sm.scan);
+#pragma unroll
+    for (int k = 0; k < BPT; ++k) {
+        const int d = tid * BPT + k;
+        if (d < nbins) {
+            sm.tile_excl[d] = tile_excl;
+            sm.goff[d] = (int)(digit_base + tile_hist[(size_t)d * tiles + tile]) - (int)tile_excl;
+        }
+        tile_excl += count[k];
+        digit_base += gcount[k];
     }
     __syncthreads();
 
-    /* rank -> position inside the tile, staged in shared memory so that the
-     * global writes below are contiguous runs per digit */
+    /* rank -> position inside the tile, staged in shared memory so that the global writes
+     * below are contiguous runs per digit */
 #pragma unroll
     for (int r = 0; r < SORT_ITEMS; ++r) {
         const int idx = base + warp * (SORT_ITEMS * 32) + r * 32 + lane;
         if (idx < n) {
             const unsigned int d = (key[r] >> shift) & mask;
-            const unsigned int lp = s_tile_excl[d] + s_warp_hist[warp][d] + rank[r];
-            s_keys[lp] = key[r];
-            s_vals[lp] = val[r];
+            const unsigned int lp = sm.tile_excl[d] + sm.warp_hist[warp][d] + rank[r];
+            sm.keys[lp] = key[r];
+            sm.vals[lp] = val[r];
         }
     }
     __syncthreads();
     const int valid_count = min(SORT_TILE, n - base);
     for (int i = tid; i < valid_count; i += SORT_THREADS) {
-        const unsigned int k = s_keys[i];
-        const int dst = s_goff[(k >> shift) & mask] + i;
+        const unsigned int k = sm.keys[i];
+        const int dst = sm.goff[(k >> shift) & mask] + i;
         keys_out[dst] = k;
-        vals_out[dst] = s_vals[i];
+        vals_out[dst] = sm.vals[i];
     }
 }
 

@@ -149,7 +149,7 @@ struct fgpu_sim {
     /* options */
     int opt_order = 1;
     int opt_graph = 1;
-    int opt_radix_bits = 8;
+    int opt_radix_bits = 9;
     int opt_stage = 0; /* block staging of PBM+message windows: correct but not yet faster (profiles/r01_notes.md) */
     int opt_stage_bytes = 36 * 1024; /* shared-memory budget for staged messages per block */
     /* CUDA graph of one iteration (static models) */
@@ -224,6 +224,7 @@ extern "C" const fgpu_model *fgpu_model_load(const char *plugin_path) {
 /* create / destroy                                                           */
 /* ------------------------------------------------------------------------- */
 static int sort_passes(int radix_bits, int max_bits) { return (radix_bits + max_bits - 1) / max_bits; }
+static size_t sort_scratch_words(int n, int key_bits, int max_bits);
 
 static int sim_alloc(fgpu_sim *s) {
     const fgpu_model *m = s->model;
@@ -272,9 +273,14 @@ static int sim_alloc(fgpu_sim *s) {
             CU(cudaMalloc(&M.cell_start, sizeof(unsigned int) * ((size_t)M.d->grid_size + 1)));
             CU(cudaMemsetAsync(M.cell_start, 0, sizeof(unsigned int) * ((size_t)M.d->grid_size + 1), s->stream));
             M.max_tiles = (M.d->buffer_size + SORT_TILE - 1) / SORT_TILE;
-            /* scratch: hist[4][256] | tickets[4] | gap_count[1] | pad | status[4][tiles][256] */
-            M.scratch_bytes = sizeof(unsigned int) * ((size_t)SORT_MAX_PASSES * SORT_BINS + 8 +
-                                                      (size_t)SORT_MAX_PASSES * M.max_tiles * SORT_BINS);
+            /* scratch: hist[4][2048] | tickets[4] | gap_count[1] | pad | status[passes][tiles][2048]
+             * (a sort of radix_bits key bits never needs more than ceil(bits/4) <= 8... passes; the status
+             * area is sized for the worst legal digit choice of this grid) */
+            size_t words = 0;
+            for (int mb = 4; mb <= SORT_MAXBITS; ++mb)
+                if (sort_passes(M.d->radix_bits, mb) <= SORT_MAX_PASSES)
+                    words = std::max(words, sort_scratch_words(M.d->buffer_size, M.d->radix_bits, mb));
+            M.scratch_bytes = sizeof(unsigned int) * words;
             CU(cudaMalloc(&M.scratch, M.scratch_bytes));
             CU(cudaMalloc(&M.gap_queue, sizeof(unsigned int) * 3 * ((size_t)M.d->grid_size / GAP_INLINE + 8)));
         }
@@ -821,39 +827,73 @@ static int choose_digit_bits(int radix_bits, int max_bits, int *passes_out) {
     return (radix_bits + passes - 1) / passes; /* balanced digits */
 }
 
+/* scratch layout (32-bit words): gap_count | pad[7] | totals[2048] | tile_hist[nbins][tiles] */
+constexpr int SCR_GAP = 0, SCR_TOTALS = 8, SCR_TILEHIST = 8 + SORT_MAX_BINS;
+
+static size_t sort_scratch_words(int n, int key_bits, int max_bits) {
+    int passes = 1;
+    const int digit_bits = choose_digit_bits(key_bits, max_bits, &passes);
+    const size_t tiles = ((size_t)n + SORT_TILE - 1) / SORT_TILE;
+    return (size_t)SCR_TILEHIST + tiles * ((size_t)1 << digit_bits);
+}
+
+template <int BITS>
+static cudaError_t launch_scatter(int tiles, cudaStream_t st, const unsigned int *kin, const unsigned int *vin, unsigned int *kout,
+                                  unsigned int *vout, int n, int shift, int digit_bits, const unsigned int *tile_hist,
+                                  const unsigned int *totals) {
+    static bool configured = false;
+    const size_t smem = sizeof(SortSmem<BITS>);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_radix_scatter<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    k_radix_scatter<BITS><<<tiles, SORT_THREADS, smem, st>>>(kin, vin, kout, vout, n, shift, digit_bits, tile_hist, totals, tiles);
+    return cudaGetLastError();
+}
+
+/* The hand-written LSD radix sort of (keys_in[i], i): replaces cub::DeviceRadixSort::SortPairs (sim:1867).
+ * Returns the index (0/1) of the ping-pong pair holding the sorted result; counts launches. */
+static int radix_sort_pairs(cudaStream_t st, const unsigned int *keys_in, int n, int key_bits, int max_bits,
+                            unsigned int *keys[2], unsigned int *vals[2], unsigned int *scratch, int *sorted_in,
+                            long long *launches) {
+    int passes = 1;
+    const int digit_bits = choose_digit_bits(key_bits, max_bits, &passes);
+    if (passes > SORT_MAX_PASSES) return set_err(FGPU_ERR_MODEL, "%d key bits need %d radix passes", key_bits, passes);
+    const int tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    const int nbins = 1 << digit_bits;
+    unsigned int *totals = scratch + SCR_TOTALS, *tile_hist = scratch + SCR_TILEHIST;
+    for (int p = 0; p < passes; ++p) {
+        const unsigned int *kin = p == 0 ? keys_in : keys[(p - 1) & 1];
+        const unsigned int *vin = p == 0 ? nullptr : vals[(p - 1) & 1];
+        const int shift = p * digit_bits;
+        k_tile_hist<<<tiles, SORT_THREADS, sizeof(unsigned int) * (size_t)nbins, st>>>(kin, n, shift, digit_bits, tile_hist, tiles);
+        k_row_scan<<<nbins, SORT_THREADS, 0, st>>>(tile_hist, tiles, totals);
+        cudaError_t e;
+        if (digit_bits <= 8) e = launch_scatter<8>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, shift, digit_bits, tile_hist, totals);
+        else if (digit_bits == 9) e = launch_scatter<9>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, shift, digit_bits, tile_hist, totals);
+        else if (digit_bits == 10) e = launch_scatter<10>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, shift, digit_bits, tile_hist, totals);
+        else e = launch_scatter<11>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, shift, digit_bits, tile_hist, totals);
+        if (e != cudaSuccess) return set_err(FGPU_ERR_CUDA, "radix pass launch -> %s", cudaGetErrorString(e));
+        (*launches) += 3;
+    }
+    *sorted_in = (passes - 1) & 1;
+    return FGPU_OK;
+}
+
 /* Spatial message build for h_count messages (simulation.xslt:1831-1892). */
 static int build_spatial(fgpu_sim *s, MsgRT &M) {
     const int n = M.h_count;
     M.built = true;
     if (n <= 0) return FGPU_OK;
-    int passes = 1;
     const int max_bits = std::min(std::max(s->opt_radix_bits, 4), SORT_MAXBITS);
-    const int digit_bits = choose_digit_bits(M.d->radix_bits, max_bits, &passes);
-    if (passes > SORT_MAX_PASSES) return set_err(FGPU_ERR_MODEL, "partition grid of %s needs %d radix passes", M.d->name, passes);
-    const int tiles = (n + SORT_TILE - 1) / SORT_TILE;
-    unsigned int *hist = M.scratch;
-    unsigned int *tickets = M.scratch + SORT_MAX_PASSES * SORT_BINS;
-    unsigned int *gap_count = tickets + 4;
-    unsigned int *status = M.scratch + SORT_MAX_PASSES * SORT_BINS + 8;
-    const size_t zero_bytes = sizeof(unsigned int) * ((size_t)SORT_MAX_PASSES * SORT_BINS + 8 + (size_t)passes * tiles * SORT_BINS);
-
+    unsigned int *gap_count = M.scratch + SCR_GAP;
     s->prof_begin(std::string("sort:") + M.d->name);
-    CU(cudaMemsetAsync(M.scratch, 0, zero_bytes, s->stream));
-    {
-        const int blocks = std::min((n + 255) / 256, 148 * 8);
-        k_radix_hist<<<blocks, 256, 0, s->stream>>>(M.keys_in, n, hist, passes, digit_bits);
-        LAUNCH_CHECK();
-    }
-    for (int p = 0; p < passes; ++p) {
-        const unsigned int *kin = p == 0 ? M.keys_in : M.keys[(p - 1) & 1];
-        const unsigned int *vin = p == 0 ? nullptr : M.vals[(p - 1) & 1];
-        k_radix_pass<<<tiles, SORT_THREADS, 0, s->stream>>>(kin, vin, M.keys[p & 1], M.vals[p & 1], n, p * digit_bits,
-                                                            digit_bits, hist + p * SORT_BINS,
-                                                            status + (size_t)p * tiles * SORT_BINS, tickets + p);
-        LAUNCH_CHECK();
-    }
+    CU(cudaMemsetAsync(gap_count, 0, sizeof(unsigned int), s->stream));
+    int in = 0;
+    int rc = radix_sort_pairs(s->stream, M.keys_in, n, M.d->radix_bits, max_bits, M.keys, M.vals, M.scratch, &in, &s->launches);
+    if (rc) return rc;
     s->prof_end();
-    const int in = (passes - 1) & 1;
     M.sorted_in = in;
     s->prof_begin(std::string("pbm:") + M.d->name);
     const int g = (n + 255) / 256;
@@ -1599,6 +1639,9 @@ extern "C" int fgpu_sim_set_option(fgpu_sim *s, const char *key, int value) {
         s->opt_stage_bytes = value;
     } else if (!strcmp(key, "radix_bits")) {
         if (value < 4 || value > SORT_MAXBITS) return set_err(FGPU_ERR_ARG, "radix_bits must be in [4,%d]", SORT_MAXBITS);
+        for (MsgRT &M : s->msgs)
+            if (M.d->partitioning == FGPU_PART_SPATIAL && sort_passes(M.d->radix_bits, value) > SORT_MAX_PASSES)
+                return set_err(FGPU_ERR_ARG, "radix_bits %d needs more than %d passes for message %s", value, SORT_MAX_PASSES, M.d->name);
         s->opt_radix_bits = value;
     } else
         return set_err(FGPU_ERR_ARG, "unknown option '%s'", key);
@@ -1644,37 +1687,32 @@ extern "C" int fgpu_debug_sort_pairs(const unsigned int *keys, int n, int key_bi
                                      unsigned int *keys_out, unsigned int *vals_out) {
     if (n < 0 || key_bits < 1 || key_bits > 32) return set_err(FGPU_ERR_ARG, "bad argument");
     if (n == 0) return FGPU_OK;
-    int passes = 1;
     const int max_bits = std::min(std::max(max_digit_bits, 1), SORT_MAXBITS);
-    const int digit_bits = choose_digit_bits(key_bits, max_bits, &passes);
-    if (passes > SORT_MAX_PASSES) return set_err(FGPU_ERR_ARG, "too many passes");
-    unsigned int *k[2], *v[2], *scratch;
-    const int tiles = (n + SORT_TILE - 1) / SORT_TILE;
-    const size_t sb = sizeof(unsigned int) * ((size_t)SORT_MAX_PASSES * SORT_BINS + 8 + (size_t)passes * tiles * SORT_BINS);
+    if (sort_passes(key_bits, max_bits) > SORT_MAX_PASSES) return set_err(FGPU_ERR_ARG, "too many passes");
+    unsigned int *kin, *k[2], *v[2], *scratch;
+    const size_t sb = sizeof(unsigned int) * sort_scratch_words(n, key_bits, max_bits);
+    CU(cudaMalloc(&kin, sizeof(unsigned int) * (size_t)n));
     for (int i = 0; i < 2; ++i) {
         CU(cudaMalloc(&k[i], sizeof(unsigned int) * (size_t)n));
         CU(cudaMalloc(&v[i], sizeof(unsigned int) * (size_t)n));
     }
     CU(cudaMalloc(&scratch, sb));
-    CU(cudaMemcpy(k[0], keys, sizeof(unsigned int) * (size_t)n, cudaMemcpyHostToDevice));
-    CU(cudaMemset(scratch, 0, sb));
-    unsigned int *hist = scratch, *tickets = scratch + SORT_MAX_PASSES * SORT_BINS, *status = scratch + SORT_MAX_PASSES * SORT_BINS + 8;
-    k_radix_hist<<<std::min((n + 255) / 256, 148 * 8), 256>>>(k[0], n, hist, passes, digit_bits);
+    CU(cudaMemcpy(kin, keys, sizeof(unsigned int) * (size_t)n, cudaMemcpyHostToDevice));
     int in = 0;
-    for (int p = 0; p < passes; ++p) {
-        k_radix_pass<<<tiles, SORT_THREADS>>>(k[in], p == 0 ? nullptr : v[in], k[in ^ 1], v[in ^ 1], n, p * digit_bits,
-                                              digit_bits, hist + p * SORT_BINS, status + (size_t)p * tiles * SORT_BINS, tickets + p);
-        in ^= 1;
+    long long launches = 0;
+    int rc = radix_sort_pairs(nullptr, kin, n, key_bits, max_bits, k, v, scratch, &in, &launches);
+    if (rc == FGPU_OK) {
+        CU(cudaDeviceSynchronize());
+        CU(cudaMemcpy(keys_out, k[in], sizeof(unsigned int) * (size_t)n, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(vals_out, v[in], sizeof(unsigned int) * (size_t)n, cudaMemcpyDeviceToHost));
     }
-    CU(cudaGetLastError());
-    CU(cudaMemcpy(keys_out, k[in], sizeof(unsigned int) * (size_t)n, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(vals_out, v[in], sizeof(unsigned int) * (size_t)n, cudaMemcpyDeviceToHost));
+    cudaFree(kin);
     for (int i = 0; i < 2; ++i) {
         cudaFree(k[i]);
         cudaFree(v[i]);
     }
     cudaFree(scratch);
-    return FGPU_OK;
+    return rc;
 }
 
 /* flags -> (positions of survivors, count); columns = one 4-byte payload column */
