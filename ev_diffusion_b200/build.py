@@ -94,7 +94,7 @@ def build_runtime(force: bool = False, verbose: bool = False) -> str:
 
 
 def build_model(xml_path: str, name: str, fmad: bool = True, force: bool = False, verbose: bool = False,
-                function_files: Optional[List[str]] = None) -> str:
+                function_files: Optional[List[str]] = None, stage: bool = False) -> str:
     """Generate and compile the plugin of one model.
 
     ``fmad=False`` builds the exact-arithmetic variant (no FMA contraction) whose
@@ -113,7 +113,8 @@ def build_model(xml_path: str, name: str, fmad: bool = True, force: bool = False
     files = codegen.emit_cuda(model, function_files, gen)
     os.makedirs(os.path.join(LIB, "models"), exist_ok=True)
     out = model_path(name)
-    cmd = [NVCC] + ARCH_FLAGS + COMMON + ["-Xptxas", "-v", "-fmad=" + ("true" if fmad else "false"),
+    cmd = [NVCC] + ARCH_FLAGS + COMMON + (["-DFGPU_STAGE=1"] if stage else []) + \
+          ["-Xptxas", "-v", "-fmad=" + ("true" if fmad else "false"),
                                           "-I", gen, "-I", INCLUDE, "-I", CSRC, "-I", mdir,
                                           files["model_glue.cu"], "-o", out,
                                           "-L", LIB, "-lfgpu_rt", "-Xlinker", "-rpath=$ORIGIN/.."]

@@ -295,7 +295,7 @@ FGPU_DEV {S}* get_next_{name}_message({S}* current, {S}_list* messages, {S}_PBM*
     else:
         out.append(f"""FGPU_DEV {S}* get_first_{name}_message({S}_list* messages){{
     if (messages->in_count == 0) return nullptr;
-    messages->base = messages->in_recs; messages->cur = 0; messages->end = messages->in_count;
+    messages->cur = 0; messages->end = messages->in_count;
     return fgpu::current_message<{S}, {T}>(messages);
 }}
 FGPU_DEV {S}* get_next_{name}_message({S}* current, {S}_list* messages){{
@@ -398,6 +398,7 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
     if spatial_in:
         M = f.input_message
         out += [
+            "#ifdef FGPU_STAGE",
             "    /* neighbourhood staging: header | 9 PBM row windows | message windows */",
             "    extern __shared__ uint4 fgpu_dsm[];",
             "    fgpu::StageShared* fgpu_sh = (fgpu::StageShared*)fgpu_dsm;",
@@ -405,6 +406,7 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
             f"    xmachine_message_{M}* fgpu_s_msgs = (xmachine_message_{M}*)(fgpu_s_cs + 9 * fgpu::STAGE_CSW);",
             f"    fgpu::stage_block<xmachine_message_{M}, fgpu_traits_{M}>(fgpu_sh, fgpu_s_cs, fgpu_s_msgs, L.stage_msgs,",
             f"        (const xmachine_message_{M}*)L.in_recs, L.in_cell_start, L.in_sorted_keys, L.order != nullptr, L.n, L.in_count);",
+            "#endif",
         ]
     out += ["    if (t >= L.n) return;",
             "    const int index = L.order ? (int)__ldg(L.order + t) : t;",
@@ -424,11 +426,14 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
         out.append(f"    xmachine_message_{M}_list inp;")
         out.append(f"    inp.in_recs = (const xmachine_message_{M}*)L.in_recs; inp.cell_start = L.in_cell_start; inp.in_count = L.in_count;")
         out.append("    inp.out_recs = nullptr; inp.out_keys = nullptr; inp.out_index = 0; inp.cur = 0; inp.end = 0;")
-        out.append("    inp.base = inp.in_recs; inp.step = 0; inp.cx = 0; inp.cy = 0; inp.cz = 0; inp.fast = 0;")
+        out.append("    inp.step = 0; inp.cx = 0; inp.cy = 0; inp.cz = 0; inp.n1lo = 0; inp.n1hi = -1; inp.n2lo = 0; inp.n2hi = -1; inp.hrow = 0; inp.interior = 0;")
+        out.append("#ifdef FGPU_STAGE")
+        out.append("    inp.base = inp.in_recs; inp.fast = 0;")
         if spatial_in:
             out.append("    inp.sh = fgpu_sh; inp.s_cs = fgpu_s_cs; inp.s_msgs = fgpu_s_msgs;")
         else:
             out.append("    inp.sh = nullptr; inp.s_cs = nullptr; inp.s_msgs = nullptr;")
+        out.append("#endif")
         call.append("&inp")
         if model.message(M).partitioning == "spatial":
             call.append(f"(xmachine_message_{M}_PBM*)nullptr")
@@ -438,8 +443,10 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
             raise ModelError(f"function '{f.name}' reads and writes message '{M}'")
         out.append(f"    xmachine_message_{M}_list outp;")
         out.append("    outp.in_recs = nullptr; outp.cell_start = nullptr; outp.in_count = 0; outp.cur = 0; outp.end = 0;")
-        out.append("    outp.base = nullptr; outp.step = 0; outp.cx = 0; outp.cy = 0; outp.cz = 0; outp.fast = 0;")
-        out.append("    outp.sh = nullptr; outp.s_cs = nullptr; outp.s_msgs = nullptr;")
+        out.append("    outp.step = 0; outp.cx = 0; outp.cy = 0; outp.cz = 0; outp.n1lo = 0; outp.n1hi = -1; outp.n2lo = 0; outp.n2hi = -1; outp.hrow = 0; outp.interior = 0;")
+        out.append("#ifdef FGPU_STAGE")
+        out.append("    outp.base = nullptr; outp.fast = 0; outp.sh = nullptr; outp.s_cs = nullptr; outp.s_msgs = nullptr;")
+        out.append("#endif")
         out.append(f"    outp.out_recs = (xmachine_message_{M}*)L.out_recs; outp.out_keys = L.out_keys; outp.out_index = L.out_base + index;")
         call.append("&outp")
     if f.rng:
@@ -462,6 +469,7 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
         out.append(f"""static void fgpu_launch_{f.name}(const fgpu_launch* a, void* stream){{
     if (a->n <= 0) return;
     const int grid = (a->n + {bs} - 1) / {bs};
+#ifdef FGPU_STAGE
     const size_t smem = (size_t)fgpu::STAGE_HDR_QUADS * 16 + 9 * fgpu::STAGE_CSW * sizeof(int)
                       + (size_t)(a->stage_msgs > 0 ? a->stage_msgs : 0) * sizeof(xmachine_message_{M});
     static size_t configured = 0;
@@ -469,6 +477,9 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
         cudaFuncSetAttribute(fgpu_k_{f.name}, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }}
+#else
+    const size_t smem = 0;
+#endif
     fgpu_k_{f.name}<<<grid, {bs}, smem, (cudaStream_t)stream>>>(*a);
 }}""")
     else:

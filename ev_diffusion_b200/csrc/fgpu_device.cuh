@@ -64,18 +64,20 @@ FGPU_DEV unsigned int cell_hash(int cx, int cy, int cz) {
     return (unsigned int)(((cz * T::DIMY) * T::DIMX) + (cy * T::DIMX) + cx);
 }
 
-/* ---- block-level staging of the neighbourhood ---------------------------------- */
+#ifdef FGPU_STAGE
+/* ---- block-level staging of the neighbourhood (build option, off by default) ---------------- */
 /* When a message consumer processes its agents in cell order (fgpu_launch.order),
  * the agents of one block occupy a short run of consecutive cells [c_lo, c_hi].
  * Their 27-cell neighbourhoods are then 9 windows of consecutive cells (one per
  * (dy,dz) row offset), i.e. 9 contiguous slices of the partition boundary
  * matrix and 9 contiguous slices of the sorted message list.  The block copies
  * those slices into shared memory once (coalesced 16-byte loads) and every
- * thread walks its neighbourhood out of shared memory: no L1/L2 misses inside
- * the divergent message loop, where one missing lane stalls the whole warp.
- * Threads whose cell is not fully interior (any wrap), lies outside the
- * block's span, or whose block does not fit the staging capacity use the
- * on-demand global walk below instead -- same visiting order, same results. */
+ * thread walks its neighbourhood out of shared memory.  Threads whose cell is
+ * not fully interior (any wrap), lies outside the block's span, or whose block
+ * does not fit the staging capacity use the global walk instead -- same visiting
+ * order, same results.  Measured in round 1 (profiles/r01_notes.md): correct but
+ * slower than the prefetching global walk (shared-memory footprint -> 20 warps/SM,
+ * generic-address loads), hence a build option. */
 constexpr int STAGE_CSW = 128;            /* staged PBM row window: span + 3 cell boundaries */
 constexpr int STAGE_HDR_QUADS = 8;        /* StageShared fits in 128 bytes */
 
@@ -149,14 +151,25 @@ FGPU_DEV void stage_block(StageShared *sh, int *s_cs, Msg *s_msgs, int stage_msg
     }
     __syncthreads();
 }
+#endif /* FGPU_STAGE */
 
 /* ---- per-thread message proxy -------------------------------------------- */
 /* `Msg` is the user-visible struct xmachine_message_<M> (16-byte aligned, payload
  * only); the sorted message list in HBM is an array of exactly that struct, so
- * get_first/next hand user code a pointer straight into the list -- or into the
- * block's staged copy of it (the reference copies every message through a
- * per-thread shared-memory slot, krn:1084-1103).  `T` holds the partition
- * constants.  The generated header derives xmachine_message_<M>_list from this. */
+ * get_first/next hand user code a pointer straight into the list (the reference
+ * copies every message through a per-thread shared-memory slot, krn:1084-1103).
+ * `T` holds the partition constants.  The generated header derives
+ * xmachine_message_<M>_list from this.
+ *
+ * Neighbourhood walk = a 3-deep software pipeline over the (up to) 9 row ranges:
+ *   range in use      [cur, end)        being iterated by the script
+ *   next range        [n1lo, n1hi)      PBM entries already loaded; its first
+ *                                       message lines are prefetched into L1 when
+ *                                       it becomes "next"
+ *   range after next  [n2lo, n2hi)      PBM loads in flight
+ * so a range switch costs no dependent load: the reference resolves each cell
+ * lazily inside the message loop (krn:1048-1081), two dependent fetches on a
+ * divergent path that stalls the whole warp. */
 template <class Msg, class T>
 struct MessageProxy {
     /* input side */
@@ -168,24 +181,74 @@ struct MessageProxy {
     unsigned int *out_keys;
     int out_index;
     /* cursor (replaces _relative_cell/_cell_index/_cell_index_max/_agent_grid_cell, hdr:170-173) */
-    const Msg *base;  /* list the open range indexes: in_recs or the staged copy */
     int cur, end;     /* current message index, end of the open range */
-    int step;         /* fast: next row (0..8); slow: next relative cell (0..26) */
-    int cx, cy, cz;   /* slow: agent grid cell; fast: cx = cell index relative to the block's span */
+    int n1lo, n1hi;   /* next range (n1hi < 0: neighbourhood exhausted) */
+    int n2lo, n2hi;   /* range after next */
+    int step;         /* next group whose PBM entries are to be fetched: interior agents count rows
+                         (0..8 / 0..2), others count relative cells (0..26 / 0..8) */
+    int cx, cy, cz;   /* agent grid cell (non-interior walk) */
+    int hrow;         /* interior walk: hash of the first cell (x-1) of the next row */
+    int interior;     /* no neighbour cell wraps: rows are hrow, hrow+DIMX, ... */
+#ifdef FGPU_STAGE
+    const Msg *base;  /* list the open range indexes: in_recs or the staged copy */
     int fast;
-    /* block-shared staging area */
     const StageShared *sh;
     const int *s_cs;
     const Msg *s_msgs;
+#endif
 };
 
-/* Opens the next non-empty range of the neighbourhood; false when exhausted.
- * Cells are visited x-fastest from (-1,-1,-1) to (1,1,1) exactly like
- * next_cell3D/next_cell2D (krn:105-154).  The three x cells of a row are
- * adjacent hashes unless x wraps, and are then opened as one range (same
- * visiting order). */
+FGPU_DEV void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+/* Issues the PBM loads of the next group of cells.  Cells are visited x-fastest
+ * from (-1,-1,-1) to (1,1,1) exactly like next_cell3D/next_cell2D (krn:105-154),
+ * each through the wrap rule of message_<M>_hash; the three x cells of a row are
+ * adjacent hashes unless x wraps, and are then fetched as ONE range (same
+ * visiting order).  hi < 0 marks the end of the neighbourhood. */
+template <class Msg, class T>
+FGPU_DEV void fetch_group(MessageProxy<Msg, T> *p, int &lo, int &hi) {
+    const int s = p->step;
+    if (p->interior) {
+        /* interior agent: the 9 (3) rows are at fixed hash strides, no wrap tests */
+        constexpr int NROWS = T::IS2D ? 3 : 9;
+        if (s >= NROWS) {
+            lo = 0;
+            hi = -1;
+            return;
+        }
+        const int h = p->hrow;
+        lo = (int)__ldg(p->cell_start + h);
+        hi = (int)__ldg(p->cell_start + h + 3);
+        p->step = s + 1;
+        p->hrow = h + ((s == 2 || s == 5) ? (T::DIMX * T::DIMY - 2 * T::DIMX) : T::DIMX);
+        return;
+    }
+    constexpr int NSTEPS = T::IS2D ? 9 : 27;
+    if (s >= NSTEPS) {
+        lo = 0;
+        hi = -1;
+        return;
+    }
+    const int rx = (s % 3) - 1;
+    const int ry = ((s / 3) % 3) - 1;
+    const int rz = T::IS2D ? -1 : (s / 9) - 1;   /* 2-D: relative z stays -1 (krn:137-154) */
+    if (rx == -1 && p->cx >= 1 && p->cx + 1 < T::DIMX) {
+        const unsigned int h = cell_hash<T>(p->cx - 1, p->cy + ry, p->cz + rz);
+        lo = (int)__ldg(p->cell_start + h);
+        hi = (int)__ldg(p->cell_start + h + 3);
+        p->step = s + 3;
+    } else {
+        const unsigned int h = cell_hash<T>(p->cx + rx, p->cy + ry, p->cz + rz);
+        lo = (int)__ldg(p->cell_start + h);
+        hi = (int)__ldg(p->cell_start + h + 1);
+        p->step = s + 1;
+    }
+}
+
+/* Opens the next non-empty range of the neighbourhood; false when exhausted. */
 template <class Msg, class T>
 FGPU_DEV bool open_next_range(MessageProxy<Msg, T> *p) {
+#ifdef FGPU_STAGE
     if (p->fast) {
         constexpr int NROWS = T::IS2D ? 3 : 9;
         while (p->step < NROWS) {
@@ -201,44 +264,38 @@ FGPU_DEV bool open_next_range(MessageProxy<Msg, T> *p) {
         }
         return false;
     }
-    constexpr int NSTEPS = T::IS2D ? 9 : 27;
-    while (p->step < NSTEPS) {
-        const int s = p->step;
-        const int rx = (s % 3) - 1;
-        const int ry = ((s / 3) % 3) - 1;
-        const int rz = T::IS2D ? -1 : (s / 9) - 1;   /* 2-D: relative z stays -1 (krn:137-154) */
-        int lo, hi;
-        if (rx == -1 && p->cx >= 1 && p->cx + 1 < T::DIMX) {
-            const unsigned int h = cell_hash<T>(p->cx - 1, p->cy + ry, p->cz + rz);
-            lo = (int)__ldg(p->cell_start + h);
-            hi = (int)__ldg(p->cell_start + h + 3);
-            p->step = s + 3;
-        } else {
-            const unsigned int h = cell_hash<T>(p->cx + rx, p->cy + ry, p->cz + rz);
-            lo = (int)__ldg(p->cell_start + h);
-            hi = (int)__ldg(p->cell_start + h + 1);
-            p->step = s + 1;
+#endif
+    while (true) {
+        const int lo = p->n1lo, hi = p->n1hi;
+        if (hi < 0) return false;
+        p->n1lo = p->n2lo;
+        p->n1hi = p->n2hi;
+        if (p->n1hi > p->n1lo) { /* the range that becomes "next": pull its first lines towards L1 */
+            const char *q = reinterpret_cast<const char *>(p->in_recs + p->n1lo);
+            prefetch_l1(q);
+            prefetch_l1(q + 128);
         }
+        fetch_group<Msg, T>(p, p->n2lo, p->n2hi);
         if (lo < hi) {
             p->cur = lo;
             p->end = hi;
             return true;
         }
     }
-    return false;
 }
 
-/* get_first: locate the agent's cell and choose the staged or the global walk. */
+/* get_first: locate the agent's cell and start the range pipeline. */
 template <class Msg, class T>
 FGPU_DEV void begin_walk(MessageProxy<Msg, T> *p, float x, float y, float z) {
     int cx, cy, cz;
     grid_position<T>(x, y, z, cx, cy, cz);
     p->step = 0;
-    p->fast = 0;
-    p->base = p->in_recs;
     p->cx = cx;
     p->cy = cy;
     p->cz = cz;
+#ifdef FGPU_STAGE
+    p->fast = 0;
+    p->base = p->in_recs;
     if (p->sh != nullptr && p->sh->ok) {
         const bool interior = (cx >= 1) && (cx + 1 < T::DIMX) && (cy >= 1) && (cy + 1 < T::DIMY) &&
                               (T::IS2D || ((cz >= 1) && (cz + 1 < T::DIMZ)));
@@ -247,14 +304,27 @@ FGPU_DEV void begin_walk(MessageProxy<Msg, T> *p, float x, float y, float z) {
             p->fast = 1;
             p->cx = c - p->sh->c_lo;
             p->base = p->s_msgs;
+            return;
         }
     }
+#endif
+    p->interior = (cx >= 1) && (cx + 1 < T::DIMX) && (cy >= 1) && (cy + 1 < T::DIMY) &&
+                  (T::IS2D || ((cz >= 1) && (cz + 1 < T::DIMZ)));
+    p->hrow = (int)cell_hash<T>(cx - 1, cy - 1, cz - 1);   /* 2-D: z-1 wraps to plane 0 */
+    fetch_group<Msg, T>(p, p->n1lo, p->n1hi);
+    fetch_group<Msg, T>(p, p->n2lo, p->n2hi);
 }
 
 /* Hands the current message to user code: a pointer straight into the list. */
 template <class Msg, class T>
 FGPU_DEV Msg *current_message(MessageProxy<Msg, T> *p) {
-    return const_cast<Msg *>(p->base + p->cur);
+#ifdef FGPU_STAGE
+    Msg *m = const_cast<Msg *>(p->base + p->cur);
+#else
+    Msg *m = const_cast<Msg *>(p->in_recs + p->cur);
+#endif
+    __builtin_assume(m != nullptr);
+    return m;
 }
 
 /* ---- rand48 ---------------------------------------------------------------- */
