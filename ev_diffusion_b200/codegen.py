@@ -426,7 +426,10 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
         out.append(f"    xmachine_message_{M}_list inp;")
         out.append(f"    inp.in_recs = (const xmachine_message_{M}*)L.in_recs; inp.cell_start = L.in_cell_start; inp.in_count = L.in_count;")
         out.append("    inp.out_recs = nullptr; inp.out_keys = nullptr; inp.out_index = 0; inp.cur = 0; inp.end = 0;")
-        out.append("    inp.step = 0; inp.cx = 0; inp.cy = 0; inp.cz = 0; inp.n1lo = 0; inp.n1hi = -1; inp.n2lo = 0; inp.n2hi = -1; inp.hrow = 0; inp.interior = 0;")
+        out.append("    inp.step = 0; inp.cx = 0; inp.cy = 0; inp.cz = 0; inp.hrow = 0; inp.interior = 0;")
+        out.append("#ifdef FGPU_WALK_PIPELINE")
+        out.append("    inp.n1lo = 0; inp.n1hi = -1; inp.n2lo = 0; inp.n2hi = -1;")
+        out.append("#endif")
         out.append("#ifdef FGPU_STAGE")
         out.append("    inp.base = inp.in_recs; inp.fast = 0;")
         if spatial_in:
@@ -443,7 +446,10 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
             raise ModelError(f"function '{f.name}' reads and writes message '{M}'")
         out.append(f"    xmachine_message_{M}_list outp;")
         out.append("    outp.in_recs = nullptr; outp.cell_start = nullptr; outp.in_count = 0; outp.cur = 0; outp.end = 0;")
-        out.append("    outp.step = 0; outp.cx = 0; outp.cy = 0; outp.cz = 0; outp.n1lo = 0; outp.n1hi = -1; outp.n2lo = 0; outp.n2hi = -1; outp.hrow = 0; outp.interior = 0;")
+        out.append("    outp.step = 0; outp.cx = 0; outp.cy = 0; outp.cz = 0; outp.hrow = 0; outp.interior = 0;")
+        out.append("#ifdef FGPU_WALK_PIPELINE")
+        out.append("    outp.n1lo = 0; outp.n1hi = -1; outp.n2lo = 0; outp.n2hi = -1;")
+        out.append("#endif")
         out.append("#ifdef FGPU_STAGE")
         out.append("    outp.base = nullptr; outp.fast = 0; outp.sh = nullptr; outp.s_cs = nullptr; outp.s_msgs = nullptr;")
         out.append("#endif")

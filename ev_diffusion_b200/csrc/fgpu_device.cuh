@@ -161,7 +161,7 @@ FGPU_DEV void stage_block(StageShared *sh, int *s_cs, Msg *s_msgs, int stage_msg
  * `T` holds the partition constants.  The generated header derives
  * xmachine_message_<M>_list from this.
  *
- * Neighbourhood walk = a 3-deep software pipeline over the (up to) 9 row ranges:
+ * Neighbourhood walk, FGPU_WALK_PIPELINE variant = a 3-deep software pipeline over the (up to) 9 row ranges:
  *   range in use      [cur, end)        being iterated by the script
  *   next range        [n1lo, n1hi)      PBM entries already loaded; its first
  *                                       message lines are prefetched into L1 when
@@ -182,8 +182,10 @@ struct MessageProxy {
     int out_index;
     /* cursor (replaces _relative_cell/_cell_index/_cell_index_max/_agent_grid_cell, hdr:170-173) */
     int cur, end;     /* current message index, end of the open range */
+#ifdef FGPU_WALK_PIPELINE
     int n1lo, n1hi;   /* next range (n1hi < 0: neighbourhood exhausted) */
     int n2lo, n2hi;   /* range after next */
+#endif
     int step;         /* next group whose PBM entries are to be fetched: interior agents count rows
                          (0..8 / 0..2), others count relative cells (0..26 / 0..8) */
     int cx, cy, cz;   /* agent grid cell (non-interior walk) */
@@ -265,6 +267,7 @@ FGPU_DEV bool open_next_range(MessageProxy<Msg, T> *p) {
         return false;
     }
 #endif
+#ifdef FGPU_WALK_PIPELINE
     while (true) {
         const int lo = p->n1lo, hi = p->n1hi;
         if (hi < 0) return false;
@@ -282,6 +285,22 @@ FGPU_DEV bool open_next_range(MessageProxy<Msg, T> *p) {
             return true;
         }
     }
+#else
+    /* The kernel is instruction-issue bound (ncu: 78 % issue-slot utilisation, 64 resident warps),
+     * so the cheapest switch wins: fetch the next group on demand and let the other warps hide the
+     * L1 latency.  The software-pipelined variant above (FGPU_WALK_PIPELINE) removes the dependent
+     * load but costs ~20 more instructions per switch and measured slower (profiles/r01_notes.md). */
+    while (true) {
+        int lo, hi;
+        fetch_group<Msg, T>(p, lo, hi);
+        if (hi < 0) return false;
+        if (lo < hi) {
+            p->cur = lo;
+            p->end = hi;
+            return true;
+        }
+    }
+#endif
 }
 
 /* get_first: locate the agent's cell and start the range pipeline. */
@@ -311,8 +330,10 @@ FGPU_DEV void begin_walk(MessageProxy<Msg, T> *p, float x, float y, float z) {
     p->interior = (cx >= 1) && (cx + 1 < T::DIMX) && (cy >= 1) && (cy + 1 < T::DIMY) &&
                   (T::IS2D || ((cz >= 1) && (cz + 1 < T::DIMZ)));
     p->hrow = (int)cell_hash<T>(cx - 1, cy - 1, cz - 1);   /* 2-D: z-1 wraps to plane 0 */
+#ifdef FGPU_WALK_PIPELINE
     fetch_group<Msg, T>(p, p->n1lo, p->n1hi);
     fetch_group<Msg, T>(p, p->n2lo, p->n2hi);
+#endif
 }
 
 /* Hands the current message to user code: a pointer straight into the list. */
