@@ -405,10 +405,10 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
             "    int* fgpu_s_cs = (int*)(fgpu_dsm + fgpu::STAGE_HDR_QUADS);",
             f"    xmachine_message_{M}* fgpu_s_msgs = (xmachine_message_{M}*)(fgpu_s_cs + 9 * fgpu::STAGE_CSW);",
             f"    fgpu::stage_block<xmachine_message_{M}, fgpu_traits_{M}>(fgpu_sh, fgpu_s_cs, fgpu_s_msgs, L.stage_msgs,",
-            f"        (const xmachine_message_{M}*)L.in_recs, L.in_cell_start, L.in_sorted_keys, L.order != nullptr, L.n, L.in_count);",
+            f"        (const xmachine_message_{M}*)L.in_recs, L.in_cell_start, L.in_sorted_keys, L.order != nullptr, (L.d_n ? *L.d_n : L.n), (L.d_in_count ? *L.d_in_count : L.in_count));",
             "#endif",
         ]
-    out += ["    if (t >= L.n) return;",
+    out += ["    if (t >= (L.d_n ? *L.d_n : L.n)) return;",
             "    const int index = L.order ? (int)__ldg(L.order + t) : t;",
             f"    xmachine_memory_{A}_list* __restrict__ agents = (xmachine_memory_{A}_list*)L.agents;",
             f"    xmachine_memory_{A} agent;"]
@@ -424,7 +424,7 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
     if f.input_message:
         M = f.input_message
         out.append(f"    xmachine_message_{M}_list inp;")
-        out.append(f"    inp.in_recs = (const xmachine_message_{M}*)L.in_recs; inp.cell_start = L.in_cell_start; inp.in_count = L.in_count;")
+        out.append(f"    inp.in_recs = (const xmachine_message_{M}*)L.in_recs; inp.cell_start = L.in_cell_start; inp.in_count = L.d_in_count ? *L.d_in_count : L.in_count;")
         out.append("    inp.out_recs = nullptr; inp.out_keys = nullptr; inp.out_index = 0; inp.cur = 0; inp.end = 0;")
         out.append("    inp.step = 0; inp.cx = 0; inp.cy = 0; inp.cz = 0; inp.hrow = 0; inp.interior = 0;")
         out.append("#ifdef FGPU_WALK_PIPELINE")

@@ -49,9 +49,10 @@ constexpr int SORT_MAX_BINS = 1 << SORT_MAXBITS;
 
 /* digit counts of one tile; tile_hist is bin-major so that k_row_scan reads rows contiguously */
 __global__ void __launch_bounds__(SORT_THREADS)
-k_tile_hist(const unsigned int *__restrict__ keys, int n, int shift, int digit_bits, unsigned int *__restrict__ tile_hist,
-            int tiles) {
+k_tile_hist(const unsigned int *__restrict__ keys, int n_host, const int *__restrict__ d_n, int shift, int digit_bits,
+            unsigned int *__restrict__ tile_hist, int tiles) {
     extern __shared__ unsigned int sh[]; /* 1 << digit_bits */
+    const int n = d_n ? *d_n : n_host; /* slab mode: the exact count lives on the device, n_host is an upper bound */
     const int nbins = 1 << digit_bits;
     for (int i = threadIdx.x; i < nbins; i += SORT_THREADS) sh[i] = 0;
     __syncthreads();
@@ -128,10 +129,11 @@ struct SortSmem {
 template <int BITS>
 __global__ void __launch_bounds__(SORT_THREADS)
 k_radix_scatter(const unsigned int *__restrict__ keys_in, const unsigned int *__restrict__ vals_in,
-                unsigned int *__restrict__ keys_out, unsigned int *__restrict__ vals_out, int n, int shift,
-                int digit_bits, const unsigned int *__restrict__ tile_hist, const unsigned int *__restrict__ totals,
-                int tiles) {
+                unsigned int *__restrict__ keys_out, unsigned int *__restrict__ vals_out, int n_host,
+                const int *__restrict__ d_n, int shift, int digit_bits, const unsigned int *__restrict__ tile_hist,
+                const unsigned int *__restrict__ totals, int tiles) {
     constexpr int BINS = 1 << BITS;
+    const int n = d_n ? *d_n : n_host;
     constexpr int BPT = BINS / SORT_THREADS; /* bins per thread: 1, 2, 4 or 8 */
     extern __shared__ __align__(16) unsigned char sort_smem_raw[];
     SortSmem<BITS> &sm = *reinterpret_cast<SortSmem<BITS> *>(sort_smem_raw);
@@ -247,17 +249,35 @@ k_radix_scatter(const unsigned int *__restrict__ keys_in, const unsigned int *__
 /* gather of packed records + partition boundary matrix                       */
 /* ------------------------------------------------------------------------- */
 constexpr int GAP_INLINE = 32;
+constexpr unsigned int GAP_LONG = 1u << 14; /* gaps longer than this are filled by the whole grid */
+constexpr int GAP_LONG_MAX = 1024;           /* capacity of the long-gap queue (>= cells / GAP_LONG for 16M cells) */
 
 __device__ __forceinline__ void fill_cells(unsigned int *cell_start, unsigned int lo, unsigned int hi /*inclusive*/,
                                            unsigned int value, unsigned int *gap_queue, unsigned int *gap_count) {
     if (hi < lo) return;
     if (hi - lo < (unsigned int)GAP_INLINE) {
         for (unsigned int c = lo; c <= hi; ++c) cell_start[c] = value;
-    } else {
+    } else if (hi - lo < GAP_LONG) {
         const unsigned int e = atomicAdd(gap_count, 1u);
-        gap_queue[3 * e + 0] = lo;
-        gap_queue[3 * e + 1] = hi;
-        gap_queue[3 * e + 2] = value;
+        gap_queue[3 * (GAP_LONG_MAX + e) + 0] = lo;
+        gap_queue[3 * (GAP_LONG_MAX + e) + 1] = hi;
+        gap_queue[3 * (GAP_LONG_MAX + e) + 2] = value;
+    } else {
+        /* long run of empty cells (e.g. the part of the grid another slab owns): its own queue, filled grid-wide;
+         * a run that does not fit the queue is cut into GAP_LONG pieces on the ordinary queue */
+        const unsigned int e = atomicAdd(gap_count + 1, 1u);
+        if (e < (unsigned int)GAP_LONG_MAX) {
+            gap_queue[3 * e + 0] = lo;
+            gap_queue[3 * e + 1] = hi;
+            gap_queue[3 * e + 2] = value;
+        } else {
+            for (unsigned int a = lo; a <= hi; a += GAP_LONG) {
+                const unsigned int q = atomicAdd(gap_count, 1u);
+                gap_queue[3 * (GAP_LONG_MAX + q) + 0] = a;
+                gap_queue[3 * (GAP_LONG_MAX + q) + 1] = min(hi, a + GAP_LONG - 1u);
+                gap_queue[3 * (GAP_LONG_MAX + q) + 2] = value;
+            }
+        }
     }
 }
 
@@ -268,10 +288,12 @@ __device__ __forceinline__ void fill_cells(unsigned int *cell_start, unsigned in
 template <int NQ>
 __global__ void __launch_bounds__(256)
 k_gather_pbm(const unsigned int *__restrict__ skeys, const unsigned int *__restrict__ svals,
-             const uint4 *__restrict__ in_recs, uint4 *__restrict__ out_recs, int n,
+             const uint4 *__restrict__ in_recs, uint4 *__restrict__ out_recs, int n_host, const int *__restrict__ d_n,
              unsigned int *__restrict__ cell_start, unsigned int cells, unsigned int *gap_queue,
              unsigned int *gap_count) {
+    const int n = d_n ? *d_n : n_host;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n == 0 && i == 0) fill_cells(cell_start, 0u, cells, 0u, gap_queue, gap_count); /* empty list: every cell empty */
     if (i >= n) return;
     const unsigned int v = svals[i];
     const unsigned int key = skeys[i];
@@ -288,13 +310,19 @@ k_gather_pbm(const unsigned int *__restrict__ skeys, const unsigned int *__restr
     if (i == n - 1) fill_cells(cell_start, key + 1u, cells, (unsigned int)n, gap_queue, gap_count);
 }
 
-/* Long runs of empty cells queued by k_gather_pbm: one block per queue entry. */
+/* Runs of empty cells queued by k_gather_pbm: long runs by the whole grid, the others one block per entry. */
 __global__ void __launch_bounds__(256)
 k_fill_gaps(unsigned int *__restrict__ cell_start, const unsigned int *__restrict__ gap_queue,
             const unsigned int *__restrict__ gap_count) {
-    const unsigned int cnt = *gap_count;
-    for (unsigned int e = blockIdx.x; e < cnt; e += gridDim.x) {
+    const unsigned int nlong = min(gap_count[1], (unsigned int)GAP_LONG_MAX);
+    for (unsigned int e = 0; e < nlong; ++e) {
         const unsigned int lo = gap_queue[3 * e + 0], hi = gap_queue[3 * e + 1], value = gap_queue[3 * e + 2];
+        for (unsigned int c = lo + blockIdx.x * blockDim.x + threadIdx.x; c <= hi; c += gridDim.x * blockDim.x) cell_start[c] = value;
+    }
+    const unsigned int cnt = gap_count[0];
+    for (unsigned int e = blockIdx.x; e < cnt; e += gridDim.x) {
+        const unsigned int *q = gap_queue + 3 * (GAP_LONG_MAX + e);
+        const unsigned int lo = q[0], hi = q[1], value = q[2];
         for (unsigned int c = lo + threadIdx.x; c <= hi; c += blockDim.x) cell_start[c] = value;
     }
 }
@@ -321,7 +349,9 @@ constexpr int COMPACT_THREADS = 1024;
 
 /* number of flagged (== 1) elements per block */
 __global__ void __launch_bounds__(COMPACT_THREADS)
-k_flag_blocksum(const int *__restrict__ flags, int n, unsigned int *__restrict__ block_sums, int match) {
+k_flag_blocksum(const int *__restrict__ flags, int n_host, const int *__restrict__ d_n, unsigned int *__restrict__ block_sums,
+                int match) {
+    const int n = d_n ? *d_n : n_host;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int f = (i < n) && (flags[i] == match);
     const int c = __syncthreads_count(f);
@@ -369,9 +399,10 @@ __global__ void __launch_bounds__(1024) k_scan_blocksums(unsigned int *block_sum
 /* stable scatter of flagged agents: dst[dst_offset + rank] = src[i] for every column */
 __global__ void __launch_bounds__(COMPACT_THREADS)
 k_compact_scatter(const char *__restrict__ src, char *__restrict__ dst, const ColSet cols, const ColSet dcols,
-                  const int *__restrict__ flags, const unsigned int *__restrict__ block_offsets, int dst_offset, int n,
-                  int match, int dst_cap, int *overflow) {
+                  const int *__restrict__ flags, const unsigned int *__restrict__ block_offsets, int dst_offset, int n_host,
+                  const int *__restrict__ d_n, int match, int dst_cap, int *overflow) {
     __shared__ unsigned int s_warp[32];
+    const int n = d_n ? *d_n : n_host;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool f = (i < n) && (flags[i] == match);
@@ -451,9 +482,10 @@ k_pack_plane(const uint4 *__restrict__ sorted_local, const unsigned int *__restr
  *   combined buffer: [ ... low halo | local block (n records at `local_at`) | high halo ... ] */
 template <int NQ>
 __global__ void __launch_bounds__(256)
-k_merge_halo(uint4 *__restrict__ combined, unsigned int *__restrict__ cell_start, int local_at, int n,
-             int own_first_cell, int own_cells, const int *__restrict__ lo_buf, int lo_first_cell,
-             const int *__restrict__ hi_buf, int hi_first_cell, int plane_cells, int *status) {
+k_merge_halo(uint4 *__restrict__ combined, unsigned int *__restrict__ cell_start, int local_at, int n_host,
+             const int *__restrict__ d_n, int own_first_cell, int own_cells, const int *__restrict__ lo_buf,
+             int lo_first_cell, const int *__restrict__ hi_buf, int hi_first_cell, int plane_cells, int *status) {
+    const int n = d_n ? *d_n : n_host;
     const int stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int lo_cnt = lo_buf[0], hi_cnt = hi_buf[0];
     if (tid == 0 && (lo_buf[1] || hi_buf[1])) atomicExch(status, 1);
@@ -481,8 +513,9 @@ k_merge_halo(uint4 *__restrict__ combined, unsigned int *__restrict__ cell_start
  * 4 = further than one slab away (reported).  The plane is the cell coordinate of
  * message_<M>_grid_position + the wrap rule of message_<M>_hash (krn:860-889). */
 __global__ void __launch_bounds__(256)
-k_owner_flags(const float *__restrict__ coord, int n, float minb, float maxb, int nplanes, int planes_per_rank, int rank,
-              int world, int *__restrict__ flags, int *status) {
+k_owner_flags(const float *__restrict__ coord, int n_host, const int *__restrict__ d_n, float minb, float maxb, int nplanes,
+              int planes_per_rank, int rank, int world, int *__restrict__ flags, int *status) {
+    const int n = d_n ? *d_n : n_host;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int p = (int)floorf(__fdiv_rn(__fmul_rn(__fsub_rn(coord[i], minb), (float)nplanes), __fsub_rn(maxb, minb)));
@@ -496,6 +529,161 @@ k_owner_flags(const float *__restrict__ coord, int n, float minb, float maxb, in
     else if (owner == (rank + 1) % world) f = 3;
     flags[i] = f;
     if (f == 4) atomicExch(status, 2);
+}
+
+/* ---- fused three-way migration split (stay / down / up) ------------------------------------------ */
+/* pass 1: owner flag of every agent + per-block counts of the three classes: block_sums[class][block] */
+__global__ void __launch_bounds__(COMPACT_THREADS)
+k_owner_count(const float *__restrict__ coord, int n_host, const int *__restrict__ d_n, float minb, float maxb, int nplanes,
+              int planes_per_rank, int rank, int world, int *__restrict__ flags, unsigned int *__restrict__ block_sums,
+              int nb, int *status) {
+    const int n = d_n ? *d_n : n_host;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int f = 0;
+    if (i < n) {
+        int p = (int)floorf(__fdiv_rn(__fmul_rn(__fsub_rn(coord[i], minb), (float)nplanes), __fsub_rn(maxb, minb)));
+        p = (p < 0) ? nplanes - 1 : p;
+        p = (p >= nplanes) ? 0 : p;
+        const int owner = min(p / planes_per_rank, world - 1);
+        const int lo_rank = (rank + world - 1) % world, hi_rank = (rank + 1) % world;
+        f = 4;
+        if (owner == rank) f = 1;
+        else if (owner == lo_rank && owner == hi_rank) f = (p < rank * planes_per_rank) ? 2 : 3; /* world == 2 */
+        else if (owner == lo_rank) f = 2;
+        else if (owner == hi_rank) f = 3;
+        flags[i] = f;
+        if (f == 4) atomicExch(status, 2);
+    }
+    const int c1 = __syncthreads_count(f == 1);
+    const int c2 = __syncthreads_count(f == 2);
+    const int c3 = __syncthreads_count(f == 3);
+    if (threadIdx.x == 0) {
+        block_sums[blockIdx.x] = (unsigned int)c1;
+        block_sums[nb + blockIdx.x] = (unsigned int)c2;
+        block_sums[2 * nb + blockIdx.x] = (unsigned int)c3;
+    }
+}
+
+/* pass 2 (3 blocks, one per class): exclusive scan of the block counts; totals -> n_stay and the send headers */
+__global__ void __launch_bounds__(1024)
+k_scan3(unsigned int *block_sums, int nb, int *n_stay, int *hdr_dn, int *hdr_up, int cap) {
+    __shared__ unsigned int s_warp[32];
+    __shared__ unsigned int s_carry;
+    unsigned int *row = block_sums + (size_t)blockIdx.x * nb;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned int v = (i < nb) ? row[i] : 0u;
+        unsigned int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const unsigned int wbase = warp ? s_warp[warp - 1] : 0u;
+        const unsigned int carry = s_carry;
+        if (i < nb) row[i] = carry + wbase + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + wbase + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int total = (int)s_carry;
+        if (blockIdx.x == 0) *n_stay = total;
+        else {
+            int *h = (blockIdx.x == 1) ? hdr_dn : hdr_up;
+            h[0] = min(total, cap);
+            h[1] = total > cap;
+            h[2] = 0;
+            h[3] = 0;
+        }
+    }
+}
+
+/* pass 3: stable scatter of every agent to its destination (stayers list / down buffer / up buffer) */
+__global__ void __launch_bounds__(COMPACT_THREADS)
+k_scatter3(const char *__restrict__ src, char *__restrict__ stay, char *__restrict__ dn, char *__restrict__ up,
+           const ColSet cols, const ColSet bcols, const int *__restrict__ flags, const unsigned int *__restrict__ block_offsets,
+           int nb, int n_host, const int *__restrict__ d_n, int cap, int *overflow) {
+    __shared__ unsigned int s_warp[3][32];
+    const int n = d_n ? *d_n : n_host;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = (i < n) ? flags[i] : 0;
+    const unsigned int b1 = __ballot_sync(0xffffffffu, f == 1), b2 = __ballot_sync(0xffffffffu, f == 2),
+                       b3 = __ballot_sync(0xffffffffu, f == 3);
+    if (lane == 0) {
+        s_warp[0][warp] = __popc(b1);
+        s_warp[1][warp] = __popc(b2);
+        s_warp[2][warp] = __popc(b3);
+    }
+    __syncthreads();
+    if (warp < 3) {
+        const unsigned int v = s_warp[warp][lane];
+        unsigned int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        s_warp[warp][lane] = inc - v;
+    }
+    __syncthreads();
+    if (f < 1 || f > 3) return;
+    const unsigned int lt = (1u << lane) - 1u;
+    const unsigned int bal = (f == 1) ? b1 : (f == 2) ? b2 : b3;
+    const size_t out = (size_t)block_offsets[(size_t)(f - 1) * nb + blockIdx.x] + s_warp[f - 1][warp] + __popc(bal & lt);
+    char *dst = (f == 1) ? stay : (f == 2) ? dn : up;
+    if (f != 1 && out >= (size_t)cap) {
+        atomicExch(overflow, 1);
+        return;
+    }
+    for (int c = 0; c < cols.ncols; ++c) {
+        const unsigned long long doff = (f == 1) ? cols.off[c] : bcols.off[c];
+        if (cols.size[c] == 4)
+            ((unsigned int *)(dst + doff))[out] = ((const unsigned int *)(src + cols.off[c]))[i];
+        else
+            ((unsigned long long *)(dst + doff))[out] = ((const unsigned long long *)(src + cols.off[c]))[i];
+    }
+}
+
+/* pass 4 (after the exchange): append both received buffers after the stayers and publish the new population */
+__global__ void __launch_bounds__(256)
+k_append_both(const char *__restrict__ rlo, const char *__restrict__ rhi, char *__restrict__ dst, const ColSet scols,
+              const ColSet dcols, const int *__restrict__ n_stay, int *__restrict__ n_new, int dst_cap, int *status) {
+    const int *hlo = (const int *)rlo, *hhi = (const int *)rhi;
+    const int clo = hlo[0], chi = hhi[0], base = *n_stay;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        if (hlo[1] || hhi[1]) atomicExch(status, 3);
+        if ((long long)base + clo + chi > (long long)dst_cap) atomicExch(status, 4);
+        *n_new = min(base + clo + chi, dst_cap);
+    }
+    if (i >= clo + chi) return;
+    const char *src = (i < clo) ? rlo : rhi;
+    const int si = (i < clo) ? i : i - clo;
+    const size_t out = (size_t)base + i;
+    if (out >= (size_t)dst_cap) return;
+    for (int c = 0; c < scols.ncols; ++c) {
+        if (scols.size[c] == 4)
+            ((unsigned int *)(dst + dcols.off[c]))[out] = ((const unsigned int *)(src + scols.off[c]))[si];
+        else
+            ((unsigned long long *)(dst + dcols.off[c]))[out] = ((const unsigned long long *)(src + scols.off[c]))[si];
+    }
 }
 
 /* header of a migrant buffer := {count (clamped), overflow} from the compaction total */

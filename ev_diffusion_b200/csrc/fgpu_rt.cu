@@ -73,6 +73,7 @@ struct AgentRT {
     ColSet cols;
     unsigned int *block_sums = nullptr;
     int *d_total = nullptr;
+    int *d_state_count = nullptr; /* slab mode: exact population of each state list, on the device */
 };
 
 struct MsgRT {
@@ -95,6 +96,7 @@ struct MsgRT {
     int sorted_in = 0; /* index of keys/vals buffer holding the final sorted pairs */
     bool built = false;
     int local_at = 0;  /* record index of the local block inside `sorted` (slab mode: halo_cap) */
+    const int *d_count = nullptr; /* slab mode: exact message count on the device (h_count is an upper bound) */
 };
 
 /* ---- 1-D slab decomposition state ---- */
@@ -124,6 +126,18 @@ struct SlabRT {
     int *h_pinned = nullptr; /* pinned mirror: status + counts */
     bool dirty = false;
     long long halo_bytes = 0, mig_bytes = 0; /* NCCL bytes sent per iteration (instrumentation) */
+    /* Asynchronous mode (models whose functions are all in-place): populations stay on the device, kernels
+     * read them there, the host only tracks upper bounds and learns the exact values a few iterations late
+     * through a ring of pinned read-backs -- no host round trip inside an iteration. */
+    bool async = false;
+    static const int RING = 4;
+    cudaEvent_t ring_ev[RING] = {nullptr, nullptr, nullptr, nullptr};
+    long long ring_mig[RING] = {-1, -1, -1, -1}; /* migration number each ring entry belongs to */
+    int *h_ring = nullptr;                        /* pinned: RING x RING_STRIDE ints (8 status + counts) */
+    static const int RING_STRIDE = 64;
+    long long migrations = 0;
+    std::vector<int> exact;       /* last exact populations seen (per migrating state list) */
+    long long exact_mig = 0;      /* ... as of this migration number */
 };
 
 struct ProfEntry {
@@ -150,10 +164,12 @@ struct fgpu_sim {
     int opt_order = 1;
     int opt_graph = 1;
     int opt_radix_bits = 9;
+    int opt_slab_async = 1;
     int opt_stage = 0; /* block staging of PBM+message windows: correct but not yet faster (profiles/r01_notes.md) */
     int opt_stage_bytes = 36 * 1024; /* shared-memory budget for staged messages per block */
     /* CUDA graph of one iteration (static models) */
     bool is_static = false;
+    bool static_kind = false; /* every function is an in-place pointer-swap function (regardless of slab mode) */
     cudaGraphExec_t graph = nullptr;
     std::vector<int> graph_counts; /* counts baked into the graph */
     long long graph_launches = 0;
@@ -190,6 +206,7 @@ struct fgpu_sim {
 };
 
 static void slab_release(fgpu_sim *s);
+static void slab_mark_exact(fgpu_sim *s);
 static size_t msg_plane_bytes(const fgpu_message *m) { return (size_t)m->rec_quads * m->buffer_size * sizeof(uint4); }
 
 /* ------------------------------------------------------------------------- */
@@ -255,8 +272,10 @@ static int sim_alloc(fgpu_sim *s) {
             A.cols.off[v] = A.d->vars[v].list_offset;
         }
         const int nb = (A.d->buffer_size + COMPACT_THREADS - 1) / COMPACT_THREADS;
-        CU(cudaMalloc(&A.block_sums, sizeof(unsigned int) * (size_t)(nb + 1)));
+        CU(cudaMalloc(&A.block_sums, sizeof(unsigned int) * 3 * (size_t)(nb + 1)));
         CU(cudaMalloc(&A.d_total, sizeof(int)));
+        CU(cudaMalloc(&A.d_state_count, sizeof(int) * (size_t)A.d->nstates));
+        CU(cudaMemsetAsync(A.d_state_count, 0, sizeof(int) * (size_t)A.d->nstates, s->stream));
     }
     s->msgs.resize(m->nmessages);
     for (int i = 0; i < m->nmessages; ++i) {
@@ -282,7 +301,7 @@ static int sim_alloc(fgpu_sim *s) {
                     words = std::max(words, sort_scratch_words(M.d->buffer_size, M.d->radix_bits, mb));
             M.scratch_bytes = sizeof(unsigned int) * words;
             CU(cudaMalloc(&M.scratch, M.scratch_bytes));
-            CU(cudaMalloc(&M.gap_queue, sizeof(unsigned int) * 3 * ((size_t)M.d->grid_size / GAP_INLINE + 8)));
+            CU(cudaMalloc(&M.gap_queue, sizeof(unsigned int) * 3 * ((size_t)GAP_LONG_MAX + (size_t)M.d->grid_size / GAP_INLINE + 8)));
         }
     }
     s->gc_count.assign(m->nfunctions, 0);
@@ -319,6 +338,7 @@ static int sim_alloc(fgpu_sim *s) {
         const fgpu_function &F = m->functions[f];
         if (!F.swappable || F.output_type != FGPU_OUT_SINGLE) s->is_static = false;
     }
+    s->static_kind = s->is_static;
     if (m->init_constants) m->init_constants();
     CU(cudaStreamSynchronize(s->stream));
     return FGPU_OK;
@@ -360,6 +380,7 @@ extern "C" void fgpu_sim_destroy(fgpu_sim *s) {
         for (char *p : A.state) cudaFree(p);
         cudaFree(A.block_sums);
         cudaFree(A.d_total);
+        cudaFree(A.d_state_count);
     }
     for (MsgRT &M : s->msgs) {
         cudaFree(M.unsorted);
@@ -388,6 +409,9 @@ extern "C" void fgpu_sim_destroy(fgpu_sim *s) {
     }
     if (s->slab.d_status) cudaFree(s->slab.d_status);
     if (s->slab.h_pinned) cudaFreeHost(s->slab.h_pinned);
+    if (s->slab.h_ring) cudaFreeHost(s->slab.h_ring);
+    for (int i = 0; i < SlabRT::RING; ++i)
+        if (s->slab.ring_ev[i]) cudaEventDestroy(s->slab.ring_ev[i]);
     slab_release(s);
     cudaFree(s->seeds);
     cudaFree(s->unpack_tmp);
@@ -445,6 +469,8 @@ static int upload_columns(fgpu_sim *s, int agent, int state, int offset, int cou
     }
     CU(cudaStreamSynchronize(s->stream));
     A.h_state_count[state] = offset + count;
+    CU(cudaMemcpy(A.d_state_count + state, &A.h_state_count[state], sizeof(int), cudaMemcpyHostToDevice));
+    slab_mark_exact(s);
     s->touch(list);
     invalidate_graph(s);
     return FGPU_OK;
@@ -797,14 +823,14 @@ extern "C" int fgpu_sim_load_states(fgpu_sim *s, const char *xml_path) {
  * the two 4-byte D2H copies after every cub scan, e.g. simulation.xslt:1476). */
 static int compact(fgpu_sim *s, AgentRT &A, const char *src, char *dst, int dst_offset, int n, const int *flags,
                    bool scatter, int *count_out, int match = 1, const ColSet *dcols = nullptr, int dst_cap = 0x7fffffff,
-                   int *overflow = nullptr) {
+                   int *overflow = nullptr, const int *d_n = nullptr) {
     if (n <= 0) {
         if (count_out) *count_out = 0;
         CU(cudaMemsetAsync(A.d_total, 0, sizeof(int), s->stream));
         return FGPU_OK;
     }
     const int nb = (n + COMPACT_THREADS - 1) / COMPACT_THREADS;
-    k_flag_blocksum<<<nb, COMPACT_THREADS, 0, s->stream>>>(flags, n, A.block_sums, match);
+    k_flag_blocksum<<<nb, COMPACT_THREADS, 0, s->stream>>>(flags, n, d_n, A.block_sums, match);
     LAUNCH_CHECK();
     k_scan_blocksums<<<1, 1024, 0, s->stream>>>(A.block_sums, nb, A.d_total);
     LAUNCH_CHECK();
@@ -814,7 +840,7 @@ static int compact(fgpu_sim *s, AgentRT &A, const char *src, char *dst, int dst_
     }
     if (scatter) {
         k_compact_scatter<<<nb, COMPACT_THREADS, 0, s->stream>>>(src, dst, A.cols, dcols ? *dcols : A.cols, flags, A.block_sums,
-                                                                 dst_offset, n, match, dst_cap, overflow);
+                                                                 dst_offset, n, d_n, match, dst_cap, overflow);
         LAUNCH_CHECK();
         s->touch(dst);
     }
@@ -839,7 +865,7 @@ static size_t sort_scratch_words(int n, int key_bits, int max_bits) {
 
 template <int BITS>
 static cudaError_t launch_scatter(int tiles, cudaStream_t st, const unsigned int *kin, const unsigned int *vin, unsigned int *kout,
-                                  unsigned int *vout, int n, int shift, int digit_bits, const unsigned int *tile_hist,
+                                  unsigned int *vout, int n, const int *d_n, int shift, int digit_bits, const unsigned int *tile_hist,
                                   const unsigned int *totals) {
     static bool configured = false;
     const size_t smem = sizeof(SortSmem<BITS>);
@@ -848,7 +874,7 @@ static cudaError_t launch_scatter(int tiles, cudaStream_t st, const unsigned int
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_radix_scatter<BITS><<<tiles, SORT_THREADS, smem, st>>>(kin, vin, kout, vout, n, shift, digit_bits, tile_hist, totals, tiles);
+    k_radix_scatter<BITS><<<tiles, SORT_THREADS, smem, st>>>(kin, vin, kout, vout, n, d_n, shift, digit_bits, tile_hist, totals, tiles);
     return cudaGetLastError();
 }
 
@@ -856,7 +882,7 @@ static cudaError_t launch_scatter(int tiles, cudaStream_t st, const unsigned int
  * Returns the index (0/1) of the ping-pong pair holding the sorted result; counts launches. */
 static int radix_sort_pairs(cudaStream_t st, const unsigned int *keys_in, int n, int key_bits, int max_bits,
                             unsigned int *keys[2], unsigned int *vals[2], unsigned int *scratch, int *sorted_in,
-                            long long *launches) {
+                            long long *launches, const int *d_n = nullptr) {
     int passes = 1;
     const int digit_bits = choose_digit_bits(key_bits, max_bits, &passes);
     if (passes > SORT_MAX_PASSES) return set_err(FGPU_ERR_MODEL, "%d key bits need %d radix passes", key_bits, passes);
@@ -867,13 +893,13 @@ static int radix_sort_pairs(cudaStream_t st, const unsigned int *keys_in, int n,
         const unsigned int *kin = p == 0 ? keys_in : keys[(p - 1) & 1];
         const unsigned int *vin = p == 0 ? nullptr : vals[(p - 1) & 1];
         const int shift = p * digit_bits;
-        k_tile_hist<<<tiles, SORT_THREADS, sizeof(unsigned int) * (size_t)nbins, st>>>(kin, n, shift, digit_bits, tile_hist, tiles);
+        k_tile_hist<<<tiles, SORT_THREADS, sizeof(unsigned int) * (size_t)nbins, st>>>(kin, n, d_n, shift, digit_bits, tile_hist, tiles);
         k_row_scan<<<nbins, SORT_THREADS, 0, st>>>(tile_hist, tiles, totals);
         cudaError_t e;
-        if (digit_bits <= 8) e = launch_scatter<8>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, shift, digit_bits, tile_hist, totals);
-        else if (digit_bits == 9) e = launch_scatter<9>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, shift, digit_bits, tile_hist, totals);
-        else if (digit_bits == 10) e = launch_scatter<10>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, shift, digit_bits, tile_hist, totals);
-        else e = launch_scatter<11>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, shift, digit_bits, tile_hist, totals);
+        if (digit_bits <= 8) e = launch_scatter<8>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals);
+        else if (digit_bits == 9) e = launch_scatter<9>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals);
+        else if (digit_bits == 10) e = launch_scatter<10>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals);
+        else e = launch_scatter<11>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals);
         if (e != cudaSuccess) return set_err(FGPU_ERR_CUDA, "radix pass launch -> %s", cudaGetErrorString(e));
         (*launches) += 3;
     }
@@ -889,9 +915,9 @@ static int build_spatial(fgpu_sim *s, MsgRT &M) {
     const int max_bits = std::min(std::max(s->opt_radix_bits, 4), SORT_MAXBITS);
     unsigned int *gap_count = M.scratch + SCR_GAP;
     s->prof_begin(std::string("sort:") + M.d->name);
-    CU(cudaMemsetAsync(gap_count, 0, sizeof(unsigned int), s->stream));
+    CU(cudaMemsetAsync(gap_count, 0, 2 * sizeof(unsigned int), s->stream));
     int in = 0;
-    int rc = radix_sort_pairs(s->stream, M.keys_in, n, M.d->radix_bits, max_bits, M.keys, M.vals, M.scratch, &in, &s->launches);
+    int rc = radix_sort_pairs(s->stream, M.keys_in, n, M.d->radix_bits, max_bits, M.keys, M.vals, M.scratch, &in, &s->launches, M.d_count);
     if (rc) return rc;
     s->prof_end();
     M.sorted_in = in;
@@ -900,7 +926,7 @@ static int build_spatial(fgpu_sim *s, MsgRT &M) {
     switch (M.d->rec_quads) {
 #define GATHER_CASE(Q)                                                                                                   \
     case Q:                                                                                                              \
-        k_gather_pbm<Q><<<g, 256, 0, s->stream>>>(M.keys[in], M.vals[in], M.unsorted, M.sorted + (size_t)M.local_at * Q, n, M.cell_start, \
+        k_gather_pbm<Q><<<g, 256, 0, s->stream>>>(M.keys[in], M.vals[in], M.unsorted, M.sorted + (size_t)M.local_at * Q, n, M.d_count, M.cell_start, \
                                                   (unsigned int)M.d->grid_size, M.gap_queue, gap_count);                 \
         break;
         GATHER_CASE(1)
@@ -916,7 +942,7 @@ static int build_spatial(fgpu_sim *s, MsgRT &M) {
             return set_err(FGPU_ERR_MODEL, "message %s: record of %d quads is not supported", M.d->name, M.d->rec_quads);
     }
     LAUNCH_CHECK();
-    k_fill_gaps<<<148, 256, 0, s->stream>>>(M.cell_start, M.gap_queue, gap_count);
+    k_fill_gaps<<<148 * 2, 256, 0, s->stream>>>(M.cell_start, M.gap_queue, gap_count);
     LAUNCH_CHECK();
     s->prof_end();
     return FGPU_OK;
@@ -1111,7 +1137,14 @@ extern "C" int fgpu_sim_slab_init(fgpu_sim *s, int rank, int world, const void *
     rc = seed_rand48(s, (unsigned long long)rank * (unsigned long long)m->buffer_size_max,
                      (unsigned long long)world * (unsigned long long)m->buffer_size_max);
     if (rc) return rc;
+    S.async = s->static_kind && s->opt_slab_async;
+    for (int i = 0; i < SlabRT::RING; ++i) CU(cudaEventCreateWithFlags(&S.ring_ev[i], cudaEventDisableTiming));
+    CU(cudaMallocHost(&S.h_ring, sizeof(int) * SlabRT::RING * SlabRT::RING_STRIDE));
+    for (int a = 0; a < m->nagents; ++a)
+        CU(cudaMemcpy(s->agents[a].d_state_count, s->agents[a].h_state_count.data(), sizeof(int) * (size_t)m->agents[a].nstates,
+                      cudaMemcpyHostToDevice));
     S.on = true;
+    slab_mark_exact(s);
     s->is_static = false; /* populations change every iteration: no graph replay in slab mode */
     invalidate_graph(s);
     return FGPU_OK;
@@ -1166,7 +1199,7 @@ static int slab_exchange_halo(fgpu_sim *s, int mi) {
     switch (Q) {
 #define MERGE_CASE(QQ)                                                                                                      \
     case QQ:                                                                                                                \
-        k_merge_halo<QQ><<<g, 256, 0, s->stream>>>(M.sorted, M.cell_start, M.local_at, n, S.p0 * PL, S.ppr * PL, X.recv_lo, \
+        k_merge_halo<QQ><<<g, 256, 0, s->stream>>>(M.sorted, M.cell_start, M.local_at, n, M.d_count, S.p0 * PL, S.ppr * PL, X.recv_lo, \
                                                    lo_first, X.recv_hi, hi_first, PL, S.d_status);                         \
         break;
         MERGE_CASE(1) MERGE_CASE(2) MERGE_CASE(3) MERGE_CASE(4) MERGE_CASE(5) MERGE_CASE(6) MERGE_CASE(7) MERGE_CASE(8)
@@ -1180,36 +1213,91 @@ static int slab_exchange_halo(fgpu_sim *s, int mi) {
 /* Migration: agents whose plane left the slab are compacted out and sent to the owning neighbour; arrivals
  * are appended after the stayers (lower neighbour's first).  One host round trip at the end learns the new
  * populations (the reference pays two blocking D2H copies after every scan, e.g. sim:1476-1477). */
+/* The host-side populations are exact right now: remember them as the base of the upper bounds. */
+static void slab_mark_exact(fgpu_sim *s) {
+    SlabRT &S = s->slab;
+    if (!S.on) return;
+    S.exact.assign(SlabRT::RING_STRIDE - 8, 0);
+    int slot = 0;
+    for (size_t a = 0; a < s->agents.size(); ++a) {
+        if (S.agents[a].axis_var < 0) continue;
+        for (int st = 0; st < s->agents[a].d->nstates; ++st, ++slot)
+            if (slot < SlabRT::RING_STRIDE - 8) S.exact[slot] = s->agents[a].h_state_count[st];
+    }
+    S.exact_mig = S.migrations;
+}
+
+/* Collects finished read-backs of the asynchronous mode: newest exact populations + error flags.
+ * `wait` blocks until everything enqueued so far has landed. */
+static int slab_poll(fgpu_sim *s, bool wait) {
+    SlabRT &S = s->slab;
+    const fgpu_model *m = s->model;
+    for (int k = 0; k < SlabRT::RING; ++k) {
+        const long long mig = S.migrations - 1 - k; /* newest first */
+        if (mig < 0) break;
+        const int slot = (int)(mig % SlabRT::RING);
+        if (S.ring_mig[slot] != mig) continue;
+        if (wait) CU(cudaEventSynchronize(S.ring_ev[slot]));
+        else if (cudaEventQuery(S.ring_ev[slot]) != cudaSuccess) continue;
+        const int *r = S.h_ring + slot * SlabRT::RING_STRIDE;
+        if (r[0] == 1 || r[1] || r[2])
+            return set_err(FGPU_ERR_OVERFLOW, "slab exchange: fixed-capacity buffer overflow (halo %d, migrants %d, status %d/%d/%d)",
+                           S.halo_cap, S.mig_cap, r[0], r[1], r[2]);
+        if (r[0] == 2) return set_err(FGPU_ERR_COMM, "slab exchange: an agent moved further than one slab in one step");
+        if (mig >= S.exact_mig) {
+            S.exact.assign(r + 8, r + SlabRT::RING_STRIDE);
+            S.exact_mig = mig + 1;
+        }
+        break;
+    }
+    /* upper bounds: each migration adds at most 2 * mig_cap agents to a list */
+    const long long lag = S.migrations - S.exact_mig;
+    int slot = 0;
+    for (int a = 0; a < m->nagents; ++a) {
+        if (S.agents[a].axis_var < 0) continue;
+        for (int st = 0; st < s->agents[a].d->nstates; ++st, ++slot) {
+            if (S.exact.empty()) continue;
+            const long long ub = (long long)S.exact[slot] + lag * 2LL * S.mig_cap;
+            if (lag == 0 && S.exact[slot] > s->agents[a].d->buffer_size)
+                return set_err(FGPU_ERR_OVERFLOW, "slab migration: %d agents exceed the buffer of %s", S.exact[slot], s->agents[a].d->name);
+            s->agents[a].h_state_count[st] = (int)std::min<long long>(ub, s->agents[a].d->buffer_size);
+        }
+    }
+    return FGPU_OK;
+}
+
+/* Migration: agents whose plane left the slab are compacted out and sent to the owning neighbour; arrivals
+ * are appended after the stayers (lower neighbour's first).  Synchronous mode: one host round trip at the
+ * end learns the new populations (the reference pays two blocking D2H copies after every scan, e.g.
+ * sim:1476-1477).  Asynchronous mode: none -- counts stay on the device. */
 static int slab_migrate(fgpu_sim *s) {
     SlabRT &S = s->slab;
     const fgpu_model *m = s->model;
     s->prof_begin("migrate");
+    const int ring = (int)(S.migrations % SlabRT::RING);
+    int *hdst = S.async ? S.h_ring + ring * SlabRT::RING_STRIDE : S.h_pinned;
+    if (S.async && S.ring_mig[ring] >= 0) CU(cudaEventSynchronize(S.ring_ev[ring])); /* RING migrations old: long done */
     int slot = 0;
     for (int a = 0; a < m->nagents; ++a) {
         AgentRT &A = s->agents[a];
         SlabAgent &X = S.agents[a];
         if (X.axis_var < 0) continue;
         for (int st = 0; st < A.d->nstates; ++st, ++slot) {
-            const int n = A.h_state_count[st];
+            if (8 + slot >= SlabRT::RING_STRIDE) return set_err(FGPU_ERR_MODEL, "too many state lists for slab mode");
+            const int n = A.h_state_count[st];           /* exact, or an upper bound in asynchronous mode */
+            const int *d_n = S.async ? A.d_state_count + st : nullptr;
             char *list = A.state[st];
             int *flags = (int *)(list + A.d->scan_offset);
             int *cnt = X.d_counts + 2 * st;
-            if (n > 0) {
-                k_owner_flags<<<(n + 255) / 256, 256, 0, s->stream>>>((const float *)(list + A.d->vars[X.axis_var].list_offset), n,
-                                                                   S.axis_min, S.axis_max, S.nplanes, S.ppr, S.rank, S.world, flags,
-                                                                   S.d_status);
-                LAUNCH_CHECK();
-            }
-            int rc = compact(s, A, list, A.swap, 0, n, flags, true, nullptr, 1);
-            if (rc) return rc;
-            CU(cudaMemcpyAsync(cnt, A.d_total, sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
-            rc = compact(s, A, list, X.send_dn, 0, n, flags, true, nullptr, 2, &X.bufcols, S.mig_cap, S.d_status + 1);
-            if (rc) return rc;
-            k_set_header<<<1, 1, 0, s->stream>>>((int *)X.send_dn, A.d_total, S.mig_cap);
+            const int nb = std::max(1, (n + COMPACT_THREADS - 1) / COMPACT_THREADS);
+            k_owner_count<<<nb, COMPACT_THREADS, 0, s->stream>>>((const float *)(list + A.d->vars[X.axis_var].list_offset), n, d_n,
+                                                                 S.axis_min, S.axis_max, S.nplanes, S.ppr, S.rank, S.world, flags,
+                                                                 A.block_sums, nb, S.d_status);
             LAUNCH_CHECK();
-            rc = compact(s, A, list, X.send_up, 0, n, flags, true, nullptr, 3, &X.bufcols, S.mig_cap, S.d_status + 1);
-            if (rc) return rc;
-            k_set_header<<<1, 1, 0, s->stream>>>((int *)X.send_up, A.d_total, S.mig_cap);
+            k_scan3<<<3, 1024, 0, s->stream>>>(A.block_sums, nb, cnt, (int *)X.send_dn, (int *)X.send_up, S.mig_cap);
+            LAUNCH_CHECK();
+            k_scatter3<<<nb, COMPACT_THREADS, 0, s->stream>>>(list, A.swap, X.send_dn, X.send_up, A.cols, X.bufcols, flags, A.block_sums,
+                                                              nb, n, d_n, S.mig_cap, S.d_status + 1);
             LAUNCH_CHECK();
             NC(g_nccl.GroupStart());
             NC(g_nccl.Send(X.send_dn, X.bytes, NCCL_INT8, S.lo_rank, S.comm, s->stream));
@@ -1218,38 +1306,51 @@ static int slab_migrate(fgpu_sim *s) {
             NC(g_nccl.Recv(X.recv_lo, X.bytes, NCCL_INT8, S.lo_rank, S.comm, s->stream));
             NC(g_nccl.GroupEnd());
             S.mig_bytes += 2 * (long long)X.bytes;
-            const int gb = (S.mig_cap + 255) / 256;
-            k_append_received<<<gb, 256, 0, s->stream>>>(X.recv_lo, (const int *)X.recv_lo, A.swap, X.bufcols, A.cols, cnt, nullptr,
-                                                         A.d->buffer_size, S.d_status + 2);
+            k_append_both<<<(2 * S.mig_cap + 255) / 256, 256, 0, s->stream>>>(X.recv_lo, X.recv_hi, A.swap, X.bufcols, A.cols, cnt,
+                                                                              A.d_state_count + st, A.d->buffer_size, S.d_status + 2);
             LAUNCH_CHECK();
-            k_append_received<<<gb, 256, 0, s->stream>>>(X.recv_hi, (const int *)X.recv_hi, A.swap, X.bufcols, A.cols, cnt,
-                                                         (const int *)X.recv_lo, A.d->buffer_size, S.d_status + 2);
-            LAUNCH_CHECK();
-            k_sum_counts<<<1, 1, 0, s->stream>>>(cnt + 1, cnt, (const int *)X.recv_lo, (const int *)X.recv_hi);
-            LAUNCH_CHECK();
-            CU(cudaMemcpyAsync(S.h_pinned + 8 + slot, cnt + 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaMemcpyAsync(hdst + 8 + slot, A.d_state_count + st, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
             std::swap(A.state[st], A.swap);
             s->touch(A.state[st]);
         }
     }
-    CU(cudaMemcpyAsync(S.h_pinned, S.d_status, sizeof(int) * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(hdst, S.d_status, sizeof(int) * 8, cudaMemcpyDeviceToHost, s->stream));
+    S.dirty = false;
+    if (S.async) {
+        CU(cudaEventRecord(S.ring_ev[ring], s->stream));
+        S.ring_mig[ring] = S.migrations;
+        S.migrations++;
+        s->prof_end();
+        return slab_poll(s, false);
+    }
+    S.migrations++;
     CU(cudaStreamSynchronize(s->stream));
     s->prof_end();
-    if (S.h_pinned[0] == 1 || S.h_pinned[1] || S.h_pinned[2])
+    if (hdst[0] == 1 || hdst[1] || hdst[2])
         return set_err(FGPU_ERR_OVERFLOW, "slab exchange: fixed-capacity buffer overflow (halo %d, migrants %d, status %d/%d/%d)",
-                       S.halo_cap, S.mig_cap, S.h_pinned[0], S.h_pinned[1], S.h_pinned[2]);
-    if (S.h_pinned[0] == 2) return set_err(FGPU_ERR_COMM, "slab exchange: an agent moved further than one slab in one step");
+                       S.halo_cap, S.mig_cap, hdst[0], hdst[1], hdst[2]);
+    if (hdst[0] == 2) return set_err(FGPU_ERR_COMM, "slab exchange: an agent moved further than one slab in one step");
     slot = 0;
     for (int a = 0; a < m->nagents; ++a) {
         if (S.agents[a].axis_var < 0) continue;
         for (int st = 0; st < s->agents[a].d->nstates; ++st, ++slot) {
-            const int nn = S.h_pinned[8 + slot];
+            const int nn = hdst[8 + slot];
             if (nn > s->agents[a].d->buffer_size)
                 return set_err(FGPU_ERR_OVERFLOW, "slab migration: %d agents exceed the buffer of %s", nn, s->agents[a].d->name);
             s->agents[a].h_state_count[st] = nn;
         }
     }
-    S.dirty = false;
+    return FGPU_OK;
+}
+
+/* After the stream has drained: make the host-side populations exact again (asynchronous slab mode). */
+static int slab_settle(fgpu_sim *s) {
+    if (!s->slab.on || !s->slab.async) return FGPU_OK;
+    int rc = slab_poll(s, true);
+    if (rc) return rc;
+    for (AgentRT &A : s->agents)
+        CU(cudaMemcpy(A.h_state_count.data(), A.d_state_count, sizeof(int) * (size_t)A.d->nstates, cudaMemcpyDeviceToHost));
+    slab_mark_exact(s);
     return FGPU_OK;
 }
 
@@ -1343,14 +1444,17 @@ static int run_function(fgpu_sim *s, int fi) {
 
     fgpu_launch L;
     memset(&L, 0, sizeof(L));
+    const bool slab_async = s->slab.on && s->slab.async;
     L.agents = A.work;
     L.n = A.h_count;
+    L.d_n = slab_async ? A.d_state_count + cur : nullptr; /* in-place function: the working list is the state list */
     L.order = nullptr;
     if (F.xagent_output >= 0) L.new_agents = s->agents[F.xagent_output].newl;
     if (Min) {
         L.in_recs = (Min->d->partitioning == FGPU_PART_SPATIAL) ? (const void *)Min->sorted : (const void *)Min->unsorted;
         L.in_cell_start = Min->cell_start;
         L.in_count = Min->h_count;
+        L.d_in_count = slab_async ? Min->d_count : nullptr;
         /* cell-coherent processing order: only when this very list produced the
          * messages (message k <-> list index k) and has not been restructured since */
         if (s->opt_order && Min->d->partitioning == FGPU_PART_SPATIAL && Min->producers == 1 &&
@@ -1386,8 +1490,11 @@ static int run_function(fgpu_sim *s, int fi) {
             Mout->producers = 1;
             Mout->producer_buf = A.work;
             Mout->producer_epoch = s->epoch_of(A.work);
+            Mout->d_count = slab_async ? L.d_n : nullptr;
         } else {
             Mout->producers++;
+            if (slab_async)
+                return set_err(FGPU_ERR_MODEL, "message %s has two producers in one iteration: not supported in asynchronous slab mode", Mout->d->name);
         }
         Mout->h_count += A.h_count;
     }
@@ -1417,7 +1524,7 @@ static int run_function(fgpu_sim *s, int fi) {
         const int nb = (pre_death_count + COMPACT_THREADS - 1) / COMPACT_THREADS;
         k_compact_scatter<<<nb, COMPACT_THREADS, 0, s->stream>>>(B.newl, B.state[st], B.cols, B.cols,
                                                                  (const int *)(B.newl + B.d->scan_offset), B.block_sums,
-                                                                 B.h_state_count[st], pre_death_count, 1, 0x7fffffff, nullptr);
+                                                                 B.h_state_count[st], pre_death_count, nullptr, 1, 0x7fffffff, nullptr);
         LAUNCH_CHECK();
         s->touch(B.state[st]);
         B.h_state_count[st] += born;
@@ -1456,6 +1563,7 @@ static int begin_iteration(fgpu_sim *s) {
         M.producers = 0;
         M.producer_buf = nullptr;
         M.built = false;
+        M.d_count = nullptr;
     }
     return FGPU_OK;
 }
@@ -1546,7 +1654,7 @@ extern "C" int fgpu_sim_sync(fgpu_sim *s) {
     if (!s) return set_err(FGPU_ERR_ARG, "null sim");
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->stream));
-    return FGPU_OK;
+    return slab_settle(s);
 }
 
 extern "C" int fgpu_sim_step(fgpu_sim *s, int n) {
@@ -1555,7 +1663,7 @@ extern "C" int fgpu_sim_step(fgpu_sim *s, int n) {
     if (rc) return rc;
     CU(cudaStreamSynchronize(s->stream));
     if (n > 0) CU(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
-    return FGPU_OK;
+    return slab_settle(s);
 }
 
 /* n iterations, each timed separately with a cudaEvent pair on the simulation
@@ -1590,6 +1698,7 @@ extern "C" int fgpu_sim_step_timed(fgpu_sim *s, int n, size_t flush_bytes, float
     }
     for (auto &e : ev) cudaEventDestroy(e);
     s->last_ms = total;
+    if (rc == FGPU_OK) rc = slab_settle(s);
     return rc;
 }
 
@@ -1604,7 +1713,7 @@ extern "C" int fgpu_sim_run_function(fgpu_sim *s, int function) {
     int rc = run_function(s, function);
     if (rc) return rc;
     CU(cudaStreamSynchronize(s->stream));
-    return FGPU_OK;
+    return slab_settle(s);
 }
 
 extern "C" unsigned int fgpu_sim_iteration(const fgpu_sim *s) { return s ? s->iteration : 0u; }
@@ -1634,6 +1743,10 @@ extern "C" int fgpu_sim_set_option(fgpu_sim *s, const char *key, int value) {
     if (!strcmp(key, "order")) s->opt_order = value ? 1 : 0;
     else if (!strcmp(key, "graph")) s->opt_graph = value ? 1 : 0;
     else if (!strcmp(key, "stage")) s->opt_stage = value ? 1 : 0;
+    else if (!strcmp(key, "slab_async")) {
+        if (s->slab.on) return set_err(FGPU_ERR_ARG, "slab_async must be set before fgpu_sim_slab_init");
+        s->opt_slab_async = value ? 1 : 0;
+    }
     else if (!strcmp(key, "stage_bytes")) {
         if (value < 0 || value > 200 * 1024) return set_err(FGPU_ERR_ARG, "stage_bytes out of range");
         s->opt_stage_bytes = value;
@@ -1664,6 +1777,8 @@ extern "C" int fgpu_sim_profile_iteration(fgpu_sim *s, const char **names, float
     s->profiling = false;
     if (rc) return rc;
     CU(cudaStreamSynchronize(s->stream));
+    rc = slab_settle(s);
+    if (rc) return rc;
     s->prof_names.clear();
     s->prof_ms.clear();
     for (ProfEntry &e : s->prof) {
@@ -1734,9 +1849,9 @@ extern "C" int fgpu_debug_compact(const int *flags, const unsigned int *payload,
     cols.ncols = 1;
     cols.size[0] = 4;
     cols.off[0] = 0;
-    k_flag_blocksum<<<nb, COMPACT_THREADS>>>(d_flags, n, d_bs, 1);
+    k_flag_blocksum<<<nb, COMPACT_THREADS>>>(d_flags, n, nullptr, d_bs, 1);
     k_scan_blocksums<<<1, 1024>>>(d_bs, nb, d_total);
-    k_compact_scatter<<<nb, COMPACT_THREADS>>>((const char *)d_in, (char *)d_out, cols, cols, d_flags, d_bs, 0, n, 1, 0x7fffffff, nullptr);
+    k_compact_scatter<<<nb, COMPACT_THREADS>>>((const char *)d_in, (char *)d_out, cols, cols, d_flags, d_bs, 0, n, nullptr, 1, 0x7fffffff, nullptr);
     CU(cudaGetLastError());
     CU(cudaMemcpy(count_out, d_total, sizeof(int), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(out, d_out, sizeof(unsigned int) * (size_t)(*count_out), cudaMemcpyDeviceToHost));

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FGPU_MODEL_ABI_VERSION 6
+#define FGPU_MODEL_ABI_VERSION 7
 
 /* One agent or message variable.  Agent lists keep the reference's SoA struct
  * layout (header.xslt:187-194): int _position[MAX]; int _scan_input[MAX];
@@ -73,6 +73,7 @@ typedef struct fgpu_message {
 typedef struct fgpu_launch {
     void *agents;                 /* working list d_<A>s */
     int n;                        /* working count (exact, host-known like h_xmachine_memory_<A>_count) */
+    const int *d_n;               /* slab mode: exact count on the device, `n` is then an upper bound; else NULL */
     const unsigned int *order;    /* processing order: thread t runs list index order[t]; NULL = identity.
                                      Always a permutation of [0,n): results never depend on it. */
     void *new_agents;             /* d_<B>s_new (sparse newborn list) or NULL */
@@ -80,6 +81,7 @@ typedef struct fgpu_launch {
     const void *in_recs;          /* xmachine_message_<M>[count], cell-sorted */
     const unsigned int *in_cell_start;  /* CSR: grid_size+1 entries */
     int in_count;                 /* h_message_<M>_count */
+    const int *d_in_count;        /* slab mode: exact message count on the device, or NULL */
     const unsigned int *in_sorted_keys; /* cell key of each sorted message (block staging), may be NULL */
     int stage_msgs;               /* shared-memory staging capacity in messages; 0 = no staging */
     /* output message (unsorted staging + cell keys) */
