@@ -259,13 +259,11 @@ def main():
         warm_ms = float(t.item())
 
     # ---- per-stage times (stream mode, one cudaEvent pair per stage) ------------
-    stage = {}
     reps = min(args.steps, 20)
-    for _ in range(reps):
-        for name, ms in sim.profile_iteration():
-            stage[name] = stage.get(name, 0.0) + ms / reps
+    sim.profile_iterations(reps)                      # warms the event pool
+    stage = dict(sim.profile_iterations(reps))        # steady state, no host sync between iterations
     classes = {"func:output_location": stage.get("func:output_location", 0.0),
-               "build:location": stage.get("sort:location", 0.0) + stage.get("pbm:location", 0.0),
+               "build:location": stage.get("sort:location", 0.0) + stage.get("pbm:location", 0.0),  # single-GPU stages
                "func:count_neighbours": stage.get("func:count_neighbours", 0.0),
                "func:move": stage.get("func:move", 0.0)}
     dom = max(classes, key=lambda k: classes[k])

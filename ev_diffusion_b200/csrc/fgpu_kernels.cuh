@@ -456,11 +456,87 @@ k_append(const char *__restrict__ src, char *__restrict__ dst, const ColSet cols
  * 4-int header: {count, overflow, 0, 0}. */
 constexpr int XHDR = 4;
 
+/* ---- peer-memory transport ------------------------------------------------------------------------
+ * In P2P mode the neighbours' receive buffers are mapped through CUDA IPC and one small kernel per
+ * exchange (k_push, grid (PUSH_BLOCKS, 2): y = 0 towards the lower neighbour, y = 1 towards the upper)
+ * stores the used part of the two local send buffers straight into them over NVLink, publishes a
+ * sequence number in the neighbour's memory (every block fences its stores to system scope after a block
+ * barrier; the last block writes the flag) and then waits until the two neighbours' flags for the same
+ * exchange have arrived.  No collective launch, no staging copy on the receiving side, and only the
+ * bytes actually used travel (the NCCL fallback has to send the fixed capacity).  The heavy producer
+ * kernels stay free of system-scope fences: fencing inside them (one fence per block of a 1280-block
+ * grid) cost 35-45 us per exchange (profiles/r01_notes.md).  Receive buffers are double-buffered by
+ * sequence parity; a rank can never be two exchanges ahead of a neighbour because each exchange also
+ * waits for that neighbour's data. */
+__device__ __forceinline__ void st_flag_sys(int *p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_flag_sys(const int *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+constexpr int PUSH_BLOCKS = 24;
+constexpr int PUSH_MAX_SEG = 48;
+/* A fixed-capacity exchange buffer = `fixed_bytes` always-used bytes (header, PBM slice) followed by
+ * segments of `cap` elements of which the first hdr[0] are used. */
+struct PushLayout {
+    int fixed_bytes; /* multiple of 16 */
+    int nseg;
+    int elem[PUSH_MAX_SEG];                /* element size in bytes (4, 8 or a multiple of 16) */
+    unsigned long long off[PUSH_MAX_SEG];  /* byte offset of the segment, 16-byte aligned */
+};
+
+__device__ __forceinline__ void push_bytes(const char *__restrict__ src, char *__restrict__ dst, size_t bytes, int tid, int nthreads) {
+    /* bytes is a multiple of 4; bulk in 16-byte pieces, tail in words */
+    const size_t q = bytes / 16;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    for (size_t i = tid; i < q; i += nthreads) d4[i] = s4[i];
+    const size_t w0 = q * 4, w1 = bytes / 4;
+    for (size_t i = w0 + tid; i < w1; i += nthreads) ((unsigned int *)dst)[i] = ((const unsigned int *)src)[i];
+}
+
+__global__ void __launch_bounds__(256)
+k_push(const char *__restrict__ send_lo, const char *__restrict__ send_hi, char *__restrict__ peer_lo, char *__restrict__ peer_hi,
+       const PushLayout L, unsigned int *done_counter, int *peer_flag_lo, int *peer_flag_hi, const int *my_flag_a,
+       const int *my_flag_b, int seq, int *status) {
+    const char *src = blockIdx.y ? send_hi : send_lo;
+    char *dst = blockIdx.y ? peer_hi : peer_lo;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    const int cnt = ((const int *)src)[0];
+    push_bytes(src, dst, (size_t)L.fixed_bytes, tid, nthreads);
+    for (int k = 0; k < L.nseg; ++k) push_bytes(src + L.off[k], dst + L.off[k], (size_t)cnt * L.elem[k], tid, nthreads);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned int t = atomicAdd(done_counter, 1u);
+        if (t == gridDim.x * gridDim.y - 1) {
+            *done_counter = 0;
+            __threadfence_system();
+            st_flag_sys(peer_flag_lo, seq);
+            st_flag_sys(peer_flag_hi, seq);
+            /* ... and wait for the neighbours' data of the same exchange (bounded spin) */
+            const long long t0 = clock64();
+            while (ld_flag_sys(my_flag_a) < seq || ld_flag_sys(my_flag_b) < seq) {
+                if (clock64() - t0 > 4000000000LL) { /* ~2 s: report instead of hanging the GPU */
+                    atomicExch(status, 5);
+                    break;
+                }
+                __nanosleep(100);
+            }
+        }
+    }
+}
+
 /* plane -> send buffer: header | (plane_cells + 1) cell_start entries rebased to 0 | records */
 template <int NQ>
 __global__ void __launch_bounds__(256)
-k_pack_plane(const uint4 *__restrict__ sorted_local, const unsigned int *__restrict__ cell_start, int first_cell,
-             int plane_cells, int cap, int *__restrict__ out) {
+k_pack_planes(const uint4 *__restrict__ sorted_local, const unsigned int *__restrict__ cell_start, int first_cell_lo,
+              int first_cell_hi, int plane_cells, int cap, int *__restrict__ out_lo, int *__restrict__ out_hi) {
+    const int first_cell = blockIdx.y ? first_cell_hi : first_cell_lo;
+    int *out = blockIdx.y ? out_hi : out_lo;
     const int lo = (int)cell_start[first_cell], hi = (int)cell_start[first_cell + plane_cells];
     const int cnt = hi - lo;
     const int stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -643,21 +719,22 @@ k_scatter3(const char *__restrict__ src, char *__restrict__ stay, char *__restri
         s_warp[warp][lane] = inc - v;
     }
     __syncthreads();
-    if (f < 1 || f > 3) return;
-    const unsigned int lt = (1u << lane) - 1u;
-    const unsigned int bal = (f == 1) ? b1 : (f == 2) ? b2 : b3;
-    const size_t out = (size_t)block_offsets[(size_t)(f - 1) * nb + blockIdx.x] + s_warp[f - 1][warp] + __popc(bal & lt);
-    char *dst = (f == 1) ? stay : (f == 2) ? dn : up;
-    if (f != 1 && out >= (size_t)cap) {
-        atomicExch(overflow, 1);
-        return;
-    }
-    for (int c = 0; c < cols.ncols; ++c) {
-        const unsigned long long doff = (f == 1) ? cols.off[c] : bcols.off[c];
-        if (cols.size[c] == 4)
-            ((unsigned int *)(dst + doff))[out] = ((const unsigned int *)(src + cols.off[c]))[i];
-        else
-            ((unsigned long long *)(dst + doff))[out] = ((const unsigned long long *)(src + cols.off[c]))[i];
+    if (f >= 1 && f <= 3) {
+        const unsigned int lt = (1u << lane) - 1u;
+        const unsigned int bal = (f == 1) ? b1 : (f == 2) ? b2 : b3;
+        const size_t out = (size_t)block_offsets[(size_t)(f - 1) * nb + blockIdx.x] + s_warp[f - 1][warp] + __popc(bal & lt);
+        char *dst = (f == 1) ? stay : (f == 2) ? dn : up;
+        if (f != 1 && out >= (size_t)cap) {
+            atomicExch(overflow, 1);
+        } else {
+            for (int c = 0; c < cols.ncols; ++c) {
+                const unsigned long long doff = (f == 1) ? cols.off[c] : bcols.off[c];
+                if (cols.size[c] == 4)
+                    ((unsigned int *)(dst + doff))[out] = ((const unsigned int *)(src + cols.off[c]))[i];
+                else
+                    ((unsigned long long *)(dst + doff))[out] = ((const unsigned long long *)(src + cols.off[c]))[i];
+            }
+        }
     }
 }
 

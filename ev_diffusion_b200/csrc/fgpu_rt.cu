@@ -28,6 +28,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <string>
 #include <vector>
@@ -129,6 +130,15 @@ struct SlabRT {
     /* Asynchronous mode (models whose functions are all in-place): populations stay on the device, kernels
      * read them there, the host only tracks upper bounds and learns the exact values a few iterations late
      * through a ring of pinned read-backs -- no host round trip inside an iteration. */
+    /* Peer-memory transport (CUDA IPC over NVLink): kernels store straight into the neighbours' receive
+     * buffers; NCCL is then only used once, to exchange the IPC handles. */
+    bool p2p = false;
+    char *xbuf = nullptr;      /* my receive area: flags | per message 4 buffers | per agent 4 buffers */
+    size_t xbuf_bytes = 0;
+    char *peer_lo = nullptr, *peer_hi = nullptr; /* the neighbours' receive areas, mapped */
+    std::vector<size_t> msg_off, agent_off;      /* offset of the first of the 4 buffers (lo0, lo1, hi0, hi1) */
+    std::vector<int> msg_seq, agent_seq;         /* exchange sequence numbers */
+    unsigned int *d_done = nullptr;              /* last-block counters */
     bool async = false;
     static const int RING = 4;
     cudaEvent_t ring_ev[RING] = {nullptr, nullptr, nullptr, nullptr};
@@ -165,6 +175,7 @@ struct fgpu_sim {
     int opt_graph = 1;
     int opt_radix_bits = 9;
     int opt_slab_async = 1;
+    int opt_slab_p2p = 1;
     int opt_stage = 0; /* block staging of PBM+message windows: correct but not yet faster (profiles/r01_notes.md) */
     int opt_stage_bytes = 36 * 1024; /* shared-memory budget for staged messages per block */
     /* CUDA graph of one iteration (static models) */
@@ -190,12 +201,22 @@ struct fgpu_sim {
         auto it = epoch.find(buf);
         return it == epoch.end() ? 0ull : it->second;
     }
+    std::vector<cudaEvent_t> ev_pool; /* events are created once and reused: no creation cost in the timed path */
+    size_t ev_used = 0;
+    cudaEvent_t pool_event() {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev_pool.push_back(e);
+        }
+        return ev_pool[ev_used++];
+    }
     void prof_begin(const std::string &name) {
         if (!profiling) return;
         ProfEntry e;
         e.name = name;
-        cudaEventCreate(&e.a);
-        cudaEventCreate(&e.b);
+        e.a = pool_event();
+        e.b = pool_event();
         cudaEventRecord(e.a, stream);
         prof.push_back(e);
     }
@@ -240,7 +261,14 @@ extern "C" const fgpu_model *fgpu_model_load(const char *plugin_path) {
 /* ------------------------------------------------------------------------- */
 /* create / destroy                                                           */
 /* ------------------------------------------------------------------------- */
-static int sort_passes(int radix_bits, int max_bits) { return (radix_bits + max_bits - 1) / max_bits; }
+/* Number of LSD passes for a key of radix_bits with digits of about max_bits: one bit wider digits are
+ * accepted when that saves a whole pass (19- and 20-bit keys sort in 2 passes of 10 bits, not 3 of 7). */
+static int sort_passes(int radix_bits, int max_bits) {
+    const int p = (radix_bits + max_bits - 1) / max_bits;
+    const int wide = std::min(max_bits + 1, 11);
+    if (p > 1 && max_bits >= 8 && (radix_bits + wide - 1) / wide < p) return p - 1;
+    return p;
+}
 static size_t sort_scratch_words(int n, int key_bits, int max_bits);
 
 static int sim_alloc(fgpu_sim *s) {
@@ -416,10 +444,7 @@ extern "C" void fgpu_sim_destroy(fgpu_sim *s) {
     cudaFree(s->seeds);
     cudaFree(s->unpack_tmp);
     cudaFree(s->flush_buf);
-    for (ProfEntry &e : s->prof) {
-        cudaEventDestroy(e.a);
-        cudaEventDestroy(e.b);
-    }
+    for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -1008,8 +1033,16 @@ int load_nccl() {
     } while (0)
 
 static void slab_release(fgpu_sim *s) {
-    if (s->slab.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->slab.comm);
-    s->slab.comm = nullptr;
+    SlabRT &S = s->slab;
+    if (S.peer_lo) cudaIpcCloseMemHandle(S.peer_lo);
+    if (S.peer_hi && S.peer_hi != S.peer_lo) cudaIpcCloseMemHandle(S.peer_hi);
+    S.peer_lo = S.peer_hi = nullptr;
+    if (S.xbuf) cudaFree(S.xbuf);
+    if (S.d_done) cudaFree(S.d_done);
+    S.xbuf = nullptr;
+    S.d_done = nullptr;
+    if (S.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(S.comm);
+    S.comm = nullptr;
 }
 
 extern "C" int fgpu_nccl_unique_id(void *out128) {
@@ -1131,12 +1164,63 @@ extern "C" int fgpu_sim_slab_init(fgpu_sim *s, int rank, int world, const void *
         CU(cudaMalloc(&X.send_up, X.bytes));
         CU(cudaMalloc(&X.recv_lo, X.bytes));
         CU(cudaMalloc(&X.recv_hi, X.bytes));
-        CU(cudaMalloc(&X.d_counts, sizeof(int) * 2 * (size_t)A.d->nstates));
-        CU(cudaMemset(X.d_counts, 0, sizeof(int) * 2 * (size_t)A.d->nstates));
+        CU(cudaMalloc(&X.d_counts, sizeof(int) * 4 * (size_t)A.d->nstates));
+        CU(cudaMemset(X.d_counts, 0, sizeof(int) * 4 * (size_t)A.d->nstates));
     }
     rc = seed_rand48(s, (unsigned long long)rank * (unsigned long long)m->buffer_size_max,
                      (unsigned long long)world * (unsigned long long)m->buffer_size_max);
     if (rc) return rc;
+    /* peer-memory transport */
+    S.msg_off.assign(m->nmessages, 0);
+    S.agent_off.assign(m->nagents, 0);
+    S.msg_seq.assign(m->nmessages, 0);
+    S.agent_seq.assign(m->nagents, 0);
+    CU(cudaMalloc(&S.d_done, sizeof(unsigned int) * 64));
+    CU(cudaMemset(S.d_done, 0, sizeof(unsigned int) * 64));
+    if (s->opt_slab_p2p) {
+        size_t off = 4096; /* flags */
+        auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        for (int i = 0; i < m->nmessages; ++i)
+            if (S.msgs[i].bytes) {
+                S.msg_off[i] = off;
+                off += 4 * align(S.msgs[i].bytes);
+            }
+        for (int a = 0; a < m->nagents; ++a)
+            if (S.agents[a].axis_var >= 0) {
+                S.agent_off[a] = off;
+                off += 4 * align(S.agents[a].bytes);
+            }
+        S.xbuf_bytes = off;
+        CU(cudaMalloc(&S.xbuf, S.xbuf_bytes));
+        CU(cudaMemset(S.xbuf, 0, S.xbuf_bytes));
+        cudaIpcMemHandle_t mine, from_lo, from_hi;
+        CU(cudaIpcGetMemHandle(&mine, S.xbuf));
+        char *hbuf = nullptr;
+        CU(cudaMalloc(&hbuf, 3 * sizeof(mine)));
+        CU(cudaMemcpy(hbuf, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+        NC(g_nccl.GroupStart());
+        NC(g_nccl.Send(hbuf, sizeof(mine), NCCL_INT8, S.lo_rank, S.comm, s->stream));
+        NC(g_nccl.Send(hbuf, sizeof(mine), NCCL_INT8, S.hi_rank, S.comm, s->stream));
+        NC(g_nccl.Recv(hbuf + 2 * sizeof(mine), sizeof(mine), NCCL_INT8, S.hi_rank, S.comm, s->stream));
+        NC(g_nccl.Recv(hbuf + sizeof(mine), sizeof(mine), NCCL_INT8, S.lo_rank, S.comm, s->stream));
+        NC(g_nccl.GroupEnd());
+        CU(cudaStreamSynchronize(s->stream));
+        CU(cudaMemcpy(&from_lo, hbuf + sizeof(mine), sizeof(mine), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&from_hi, hbuf + 2 * sizeof(mine), sizeof(mine), cudaMemcpyDeviceToHost));
+        cudaFree(hbuf);
+        cudaError_t e = cudaIpcOpenMemHandle((void **)&S.peer_lo, from_lo, cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) {
+            if (S.lo_rank == S.hi_rank) S.peer_hi = S.peer_lo;
+            else e = cudaIpcOpenMemHandle((void **)&S.peer_hi, from_hi, cudaIpcMemLazyEnablePeerAccess);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            fprintf(stderr, "fgpu: CUDA IPC unavailable (%s): slab exchange falls back to NCCL send/recv\n", cudaGetErrorString(e));
+            S.peer_lo = S.peer_hi = nullptr;
+        } else {
+            S.p2p = true;
+        }
+    }
     S.async = s->static_kind && s->opt_slab_async;
     for (int i = 0; i < SlabRT::RING; ++i) CU(cudaEventCreateWithFlags(&S.ring_ev[i], cudaEventDisableTiming));
     CU(cudaMallocHost(&S.h_ring, sizeof(int) * SlabRT::RING * SlabRT::RING_STRIDE));
@@ -1160,7 +1244,7 @@ extern "C" int fgpu_sim_slab_info(fgpu_sim *s, int *out8) {
     out8[4] = S.p1;
     out8[5] = S.halo_cap;
     out8[6] = S.mig_cap;
-    out8[7] = S.plane_cells;
+    out8[7] = S.plane_cells + (S.p2p ? (1 << 30) : 0); /* bit 30: peer-memory transport active */
     return FGPU_OK;
 }
 
@@ -1173,34 +1257,58 @@ static int slab_exchange_halo(fgpu_sim *s, int mi) {
     const int n = M.h_count, PL = S.plane_cells, Q = M.d->rec_quads;
     if (n == 0) CU(cudaMemsetAsync(M.cell_start, 0, sizeof(unsigned int) * ((size_t)M.d->grid_size + 1), s->stream));
     const uint4 *local = M.sorted + (size_t)M.local_at * Q;
-    s->prof_begin(std::string("halo:") + M.d->name);
+    s->prof_begin(std::string("halo_pack:") + M.d->name);
     const int g = std::min(148 * 4, (std::max(S.halo_cap * Q, PL) + 255) / 256);
+    const size_t A4 = (X.bytes + 255) & ~(size_t)255;
+    const int seq = ++S.msg_seq[mi], par = seq & 1;
+    const int *in_lo = X.recv_lo, *in_hi = X.recv_hi;  /* where the neighbours' planes arrive */
     switch (Q) {
 #define PACK_CASE(QQ)                                                                                                       \
     case QQ:                                                                                                                \
-        k_pack_plane<QQ><<<g, 256, 0, s->stream>>>(local, M.cell_start, S.p0 * PL, PL, S.halo_cap, X.send_lo);              \
-        k_pack_plane<QQ><<<g, 256, 0, s->stream>>>(local, M.cell_start, (S.p1 - 1) * PL, PL, S.halo_cap, X.send_hi);        \
+        k_pack_planes<QQ><<<dim3(g, 2), 256, 0, s->stream>>>(local, M.cell_start, S.p0 * PL, (S.p1 - 1) * PL, PL, S.halo_cap, \
+                                                             X.send_lo, X.send_hi);                                         \
         break;
         PACK_CASE(1) PACK_CASE(2) PACK_CASE(3) PACK_CASE(4) PACK_CASE(5) PACK_CASE(6) PACK_CASE(7) PACK_CASE(8)
 #undef PACK_CASE
         default:
             return set_err(FGPU_ERR_MODEL, "record of %d quads unsupported", Q);
     }
-    s->launches += 2;
-    CU(cudaGetLastError());
-    NC(g_nccl.GroupStart());
-    NC(g_nccl.Send(X.send_lo, X.bytes, NCCL_INT8, S.lo_rank, S.comm, s->stream));
-    NC(g_nccl.Send(X.send_hi, X.bytes, NCCL_INT8, S.hi_rank, S.comm, s->stream));
-    NC(g_nccl.Recv(X.recv_hi, X.bytes, NCCL_INT8, S.hi_rank, S.comm, s->stream));
-    NC(g_nccl.Recv(X.recv_lo, X.bytes, NCCL_INT8, S.lo_rank, S.comm, s->stream));
-    NC(g_nccl.GroupEnd());
+    LAUNCH_CHECK();
+    s->prof_end();
+    s->prof_begin(std::string("halo_xfer:") + M.d->name);
+    if (S.p2p) {
+        /* my low plane is the lower neighbour's HIGH halo and vice versa */
+        PushLayout PLY;
+        PLY.fixed_bytes = (int)(sizeof(int) * (XHDR + ((PL + 1 + 3) & ~3)));
+        PLY.nseg = 1;
+        PLY.elem[0] = Q * 16;
+        PLY.off[0] = (unsigned long long)PLY.fixed_bytes;
+        in_lo = (const int *)(S.xbuf + S.msg_off[mi] + (0 + par) * A4);
+        in_hi = (const int *)(S.xbuf + S.msg_off[mi] + (2 + par) * A4);
+        k_push<<<dim3(PUSH_BLOCKS, 2), 256, 0, s->stream>>>((const char *)X.send_lo, (const char *)X.send_hi,
+                                                            S.peer_lo + S.msg_off[mi] + (2 + par) * A4,
+                                                            S.peer_hi + S.msg_off[mi] + (0 + par) * A4, PLY, S.d_done + mi,
+                                                            (int *)(S.peer_lo + 16 * mi) + 1, (int *)(S.peer_hi + 16 * mi) + 0,
+                                                            (const int *)(S.xbuf + 16 * mi), (const int *)(S.xbuf + 16 * mi) + 1, seq,
+                                                            S.d_status + 3);
+        LAUNCH_CHECK();
+    } else {
+        NC(g_nccl.GroupStart());
+        NC(g_nccl.Send(X.send_lo, X.bytes, NCCL_INT8, S.lo_rank, S.comm, s->stream));
+        NC(g_nccl.Send(X.send_hi, X.bytes, NCCL_INT8, S.hi_rank, S.comm, s->stream));
+        NC(g_nccl.Recv(X.recv_hi, X.bytes, NCCL_INT8, S.hi_rank, S.comm, s->stream));
+        NC(g_nccl.Recv(X.recv_lo, X.bytes, NCCL_INT8, S.lo_rank, S.comm, s->stream));
+        NC(g_nccl.GroupEnd());
+    }
     S.halo_bytes += 2 * (long long)X.bytes;
+    s->prof_end();
+    s->prof_begin(std::string("halo_merge:") + M.d->name);
     const int lo_first = ((S.p0 - 1 + S.nplanes) % S.nplanes) * PL, hi_first = (S.p1 % S.nplanes) * PL;
     switch (Q) {
 #define MERGE_CASE(QQ)                                                                                                      \
     case QQ:                                                                                                                \
-        k_merge_halo<QQ><<<g, 256, 0, s->stream>>>(M.sorted, M.cell_start, M.local_at, n, M.d_count, S.p0 * PL, S.ppr * PL, X.recv_lo, \
-                                                   lo_first, X.recv_hi, hi_first, PL, S.d_status);                         \
+        k_merge_halo<QQ><<<g, 256, 0, s->stream>>>(M.sorted, M.cell_start, M.local_at, n, M.d_count, S.p0 * PL, S.ppr * PL, in_lo, \
+                                                   lo_first, in_hi, hi_first, PL, S.d_status);                              \
         break;
         MERGE_CASE(1) MERGE_CASE(2) MERGE_CASE(3) MERGE_CASE(4) MERGE_CASE(5) MERGE_CASE(6) MERGE_CASE(7) MERGE_CASE(8)
 #undef MERGE_CASE
@@ -1244,6 +1352,7 @@ static int slab_poll(fgpu_sim *s, bool wait) {
             return set_err(FGPU_ERR_OVERFLOW, "slab exchange: fixed-capacity buffer overflow (halo %d, migrants %d, status %d/%d/%d)",
                            S.halo_cap, S.mig_cap, r[0], r[1], r[2]);
         if (r[0] == 2) return set_err(FGPU_ERR_COMM, "slab exchange: an agent moved further than one slab in one step");
+        if (r[3]) return set_err(FGPU_ERR_COMM, "slab exchange: timed out waiting for a neighbour's data (peer-memory transport)");
         if (mig >= S.exact_mig) {
             S.exact.assign(r + 8, r + SlabRT::RING_STRIDE);
             S.exact_mig = mig + 1;
@@ -1273,7 +1382,6 @@ static int slab_poll(fgpu_sim *s, bool wait) {
 static int slab_migrate(fgpu_sim *s) {
     SlabRT &S = s->slab;
     const fgpu_model *m = s->model;
-    s->prof_begin("migrate");
     const int ring = (int)(S.migrations % SlabRT::RING);
     int *hdst = S.async ? S.h_ring + ring * SlabRT::RING_STRIDE : S.h_pinned;
     if (S.async && S.ring_mig[ring] >= 0) CU(cudaEventSynchronize(S.ring_ev[ring])); /* RING migrations old: long done */
@@ -1288,27 +1396,60 @@ static int slab_migrate(fgpu_sim *s) {
             const int *d_n = S.async ? A.d_state_count + st : nullptr;
             char *list = A.state[st];
             int *flags = (int *)(list + A.d->scan_offset);
-            int *cnt = X.d_counts + 2 * st;
+            int *cnt = X.d_counts + 4 * st; /* {n_stay, -, total down, total up} */
             const int nb = std::max(1, (n + COMPACT_THREADS - 1) / COMPACT_THREADS);
+            s->prof_begin("mig:flags");
             k_owner_count<<<nb, COMPACT_THREADS, 0, s->stream>>>((const float *)(list + A.d->vars[X.axis_var].list_offset), n, d_n,
                                                                  S.axis_min, S.axis_max, S.nplanes, S.ppr, S.rank, S.world, flags,
                                                                  A.block_sums, nb, S.d_status);
             LAUNCH_CHECK();
+            s->prof_end();
+            const size_t A4 = (X.bytes + 255) & ~(size_t)255;
+            const int seq = ++S.agent_seq[a], par = seq & 1;
+            const char *in_lo = X.recv_lo, *in_hi = X.recv_hi;
+            s->prof_begin("mig:scan");
             k_scan3<<<3, 1024, 0, s->stream>>>(A.block_sums, nb, cnt, (int *)X.send_dn, (int *)X.send_up, S.mig_cap);
             LAUNCH_CHECK();
-            k_scatter3<<<nb, COMPACT_THREADS, 0, s->stream>>>(list, A.swap, X.send_dn, X.send_up, A.cols, X.bufcols, flags, A.block_sums,
-                                                              nb, n, d_n, S.mig_cap, S.d_status + 1);
+            s->prof_end();
+            s->prof_begin("mig:scatter");
+            k_scatter3<<<nb, COMPACT_THREADS, 0, s->stream>>>(list, A.swap, X.send_dn, X.send_up, A.cols, X.bufcols, flags, A.block_sums, nb, n,
+                                                              d_n, S.mig_cap, S.d_status + 1);
             LAUNCH_CHECK();
-            NC(g_nccl.GroupStart());
-            NC(g_nccl.Send(X.send_dn, X.bytes, NCCL_INT8, S.lo_rank, S.comm, s->stream));
-            NC(g_nccl.Send(X.send_up, X.bytes, NCCL_INT8, S.hi_rank, S.comm, s->stream));
-            NC(g_nccl.Recv(X.recv_hi, X.bytes, NCCL_INT8, S.hi_rank, S.comm, s->stream));
-            NC(g_nccl.Recv(X.recv_lo, X.bytes, NCCL_INT8, S.lo_rank, S.comm, s->stream));
-            NC(g_nccl.GroupEnd());
+            s->prof_end();
+            s->prof_begin("mig:xfer");
+            if (S.p2p) {
+                PushLayout PLY;
+                PLY.fixed_bytes = 16;
+                PLY.nseg = X.bufcols.ncols;
+                for (int c = 0; c < X.bufcols.ncols; ++c) {
+                    PLY.elem[c] = X.bufcols.size[c];
+                    PLY.off[c] = X.bufcols.off[c];
+                }
+                in_lo = S.xbuf + S.agent_off[a] + (0 + par) * A4;
+                in_hi = S.xbuf + S.agent_off[a] + (2 + par) * A4;
+                /* I am the lower neighbour's upper neighbour: my "down" migrants land in its recv_hi */
+                k_push<<<dim3(PUSH_BLOCKS, 2), 256, 0, s->stream>>>(X.send_dn, X.send_up, S.peer_lo + S.agent_off[a] + (2 + par) * A4,
+                                                                    S.peer_hi + S.agent_off[a] + (0 + par) * A4, PLY, S.d_done + 32 + a,
+                                                                    (int *)(S.peer_lo + 2048 + 16 * a) + 1,
+                                                                    (int *)(S.peer_hi + 2048 + 16 * a) + 0,
+                                                                    (const int *)(S.xbuf + 2048 + 16 * a),
+                                                                    (const int *)(S.xbuf + 2048 + 16 * a) + 1, seq, S.d_status + 3);
+                LAUNCH_CHECK();
+            } else {
+                NC(g_nccl.GroupStart());
+                NC(g_nccl.Send(X.send_dn, X.bytes, NCCL_INT8, S.lo_rank, S.comm, s->stream));
+                NC(g_nccl.Send(X.send_up, X.bytes, NCCL_INT8, S.hi_rank, S.comm, s->stream));
+                NC(g_nccl.Recv(X.recv_hi, X.bytes, NCCL_INT8, S.hi_rank, S.comm, s->stream));
+                NC(g_nccl.Recv(X.recv_lo, X.bytes, NCCL_INT8, S.lo_rank, S.comm, s->stream));
+                NC(g_nccl.GroupEnd());
+            }
             S.mig_bytes += 2 * (long long)X.bytes;
-            k_append_both<<<(2 * S.mig_cap + 255) / 256, 256, 0, s->stream>>>(X.recv_lo, X.recv_hi, A.swap, X.bufcols, A.cols, cnt,
+            s->prof_end();
+            s->prof_begin("mig:append");
+            k_append_both<<<(2 * S.mig_cap + 255) / 256, 256, 0, s->stream>>>(in_lo, in_hi, A.swap, X.bufcols, A.cols, cnt,
                                                                               A.d_state_count + st, A.d->buffer_size, S.d_status + 2);
             LAUNCH_CHECK();
+            s->prof_end();
             CU(cudaMemcpyAsync(hdst + 8 + slot, A.d_state_count + st, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
             std::swap(A.state[st], A.swap);
             s->touch(A.state[st]);
@@ -1320,16 +1461,15 @@ static int slab_migrate(fgpu_sim *s) {
         CU(cudaEventRecord(S.ring_ev[ring], s->stream));
         S.ring_mig[ring] = S.migrations;
         S.migrations++;
-        s->prof_end();
         return slab_poll(s, false);
     }
     S.migrations++;
     CU(cudaStreamSynchronize(s->stream));
-    s->prof_end();
     if (hdst[0] == 1 || hdst[1] || hdst[2])
         return set_err(FGPU_ERR_OVERFLOW, "slab exchange: fixed-capacity buffer overflow (halo %d, migrants %d, status %d/%d/%d)",
                        S.halo_cap, S.mig_cap, hdst[0], hdst[1], hdst[2]);
     if (hdst[0] == 2) return set_err(FGPU_ERR_COMM, "slab exchange: an agent moved further than one slab in one step");
+    if (hdst[3]) return set_err(FGPU_ERR_COMM, "slab exchange: timed out waiting for a neighbour's data (peer-memory transport)");
     slot = 0;
     for (int a = 0; a < m->nagents; ++a) {
         if (S.agents[a].axis_var < 0) continue;
@@ -1682,12 +1822,19 @@ extern "C" int fgpu_sim_step_timed(fgpu_sim *s, int n, size_t flush_bytes, float
     std::vector<cudaEvent_t> ev(2 * (size_t)n);
     for (auto &e : ev) CU(cudaEventCreate(&e));
     int rc = FGPU_OK;
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int i = 0; i < n && rc == FGPU_OK; ++i) {
         if (flush_bytes) CU(cudaMemsetAsync(s->flush_buf, i & 0xff, flush_bytes, s->stream));
         CU(cudaEventRecord(ev[2 * i], s->stream));
         rc = step_async(s, 1);
         CU(cudaEventRecord(ev[2 * i + 1], s->stream));
     }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (getenv("FGPU_DEBUG_TIMING"))
+        fprintf(stderr, "fgpu: enqueue of %d iterations took %.3f ms of host time (%.1f us / iteration)\n", n,
+                (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6,
+                ((t1.tv_sec - t0.tv_sec) * 1e6 + (t1.tv_nsec - t0.tv_nsec) * 1e-3) / std::max(n, 1));
     CU(cudaStreamSynchronize(s->stream));
     float total = 0.f;
     for (int i = 0; i < n; ++i) {
@@ -1743,7 +1890,10 @@ extern "C" int fgpu_sim_set_option(fgpu_sim *s, const char *key, int value) {
     if (!strcmp(key, "order")) s->opt_order = value ? 1 : 0;
     else if (!strcmp(key, "graph")) s->opt_graph = value ? 1 : 0;
     else if (!strcmp(key, "stage")) s->opt_stage = value ? 1 : 0;
-    else if (!strcmp(key, "slab_async")) {
+    else if (!strcmp(key, "slab_p2p")) {
+        if (s->slab.on) return set_err(FGPU_ERR_ARG, "slab_p2p must be set before fgpu_sim_slab_init");
+        s->opt_slab_p2p = value ? 1 : 0;
+    } else if (!strcmp(key, "slab_async")) {
         if (s->slab.on) return set_err(FGPU_ERR_ARG, "slab_async must be set before fgpu_sim_slab_init");
         s->opt_slab_async = value ? 1 : 0;
     }
@@ -1762,18 +1912,18 @@ extern "C" int fgpu_sim_set_option(fgpu_sim *s, const char *key, int value) {
     return FGPU_OK;
 }
 
-/* One iteration in stream mode with a cudaEvent pair around every stage
- * (INSTRUMENT_AGENT_FUNCTIONS, simulation.xslt:898-914, at stage granularity). */
-extern "C" int fgpu_sim_profile_iteration(fgpu_sim *s, const char **names, float *ms, int cap) {
-    if (!s) return set_err(FGPU_ERR_ARG, "null sim");
+/* `iters` iterations in stream mode with a cudaEvent pair around every stage
+ * (INSTRUMENT_AGENT_FUNCTIONS, simulation.xslt:898-914, at stage granularity).  The iterations are
+ * enqueued back to back without host synchronisation and the events come from a reused pool, so the
+ * reported times are device times of the steady state; stages are averaged by name. */
+extern "C" int fgpu_sim_profile_iterations(fgpu_sim *s, int iters, const char **names, float *ms, int cap) {
+    if (!s || iters < 1) return set_err(FGPU_ERR_ARG, "bad argument");
     CU(cudaSetDevice(s->device));
-    for (ProfEntry &e : s->prof) {
-        cudaEventDestroy(e.a);
-        cudaEventDestroy(e.b);
-    }
     s->prof.clear();
+    s->ev_used = 0;
     s->profiling = true;
-    int rc = single_iteration(s);
+    int rc = FGPU_OK;
+    for (int i = 0; i < iters && rc == FGPU_OK; ++i) rc = single_iteration(s);
     s->profiling = false;
     if (rc) return rc;
     CU(cudaStreamSynchronize(s->stream));
@@ -1784,8 +1934,13 @@ extern "C" int fgpu_sim_profile_iteration(fgpu_sim *s, const char **names, float
     for (ProfEntry &e : s->prof) {
         float t = 0.f;
         cudaEventElapsedTime(&t, e.a, e.b);
-        s->prof_names.push_back(e.name);
-        s->prof_ms.push_back(t);
+        size_t k = 0;
+        while (k < s->prof_names.size() && s->prof_names[k] != e.name) ++k;
+        if (k == s->prof_names.size()) {
+            s->prof_names.push_back(e.name);
+            s->prof_ms.push_back(0.f);
+        }
+        s->prof_ms[k] += t / iters;
     }
     const int n = std::min(cap, (int)s->prof_names.size());
     for (int i = 0; i < n; ++i) {
@@ -1793,6 +1948,10 @@ extern "C" int fgpu_sim_profile_iteration(fgpu_sim *s, const char **names, float
         if (ms) ms[i] = s->prof_ms[i];
     }
     return n;
+}
+
+extern "C" int fgpu_sim_profile_iteration(fgpu_sim *s, const char **names, float *ms, int cap) {
+    return fgpu_sim_profile_iterations(s, 1, names, ms, cap);
 }
 
 /* ------------------------------------------------------------------------- */

@@ -408,6 +408,8 @@ def load_runtime() -> C.CDLL:
     lib.fgpu_sim_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     lib.fgpu_sim_profile_iteration.restype = C.c_int
     lib.fgpu_sim_profile_iteration.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+    lib.fgpu_sim_profile_iterations.restype = C.c_int
+    lib.fgpu_sim_profile_iterations.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     lib.fgpu_sim_device_agents.restype = C.c_void_p
     lib.fgpu_sim_device_agents.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.fgpu_nccl_unique_id.restype = C.c_int
@@ -481,13 +483,20 @@ class Simulation(SimBase):
         out = np.zeros(8, dtype=np.int32)
         self._check(self._lib.fgpu_sim_slab_info(self._h, out.ctypes.data))
         keys = ("enabled", "axis", "nplanes", "p0", "p1", "halo_cap", "mig_cap", "plane_cells")
-        return dict(zip(keys, (int(v) for v in out)))
+        d = dict(zip(keys, (int(v) for v in out)))
+        d["p2p"] = bool(d["plane_cells"] >> 30)
+        d["plane_cells"] &= (1 << 30) - 1
+        return d
 
     def profile_iteration(self):
+        return self.profile_iterations(1)
+
+    def profile_iterations(self, iters: int):
+        """Steady-state device time per stage over `iters` back-to-back iterations (stream mode)."""
         cap = 256
         names = (C.c_char_p * cap)()
         ms = (C.c_float * cap)()
-        n = self._check(self._lib.fgpu_sim_profile_iteration(self._h, names, ms, cap))
+        n = self._check(self._lib.fgpu_sim_profile_iterations(self._h, int(iters), names, ms, cap))
         return [(names[i].decode(), float(ms[i])) for i in range(n)]
 
 

@@ -129,6 +129,9 @@ int fgpu_sim_set_option(fgpu_sim *sim, const char *key, int value);
 /* Per-kernel-class device time of the most recent profiled iteration.
  * Writes up to `cap` (name,ms) pairs; returns the number written. */
 int fgpu_sim_profile_iteration(fgpu_sim *sim, const char **names, float *ms, int cap);
+/* Same over `iters` back-to-back iterations (no host synchronisation in between, pooled events):
+ * steady-state device time per stage, averaged by stage name. */
+int fgpu_sim_profile_iterations(fgpu_sim *sim, int iters, const char **names, float *ms, int cap);
 
 /* ---- kernel-level entry points for the parity tests ---------------------- */
 /* The hand-written LSD radix sort (replaces cub::DeviceRadixSort::SortPairs,
