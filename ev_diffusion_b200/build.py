@@ -94,12 +94,15 @@ def build_runtime(force: bool = False, verbose: bool = False) -> str:
 
 
 def build_model(xml_path: str, name: str, fmad: bool = True, force: bool = False, verbose: bool = False,
-                function_files: Optional[List[str]] = None, stage: bool = False) -> str:
+                function_files: Optional[List[str]] = None, extra_flags: Optional[List[str]] = None,
+                rewrite_loops: bool = True) -> str:
     """Generate and compile the plugin of one model.
 
     ``fmad=False`` builds the exact-arithmetic variant (no FMA contraction) whose
     float results are bit-comparable with the host oracle compiled with
-    ``-ffp-contract=off``.
+    ``-ffp-contract=off``.  ``rewrite_loops=False`` compiles the
+    scripts byte for byte (generic get_next) instead of the loop-restructured
+    copies (looprewrite.py); results are identical either way.
     """
     build_runtime()   # the plugin's Face-2 shim links against libfgpu_rt.so
     model = xmml.parse_model(xml_path)
@@ -110,24 +113,32 @@ def build_model(xml_path: str, name: str, fmad: bool = True, force: bool = False
         if not os.path.exists(f):
             raise BuildError(f"function file {f} not found")
     gen = os.path.join(GEN, name)
-    files = codegen.emit_cuda(model, function_files, gen)
+    files = codegen.emit_cuda(model, function_files, gen, rewrite_loops=rewrite_loops)
     os.makedirs(os.path.join(LIB, "models"), exist_ok=True)
     out = model_path(name)
-    cmd = [NVCC] + ARCH_FLAGS + COMMON + (["-DFGPU_STAGE=1"] if stage else []) + \
-          ["-Xptxas", "-v", "-fmad=" + ("true" if fmad else "false"),
+    cmd = [NVCC] + ARCH_FLAGS + COMMON + list(extra_flags or []) + ["-Xptxas", "-v", "-fmad=" + ("true" if fmad else "false"),
                                           "-I", gen, "-I", INCLUDE, "-I", CSRC, "-I", mdir,
                                           files["model_glue.cu"], "-o", out,
                                           "-L", LIB, "-lfgpu_rt", "-Xlinker", "-rpath=$ORIGIN/.."]
-    deps = [files["header.h"], files["model_glue.cu"], os.path.join(CSRC, "fgpu_device.cuh"),
+    deps = sorted(files.values()) + [os.path.join(CSRC, "fgpu_device.cuh"),
             os.path.join(CSRC, "fgpu_glm.h"), os.path.join(INCLUDE, "fgpu_model.h"), os.path.join(INCLUDE, "fgpu.h")] + list(function_files)
     stamp = _stamp(deps, " ".join(cmd))
-    if not force and _fresh(out, stamp):
+    # scripts from outside this repository (the reference's examples) are compiled where they lie; their
+    # loop-rewritten copies are compiler input only and do not stay in the tree
+    transient = [p for k, p in files.items() if k.startswith("rewritten_")] \
+        if any(not os.path.abspath(f).startswith(ROOT + os.sep) for f in function_files) else []
+    try:
+        if not force and _fresh(out, stamp):
+            return out
+        text = _run(cmd, log=out + ".log")
+        if verbose:
+            print(text)
+        _mark(out, stamp)
         return out
-    text = _run(cmd, log=out + ".log")
-    if verbose:
-        print(text)
-    _mark(out, stamp)
-    return out
+    finally:
+        for p in transient:
+            if os.path.exists(p):
+                os.remove(p)
 
 
 def build_driver(source: str, model_name: str, out_name: str, force: bool = False) -> str:

@@ -19,6 +19,7 @@ import os
 import re
 from typing import Dict, List, Optional, Set, Tuple
 
+from .looprewrite import rewrite_message_loops
 from .xmml import Agent, Function, Message, Model, ModelError, Variable, _f32
 
 # --------------------------------------------------------------------------
@@ -282,27 +283,27 @@ def _cuda_message_api(m: Message) -> str:
     (void)partition_matrix;
     if (messages->in_count == 0) return nullptr;   /* krn:1117 */
     fgpu::begin_walk<{S}, {T}>(messages, x, y, z);
-    if (!fgpu::open_next_range<{S}, {T}>(messages)) return nullptr;
-    return fgpu::current_message<{S}, {T}>(messages);
+    return fgpu::open_next_range<{S}, {T}>(messages);
 }}
 FGPU_DEV {S}* get_next_{name}_message({S}* current, {S}_list* messages, {S}_PBM* partition_matrix){{
-    (void)current; (void)partition_matrix;
-    if (++messages->cur >= messages->end) {{
-        if (!fgpu::open_next_range<{S}, {T}>(messages)) return nullptr;
-    }}
-    return fgpu::current_message<{S}, {T}>(messages);
-}}""")
+    (void)partition_matrix;
+    return fgpu::next_message<{S}, {T}>(current, messages);
+}}
+/* the two levels of the walk, for message loops rewritten by looprewrite.py */
+FGPU_DEV {S}* fgpu_range_end_{name}({S}_list* messages){{ return const_cast<{S}*>(messages->end); }}
+FGPU_DEV {S}* fgpu_next_range_{name}({S}_list* messages){{ return fgpu::open_next_range<{S}, {T}>(messages); }}""")
     else:
         out.append(f"""FGPU_DEV {S}* get_first_{name}_message({S}_list* messages){{
     if (messages->in_count == 0) return nullptr;
-    messages->cur = 0; messages->end = messages->in_count;
-    return fgpu::current_message<{S}, {T}>(messages);
+    messages->end = messages->in_recs + messages->in_count;
+    return const_cast<{S}*>(messages->in_recs);
 }}
 FGPU_DEV {S}* get_next_{name}_message({S}* current, {S}_list* messages){{
-    (void)current;
-    if (++messages->cur >= messages->end) return nullptr;
-    return fgpu::current_message<{S}, {T}>(messages);
-}}""")
+    {S}* next = current + 1;
+    return next != messages->end ? next : nullptr;
+}}
+FGPU_DEV {S}* fgpu_range_end_{name}({S}_list* messages){{ return const_cast<{S}*>(messages->end); }}
+FGPU_DEV {S}* fgpu_next_range_{name}({S}_list* messages){{ (void)messages; return nullptr; }}""")
     return "\n".join(out) + "\n"
 
 
@@ -391,23 +392,9 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
     a = model.agent(f.agent)
     A = a.name
     bs = 128 if f.input_message else 256
-    spatial_in = bool(f.input_message) and model.message(f.input_message).partitioning == "spatial"
     out = [f"/* GPUFLAME_{f.name} (krn:1320-1387) */",
            f"__global__ void __launch_bounds__({bs}) fgpu_k_{f.name}(const fgpu_launch L)\n{{",
            "    const int t = blockIdx.x * blockDim.x + threadIdx.x;"]
-    if spatial_in:
-        M = f.input_message
-        out += [
-            "#ifdef FGPU_STAGE",
-            "    /* neighbourhood staging: header | 9 PBM row windows | message windows */",
-            "    extern __shared__ uint4 fgpu_dsm[];",
-            "    fgpu::StageShared* fgpu_sh = (fgpu::StageShared*)fgpu_dsm;",
-            "    int* fgpu_s_cs = (int*)(fgpu_dsm + fgpu::STAGE_HDR_QUADS);",
-            f"    xmachine_message_{M}* fgpu_s_msgs = (xmachine_message_{M}*)(fgpu_s_cs + 9 * fgpu::STAGE_CSW);",
-            f"    fgpu::stage_block<xmachine_message_{M}, fgpu_traits_{M}>(fgpu_sh, fgpu_s_cs, fgpu_s_msgs, L.stage_msgs,",
-            f"        (const xmachine_message_{M}*)L.in_recs, L.in_cell_start, L.in_sorted_keys, L.order != nullptr, (L.d_n ? *L.d_n : L.n), (L.d_in_count ? *L.d_in_count : L.in_count));",
-            "#endif",
-        ]
     out += ["    if (t >= (L.d_n ? *L.d_n : L.n)) return;",
             "    const int index = L.order ? (int)__ldg(L.order + t) : t;",
             f"    xmachine_memory_{A}_list* __restrict__ agents = (xmachine_memory_{A}_list*)L.agents;",
@@ -425,18 +412,8 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
         M = f.input_message
         out.append(f"    xmachine_message_{M}_list inp;")
         out.append(f"    inp.in_recs = (const xmachine_message_{M}*)L.in_recs; inp.cell_start = L.in_cell_start; inp.in_count = L.d_in_count ? *L.d_in_count : L.in_count;")
-        out.append("    inp.out_recs = nullptr; inp.out_keys = nullptr; inp.out_index = 0; inp.cur = 0; inp.end = 0;")
-        out.append("    inp.step = 0; inp.cx = 0; inp.cy = 0; inp.cz = 0; inp.hrow = 0; inp.interior = 0;")
-        out.append("#ifdef FGPU_WALK_PIPELINE")
-        out.append("    inp.n1lo = 0; inp.n1hi = -1; inp.n2lo = 0; inp.n2hi = -1;")
-        out.append("#endif")
-        out.append("#ifdef FGPU_STAGE")
-        out.append("    inp.base = inp.in_recs; inp.fast = 0;")
-        if spatial_in:
-            out.append("    inp.sh = fgpu_sh; inp.s_cs = fgpu_s_cs; inp.s_msgs = fgpu_s_msgs;")
-        else:
-            out.append("    inp.sh = nullptr; inp.s_cs = nullptr; inp.s_msgs = nullptr;")
-        out.append("#endif")
+        out.append("    inp.out_recs = nullptr; inp.out_keys = nullptr; inp.out_index = 0; inp.end = nullptr;")
+        out.append("    inp.step = 0; inp.cx = 0; inp.cy = 0; inp.cz = 0; inp.nrows = -1; inp.nlo = 0; inp.nhi = 0;")
         call.append("&inp")
         if model.message(M).partitioning == "spatial":
             call.append(f"(xmachine_message_{M}_PBM*)nullptr")
@@ -445,14 +422,8 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
         if f.input_message == M:
             raise ModelError(f"function '{f.name}' reads and writes message '{M}'")
         out.append(f"    xmachine_message_{M}_list outp;")
-        out.append("    outp.in_recs = nullptr; outp.cell_start = nullptr; outp.in_count = 0; outp.cur = 0; outp.end = 0;")
-        out.append("    outp.step = 0; outp.cx = 0; outp.cy = 0; outp.cz = 0; outp.hrow = 0; outp.interior = 0;")
-        out.append("#ifdef FGPU_WALK_PIPELINE")
-        out.append("    outp.n1lo = 0; outp.n1hi = -1; outp.n2lo = 0; outp.n2hi = -1;")
-        out.append("#endif")
-        out.append("#ifdef FGPU_STAGE")
-        out.append("    outp.base = nullptr; outp.fast = 0; outp.sh = nullptr; outp.s_cs = nullptr; outp.s_msgs = nullptr;")
-        out.append("#endif")
+        out.append("    outp.in_recs = nullptr; outp.cell_start = nullptr; outp.in_count = 0; outp.end = nullptr;")
+        out.append("    outp.step = 0; outp.cx = 0; outp.cy = 0; outp.cz = 0; outp.nrows = -1; outp.nlo = 0; outp.nhi = 0;")
         out.append(f"    outp.out_recs = (xmachine_message_{M}*)L.out_recs; outp.out_keys = L.out_keys; outp.out_index = L.out_base + index;")
         call.append("&outp")
     if f.rng:
@@ -470,26 +441,7 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
     if f.rng:
         out.append("    ((uint2*)L.seeds)[index] = make_uint2(rng.sx, rng.sy);")
     out.append("}")
-    if spatial_in:
-        M = f.input_message
-        out.append(f"""static void fgpu_launch_{f.name}(const fgpu_launch* a, void* stream){{
-    if (a->n <= 0) return;
-    const int grid = (a->n + {bs} - 1) / {bs};
-#ifdef FGPU_STAGE
-    const size_t smem = (size_t)fgpu::STAGE_HDR_QUADS * 16 + 9 * fgpu::STAGE_CSW * sizeof(int)
-                      + (size_t)(a->stage_msgs > 0 ? a->stage_msgs : 0) * sizeof(xmachine_message_{M});
-    static size_t configured = 0;
-    if (smem > configured) {{
-        cudaFuncSetAttribute(fgpu_k_{f.name}, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }}
-#else
-    const size_t smem = 0;
-#endif
-    fgpu_k_{f.name}<<<grid, {bs}, smem, (cudaStream_t)stream>>>(*a);
-}}""")
-    else:
-        out.append(f"""static void fgpu_launch_{f.name}(const fgpu_launch* a, void* stream){{
+    out.append(f"""static void fgpu_launch_{f.name}(const fgpu_launch* a, void* stream){{
     if (a->n <= 0) return;
     const int grid = (a->n + {bs} - 1) / {bs};
     fgpu_k_{f.name}<<<grid, {bs}, 0, (cudaStream_t)stream>>>(*a);
@@ -719,13 +671,15 @@ extern "C" const fgpu_model* fgpu_model_get(void){{ return &fgpu_the_model; }}
     return "\n".join(out)
 
 
-def emit_cuda_glue(model: Model, function_files: List[str]) -> str:
+def emit_cuda_glue(model: Model, function_files: List[str], include_files: Optional[List[str]] = None) -> str:
+    """`function_files` are the author's scripts (analysed for write sets etc.); `include_files` the files
+    actually compiled in their place (the loop-rewritten copies), default the scripts themselves."""
     sources = [open(p, "r", errors="replace").read() for p in function_files]
     out = ["/* generated by ev_diffusion_b200.codegen -- model plugin for sm_100a */",
            "#include <cstddef>\n#include <cstring>\n#include <cstdio>\n#include <cmath>",
            '#include "header.h"',
            '#include "fgpu_model.h"']
-    for p in function_files:
+    for p in (include_files or function_files):
         out.append(f'#include "{os.path.abspath(p)}"')
     for f in model.all_functions():
         a = model.agent(f.agent)
@@ -740,9 +694,25 @@ def emit_cuda_glue(model: Model, function_files: List[str]) -> str:
     return "\n".join(out) + "\n"
 
 
-def emit_cuda(model: Model, function_files: List[str], outdir: str) -> Dict[str, str]:
+def emit_cuda(model: Model, function_files: List[str], outdir: str, rewrite_loops: bool = True) -> Dict[str, str]:
+    """Writes header.h, model_glue.cu and -- unless `rewrite_loops` is off -- a copy of every script with
+    its canonical message loops restructured (looprewrite.py), which is what model_glue.cu then includes.
+    `loops.txt` lists every message loop found and whether it was rewritten."""
     os.makedirs(outdir, exist_ok=True)
-    files = {"header.h": emit_cuda_header(model), "model_glue.cu": emit_cuda_glue(model, function_files)}
+    files: Dict[str, str] = {}
+    include_files = None
+    if rewrite_loops:
+        include_files, log = [], []
+        for i, p in enumerate(function_files):
+            text, reports = rewrite_message_loops(open(p, "r", errors="replace").read(), [m.name for m in model.messages])
+            name = f"rewritten_{i}_{os.path.basename(p)}"
+            files[name] = f'#line 1 "{os.path.abspath(p)}"\n' + text
+            include_files.append(os.path.join(outdir, name))
+            for r in reports:
+                log.append(f"{p}:{r.line}: message {r.message}: " + ("rewritten" if r.rewritten else f"generic get_next ({r.reason})"))
+        files["loops.txt"] = "\n".join(log) + "\n"
+    files["header.h"] = emit_cuda_header(model)
+    files["model_glue.cu"] = emit_cuda_glue(model, function_files, include_files)
     for name, text in files.items():
         path = os.path.join(outdir, name)
         if not os.path.exists(path) or open(path).read() != text:

@@ -176,8 +176,6 @@ struct fgpu_sim {
     int opt_radix_bits = 9;
     int opt_slab_async = 1;
     int opt_slab_p2p = 1;
-    int opt_stage = 0; /* block staging of PBM+message windows: correct but not yet faster (profiles/r01_notes.md) */
-    int opt_stage_bytes = 36 * 1024; /* shared-memory budget for staged messages per block */
     /* CUDA graph of one iteration (static models) */
     bool is_static = false;
     bool static_kind = false; /* every function is an in-place pointer-swap function (regardless of slab mode) */
@@ -1601,10 +1599,6 @@ static int run_function(fgpu_sim *s, int fi) {
             Min->producer_buf == A.work && Min->producer_epoch == s->epoch_of(A.work) && Min->h_count == A.h_count &&
             Min->built) {
             L.order = Min->vals[Min->sorted_in];
-            if (s->opt_stage) {
-                L.in_sorted_keys = Min->keys[Min->sorted_in];
-                L.stage_msgs = s->opt_stage_bytes / (Min->d->rec_quads * 16);
-            }
         }
     }
     if (Mout) {
@@ -1735,8 +1729,6 @@ static std::vector<int> current_counts(fgpu_sim *s) {
         for (int v : A.h_state_count) c.push_back(v);
     c.push_back(s->opt_order);
     c.push_back(s->opt_radix_bits);
-    c.push_back(s->opt_stage);
-    c.push_back(s->opt_stage_bytes);
     return c;
 }
 
@@ -1889,17 +1881,12 @@ extern "C" int fgpu_sim_set_option(fgpu_sim *s, const char *key, int value) {
     if (!s || !key) return set_err(FGPU_ERR_ARG, "bad argument");
     if (!strcmp(key, "order")) s->opt_order = value ? 1 : 0;
     else if (!strcmp(key, "graph")) s->opt_graph = value ? 1 : 0;
-    else if (!strcmp(key, "stage")) s->opt_stage = value ? 1 : 0;
     else if (!strcmp(key, "slab_p2p")) {
         if (s->slab.on) return set_err(FGPU_ERR_ARG, "slab_p2p must be set before fgpu_sim_slab_init");
         s->opt_slab_p2p = value ? 1 : 0;
     } else if (!strcmp(key, "slab_async")) {
         if (s->slab.on) return set_err(FGPU_ERR_ARG, "slab_async must be set before fgpu_sim_slab_init");
         s->opt_slab_async = value ? 1 : 0;
-    }
-    else if (!strcmp(key, "stage_bytes")) {
-        if (value < 0 || value > 200 * 1024) return set_err(FGPU_ERR_ARG, "stage_bytes out of range");
-        s->opt_stage_bytes = value;
     } else if (!strcmp(key, "radix_bits")) {
         if (value < 4 || value > SORT_MAXBITS) return set_err(FGPU_ERR_ARG, "radix_bits must be in [4,%d]", SORT_MAXBITS);
         for (MsgRT &M : s->msgs)

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FGPU_MODEL_ABI_VERSION 7
+#define FGPU_MODEL_ABI_VERSION 8
 
 /* One agent or message variable.  Agent lists keep the reference's SoA struct
  * layout (header.xslt:187-194): int _position[MAX]; int _scan_input[MAX];
@@ -82,8 +82,6 @@ typedef struct fgpu_launch {
     const unsigned int *in_cell_start;  /* CSR: grid_size+1 entries */
     int in_count;                 /* h_message_<M>_count */
     const int *d_in_count;        /* slab mode: exact message count on the device, or NULL */
-    const unsigned int *in_sorted_keys; /* cell key of each sorted message (block staging), may be NULL */
-    int stage_msgs;               /* shared-memory staging capacity in messages; 0 = no staging */
     /* output message (unsorted staging + cell keys) */
     void *out_recs;
     unsigned int *out_keys;

@@ -81,6 +81,30 @@ def test_many_iterations_exact(order, graph):
     orc.close()
 
 
+def test_generic_get_next_build_is_bit_identical():
+    """The same functions.c compiled byte for byte (flat get_first/get_next cursor, looprewrite off): the
+    loop-restructured build every other test uses and this one must both match the oracle exactly."""
+    import os
+    from common import build
+    cfg = W.BROWNIAN["c2_tiny"]
+    path = build.model_path(cfg.name + "_generic")
+    if not os.path.exists(path):
+        path = build.build_model(W.brownian_xml(cfg), cfg.name + "_generic", fmad=False,
+                                 function_files=W.brownian_function_files(), rewrite_loops=False)
+    assert "rewritten_" not in open(os.path.join(build.GEN, cfg.name + "_generic", "model_glue.cu")).read()
+    assert "rewritten_" in open(os.path.join(build.GEN, cfg.name + "_exact", "model_glue.cu")).read()
+    gpu = Simulation(path)
+    orc = brownian_oracle("c2_tiny")
+    st = W.brownian_state(cfg)
+    for s_ in (gpu, orc):
+        s_.set_agents("Particle", "default", st)
+        s_.step(25)
+    _assert_same_state(gpu, orc, exact=True)
+    assert np.array_equal(gpu.seeds(), orc.seeds())
+    gpu.close()
+    orc.close()
+
+
 def test_default_build_within_ulp_bound():
     """nvcc contracts a*b+c into FMA (-fmad=true, the reference's build default,
     tools/common.mk:132-153); the oracle is built -ffp-contract=off.  Each `move`

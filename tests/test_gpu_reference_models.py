@@ -64,10 +64,12 @@ def _oracle_snapshot(orc):
     return out
 
 
-@pytest.mark.parametrize("name", ["CirclesPartitioning_float", "Boids_Partitioning"])
+@pytest.mark.parametrize("name", ["CirclesPartitioning_float", "Boids_Partitioning", "Boids_Partitioning_generic"])
 def test_exact_build_matches_golden_bit_for_bit(name):
-    """-fmad=false build: + - * / sqrt only (and fp64 subexpressions in Circles) -> bit-exact."""
+    """-fmad=false build: + - * / sqrt only (and fp64 subexpressions in Circles) -> bit-exact.
+    `_generic` = the script compiled without the message-loop restructuring (looprewrite.py)."""
     sim = Simulation(_plugin(name, exact=True))
+    name = name.replace("_generic", "")
     _start(sim, name)
     sim.step(CASES[name])
     _compare(sim, np.load(os.path.join(GOLDEN, f"{name}_iter{CASES[name]}.npz")), exact=True, label=name)

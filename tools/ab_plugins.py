@@ -1,0 +1,28 @@
+"""A/B helper: steady-state stage times of several builds of the C2 Brownian plugin on one GPU.
+
+usage: python tools/ab_plugins.py Brownian Brownian_x ...   (names under ev_diffusion_b200/_lib/models)
+"""
+import sys
+
+import numpy as np
+
+from ev_diffusion_b200 import build as B, workloads as W
+from ev_diffusion_b200.runtime import Simulation
+
+cfg = W.BROWNIAN["c2"]
+state = W.brownian_state(cfg)
+ref = None
+for name in sys.argv[1:]:
+    sim = Simulation(B.model_path(name), device=0)
+    sim.set_agents("Particle", "default", state)
+    sim.step(5)
+    sim.profile_iterations(5)
+    st = sim.profile_iterations(20)
+    ms = sim.step_timed(50, 256 << 20)
+    nbr = sim.agent_var("Particle", "default", "nbr")
+    x = sim.agent_var("Particle", "default", "x")
+    if ref is None:
+        ref = (nbr.copy(), x.copy())
+    same = bool(np.array_equal(ref[0], nbr) and np.array_equal(ref[1], x))
+    print(name, "cold ms/iter %.4f" % float(np.mean(ms)), {k: round(v * 1e3, 1) for k, v in st}, "identical to first:", same,
+          flush=True)
