@@ -281,22 +281,24 @@ def main():
 
     # ---- end to end through the public API with host buffers --------------------
     e2e_steps = min(args.steps, 20)
-    try:
-        import torch
-        pin = {k: torch.from_numpy(v.copy()).pin_memory().numpy() for k, v in state.items()}
-    except Exception:
-        pin = {k: v.copy() for k, v in state.items()}
+    import torch
+    pin = {k: torch.from_numpy(v.copy()).pin_memory().numpy() for k, v in state.items()}
+    out = {k: torch.empty(len(state[k]) + 65536, dtype=torch.from_numpy(state[k]).dtype).pin_memory().numpy() for k in ("x", "y", "z", "nbr")}
     h2d = sum(v.nbytes for v in pin.values())
     d2h = 0
+    for _ in range(2):   # untimed: first-touch of the pinned pages, graph capture
+        sim.set_agents("Particle", "default", pin)
+        sim.step(1)
+        sim.read_agents("Particle", "default", out)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        sim.set_agents("Particle", "default", pin)
-        sim.step(1)
-        out = [sim.agent_var("Particle", "default", k) for k in ("x", "y", "z", "nbr")]
+        sim.set_agents("Particle", "default", pin)                 # H2D: the whole population, 5 columns
+        sim.step(1)                                                # one iteration
+        got = sim.read_agents("Particle", "default", out)          # D2H: x, y, z, nbr
     barrier()
     e2e_dt = time.perf_counter() - t0
-    d2h = sum(o.nbytes for o in out)
+    d2h = sum(got * o.itemsize for o in out.values())
     if dist is not None:
         import torch
         t = torch.tensor([e2e_dt], device="cuda")

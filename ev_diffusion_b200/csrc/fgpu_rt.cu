@@ -490,12 +490,16 @@ static int upload_columns(fgpu_sim *s, int agent, int state, int offset, int cou
             CU(cudaStreamSynchronize(s->stream));
         }
     }
-    CU(cudaStreamSynchronize(s->stream));
+    const bool same_count = (A.h_state_count[state] == offset + count);
     A.h_state_count[state] = offset + count;
-    CU(cudaMemcpy(A.d_state_count + state, &A.h_state_count[state], sizeof(int), cudaMemcpyHostToDevice));
+    if (!same_count || s->slab.on) /* d_state_count already holds this value otherwise */
+        CU(cudaMemcpyAsync(A.d_state_count + state, &A.h_state_count[state], sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
     slab_mark_exact(s);
     s->touch(list);
-    invalidate_graph(s);
+    /* a captured iteration depends on the list sizes, not on the values: new values of the same
+     * population keep it valid */
+    if (!same_count) invalidate_graph(s);
     return FGPU_OK;
 }
 
@@ -526,6 +530,21 @@ extern "C" int fgpu_sim_read_agent_var(fgpu_sim *s, int agent, int state, int va
     CU(cudaSetDevice(s->device));
     const fgpu_var &V = A.d->vars[var];
     CU(cudaMemcpyAsync(dst, A.state[state] + V.list_offset, (size_t)count * V.size, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FGPU_OK;
+}
+
+extern "C" int fgpu_sim_read_agents(fgpu_sim *s, int agent, int state, int count, void *const *columns) {
+    if (!s || !columns || agent < 0 || agent >= (int)s->agents.size()) return set_err(FGPU_ERR_ARG, "bad argument");
+    AgentRT &A = s->agents[agent];
+    if (state < 0 || state >= A.d->nstates) return set_err(FGPU_ERR_ARG, "bad index");
+    if (count < 0 || count > A.d->buffer_size) return set_err(FGPU_ERR_ARG, "bad count");
+    CU(cudaSetDevice(s->device));
+    for (int v = 0; v < A.d->nvars; ++v) {
+        if (!columns[v]) continue;
+        const fgpu_var &V = A.d->vars[v];
+        CU(cudaMemcpyAsync(columns[v], A.state[state] + V.list_offset, (size_t)count * V.size, cudaMemcpyDeviceToHost, s->stream));
+    }
     CU(cudaStreamSynchronize(s->stream));
     return FGPU_OK;
 }

@@ -410,6 +410,8 @@ def load_runtime() -> C.CDLL:
     lib.fgpu_sim_profile_iteration.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     lib.fgpu_sim_profile_iterations.restype = C.c_int
     lib.fgpu_sim_profile_iterations.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+    lib.fgpu_sim_read_agents.restype = C.c_int
+    lib.fgpu_sim_read_agents.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.fgpu_sim_device_agents.restype = C.c_void_p
     lib.fgpu_sim_device_agents.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.fgpu_nccl_unique_id.restype = C.c_int
@@ -453,6 +455,23 @@ class Simulation(SimBase):
 
     def step_async(self, n: int = 1) -> None:
         self._check(self._lib.fgpu_sim_step_async(self._h, int(n)))
+
+    def read_agents(self, agent, state, out: Dict[str, np.ndarray], count: Optional[int] = None) -> int:
+        """Fill caller-owned arrays (ideally pinned) with the named variables of a state list: all copies
+        are issued before one synchronisation (fgpu_sim_read_agents).  Returns the number of agents read."""
+        agent = self._agent(agent)
+        state = self._state(agent, state)
+        a = self.model.agents[agent]
+        if count is None:
+            count = self.agent_count(agent, state)
+        ptrs = (C.c_void_p * len(a.vars))()
+        for name, arr in out.items():
+            vi = a.var_index(name)
+            if arr.dtype != a.vars[vi].dtype or arr.size < count or not arr.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"read_agents: bad destination for '{name}'")
+            ptrs[vi] = arr.ctypes.data
+        self._check(self._lib.fgpu_sim_read_agents(self._h, agent, state, count, ptrs))
+        return count
 
     def sync(self) -> None:
         self._check(self._lib.fgpu_sim_sync(self._h))

@@ -93,6 +93,10 @@ unsigned int fgpu_sim_iteration(const fgpu_sim *sim);      /* getIterationNumber
 int fgpu_sim_agent_count(fgpu_sim *sim, int agent, int state);
 /* Copies variable `var` of the first `count` agents of a state list to `dst`. */
 int fgpu_sim_read_agent_var(fgpu_sim *sim, int agent, int state, int var, void *dst, int count);
+/* The read-back counterpart of fgpu_sim_set_agents: columns[v] receives variable v of the first `count`
+ * agents of the state list, NULL entries are skipped.  All copies are issued before one synchronisation,
+ * so pinned destinations are filled at bus speed. */
+int fgpu_sim_read_agents(fgpu_sim *sim, int agent, int state, int count, void *const *columns);
 /* get_<A>_<S>_variable_<v>(index) (header.xslt:645): one element of a state list. */
 int fgpu_sim_read_agent_value(fgpu_sim *sim, int agent, int state, int var, unsigned int index, void *dst);
 /* get_device_<A>_<S>_agents(): borrowed device pointer to a list in the

@@ -126,6 +126,33 @@ def test_default_build_within_ulp_bound():
     orc.close()
 
 
+def test_reupload_same_size_keeps_graph_and_read_agents_fills_caller_buffers():
+    """A new population of the same size reuses the captured iteration (only values changed); the
+    multi-column read-back fills caller-owned arrays."""
+    cfg, gpu, orc = _pair("c2_tiny", exact=True)
+    gpu.step(3)
+    orc.step(3)
+    launches_per_step = gpu.launch_count
+    st = W.brownian_state(cfg)
+    st["x"] = st["x"][::-1].copy()
+    st["z"] = (cfg.dims[2] - st["z"]).astype(np.float32)
+    for s_ in (gpu, orc):
+        s_.set_agents("Particle", "default", st)
+        s_.step(4)
+    _assert_same_state(gpu, orc, exact=True)
+    assert gpu.launch_count - launches_per_step == 4 * (launches_per_step // 3)
+    n = gpu.agent_count("Particle", "default")
+    out = {"x": np.full(n + 7, -1.0, np.float32), "nbr": np.full(n, -1, np.int32)}
+    assert gpu.read_agents("Particle", "default", out) == n
+    ref = orc.agents("Particle")
+    assert np.array_equal(out["x"][:n].view(np.uint32), ref["x"].view(np.uint32)) and np.all(out["x"][n:] == -1.0)
+    assert np.array_equal(out["nbr"], ref["nbr"])
+    with pytest.raises(ValueError):
+        gpu.read_agents("Particle", "default", {"x": np.zeros(n, np.float64)})
+    gpu.close()
+    orc.close()
+
+
 def test_empty_population_and_zero_messages():
     cfg, gpu, orc = _pair("c2_tiny", exact=True, count=0)
     gpu.step(3)

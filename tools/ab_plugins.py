@@ -1,6 +1,6 @@
 """A/B helper: steady-state stage times of several builds of the C2 Brownian plugin on one GPU.
 
-usage: python tools/ab_plugins.py Brownian Brownian_x ...   (names under ev_diffusion_b200/_lib/models)
+usage: python tools/ab_plugins.py Brownian Brownian_generic:sm_local=0 ...   (plugin[:option=value]...)
 """
 import sys
 
@@ -12,8 +12,12 @@ from ev_diffusion_b200.runtime import Simulation
 cfg = W.BROWNIAN["c2"]
 state = W.brownian_state(cfg)
 ref = None
-for name in sys.argv[1:]:
+for spec in sys.argv[1:]:
+    name, *opts = spec.split(":")          # Brownian:sm_local=0:order=1
     sim = Simulation(B.model_path(name), device=0)
+    for kv in opts:
+        k, v = kv.split("=")
+        sim.set_option(k, int(v))
     sim.set_agents("Particle", "default", state)
     sim.step(5)
     sim.profile_iterations(5)
@@ -24,5 +28,5 @@ for name in sys.argv[1:]:
     if ref is None:
         ref = (nbr.copy(), x.copy())
     same = bool(np.array_equal(ref[0], nbr) and np.array_equal(ref[1], x))
-    print(name, "cold ms/iter %.4f" % float(np.mean(ms)), {k: round(v * 1e3, 1) for k, v in st}, "identical to first:", same,
+    print(spec, "cold ms/iter %.4f" % float(np.mean(ms)), {k: round(v * 1e3, 1) for k, v in st}, "identical to first:", same,
           flush=True)
