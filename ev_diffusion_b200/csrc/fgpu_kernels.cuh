@@ -50,7 +50,7 @@ constexpr int SORT_MAX_BINS = 1 << SORT_MAXBITS;
 /* digit counts of one tile; tile_hist is bin-major so that k_row_scan reads rows contiguously */
 __global__ void __launch_bounds__(SORT_THREADS)
 k_tile_hist(const unsigned int *__restrict__ keys, int n_host, const int *__restrict__ d_n, int shift, int digit_bits,
-            unsigned int *__restrict__ tile_hist, int tiles) {
+            unsigned int *__restrict__ tile_hist, int tiles, unsigned int key_base, unsigned int key_span, int *range_error) {
     extern __shared__ unsigned int sh[]; /* 1 << digit_bits */
     const int n = d_n ? *d_n : n_host; /* slab mode: the exact count lives on the device, n_host is an upper bound */
     const int nbins = 1 << digit_bits;
@@ -67,7 +67,13 @@ k_tile_hist(const unsigned int *__restrict__ keys, int n_host, const int *__rest
 #pragma unroll
     for (int r = 0; r < SORT_ITEMS; ++r) {
         const int idx = base + r * SORT_THREADS + threadIdx.x;
-        if (idx < n) atomicAdd(&sh[(k[r] >> shift) & mask], 1u);
+        if (idx < n) {
+            /* slab mode sorts on the key relative to the first owned cell (fewer digits); a key outside
+             * the owned cells would be mis-sorted silently, so the first pass reports it */
+            const unsigned int rel = k[r] - key_base;
+            if (range_error != nullptr && rel >= key_span) *range_error = 1;
+            atomicAdd(&sh[(rel >> shift) & mask], 1u);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nbins; i += SORT_THREADS) tile_hist[(size_t)i * tiles + blockIdx.x] = sh[i];
@@ -131,7 +137,7 @@ __global__ void __launch_bounds__(SORT_THREADS)
 k_radix_scatter(const unsigned int *__restrict__ keys_in, const unsigned int *__restrict__ vals_in,
                 unsigned int *__restrict__ keys_out, unsigned int *__restrict__ vals_out, int n_host,
                 const int *__restrict__ d_n, int shift, int digit_bits, const unsigned int *__restrict__ tile_hist,
-                const unsigned int *__restrict__ totals, int tiles) {
+                const unsigned int *__restrict__ totals, int tiles, unsigned int key_base) {
     constexpr int BINS = 1 << BITS;
     const int n = d_n ? *d_n : n_host;
     constexpr int BPT = BINS / SORT_THREADS; /* bins per thread: 1, 2, 4 or 8 */
@@ -167,7 +173,7 @@ k_radix_scatter(const unsigned int *__restrict__ keys_in, const unsigned int *__
     for (int r = 0; r < SORT_ITEMS; ++r) {
         const int idx = base + warp * (SORT_ITEMS * 32) + r * 32 + lane;
         const bool valid = idx < n;
-        const unsigned int d = (key[r] >> shift) & mask;
+        const unsigned int d = ((key[r] - key_base) >> shift) & mask;
         unsigned int peers = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
         for (int b = 0; b < BITS; ++b) {
@@ -229,7 +235,7 @@ k_radix_scatter(const unsigned int *__restrict__ keys_in, const unsigned int *__
     for (int r = 0; r < SORT_ITEMS; ++r) {
         const int idx = base + warp * (SORT_ITEMS * 32) + r * 32 + lane;
         if (idx < n) {
-            const unsigned int d = (key[r] >> shift) & mask;
+            const unsigned int d = ((key[r] - key_base) >> shift) & mask;
             const unsigned int lp = sm.tile_excl[d] + sm.warp_hist[warp][d] + rank[r];
             sm.keys[lp] = key[r];
             sm.vals[lp] = val[r];
@@ -239,7 +245,7 @@ k_radix_scatter(const unsigned int *__restrict__ keys_in, const unsigned int *__
     const int valid_count = min(SORT_TILE, n - base);
     for (int i = tid; i < valid_count; i += SORT_THREADS) {
         const unsigned int k = sm.keys[i];
-        const int dst = sm.goff[(k >> shift) & mask] + i;
+        const int dst = sm.goff[((k - key_base) >> shift) & mask] + i;
         keys_out[dst] = k;
         vals_out[dst] = sm.vals[i];
     }

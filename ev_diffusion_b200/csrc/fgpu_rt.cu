@@ -908,7 +908,7 @@ static size_t sort_scratch_words(int n, int key_bits, int max_bits) {
 template <int BITS>
 static cudaError_t launch_scatter(int tiles, cudaStream_t st, const unsigned int *kin, const unsigned int *vin, unsigned int *kout,
                                   unsigned int *vout, int n, const int *d_n, int shift, int digit_bits, const unsigned int *tile_hist,
-                                  const unsigned int *totals) {
+                                  const unsigned int *totals, unsigned int key_base) {
     static bool configured = false;
     const size_t smem = sizeof(SortSmem<BITS>);
     if (!configured) {
@@ -916,7 +916,7 @@ static cudaError_t launch_scatter(int tiles, cudaStream_t st, const unsigned int
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_radix_scatter<BITS><<<tiles, SORT_THREADS, smem, st>>>(kin, vin, kout, vout, n, d_n, shift, digit_bits, tile_hist, totals, tiles);
+    k_radix_scatter<BITS><<<tiles, SORT_THREADS, smem, st>>>(kin, vin, kout, vout, n, d_n, shift, digit_bits, tile_hist, totals, tiles, key_base);
     return cudaGetLastError();
 }
 
@@ -924,7 +924,8 @@ static cudaError_t launch_scatter(int tiles, cudaStream_t st, const unsigned int
  * Returns the index (0/1) of the ping-pong pair holding the sorted result; counts launches. */
 static int radix_sort_pairs(cudaStream_t st, const unsigned int *keys_in, int n, int key_bits, int max_bits,
                             unsigned int *keys[2], unsigned int *vals[2], unsigned int *scratch, int *sorted_in,
-                            long long *launches, const int *d_n = nullptr) {
+                            long long *launches, const int *d_n = nullptr, unsigned int key_base = 0, unsigned int key_span = 0,
+                            int *range_error = nullptr) {
     int passes = 1;
     const int digit_bits = choose_digit_bits(key_bits, max_bits, &passes);
     if (passes > SORT_MAX_PASSES) return set_err(FGPU_ERR_MODEL, "%d key bits need %d radix passes", key_bits, passes);
@@ -935,13 +936,14 @@ static int radix_sort_pairs(cudaStream_t st, const unsigned int *keys_in, int n,
         const unsigned int *kin = p == 0 ? keys_in : keys[(p - 1) & 1];
         const unsigned int *vin = p == 0 ? nullptr : vals[(p - 1) & 1];
         const int shift = p * digit_bits;
-        k_tile_hist<<<tiles, SORT_THREADS, sizeof(unsigned int) * (size_t)nbins, st>>>(kin, n, d_n, shift, digit_bits, tile_hist, tiles);
+        k_tile_hist<<<tiles, SORT_THREADS, sizeof(unsigned int) * (size_t)nbins, st>>>(kin, n, d_n, shift, digit_bits, tile_hist, tiles, key_base,
+                                                                                       key_span, p == 0 ? range_error : nullptr);
         k_row_scan<<<nbins, SORT_THREADS, 0, st>>>(tile_hist, tiles, totals);
         cudaError_t e;
-        if (digit_bits <= 8) e = launch_scatter<8>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals);
-        else if (digit_bits == 9) e = launch_scatter<9>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals);
-        else if (digit_bits == 10) e = launch_scatter<10>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals);
-        else e = launch_scatter<11>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals);
+        if (digit_bits <= 8) e = launch_scatter<8>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals, key_base);
+        else if (digit_bits == 9) e = launch_scatter<9>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals, key_base);
+        else if (digit_bits == 10) e = launch_scatter<10>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals, key_base);
+        else e = launch_scatter<11>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals, key_base);
         if (e != cudaSuccess) return set_err(FGPU_ERR_CUDA, "radix pass launch -> %s", cudaGetErrorString(e));
         (*launches) += 3;
     }
@@ -959,7 +961,22 @@ static int build_spatial(fgpu_sim *s, MsgRT &M) {
     s->prof_begin(std::string("sort:") + M.d->name);
     CU(cudaMemsetAsync(gap_count, 0, 2 * sizeof(unsigned int), s->stream));
     int in = 0;
-    int rc = radix_sort_pairs(s->stream, M.keys_in, n, M.d->radix_bits, max_bits, M.keys, M.vals, M.scratch, &in, &s->launches, M.d_count);
+    int key_bits = M.d->radix_bits;
+    unsigned int key_base = 0, key_span = 0;
+    int *range_error = nullptr;
+    if (s->slab.on) {
+        /* every local message lies in an owned plane (agents migrate before they output): sort on the key
+         * relative to the first owned cell, which needs log2(owned cells) bits whatever the world size */
+        const SlabRT &S = s->slab;
+        key_base = (unsigned int)S.p0 * (unsigned int)S.plane_cells;
+        key_span = (unsigned int)S.ppr * (unsigned int)S.plane_cells;
+        key_bits = 1;
+        while (key_bits < 32 && (1u << key_bits) < key_span) ++key_bits;
+        key_bits = std::min(key_bits, M.d->radix_bits);
+        range_error = S.d_status + 4;
+    }
+    int rc = radix_sort_pairs(s->stream, M.keys_in, n, key_bits, max_bits, M.keys, M.vals, M.scratch, &in, &s->launches, M.d_count, key_base,
+                              key_span, range_error);
     if (rc) return rc;
     s->prof_end();
     M.sorted_in = in;
@@ -1370,6 +1387,7 @@ static int slab_poll(fgpu_sim *s, bool wait) {
                            S.halo_cap, S.mig_cap, r[0], r[1], r[2]);
         if (r[0] == 2) return set_err(FGPU_ERR_COMM, "slab exchange: an agent moved further than one slab in one step");
         if (r[3]) return set_err(FGPU_ERR_COMM, "slab exchange: timed out waiting for a neighbour's data (peer-memory transport)");
+        if (r[4]) return set_err(FGPU_ERR_MODEL, "slab mode: a message was output outside the planes its rank owns (messages must be emitted at the agent's position)");
         if (mig >= S.exact_mig) {
             S.exact.assign(r + 8, r + SlabRT::RING_STRIDE);
             S.exact_mig = mig + 1;
@@ -1487,6 +1505,7 @@ static int slab_migrate(fgpu_sim *s) {
                        S.halo_cap, S.mig_cap, hdst[0], hdst[1], hdst[2]);
     if (hdst[0] == 2) return set_err(FGPU_ERR_COMM, "slab exchange: an agent moved further than one slab in one step");
     if (hdst[3]) return set_err(FGPU_ERR_COMM, "slab exchange: timed out waiting for a neighbour's data (peer-memory transport)");
+    if (hdst[4]) return set_err(FGPU_ERR_MODEL, "slab mode: a message was output outside the planes its rank owns (messages must be emitted at the agent's position)");
     slot = 0;
     for (int a = 0; a < m->nagents; ++a) {
         if (S.agents[a].axis_var < 0) continue;
