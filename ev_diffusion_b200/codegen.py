@@ -694,7 +694,8 @@ def emit_cuda_glue(model: Model, function_files: List[str], include_files: Optio
     return "\n".join(out) + "\n"
 
 
-def emit_cuda(model: Model, function_files: List[str], outdir: str, rewrite_loops: bool = True) -> Dict[str, str]:
+def emit_cuda(model: Model, function_files: List[str], outdir: str, rewrite_loops: bool = True,
+              loop_unroll: Optional[int] = None) -> Dict[str, str]:
     """Writes header.h, model_glue.cu and -- unless `rewrite_loops` is off -- a copy of every script with
     its canonical message loops restructured (looprewrite.py), which is what model_glue.cu then includes.
     `loops.txt` lists every message loop found and whether it was rewritten."""
@@ -704,7 +705,8 @@ def emit_cuda(model: Model, function_files: List[str], outdir: str, rewrite_loop
     if rewrite_loops:
         include_files, log = [], []
         for i, p in enumerate(function_files):
-            text, reports = rewrite_message_loops(open(p, "r", errors="replace").read(), [m.name for m in model.messages])
+            text, reports = rewrite_message_loops(open(p, "r", errors="replace").read(), [m.name for m in model.messages],
+                                                  unroll=loop_unroll)
             name = f"rewritten_{i}_{os.path.basename(p)}"
             files[name] = f'#line 1 "{os.path.abspath(p)}"\n' + text
             include_files.append(os.path.join(outdir, name))

@@ -124,8 +124,10 @@ class LoopReport:
     reason: str = ""
 
 
-def rewrite_message_loops(src: str, message_names: List[str]) -> Tuple[str, List[LoopReport]]:
-    """Rewrite every canonical message loop of `src`; returns the new text and one report per get_next call."""
+def rewrite_message_loops(src: str, message_names: List[str], unroll: Optional[int] = None) -> Tuple[str, List[LoopReport]]:
+    """Rewrite every canonical message loop of `src`; returns the new text and one report per get_next call.
+    `unroll` puts an unroll pragma on the inner loop (tuning knob; default: the compiler decides)."""
+    pragma = ('_Pragma("unroll %d") ' % unroll) if unroll else ""
     masked = mask_comments_and_strings(src)
     names = "|".join(re.escape(m) for m in sorted(message_names, key=len, reverse=True))
     if not names:
@@ -188,7 +190,7 @@ def rewrite_message_loops(src: str, message_names: List[str]) -> Tuple[str, List
         serial += 1
         S = f"xmachine_message_{msg}"
         k = serial
-        prologue = (f" {S}* const fgpu_end{k} = fgpu_range_end_{msg}({lst}); {S}* fgpu_cur{k} = {var}; do {{ "
+        prologue = (f" {S}* const fgpu_end{k} = fgpu_range_end_{msg}({lst}); {S}* fgpu_cur{k} = {var}; {pragma}do {{ "
                     f"{S} fgpu_msg{k} = fgpu::load_message(fgpu_cur{k}); {S}* {var} = &fgpu_msg{k}; {{")
         epilogue = f"}} }} while (++fgpu_cur{k} != fgpu_end{k}); {var} = fgpu_next_range_{msg}({lst});"
         edits.append((body_open + 1, body_open + 1, prologue))
