@@ -271,8 +271,17 @@ def main():
     dom_ms = classes[dom]
     n_kernel = sim.agent_count("Particle", "default")   # units one launch of the dominant kernel processes
     achieved = B_ALG[dom] * n_kernel / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    # DRAM bytes per launch of that kernel from the committed ncu capture (not measurable here without ncu)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            rec = json.load(fh).get(args.workload, {}).get(dom)
+        if rec and world == 1:
+            traffic = rec["dram_read_bytes"] + rec["dram_write_bytes"]
+    except (OSError, ValueError, KeyError):
+        traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_agent": B_ALG[dom], "kernel_ms": dom_ms,
                 "stage_ms": {k: round(v, 5) for k, v in stage.items()},
                 "iteration": {"alg_bytes_per_agent_step": B_ALG_ITERATION,
