@@ -295,7 +295,10 @@ static void orc_filter_{f.name}(const fgpu_filter* F, void*){{
 
 def emit_glue(model: Model, function_files: List[str]) -> str:
     out = ["/* generated by oracle/gen_oracle.py -- CPU ORACLE glue (test infrastructure) */",
-           "#include <cstddef>",
+           "/* every standard header the runtime needs comes BEFORE the scripts: a script may define macros",
+           " * such as `length(x)` that would otherwise rewrite libstdc++ itself */",
+           "#include <cstddef>\n#include <algorithm>\n#include <cmath>\n#include <cstdarg>\n#include <cstdio>\n#include <cstdlib>",
+           "#include <cstring>\n#include <string>\n#include <vector>\n#include <omp.h>",
            '#include "header.h"',
            '#include "fgpu_model.h"',
            "thread_local int orc_tid = 0;",

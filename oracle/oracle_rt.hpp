@@ -247,11 +247,15 @@ static void orc_build_spatial(OrcMessage &M) {
     int *end_or_count = (int *)(M.pbm + M.hooks->pbm_end_offset);
     memset(M.pbm, 0, M.hooks->pbm_bytes); /* sim:1835 */
     if (n > 0) {
-        const float *x = (const float *)(M.list + d->vars[d->xvar].list_offset);
-        const float *y = (const float *)(M.list + d->vars[d->yvar].list_offset);
-        const float *z = (const float *)(M.list + d->vars[d->zvar].list_offset);
+        /* krn:944-953: glm::vec3(messages->x[index], ...) -- the variable's own type (float or double)
+         * converted to float */
+        auto coord = [&](int var, int i) -> float {
+            const fgpu_var &V = d->vars[var];
+            const char *col = M.list + V.list_offset;
+            return V.size == 8 ? (float)((const double *)col)[i] : ((const float *)col)[i];
+        };
         for (int i = 0; i < n; ++i) {
-            M.keys[i] = orc_cell_hash(d, x[i], y[i], z[i]);
+            M.keys[i] = orc_cell_hash(d, coord(d->xvar, i), coord(d->yvar, i), coord(d->zvar, i));
             M.keys_unsorted[i] = M.keys[i];
             M.values[i] = (unsigned int)i;
         }

@@ -29,7 +29,10 @@ from oracle.oracle import OracleSimulation  # noqa: E402
 from oracle.xml_states import read_states  # noqa: E402
 
 REF = "/root/reference/examples"
-CASES = [("CirclesPartitioning_float", 100), ("Boids_Partitioning", 50), ("Keratinocyte", 200)]
+CASES = [("CirclesPartitioning_float", 100), ("Boids_Partitioning", 50), ("Keratinocyte", 200),
+         # second batch: brute-force (non-partitioned) messages, double-precision variables, a second spatial model
+         ("CirclesBruteForce_float", 20), ("CirclesBruteForce_double", 20), ("CirclesPartitioning_double", 50),
+         ("SocialParticleSimulation", 20), ("EmptyExample", 5)]
 
 
 def snapshot(sim):

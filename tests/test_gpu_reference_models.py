@@ -15,7 +15,9 @@ from ev_diffusion_b200.runtime import Simulation
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-CASES = {"CirclesPartitioning_float": 100, "Boids_Partitioning": 50, "Keratinocyte": 200}
+CASES = {"CirclesPartitioning_float": 100, "Boids_Partitioning": 50, "Keratinocyte": 200,
+         "CirclesBruteForce_float": 20, "CirclesBruteForce_double": 20, "CirclesPartitioning_double": 50,
+         "SocialParticleSimulation": 20, "EmptyExample": 5}
 
 
 def _plugin(name, exact):
@@ -64,7 +66,9 @@ def _oracle_snapshot(orc):
     return out
 
 
-@pytest.mark.parametrize("name", ["CirclesPartitioning_float", "Boids_Partitioning", "Boids_Partitioning_generic"])
+@pytest.mark.parametrize("name", ["CirclesPartitioning_float", "Boids_Partitioning", "Boids_Partitioning_generic",
+                                  "CirclesBruteForce_float", "CirclesBruteForce_double", "CirclesPartitioning_double",
+                                  "SocialParticleSimulation", "EmptyExample"])
 def test_exact_build_matches_golden_bit_for_bit(name):
     """-fmad=false build: + - * / sqrt only (and fp64 subexpressions in Circles) -> bit-exact.
     `_generic` = the script compiled without the message-loop restructuring (looprewrite.py)."""
@@ -98,7 +102,8 @@ def test_default_build_within_tolerance(name, iters, rtol, atol):
     orc.close()
 
 
-@pytest.mark.parametrize("name", ["CirclesPartitioning_float", "Boids_Partitioning"])
+@pytest.mark.parametrize("name", ["CirclesPartitioning_float", "Boids_Partitioning", "CirclesBruteForce_float",
+                                  "CirclesPartitioning_double", "SocialParticleSimulation"])
 def test_every_function_against_live_oracle(name):
     so = gen_oracle.oracle_path(name)
     if not os.path.exists(so):
