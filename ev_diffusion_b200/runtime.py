@@ -410,6 +410,11 @@ def load_runtime() -> C.CDLL:
     lib.fgpu_sim_profile_iteration.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     lib.fgpu_sim_profile_iterations.restype = C.c_int
     lib.fgpu_sim_profile_iterations.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+    for fn in ("fgpu_sim_save_snapshot", "fgpu_sim_load_snapshot"):
+        getattr(lib, fn).restype = C.c_int
+        getattr(lib, fn).argtypes = [C.c_void_p, C.c_char_p]
+    lib.fgpu_sim_save_states.restype = C.c_int
+    lib.fgpu_sim_save_states.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     lib.fgpu_sim_read_agents.restype = C.c_int
     lib.fgpu_sim_read_agents.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.fgpu_sim_device_agents.restype = C.c_void_p
@@ -472,6 +477,18 @@ class Simulation(SimBase):
             ptrs[vi] = arr.ctypes.data
         self._check(self._lib.fgpu_sim_read_agents(self._h, agent, state, count, ptrs))
         return count
+
+    def save_states(self, outputpath: str, iteration_number: int) -> str:
+        """saveIterationData(): writes <outputpath><iteration_number>.xml in the reference's format."""
+        self._check(self._lib.fgpu_sim_save_states(self._h, os.fsencode(outputpath), int(iteration_number)))
+        return f"{outputpath}{int(iteration_number)}.xml"
+
+    def save_snapshot(self, path: str) -> None:
+        """Exact binary checkpoint: state lists, rand48 seeds, environment constants, iteration counter."""
+        self._check(self._lib.fgpu_sim_save_snapshot(self._h, os.fsencode(path)))
+
+    def load_snapshot(self, path: str) -> None:
+        self._check(self._lib.fgpu_sim_load_snapshot(self._h, os.fsencode(path)))
 
     def sync(self) -> None:
         self._check(self._lib.fgpu_sim_sync(self._h))

@@ -55,6 +55,17 @@ void fgpu_sim_destroy(fgpu_sim *sim);
  * lists, apply <environment> constants, upload. */
 int fgpu_sim_load_states(fgpu_sim *sim, const char *xml_path);
 
+/* saveIterationData() (io.xslt:124-200): writes <outputpath><iteration_number>.xml in the reference's
+ * format -- <states><itno/><environment/> then one <xagent> per agent, per agent type and state in model
+ * order, every value through the reference's format specifier (%f for float/double: lossy, like the
+ * reference).  A file written here is readable by fgpu_sim_load_states and by the reference's reader. */
+int fgpu_sim_save_states(fgpu_sim *sim, const char *outputpath, int iteration_number);
+/* Exact checkpoint / resume (the XML route loses float bits, the rand48 state and the iteration number):
+ * a little-endian binary image of every state list, the rand48 seeds, the environment constants and the
+ * iteration counter.  Loading checks the model name and the variable layout. */
+int fgpu_sim_save_snapshot(fgpu_sim *sim, const char *path);
+int fgpu_sim_load_snapshot(fgpu_sim *sim, const char *path);
+
 /* Direct upload of one state list from host SoA columns (one pointer per
  * agent variable, XML order; NULL = defaultValue).  Replaces the malloc +
  * cudaMemcpy H2D of the whole list struct (simulation.xslt:568-581). */

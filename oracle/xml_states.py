@@ -111,3 +111,40 @@ def read_states(path: str, agents: List[Tuple[str, List[Tuple[str, str, float]]]
     np_types = {"float": np.float32, "double": np.float64, "int": np.int32, "unsigned int": np.uint32}
     res = {a: {v: np.array(out[a][v], dtype=np_types[types[a][v]]) for v in out[a]} for a in out}
     return res, env
+
+
+_INT_FORMATS = {"bool": "%d", "char": "%d", "unsigned char": "%u", "short": "%d", "unsigned short": "%u", "int": "%d",
+                "unsigned int": "%u", "long long int": "%d", "unsigned long long int": "%u"}
+
+
+def _format(ctype: str, value) -> str:
+    """formatSpecifier (_common_templates.xslt:25-60): integers by type, anything else ``%f`` (C promotes a
+    float argument to double, so ``%f`` of the float32 value is what ``sprintf`` prints)."""
+    if ctype in _INT_FORMATS:
+        return "%d" % int(value)
+    return "%f" % float(value)
+
+
+def write_states(path: str, iteration: int, agents, states, constants=()) -> None:
+    """Python restatement of ``saveIterationData`` (io.xslt:124-200).
+
+    agents:    [(agent name, [(state name, [(var name, ctype)])...])] in model order; ``states`` maps
+               (agent, state) -> {var: array}.  constants: [(name, ctype, value-or-array)].
+    """
+    out = ["<states>\n<itno>%i</itno>\n<environment>\n" % iteration]
+    for name, ctype, value in constants:
+        vals = np.atleast_1d(value)
+        out.append("\t<%s>%s</%s>\n" % (name, ",".join(_format(ctype, v) for v in vals), name))
+    out.append("</environment>\n")
+    for aname, st_list in agents:
+        for sname, variables in st_list:
+            cols = states[(aname, sname)]
+            n = len(cols[variables[0][0]]) if variables else 0
+            for i in range(n):
+                out.append("<xagent>\n<name>%s</name>\n" % aname)
+                for vname, ctype in variables:
+                    out.append("<%s>%s</%s>\n" % (vname, _format(ctype, cols[vname][i]), vname))
+                out.append("</xagent>\n")
+    out.append("</states>\n")
+    with open(path, "w") as fh:
+        fh.write("".join(out))
