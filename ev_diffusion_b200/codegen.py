@@ -385,7 +385,34 @@ def _host_api_decls(model: Model) -> str:
             for v in a.variables:
                 if not v.array_length:
                     out.append(f"{v.type} get_{a.name}_{s}_variable_{v.name}(unsigned int index);")
+                    # analytics (header.xslt:729-751): sum for every scalar, count for integers, min/max for non-vectors
+                    out.append(f"{v.type} reduce_{a.name}_{s}_{v.name}_variable();")
+                    if "int" in v.type:
+                        out.append(f"{v.type} count_{a.name}_{s}_{v.name}_variable({v.type} count_value);")
+                    if "vec" not in v.type:
+                        out.append(f"{v.type} min_{a.name}_{s}_{v.name}_variable();")
+                        out.append(f"{v.type} max_{a.name}_{s}_{v.name}_variable();")
     return "\n".join(out)
+
+
+def _reduction_defs(model: Model, call: str) -> List[str]:
+    """Definitions of reduce_/count_/min_/max_<A>_<S>_<v>_variable() (simulation.xslt:1325-1357) over
+    `call`(agent, state, var, op, count_value*, result*) -> status."""
+    out = []
+    for ai, a in enumerate(model.agents):
+        for si, st in enumerate(a.states):
+            for vi, v in enumerate(a.variables):
+                if v.array_length:
+                    continue
+                def body(op, arg="nullptr"):
+                    return (f"{{ {v.type} t = 0; if ({call}({ai}, {si}, {vi}, {op}, {arg}, &t) != 0) fgpu_die(); return t; }}")
+                out.append(f"{v.type} reduce_{a.name}_{st}_{v.name}_variable(){body(0)}")
+                if "int" in v.type:
+                    out.append(f"{v.type} count_{a.name}_{st}_{v.name}_variable({v.type} count_value){body(3, '&count_value')}")
+                if "vec" not in v.type:
+                    out.append(f"{v.type} min_{a.name}_{st}_{v.name}_variable(){body(1)}")
+                    out.append(f"{v.type} max_{a.name}_{st}_{v.name}_variable(){body(2)}")
+    return out
 
 
 def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
@@ -643,6 +670,8 @@ void cleanup(){ fgpu_sim_run_exit_functions(fgpu_cur); fgpu_sim_destroy(fgpu_cur
                 if not v.array_length:
                     out.append(f"{v.type} get_{a.name}_{st}_variable_{v.name}(unsigned int index){{ {v.type} t = 0; "
                                f"if (fgpu_sim_read_agent_value(fgpu_cur, {ai}, {si}, {vi}, index, &t) != FGPU_OK) fgpu_die(); return t; }}")
+    out.append("static int fgpu_reduce_cur(int a, int s, int v, int op, const void* cv, void* r){ return fgpu_sim_reduce_agent_var(fgpu_cur, a, s, v, op, cv, r); }")
+    out += _reduction_defs(model, "fgpu_reduce_cur")
     return "\n".join(out) + "\n"
 
 

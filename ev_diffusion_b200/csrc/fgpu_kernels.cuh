@@ -457,6 +457,59 @@ k_append(const char *__restrict__ src, char *__restrict__ dst, const ColSet cols
 /* ------------------------------------------------------------------------- */
 /* 1-D slab decomposition: halo planes of the sorted message list, migrants    */
 /* ------------------------------------------------------------------------- */
+/* host-API reductions over one agent variable (simulation.xslt:1325-1357)    */
+/* ------------------------------------------------------------------------- */
+/* reduce_/count_/min_/max_<A>_<S>_<v>_variable(): thrust::reduce / count / min_element / max_element in the
+ * reference.  Two launches: grid-stride partials per block in a fixed order (so a float sum is the same
+ * from run to run, which thrust does not promise), then one block folds the partials. */
+enum { RED_SUM = 0, RED_MIN = 1, RED_MAX = 2, RED_COUNT = 3 };
+constexpr int RED_THREADS = 256;
+constexpr int RED_MAX_BLOCKS = 1024;
+
+template <typename T, int OP>
+__device__ __forceinline__ T red_combine(T a, T b) {
+    if (OP == RED_MIN) return b < a ? b : a;
+    if (OP == RED_MAX) return a < b ? b : a;
+    return a + b;
+}
+
+template <typename T, int OP>
+__device__ __forceinline__ T red_block(T v, T *s_part /*[RED_THREADS]*/) {
+    s_part[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = RED_THREADS / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) s_part[threadIdx.x] = red_combine<T, OP>(s_part[threadIdx.x], s_part[threadIdx.x + o]);
+        __syncthreads();
+    }
+    return s_part[0];
+}
+
+/* identity: 0 for sum/count, the first element for min/max (n > 0 is checked by the caller) */
+template <typename T, int OP>
+__global__ void __launch_bounds__(RED_THREADS)
+k_reduce_partial(const T *__restrict__ col, int n, T count_value, T *__restrict__ partial) {
+    __shared__ T s_part[RED_THREADS];
+    T acc = (OP == RED_MIN || OP == RED_MAX) ? col[0] : (T)0;
+    for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += gridDim.x * RED_THREADS) {
+        const T v = col[i];
+        if (OP == RED_COUNT) acc += (v == count_value) ? (T)1 : (T)0;
+        else acc = red_combine<T, OP>(acc, v);
+    }
+    const T r = red_block<T, (OP == RED_COUNT ? RED_SUM : OP)>(acc, s_part);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(RED_THREADS)
+k_reduce_final(const T *__restrict__ partial, int nparts, T *__restrict__ result) {
+    __shared__ T s_part[RED_THREADS];
+    T acc = (OP == RED_MIN || OP == RED_MAX) ? partial[0] : (T)0;
+    for (int i = threadIdx.x; i < nparts; i += RED_THREADS) acc = red_combine<T, OP>(acc, partial[i]);
+    const T r = red_block<T, OP>(acc, s_part);
+    if (threadIdx.x == 0) *result = r;
+}
+
+/* ------------------------------------------------------------------------- */
 /* Exchange buffers have a fixed capacity so that the NCCL message sizes are
  * known on the host without a device round trip; the true counts travel in a
  * 4-int header: {count, overflow, 0, 0}. */

@@ -2118,6 +2118,63 @@ extern "C" int fgpu_sim_load_snapshot(fgpu_sim *s, const char *path) {
     return FGPU_OK;
 }
 
+namespace {
+template <typename T>
+int reduce_typed(fgpu_sim *s, const char *col, int n, int op, const void *count_value, void *result) {
+    if (s->unpack_tmp_n < (size_t)RED_MAX_BLOCKS * 2 + 4) {
+        int rc = ensure_tmp(s, (size_t)RED_MAX_BLOCKS * 2 + 4);
+        if (rc) return rc;
+    }
+    T *partial = reinterpret_cast<T *>(s->unpack_tmp); /* 8-byte elements fit: 2 words each */
+    T *out = partial + RED_MAX_BLOCKS;
+    const T *c = reinterpret_cast<const T *>(col);
+    const int blocks = std::max(1, std::min(RED_MAX_BLOCKS, (n + RED_THREADS * 4 - 1) / (RED_THREADS * 4)));
+    T cv = (T)0;
+    if (op == RED_COUNT) memcpy(&cv, count_value, sizeof(T));
+    switch (op) {
+#define RED_CASE(OP)                                                                            \
+    case OP:                                                                                    \
+        k_reduce_partial<T, OP><<<blocks, RED_THREADS, 0, s->stream>>>(c, n, cv, partial);      \
+        k_reduce_final<T, (OP == RED_COUNT ? RED_SUM : OP)><<<1, RED_THREADS, 0, s->stream>>>(partial, blocks, out); \
+        break;
+        RED_CASE(RED_SUM) RED_CASE(RED_MIN) RED_CASE(RED_MAX) RED_CASE(RED_COUNT)
+#undef RED_CASE
+        default:
+            return set_err(FGPU_ERR_ARG, "unknown reduction %d", op);
+    }
+    s->launches += 2;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_err(FGPU_ERR_CUDA, "reduction launch -> %s", cudaGetErrorString(e));
+    CU(cudaMemcpyAsync(result, out, sizeof(T), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FGPU_OK;
+}
+}  // namespace
+
+extern "C" int fgpu_sim_reduce_agent_var(fgpu_sim *s, int agent, int state, int var, int op, const void *count_value, void *result) {
+    if (!s || !result || agent < 0 || agent >= (int)s->agents.size()) return set_err(FGPU_ERR_ARG, "bad argument");
+    AgentRT &A = s->agents[agent];
+    if (state < 0 || state >= A.d->nstates || var < 0 || var >= A.d->nvars) return set_err(FGPU_ERR_ARG, "bad index");
+    if (op == FGPU_REDUCE_COUNT && !count_value) return set_err(FGPU_ERR_ARG, "count needs a value");
+    CU(cudaSetDevice(s->device));
+    int rc = slab_settle(s);
+    if (rc) return rc;
+    const fgpu_var &V = A.d->vars[var];
+    const int n = A.h_state_count[state];
+    if (op == FGPU_REDUCE_COUNT && V.is_float) return set_err(FGPU_ERR_ARG, "count_ is defined for integer variables only (header.xslt:735)");
+    if (n == 0) {
+        if (op == FGPU_REDUCE_MIN || op == FGPU_REDUCE_MAX) return set_err(FGPU_ERR_ARG, "min/max of an empty %s list", A.d->name);
+        memset(result, 0, (size_t)V.size);
+        return FGPU_OK;
+    }
+    const char *col = A.state[state] + V.list_offset;
+    const bool uns = strstr(V.ctype, "unsigned") != nullptr;
+    if (V.is_float) return V.size == 8 ? reduce_typed<double>(s, col, n, op, count_value, result) : reduce_typed<float>(s, col, n, op, count_value, result);
+    if (V.size == 8) return uns ? reduce_typed<unsigned long long>(s, col, n, op, count_value, result) : reduce_typed<long long>(s, col, n, op, count_value, result);
+    if (V.size == 4) return uns ? reduce_typed<unsigned int>(s, col, n, op, count_value, result) : reduce_typed<int>(s, col, n, op, count_value, result);
+    return set_err(FGPU_ERR_MODEL, "reduction over a %d-byte variable is not supported", V.size);
+}
+
 extern "C" int fgpu_sim_set_option(fgpu_sim *s, const char *key, int value) {
     if (!s || !key) return set_err(FGPU_ERR_ARG, "bad argument");
     if (!strcmp(key, "order")) s->opt_order = value ? 1 : 0;

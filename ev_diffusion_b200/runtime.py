@@ -183,6 +183,7 @@ def bind_sim_api(lib: C.CDLL, prefix: str) -> None:
     sig("sim_iteration", C.c_uint, vp)
     sig("sim_agent_count", ci, vp, ci, ci)
     sig("sim_read_agent_var", ci, vp, ci, ci, ci, vp, ci)
+    sig("sim_reduce_agent_var", ci, vp, ci, ci, ci, ci, vp, vp)
     sig("sim_message_count", ci, vp, ci)
     sig("sim_read_message_var", ci, vp, ci, ci, vp, ci)
     sig("sim_read_pbm", ci, vp, ci, vp, vp)
@@ -362,6 +363,22 @@ class SimBase:
         out = np.empty(4, dtype=np.uint32)
         self._check(self._fn("sim_rand48_constants")(self._h, out.ctypes.data))
         return out
+
+    REDUCE_OPS = {"sum": 0, "min": 1, "max": 2, "count": 3}
+
+    def reduce(self, agent, state, var, op: str, count_value=None):
+        """reduce_/min_/max_/count_<A>_<S>_<v>_variable(): one agent variable folded over a state list;
+        the result has the variable's own type."""
+        agent = self._agent(agent)
+        state = self._state(agent, state)
+        a = self.model.agents[agent]
+        vi = a.var_index(var) if isinstance(var, str) else int(var)
+        dt = a.vars[vi].dtype
+        res = np.zeros(1, dtype=dt)
+        cv = np.asarray([0 if count_value is None else count_value], dtype=dt)
+        self._check(self._fn("sim_reduce_agent_var")(self._h, agent, state, vi, self.REDUCE_OPS[op],
+                                                     cv.ctypes.data if op == "count" else None, res.ctypes.data))
+        return res[0]
 
     def set_constant(self, name: str, value) -> None:
         ctype = {c[0]: c[1] for c in self.model.constants}[name]

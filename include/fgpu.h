@@ -110,6 +110,13 @@ int fgpu_sim_read_agent_var(fgpu_sim *sim, int agent, int state, int var, void *
 int fgpu_sim_read_agents(fgpu_sim *sim, int agent, int state, int count, void *const *columns);
 /* get_<A>_<S>_variable_<v>(index) (header.xslt:645): one element of a state list. */
 int fgpu_sim_read_agent_value(fgpu_sim *sim, int agent, int state, int var, unsigned int index, void *dst);
+/* reduce_/min_/max_/count_<A>_<S>_<v>_variable() (header.xslt:729-751, simulation.xslt:1325-1357): one scalar
+ * agent variable of a state list folded on the device.  `result` (and `count_value`, FGPU_REDUCE_COUNT only)
+ * have the variable's own C type; the count is returned in that type too, like the reference.  Integer results
+ * are exact; a float SUM is a fixed-order tree (the reference's thrust::reduce leaves the order open).
+ * MIN/MAX of an empty list is an error. */
+enum { FGPU_REDUCE_SUM = 0, FGPU_REDUCE_MIN = 1, FGPU_REDUCE_MAX = 2, FGPU_REDUCE_COUNT = 3 };
+int fgpu_sim_reduce_agent_var(fgpu_sim *sim, int agent, int state, int var, int op, const void *count_value, void *result);
 /* get_device_<A>_<S>_agents(): borrowed device pointer to a list in the
  * reference's xmachine_memory_<A>_list layout; invalidated by the next step. */
 void *fgpu_sim_device_agents(fgpu_sim *sim, int agent, int state);

@@ -213,6 +213,8 @@ def emit_header(model: Model) -> str:
         out.append(f"extern {c.type} h_env_{c.name}{dim};")
         out.append(f"void set_{c.name}({c.type}* h_{c.name});")
         out.append(f"const {c.type}* get_{c.name}();")
+    # host API the scripts' init/step/exit functions may call; the oracle defines the counts and the analytics
+    out.append(codegen._host_api_decls(model))
     out.append("#endif")
     return "\n".join(out) + "\n"
 
@@ -387,6 +389,14 @@ template <int AGENT_TYPE> void add_{a.name}_agent(xmachine_memory_{a.name}_list*
         else:
             rows.append(f"    {{sizeof({S}_list), 0, 0, &d_message_{m.name}_count, &d_message_{m.name}_output_type}},")
     out.append('#include "oracle_rt.hpp"')
+    # host API the scripts' init/step/exit functions may call (header.xslt:588-596, 729-751), on the oracle's lists
+    out.append('static void fgpu_die(){ fprintf(stderr, "%s\\n", orc_last_error()); exit(EXIT_FAILURE); }')
+    out.append("unsigned int getIterationNumber(){ return orc_cur ? orc_cur->iteration : 0u; }")
+    for ai, a in enumerate(model.agents):
+        out.append(f"int get_agent_{a.name}_MAX_count(){{ return xmachine_memory_{a.name}_MAX; }}")
+        for si, st in enumerate(a.states):
+            out.append(f"int get_agent_{a.name}_{st}_count(){{ return orc_sim_agent_count(orc_cur, {ai}, {si}); }}")
+    out += codegen._reduction_defs(model, "orc_host_reduce")
     out.append("const orc_message_hooks orc_hooks[] = {\n" + "\n".join(rows) + "\n    {0, 0, 0, nullptr, nullptr}\n};")
     return "\n".join(out) + "\n"
 

@@ -93,6 +93,9 @@ struct orc_sim {
 static inline int *orc_col_i(char *list, size_t off) { return (int *)(list + off); }
 
 /* ---- create: initialise() minus the XML read, sim:472-747 ------------------ */
+/* the simulation whose init/step/exit function is running (the reference's host API is global state) */
+static orc_sim *orc_cur = nullptr;
+
 static orc_sim *orc_create_impl(const fgpu_model *m) {
     orc_sim *s = new orc_sim();
     s->model = m;
@@ -438,10 +441,60 @@ static int orc_single_iteration(orc_sim *s) {
             int rc = orc_run_function(s, m->layers[l].functions[k]);
             if (rc) return rc;
         }
+    orc_cur = s;
     for (int k = 0; k < m->nstep_functions; ++k) m->step_functions[k]();
     return 0;
 }
 
+/* integer sums wrap like the device's (signed overflow is undefined in host C++) */
+template <typename T>
+static T orc_wrap_add(T a, T b) { return (T)(a + b); }
+template <>
+int orc_wrap_add<int>(int a, int b) { return (int)((unsigned int)a + (unsigned int)b); }
+template <>
+long long orc_wrap_add<long long>(long long a, long long b) { return (long long)((unsigned long long)a + (unsigned long long)b); }
+
+template <typename T>
+static void orc_reduce_typed(const char *col, int n, int op, const void *count_value, void *result) {
+    const T *c = (const T *)col;
+    T acc = (op == 1 || op == 2) ? c[0] : (T)0;
+    T cv = (T)0;
+    if (op == 3) memcpy(&cv, count_value, sizeof(T));
+    for (int i = 0; i < n; ++i) {
+        if (op == 0) acc = orc_wrap_add(acc, c[i]);
+        else if (op == 1) acc = c[i] < acc ? c[i] : acc;
+        else if (op == 2) acc = acc < c[i] ? c[i] : acc;
+        else acc = (T)(acc + (c[i] == cv ? (T)1 : (T)0));
+    }
+    memcpy(result, &acc, sizeof(T));
+}
+/* reduce_/count_/min_/max_<A>_<S>_<v>_variable() on the oracle's lists; op as in FGPU_REDUCE_* */
+int orc_host_reduce(int agent, int state, int var, int op, const void *count_value, void *result) {
+    orc_sim *s = orc_cur;
+    if (!s || agent < 0 || agent >= (int)s->agents.size()) return orc_set_err(-1, "bad index");
+    OrcAgent &A = s->agents[agent];
+    if (state < 0 || state >= A.d->nstates || var < 0 || var >= A.d->nvars) return orc_set_err(-1, "bad index");
+    const fgpu_var &V = A.d->vars[var];
+    const int n = A.h_state_count[state];
+    if (n == 0) {
+        if (op == 1 || op == 2) return orc_set_err(-1, "min/max of an empty list");
+        memset(result, 0, (size_t)V.size);
+        return 0;
+    }
+    const char *col = A.state[state] + V.list_offset;
+    const bool uns = strstr(V.ctype, "unsigned") != nullptr;
+    if (V.is_float) {
+        if (V.size == 8) orc_reduce_typed<double>(col, n, op, count_value, result);
+        else orc_reduce_typed<float>(col, n, op, count_value, result);
+    } else if (V.size == 8) {
+        if (uns) orc_reduce_typed<unsigned long long>(col, n, op, count_value, result);
+        else orc_reduce_typed<long long>(col, n, op, count_value, result);
+    } else {
+        if (uns) orc_reduce_typed<unsigned int>(col, n, op, count_value, result);
+        else orc_reduce_typed<int>(col, n, op, count_value, result);
+    }
+    return 0;
+}
 /* ---- C ABI (same shapes as include/fgpu.h, prefix orc_) ------------------------ */
 extern "C" {
 
@@ -489,6 +542,7 @@ int orc_sim_add_agents(void *p, int agent, int state, int count, const void *con
 int orc_sim_load_states(void *, const char *) { return orc_set_err(-4, "the oracle reads states through oracle/xml_states.py"); }
 int orc_sim_run_init_functions(void *p) {
     orc_sim *s = (orc_sim *)p;
+    orc_cur = s;
     for (int k = 0; k < s->model->ninit_functions; ++k) s->model->init_functions[k]();
     return 0;
 }
@@ -513,6 +567,10 @@ int orc_sim_agent_count(void *p, int agent, int state) {
     orc_sim *s = (orc_sim *)p;
     if (agent < 0 || agent >= (int)s->agents.size() || state < 0 || state >= s->agents[agent].d->nstates) return orc_set_err(-1, "bad index");
     return s->agents[agent].h_state_count[state];
+}
+int orc_sim_reduce_agent_var(void *p, int agent, int state, int var, int op, const void *count_value, void *result) {
+    orc_cur = (orc_sim *)p;
+    return orc_host_reduce(agent, state, var, op, count_value, result);
 }
 int orc_sim_read_agent_var(void *p, int agent, int state, int var, void *dst, int count) {
     orc_sim *s = (orc_sim *)p;

@@ -32,7 +32,9 @@ REF = "/root/reference/examples"
 CASES = [("CirclesPartitioning_float", 100), ("Boids_Partitioning", 50), ("Keratinocyte", 200),
          # second batch: brute-force (non-partitioned) messages, double-precision variables, a second spatial model
          ("CirclesBruteForce_float", 20), ("CirclesBruteForce_double", 20), ("CirclesPartitioning_double", 50),
-         ("SocialParticleSimulation", 20), ("EmptyExample", 5)]
+         ("SocialParticleSimulation", 20), ("EmptyExample", 5),
+         # init/step/exit functions calling the host analytics API (reduce_/min_/max_)
+         ("Analytics", 10)]
 
 
 def snapshot(sim):

@@ -1,0 +1,80 @@
+"""Host-side analytics API: reduce_/min_/max_/count_<A>_<S>_<v>_variable()
+(header.xslt:729-751, simulation.xslt:1325-1357) as device reductions behind fgpu_sim_reduce_agent_var, and
+through the generated names when a script's step function calls them (examples/Analytics)."""
+import os
+
+import numpy as np
+import pytest
+
+from common import W, brownian_oracle, brownian_plugin, build
+from ev_diffusion_b200.runtime import FgpuError, Simulation
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("key,count", [("c2_tiny", 1), ("c2_tiny", 4096), ("c2", None)])
+def test_reductions_against_numpy_and_oracle(key, count):
+    cfg = W.BROWNIAN[key]
+    st = W.brownian_state(cfg, count)
+    sim = Simulation(brownian_plugin(key))
+    sim.set_agents("Particle", "default", st)
+    sim.step(2)
+    a = sim.agents("Particle")
+    # integers: exact, with the wrap-around of the variable's own type (the reference returns thrust::reduce<int>)
+    wrapped = np.array(a["id"].astype(np.int64).sum() & 0xFFFFFFFF, dtype=np.uint32).astype(np.int32)
+    assert sim.reduce("Particle", "default", "id", "sum") == wrapped
+    for k in ("id", "nbr"):
+        assert sim.reduce("Particle", "default", k, "min") == a[k].min()
+        assert sim.reduce("Particle", "default", k, "max") == a[k].max()
+    for v in (0, int(a["nbr"].max()), 12345678):
+        assert sim.reduce("Particle", "default", "nbr", "count", v) == np.count_nonzero(a["nbr"] == v)
+    # floats: min/max exact, the sum a fixed-order float32 tree (reference: order unspecified)
+    for k in "xyz":
+        assert sim.reduce("Particle", "default", k, "min") == a[k].min()
+        assert sim.reduce("Particle", "default", k, "max") == a[k].max()
+        s1 = sim.reduce("Particle", "default", k, "sum")
+        assert s1 == sim.reduce("Particle", "default", k, "sum")          # deterministic
+        assert abs(float(s1) - a[k].astype(np.float64).sum()) <= 2e-6 * max(1.0, a[k].astype(np.float64).sum())
+    if key == "c2_tiny":
+        orc = brownian_oracle(key)
+        orc.set_agents("Particle", "default", st)
+        orc.step(2)
+        for k, op in (("id", "sum"), ("nbr", "max"), ("x", "min"), ("z", "max")):
+            assert orc.reduce("Particle", "default", k, op) == sim.reduce("Particle", "default", k, op)
+        assert orc.reduce("Particle", "default", "nbr", "count", 3) == sim.reduce("Particle", "default", "nbr", "count", 3)
+        orc.close()
+    sim.close()
+
+
+def test_reduction_edge_cases():
+    sim = Simulation(brownian_plugin("c2_tiny"))
+    assert sim.reduce("Particle", "default", "x", "sum") == 0.0          # empty list
+    assert sim.reduce("Particle", "default", "nbr", "count", 0) == 0
+    with pytest.raises(FgpuError, match="empty"):
+        sim.reduce("Particle", "default", "x", "min")
+    sim.set_agents("Particle", "default", W.brownian_state(W.BROWNIAN["c2_tiny"], 10))
+    with pytest.raises(FgpuError, match="integer"):
+        sim.reduce("Particle", "default", "x", "count", 1.0)
+    sim.close()
+
+
+def test_analytics_step_function_runs_the_generated_names(capfd):
+    """examples/Analytics: its step function prints mean/min/max positions through reduce_/min_/max_."""
+    p = build.model_path("Analytics_exact")
+    if not os.path.exists(p):
+        pytest.skip("Analytics plugin not prebuilt (needs /root/reference at build time)")
+    sim = Simulation(p)
+    rng = np.random.default_rng(1)
+    n = 500
+    cols = {v.name: np.zeros(n, v.dtype) for v in sim.model.agents[0].vars}
+    cols["id"] = np.arange(n, dtype=np.int32)
+    cols["x"] = (rng.random(n, dtype=np.float32) * 20 - 10).astype(np.float32)
+    cols["y"] = (rng.random(n, dtype=np.float32) * 20 - 10).astype(np.float32)
+    sim.set_agents(0, 0, cols)
+    sim.run_init_functions()
+    sim.step(1)
+    a = sim.agents(0)
+    out = capfd.readouterr().out
+    assert "FLAME GPU Step function. Min circle position is (%f, %f, %f)" % (a["x"].min(), a["y"].min(), a["z"].min()) in out
+    assert "FLAME GPU Step function. Max circle position is (%f, %f, %f)" % (a["x"].max(), a["y"].max(), a["z"].max()) in out
+    sim.close()

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 CASES = {"CirclesPartitioning_float": 100, "Boids_Partitioning": 50, "Keratinocyte": 200,
          "CirclesBruteForce_float": 20, "CirclesBruteForce_double": 20, "CirclesPartitioning_double": 50,
-         "SocialParticleSimulation": 20, "EmptyExample": 5}
+         "SocialParticleSimulation": 20, "EmptyExample": 5, "Analytics": 10}
 
 
 def _plugin(name, exact):
@@ -68,7 +68,7 @@ def _oracle_snapshot(orc):
 
 @pytest.mark.parametrize("name", ["CirclesPartitioning_float", "Boids_Partitioning", "Boids_Partitioning_generic",
                                   "CirclesBruteForce_float", "CirclesBruteForce_double", "CirclesPartitioning_double",
-                                  "SocialParticleSimulation", "EmptyExample"])
+                                  "SocialParticleSimulation", "EmptyExample", "Analytics"])
 def test_exact_build_matches_golden_bit_for_bit(name):
     """-fmad=false build: + - * / sqrt only (and fp64 subexpressions in Circles) -> bit-exact.
     `_generic` = the script compiled without the message-loop restructuring (looprewrite.py)."""
