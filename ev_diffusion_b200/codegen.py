@@ -277,6 +277,7 @@ def _cuda_message_api(m: Message) -> str:
         out.append("    int _cx, _cy, _cz;")
         out.append(f"    fgpu::grid_position<{T}>((float)x, (float)y, (float)z, _cx, _cy, _cz);")
         out.append(f"    messages->out_keys[messages->out_index] = fgpu::cell_hash<{T}>(_cx, _cy, _cz);")
+    out.append("    if (messages->out_flags != nullptr) messages->out_flags[messages->out_index] = 1;   /* optional_message, krn:394-397 */")
     out.append("}")
     if m.partitioning == "spatial":
         out.append(f"""FGPU_DEV {S}* get_first_{name}_message({S}_list* messages, {S}_PBM* partition_matrix, float x, float y, float z){{
@@ -439,7 +440,7 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
         M = f.input_message
         out.append(f"    xmachine_message_{M}_list inp;")
         out.append(f"    inp.in_recs = (const xmachine_message_{M}*)L.in_recs; inp.cell_start = L.in_cell_start; inp.in_count = L.d_in_count ? *L.d_in_count : L.in_count;")
-        out.append("    inp.out_recs = nullptr; inp.out_keys = nullptr; inp.out_index = 0; inp.end = nullptr;")
+        out.append("    inp.out_recs = nullptr; inp.out_keys = nullptr; inp.out_flags = nullptr; inp.out_index = 0; inp.end = nullptr;")
         out.append("    inp.step = 0; inp.cx = 0; inp.cy = 0; inp.cz = 0; inp.nrows = -1; inp.nlo = 0; inp.nhi = 0;")
         call.append("&inp")
         if model.message(M).partitioning == "spatial":
@@ -451,7 +452,7 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
         out.append(f"    xmachine_message_{M}_list outp;")
         out.append("    outp.in_recs = nullptr; outp.cell_start = nullptr; outp.in_count = 0; outp.end = nullptr;")
         out.append("    outp.step = 0; outp.cx = 0; outp.cy = 0; outp.cz = 0; outp.nrows = -1; outp.nlo = 0; outp.nhi = 0;")
-        out.append(f"    outp.out_recs = (xmachine_message_{M}*)L.out_recs; outp.out_keys = L.out_keys; outp.out_index = L.out_base + index;")
+        out.append(f"    outp.out_recs = (xmachine_message_{M}*)L.out_recs; outp.out_keys = L.out_keys; outp.out_flags = L.out_flags; outp.out_index = L.out_base + index;")
         call.append("&outp")
     if f.rng:
         out.append("    RNG_rand48 rng; rng.Ax = L.Ax; rng.Ay = L.Ay; rng.Cx = L.Cx; rng.Cy = L.Cy;")

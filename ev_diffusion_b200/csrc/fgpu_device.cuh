@@ -94,6 +94,7 @@ struct MessageProxy {
     /* output side */
     Msg *out_recs;
     unsigned int *out_keys;
+    int *out_flags;   /* optional_message output: one flag per slot, or nullptr */
     int out_index;
     /* cursor (replaces _relative_cell/_cell_index/_cell_index_max/_agent_grid_cell, hdr:170-173) */
     const Msg *end;   /* one past the last message of the open range; the cursor itself is the pointer

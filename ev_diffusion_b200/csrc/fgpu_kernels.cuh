@@ -440,6 +440,39 @@ k_compact_scatter(const char *__restrict__ src, char *__restrict__ dst, const Co
     }
 }
 
+/* optional_message outputs (scatter_optional_<M>_messages, krn:411-428): stable compaction of the flagged
+ * slots of the sparse staging list -- 16-byte records and, for partitioned messages, their cell keys -- to
+ * dst_offset of the message list.  Uses the block offsets of k_flag_blocksum + k_scan_blocksums. */
+template <int NQ>
+__global__ void __launch_bounds__(COMPACT_THREADS)
+k_compact_records(const uint4 *__restrict__ src_recs, const unsigned int *__restrict__ src_keys, uint4 *__restrict__ dst_recs,
+                  unsigned int *__restrict__ dst_keys, const int *__restrict__ flags, const unsigned int *__restrict__ block_offsets,
+                  int dst_offset, int n) {
+    __shared__ unsigned int s_warp[32];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool f = (i < n) && (flags[i] == 1);
+    const unsigned int ballot = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned int v = s_warp[lane];
+        unsigned int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        s_warp[lane] = inc - v;
+    }
+    __syncthreads();
+    if (!f) return;
+    const size_t out = (size_t)dst_offset + block_offsets[blockIdx.x] + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u));
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) dst_recs[out * NQ + q] = src_recs[(size_t)i * NQ + q];
+    if (src_keys != nullptr) dst_keys[out] = src_keys[i];
+}
+
 /* append_<A>_Agents (krn:265-280) */
 __global__ void __launch_bounds__(256)
 k_append(const char *__restrict__ src, char *__restrict__ dst, const ColSet cols, int dst_offset, int n) {

@@ -82,6 +82,10 @@ struct MsgRT {
     uint4 *unsorted = nullptr; /* staging written by add_<M>_message */
     uint4 *sorted = nullptr;   /* cell-ordered list read by get_first/next */
     unsigned int *keys_in = nullptr; /* cell key of each unsorted message (written by add_<M>_message) */
+    /* optional_message producers write a sparse staging list first (allocated on first use) */
+    uint4 *opt_recs = nullptr;
+    unsigned int *opt_keys = nullptr;
+    int *opt_flags = nullptr;
     unsigned int *keys[2] = {nullptr, nullptr}; /* radix ping-pong */
     unsigned int *vals[2] = {nullptr, nullptr};
     unsigned int *cell_start = nullptr; /* CSR, grid_size + 1 */
@@ -412,6 +416,9 @@ extern "C" void fgpu_sim_destroy(fgpu_sim *s) {
         cudaFree(M.unsorted);
         cudaFree(M.sorted);
         cudaFree(M.keys_in);
+        cudaFree(M.opt_recs);
+        cudaFree(M.opt_keys);
+        cudaFree(M.opt_flags);
         for (int k = 0; k < 2; ++k) {
             cudaFree(M.keys[k]);
             cudaFree(M.vals[k]);
@@ -1615,8 +1622,18 @@ static int run_function(fgpu_sim *s, int fi) {
     MsgRT *Min = F.input_message >= 0 ? &s->msgs[F.input_message] : nullptr;
     if (Mout && Mout->h_count + A.h_count > Mout->d->buffer_size) /* sim:1607-1613 */
         return set_err(FGPU_ERR_OVERFLOW, "Error: Buffer size of %s message will be exceeded in function %s", Mout->d->name, F.name);
-    if (Mout && F.output_type != FGPU_OUT_SINGLE)
-        return set_err(FGPU_ERR_MODEL, "function %s: optional_message output is not implemented yet", F.name);
+    const bool optional_out = Mout && F.output_type == FGPU_OUT_OPTIONAL;
+    if (optional_out) {
+        if (Mout->h_count > 0) /* the reference swaps the list away under an earlier producer (sim:1709-1716) */
+            return set_err(FGPU_ERR_MODEL, "function %s: an optional_message output must be the first producer of message %s in an iteration", F.name,
+                           Mout->d->name);
+        if (s->slab.on) return set_err(FGPU_ERR_MODEL, "function %s: optional_message outputs are not supported in slab mode", F.name);
+        if (!Mout->opt_recs) {
+            CU(cudaMalloc(&Mout->opt_recs, msg_plane_bytes(Mout->d)));
+            CU(cudaMalloc(&Mout->opt_keys, sizeof(unsigned int) * (size_t)Mout->d->buffer_size));
+            CU(cudaMalloc(&Mout->opt_flags, sizeof(int) * (size_t)Mout->d->buffer_size));
+        }
+    }
 
     fgpu_launch L;
     memset(&L, 0, sizeof(L));
@@ -1643,6 +1660,14 @@ static int run_function(fgpu_sim *s, int fi) {
         L.out_recs = Mout->unsorted;
         L.out_keys = Mout->keys_in;
         L.out_base = Mout->h_count; /* a second producer appends; the whole list is re-binned (sim:1836-1837) */
+        if (optional_out) {
+            /* reset_<M>_swaps (sim:1666-1672), then every agent that calls add_<M>_message flags its own slot */
+            CU(cudaMemsetAsync(Mout->opt_flags, 0, sizeof(int) * (size_t)std::max(A.h_count, 1), s->stream));
+            L.out_recs = Mout->opt_recs;
+            L.out_keys = Mout->opt_keys;
+            L.out_flags = Mout->opt_flags;
+            L.out_base = 0;
+        }
     }
     if (F.rng) {
         L.seeds = s->seeds;
@@ -1656,7 +1681,36 @@ static int run_function(fgpu_sim *s, int fi) {
     LAUNCH_CHECK();
     s->prof_end();
 
-    if (Mout) {
+    if (optional_out) {
+        /* exclusive scan of the flags + scatter_optional_<M>_messages + the count read-back the reference also
+         * pays (sim:1709-1750): the message list is the stable compaction of the flagged slots */
+        s->prof_begin(std::string("optional:") + F.name);
+        int produced = 0;
+        int rc = compact(s, A, nullptr, nullptr, 0, A.h_count, Mout->opt_flags, false, &produced);
+        if (rc) return rc;
+        if (A.h_count > 0) {
+            const int nb = (A.h_count + COMPACT_THREADS - 1) / COMPACT_THREADS;
+            const bool spatial = Mout->d->partitioning == FGPU_PART_SPATIAL;
+            switch (Mout->d->rec_quads) {
+#define OPT_CASE(QQ)                                                                                                                      \
+    case QQ:                                                                                                                              \
+        k_compact_records<QQ><<<nb, COMPACT_THREADS, 0, s->stream>>>(Mout->opt_recs, spatial ? Mout->opt_keys : nullptr, Mout->unsorted, \
+                                                                     Mout->keys_in, Mout->opt_flags, A.block_sums, 0, A.h_count);        \
+        break;
+                OPT_CASE(1) OPT_CASE(2) OPT_CASE(3) OPT_CASE(4) OPT_CASE(5) OPT_CASE(6) OPT_CASE(7) OPT_CASE(8)
+#undef OPT_CASE
+                default:
+                    return set_err(FGPU_ERR_MODEL, "message %s: record of %d quads is not supported", Mout->d->name, Mout->d->rec_quads);
+            }
+            LAUNCH_CHECK();
+        }
+        Mout->producers = 1;
+        Mout->producer_buf = nullptr; /* message k is no longer the message of list index k: no cell-coherent order */
+        Mout->producer_epoch = 0;
+        Mout->d_count = nullptr;
+        Mout->h_count = produced;
+        s->prof_end();
+    } else if (Mout) {
         /* sim:1734-1754 */
         if (Mout->h_count == 0) {
             Mout->producers = 1;

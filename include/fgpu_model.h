@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FGPU_MODEL_ABI_VERSION 8
+#define FGPU_MODEL_ABI_VERSION 9
 
 /* One agent or message variable.  Agent lists keep the reference's SoA struct
  * layout (header.xslt:187-194): int _position[MAX]; int _scan_input[MAX];
@@ -85,6 +85,8 @@ typedef struct fgpu_launch {
     /* output message (unsorted staging + cell keys) */
     void *out_recs;
     unsigned int *out_keys;
+    int *out_flags;               /* optional_message output: add_<M>_message sets out_flags[slot] = 1 (zeroed before
+                                     the launch); NULL for single_message */
     int out_base;                 /* d_message_<M>_count before this function (krn:385) */
     /* rand48 (simulation.xslt:661-688) */
     void *seeds;                  /* uint2[buffer_size_MAX], .x low 24 bits, .y high 24 bits */

@@ -362,7 +362,17 @@ static int orc_run_function(orc_sim *s, int fi) {
     OrcMessage *Min = F.input_message >= 0 ? &s->msgs[F.input_message] : nullptr;
     if (Mout && Mout->h_count + A.h_count > Mout->d->buffer_size) /* sim:1607-1613 */
         return orc_set_err(-3, "Error: Buffer size of %s message will be exceeded in function %s", Mout->d->name, F.name);
-    if (Mout && F.output_type != FGPU_OUT_SINGLE) return orc_set_err(-5, "optional messages not implemented in the oracle");
+    const bool optional_out = Mout && F.output_type == FGPU_OUT_OPTIONAL;
+    if (optional_out && Mout->h_count > 0) /* sim:1709-1716 swaps the list away under an earlier producer */
+        return orc_set_err(-5, "function %s: an optional_message output must be the first producer of message %s in an iteration", F.name,
+                           Mout->d->name);
+    int *const msg_position = Mout ? (int *)Mout->list : nullptr;                       /* int _position[MAX]  */
+    int *const msg_scan_input = Mout ? (int *)Mout->list + Mout->d->buffer_size : nullptr; /* int _scan_input[MAX] */
+    if (optional_out) /* reset_<M>_swaps(d_<M>s), sim:1666-1672 + krn:434-441 */
+        for (int i = 0; i < state_list_size; ++i) {
+            msg_position[i] = 0;
+            msg_scan_input[i] = 0;
+        }
 
     if (Mout) *Mout->hooks->output_type_symbol = F.output_type; /* sim:1660-1672 */
     if (F.reallocate) orc_reset_scan_input(A, A.work, state_list_size); /* sim:1675-1681 */
@@ -387,7 +397,29 @@ static int orc_run_function(orc_sim *s, int fi) {
 #endif
     F.launch(&L, nullptr); /* GPUFLAME_<f>, sim:1688-1692 */
 
-    if (Mout) { /* sim:1734-1754 */
+    if (optional_out) {
+        /* sim:1709-1750: swap the lists, exclusive sum of the sparse list's flags over the agents,
+         * scatter_optional_<M>_messages (krn:411-428), count from the last prefix sum */
+        std::swap(Mout->list, Mout->swap);
+        const int *sparse_flag = (const int *)Mout->swap + Mout->d->buffer_size;
+        int *sparse_pos = (int *)Mout->swap;
+        int running = 0;
+        for (int i = 0; i < A.h_count; ++i) {
+            sparse_pos[i] = running;
+            running += sparse_flag[i];
+        }
+        for (int index = 0; index < A.h_count; ++index) {
+            if (sparse_flag[index] != 1) continue;
+            const int output_index = sparse_pos[index] + Mout->h_count;
+            ((int *)Mout->list)[output_index] = output_index;
+            for (int v = 0; v < Mout->d->nvars; ++v) {
+                const fgpu_var &V = Mout->d->vars[v];
+                memcpy(Mout->list + V.list_offset + (size_t)output_index * V.size, Mout->swap + V.list_offset + (size_t)index * V.size, V.size);
+            }
+        }
+        if (A.h_count > 0) Mout->h_count += sparse_pos[A.h_count - 1] + (sparse_flag[A.h_count - 1] == 1 ? 1 : 0);
+        *Mout->hooks->count_symbol = Mout->h_count;
+    } else if (Mout) { /* sim:1734-1754 */
         Mout->h_count += A.h_count;
         *Mout->hooks->count_symbol = Mout->h_count;
     }
