@@ -295,11 +295,13 @@ template <int NQ>
 __global__ void __launch_bounds__(256)
 k_gather_pbm(const unsigned int *__restrict__ skeys, const unsigned int *__restrict__ svals,
              const uint4 *__restrict__ in_recs, uint4 *__restrict__ out_recs, int n_host, const int *__restrict__ d_n,
-             unsigned int *__restrict__ cell_start, unsigned int cells, unsigned int *gap_queue,
-             unsigned int *gap_count) {
+             unsigned int *__restrict__ cell_start, unsigned int first_cell, unsigned int cells, unsigned int value_offset,
+             unsigned int *gap_queue, unsigned int *gap_count) {
+    /* boundaries are written for the cells [first_cell, cells] only (slab mode: the owned planes) and hold
+     * value_offset + sorted index (slab mode: the local block sits behind the low halo in the combined list) */
     const int n = d_n ? *d_n : n_host;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n == 0 && i == 0) fill_cells(cell_start, 0u, cells, 0u, gap_queue, gap_count); /* empty list: every cell empty */
+    if (n == 0 && i == 0) fill_cells(cell_start, first_cell, cells, value_offset, gap_queue, gap_count); /* empty list: every cell empty */
     if (i >= n) return;
     const unsigned int v = svals[i];
     const unsigned int key = skeys[i];
@@ -308,12 +310,12 @@ k_gather_pbm(const unsigned int *__restrict__ skeys, const unsigned int *__restr
 #pragma unroll
     for (int q = 0; q < NQ; ++q) out_recs[(size_t)i * NQ + q] = __ldg(in_recs + (size_t)v * NQ + q);
     if (i == 0) {
-        fill_cells(cell_start, 0u, key, 0u, gap_queue, gap_count);
+        fill_cells(cell_start, first_cell, key, value_offset, gap_queue, gap_count);
     } else {
         const unsigned int prev = skeys[i - 1];
-        if (prev != key) fill_cells(cell_start, prev + 1u, key, (unsigned int)i, gap_queue, gap_count);
+        if (prev != key) fill_cells(cell_start, prev + 1u, key, value_offset + (unsigned int)i, gap_queue, gap_count);
     }
-    if (i == n - 1) fill_cells(cell_start, key + 1u, cells, (unsigned int)n, gap_queue, gap_count);
+    if (i == n - 1) fill_cells(cell_start, key + 1u, cells, value_offset + (unsigned int)n, gap_queue, gap_count);
 }
 
 /* Runs of empty cells queued by k_gather_pbm: long runs by the whole grid, the others one block per entry. */
@@ -658,9 +660,7 @@ k_merge_halo(uint4 *__restrict__ combined, unsigned int *__restrict__ cell_start
     const int lo_cnt = lo_buf[0], hi_cnt = hi_buf[0];
     if (tid == 0 && (lo_buf[1] || hi_buf[1])) atomicExch(status, 1);
     const int pad = (plane_cells + 1 + 3) & ~3;
-    /* owned planes (including the closing boundary) */
-    for (int i = tid; i <= own_cells; i += stride) cell_start[own_first_cell + i] += (unsigned int)local_at;
-    __threadfence();
+    /* the owned planes' entries (closing boundary included) were written with local_at added by the build */
     /* low halo sits immediately below the local block, high halo immediately above */
     const int lo_at = local_at - lo_cnt, hi_at = local_at + n;
     /* a halo plane adjacent in hash order shares its boundary entry with the owned block; that entry already
@@ -677,120 +677,100 @@ k_merge_halo(uint4 *__restrict__ combined, unsigned int *__restrict__ cell_start
     for (int i = tid; i < hi_cnt * NQ; i += stride) combined[(size_t)hi_at * NQ + i] = hi_recs[i];
 }
 
-/* Owner of each agent along the slab axis: 1 = stays, 2 = lower neighbour, 3 = upper neighbour,
+/* ---- fused three-way migration split (stay / down / up) ------------------------------------------ */
+/* Owner class of an agent along the slab axis: 1 = stays, 2 = lower neighbour, 3 = upper neighbour,
  * 4 = further than one slab away (reported).  The plane is the cell coordinate of
  * message_<M>_grid_position + the wrap rule of message_<M>_hash (krn:860-889). */
+/* pass 1: owner flag of every agent + per-block counts of the three classes: block_sums[class][block].
+ * A block covers COMPACT_THREADS consecutive agents (the unit of the stable scatter below) with 256 threads
+ * x 4 rounds: a quarter of the thread launches of one-thread-per-agent. */
 __global__ void __launch_bounds__(256)
-k_owner_flags(const float *__restrict__ coord, int n_host, const int *__restrict__ d_n, float minb, float maxb, int nplanes,
-              int planes_per_rank, int rank, int world, int *__restrict__ flags, int *status) {
-    const int n = d_n ? *d_n : n_host;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int p = (int)floorf(__fdiv_rn(__fmul_rn(__fsub_rn(coord[i], minb), (float)nplanes), __fsub_rn(maxb, minb)));
-    p = (p < 0) ? nplanes - 1 : p;
-    p = (p >= nplanes) ? 0 : p;
-    const int owner = min(p / planes_per_rank, world - 1);
-    int f = 4;
-    if (owner == rank) f = 1;
-    else if (owner == (rank + world - 1) % world && owner == (rank + 1) % world) f = (p < rank * planes_per_rank) ? 2 : 3; /* world == 2 */
-    else if (owner == (rank + world - 1) % world) f = 2;
-    else if (owner == (rank + 1) % world) f = 3;
-    flags[i] = f;
-    if (f == 4) atomicExch(status, 2);
-}
-
-/* ---- fused three-way migration split (stay / down / up) ------------------------------------------ */
-/* pass 1: owner flag of every agent + per-block counts of the three classes: block_sums[class][block] */
-__global__ void __launch_bounds__(COMPACT_THREADS)
 k_owner_count(const float *__restrict__ coord, int n_host, const int *__restrict__ d_n, float minb, float maxb, int nplanes,
               int planes_per_rank, int rank, int world, int *__restrict__ flags, unsigned int *__restrict__ block_sums,
               int nb, int *status) {
+    __shared__ unsigned int s_cnt[3];
     const int n = d_n ? *d_n : n_host;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int f = 0;
-    if (i < n) {
-        int p = (int)floorf(__fdiv_rn(__fmul_rn(__fsub_rn(coord[i], minb), (float)nplanes), __fsub_rn(maxb, minb)));
-        p = (p < 0) ? nplanes - 1 : p;
-        p = (p >= nplanes) ? 0 : p;
-        const int owner = min(p / planes_per_rank, world - 1);
-        const int lo_rank = (rank + world - 1) % world, hi_rank = (rank + 1) % world;
-        f = 4;
-        if (owner == rank) f = 1;
-        else if (owner == lo_rank && owner == hi_rank) f = (p < rank * planes_per_rank) ? 2 : 3; /* world == 2 */
-        else if (owner == lo_rank) f = 2;
-        else if (owner == hi_rank) f = 3;
-        flags[i] = f;
-        if (f == 4) atomicExch(status, 2);
+    if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int lo_rank = (rank + world - 1) % world, hi_rank = (rank + 1) % world;
+    const float scale = (float)nplanes, range = __fsub_rn(maxb, minb);
+    unsigned int c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+    for (int r = 0; r < COMPACT_THREADS / 256; ++r) {
+        const int i = blockIdx.x * COMPACT_THREADS + r * 256 + threadIdx.x;
+        int f = 0;
+        if (i < n) {
+            int p = (int)floorf(__fdiv_rn(__fmul_rn(__fsub_rn(coord[i], minb), scale), range));
+            p = (p < 0) ? nplanes - 1 : p;
+            p = (p >= nplanes) ? 0 : p;
+            const int owner = min(p / planes_per_rank, world - 1);
+            f = 4;
+            if (owner == rank) f = 1;
+            else if (owner == lo_rank && owner == hi_rank) f = (p < rank * planes_per_rank) ? 2 : 3; /* world == 2 */
+            else if (owner == lo_rank) f = 2;
+            else if (owner == hi_rank) f = 3;
+            flags[i] = f;
+            if (f == 4) atomicExch(status, 2);
+        }
+        c1 += __popc(__ballot_sync(0xffffffffu, f == 1));
+        c2 += __popc(__ballot_sync(0xffffffffu, f == 2));
+        c3 += __popc(__ballot_sync(0xffffffffu, f == 3));
     }
-    const int c1 = __syncthreads_count(f == 1);
-    const int c2 = __syncthreads_count(f == 2);
-    const int c3 = __syncthreads_count(f == 3);
-    if (threadIdx.x == 0) {
-        block_sums[blockIdx.x] = (unsigned int)c1;
-        block_sums[nb + blockIdx.x] = (unsigned int)c2;
-        block_sums[2 * nb + blockIdx.x] = (unsigned int)c3;
+    if ((threadIdx.x & 31) == 0) {
+        if (c1) atomicAdd(&s_cnt[0], c1);
+        if (c2) atomicAdd(&s_cnt[1], c2);
+        if (c3) atomicAdd(&s_cnt[2], c3);
     }
+    __syncthreads();
+    if (threadIdx.x < 3) block_sums[threadIdx.x * nb + blockIdx.x] = s_cnt[threadIdx.x];
 }
 
-/* pass 2 (3 blocks, one per class): exclusive scan of the block counts; totals -> n_stay and the send headers */
-__global__ void __launch_bounds__(1024)
-k_scan3(unsigned int *block_sums, int nb, int *n_stay, int *hdr_dn, int *hdr_up, int cap) {
-    __shared__ unsigned int s_warp[32];
-    __shared__ unsigned int s_carry;
-    unsigned int *row = block_sums + (size_t)blockIdx.x * nb;
+/* pass 2: stable scatter of every agent to its destination (stayers list / down buffer / up buffer).
+ * The offset of a block is the sum of the counts of the blocks before it, which every block adds up for
+ * itself (at most a few thousand values; no scan launch, no chain between blocks); the last block also
+ * publishes the totals: *n_stay and the headers of the two send buffers. */
+__global__ void __launch_bounds__(COMPACT_THREADS)
+k_scatter3(const char *__restrict__ src, char *__restrict__ stay, char *__restrict__ dn, char *__restrict__ up,
+           const ColSet cols, const ColSet bcols, const int *__restrict__ flags, const unsigned int *__restrict__ block_sums,
+           int nb, int n_host, const int *__restrict__ d_n, int cap, int *overflow, int *n_stay, int *hdr_dn, int *hdr_up) {
+    __shared__ unsigned int s_warp[3][32];
+    __shared__ unsigned int s_off[3];
+    const int n = d_n ? *d_n : n_host;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
+    if (threadIdx.x < 3) s_off[threadIdx.x] = 0;
     __syncthreads();
-    for (int base = 0; base < nb; base += 1024) {
-        const int i = base + threadIdx.x;
-        const unsigned int v = (i < nb) ? row[i] : 0u;
-        unsigned int inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
+    {
+        unsigned int p0 = 0, p1 = 0, p2 = 0;
+        for (int b = threadIdx.x; b < (int)blockIdx.x; b += COMPACT_THREADS) {
+            p0 += block_sums[b];
+            p1 += block_sums[nb + b];
+            p2 += block_sums[2 * nb + b];
         }
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned int w = s_warp[lane];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned int t = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += t;
-            }
-            s_warp[lane] = w;
+        for (int o = 16; o > 0; o >>= 1) {
+            p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+            p2 += __shfl_xor_sync(0xffffffffu, p2, o);
         }
-        __syncthreads();
-        const unsigned int wbase = warp ? s_warp[warp - 1] : 0u;
-        const unsigned int carry = s_carry;
-        if (i < nb) row[i] = carry + wbase + inc - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = carry + wbase + inc;
-        __syncthreads();
+        if (lane == 0) {
+            if (p0) atomicAdd(&s_off[0], p0);
+            if (p1) atomicAdd(&s_off[1], p1);
+            if (p2) atomicAdd(&s_off[2], p2);
+        }
     }
-    if (threadIdx.x == 0) {
-        const int total = (int)s_carry;
-        if (blockIdx.x == 0) *n_stay = total;
+    __syncthreads();
+    if (blockIdx.x == (unsigned int)nb - 1 && threadIdx.x < 3) {
+        const int total = (int)(s_off[threadIdx.x] + block_sums[threadIdx.x * nb + blockIdx.x]);
+        if (threadIdx.x == 0) *n_stay = total;
         else {
-            int *h = (blockIdx.x == 1) ? hdr_dn : hdr_up;
+            int *h = (threadIdx.x == 1) ? hdr_dn : hdr_up;
             h[0] = min(total, cap);
             h[1] = total > cap;
             h[2] = 0;
             h[3] = 0;
         }
     }
-}
-
-/* pass 3: stable scatter of every agent to its destination (stayers list / down buffer / up buffer) */
-__global__ void __launch_bounds__(COMPACT_THREADS)
-k_scatter3(const char *__restrict__ src, char *__restrict__ stay, char *__restrict__ dn, char *__restrict__ up,
-           const ColSet cols, const ColSet bcols, const int *__restrict__ flags, const unsigned int *__restrict__ block_offsets,
-           int nb, int n_host, const int *__restrict__ d_n, int cap, int *overflow) {
-    __shared__ unsigned int s_warp[3][32];
-    const int n = d_n ? *d_n : n_host;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = (i < n) ? flags[i] : 0;
     const unsigned int b1 = __ballot_sync(0xffffffffu, f == 1), b2 = __ballot_sync(0xffffffffu, f == 2),
                        b3 = __ballot_sync(0xffffffffu, f == 3);
@@ -814,7 +794,7 @@ k_scatter3(const char *__restrict__ src, char *__restrict__ stay, char *__restri
     if (f >= 1 && f <= 3) {
         const unsigned int lt = (1u << lane) - 1u;
         const unsigned int bal = (f == 1) ? b1 : (f == 2) ? b2 : b3;
-        const size_t out = (size_t)block_offsets[(size_t)(f - 1) * nb + blockIdx.x] + s_warp[f - 1][warp] + __popc(bal & lt);
+        const size_t out = (size_t)s_off[f - 1] + s_warp[f - 1][warp] + __popc(bal & lt);
         char *dst = (f == 1) ? stay : (f == 2) ? dn : up;
         if (f != 1 && out >= (size_t)cap) {
             atomicExch(overflow, 1);

@@ -993,7 +993,8 @@ static int build_spatial(fgpu_sim *s, MsgRT &M) {
 #define GATHER_CASE(Q)                                                                                                   \
     case Q:                                                                                                              \
         k_gather_pbm<Q><<<g, 256, 0, s->stream>>>(M.keys[in], M.vals[in], M.unsorted, M.sorted + (size_t)M.local_at * Q, n, M.d_count, M.cell_start, \
-                                                  (unsigned int)M.d->grid_size, M.gap_queue, gap_count);                 \
+                                                  key_base, key_base + (key_span ? key_span : (unsigned int)M.d->grid_size),        \
+                                                  (unsigned int)M.local_at, M.gap_queue, gap_count);                           \
         break;
         GATHER_CASE(1)
         GATHER_CASE(2)
@@ -1297,7 +1298,7 @@ static int slab_exchange_halo(fgpu_sim *s, int mi) {
     SlabMsg &X = S.msgs[mi];
     const int n = M.h_count, PL = S.plane_cells, Q = M.d->rec_quads;
     if (n == 0) CU(cudaMemsetAsync(M.cell_start, 0, sizeof(unsigned int) * ((size_t)M.d->grid_size + 1), s->stream));
-    const uint4 *local = M.sorted + (size_t)M.local_at * Q;
+    const uint4 *local = M.sorted; /* cell_start of the owned planes already counts from the start of the combined list */
     s->prof_begin(std::string("halo_pack:") + M.d->name);
     const int g = std::min(148 * 4, (std::max(S.halo_cap * Q, PL) + 255) / 256);
     const size_t A4 = (X.bytes + 255) & ~(size_t)255;
@@ -1441,7 +1442,7 @@ static int slab_migrate(fgpu_sim *s) {
             int *cnt = X.d_counts + 4 * st; /* {n_stay, -, total down, total up} */
             const int nb = std::max(1, (n + COMPACT_THREADS - 1) / COMPACT_THREADS);
             s->prof_begin("mig:flags");
-            k_owner_count<<<nb, COMPACT_THREADS, 0, s->stream>>>((const float *)(list + A.d->vars[X.axis_var].list_offset), n, d_n,
+            k_owner_count<<<nb, 256, 0, s->stream>>>((const float *)(list + A.d->vars[X.axis_var].list_offset), n, d_n,
                                                                  S.axis_min, S.axis_max, S.nplanes, S.ppr, S.rank, S.world, flags,
                                                                  A.block_sums, nb, S.d_status);
             LAUNCH_CHECK();
@@ -1449,13 +1450,9 @@ static int slab_migrate(fgpu_sim *s) {
             const size_t A4 = (X.bytes + 255) & ~(size_t)255;
             const int seq = ++S.agent_seq[a], par = seq & 1;
             const char *in_lo = X.recv_lo, *in_hi = X.recv_hi;
-            s->prof_begin("mig:scan");
-            k_scan3<<<3, 1024, 0, s->stream>>>(A.block_sums, nb, cnt, (int *)X.send_dn, (int *)X.send_up, S.mig_cap);
-            LAUNCH_CHECK();
-            s->prof_end();
             s->prof_begin("mig:scatter");
             k_scatter3<<<nb, COMPACT_THREADS, 0, s->stream>>>(list, A.swap, X.send_dn, X.send_up, A.cols, X.bufcols, flags, A.block_sums, nb, n,
-                                                              d_n, S.mig_cap, S.d_status + 1);
+                                                              d_n, S.mig_cap, S.d_status + 1, cnt, (int *)X.send_dn, (int *)X.send_up);
             LAUNCH_CHECK();
             s->prof_end();
             s->prof_begin("mig:xfer");
