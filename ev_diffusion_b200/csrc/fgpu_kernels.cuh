@@ -595,7 +595,7 @@ __device__ __forceinline__ void push_bytes(const char *__restrict__ src, char *_
 __global__ void __launch_bounds__(256)
 k_push(const char *__restrict__ send_lo, const char *__restrict__ send_hi, char *__restrict__ peer_lo, char *__restrict__ peer_hi,
        const PushLayout L, unsigned int *done_counter, int *peer_flag_lo, int *peer_flag_hi, const int *my_flag_a,
-       const int *my_flag_b, int seq, int *status) {
+       const int *my_flag_b, int *seq_counter, int *status) {
     const char *src = blockIdx.y ? send_hi : send_lo;
     char *dst = blockIdx.y ? peer_hi : peer_lo;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
@@ -608,6 +608,10 @@ k_push(const char *__restrict__ send_lo, const char *__restrict__ send_hi, char 
         const unsigned int t = atomicAdd(done_counter, 1u);
         if (t == gridDim.x * gridDim.y - 1) {
             *done_counter = 0;
+            /* the exchange number lives on the device (one counter per exchange stream, touched by this
+             * thread only), so a captured CUDA graph of the iteration can be replayed */
+            const int seq = *seq_counter + 1;
+            *seq_counter = seq;
             __threadfence_system();
             st_flag_sys(peer_flag_lo, seq);
             st_flag_sys(peer_flag_hi, seq);

@@ -143,6 +143,7 @@ struct SlabRT {
     std::vector<size_t> msg_off, agent_off;      /* offset of the first of the 4 buffers (lo0, lo1, hi0, hi1) */
     std::vector<int> msg_seq, agent_seq;         /* exchange sequence numbers */
     unsigned int *d_done = nullptr;              /* last-block counters */
+    int *d_seq = nullptr;                        /* exchange numbers on the device (same slots as d_done) */
     bool async = false;
     static const int RING = 4;
     cudaEvent_t ring_ev[RING] = {nullptr, nullptr, nullptr, nullptr};
@@ -150,6 +151,7 @@ struct SlabRT {
     int *h_ring = nullptr;                        /* pinned: RING x RING_STRIDE ints (8 status + counts) */
     static const int RING_STRIDE = 64;
     long long migrations = 0;
+    bool graph_bounds = false;    /* graph replay: host-side populations are pinned to the buffer capacity until settled */
     std::vector<int> exact;       /* last exact populations seen (per migrating state list) */
     long long exact_mig = 0;      /* ... as of this migration number */
 };
@@ -187,6 +189,23 @@ struct fgpu_sim {
     std::vector<int> graph_counts; /* counts baked into the graph */
     long long graph_launches = 0;
     bool capturing = false;
+    /* slab mode: captured iterations keyed by the host-side configuration they start from (list pointers
+     * alternate between two buffers from one iteration to the next, so do the receive-buffer parities) */
+    struct IterationGraph {
+        cudaGraphExec_t exec = nullptr;
+        long long launches = 0;
+        /* host state after the iteration: absolute values ... */
+        std::vector<char *> agent_ptrs; /* per agent: work, swap, state[0..] */
+        std::vector<int> agent_h_count;
+        std::vector<int> msg_ints;      /* per message: h_count, producers, sorted_in, built */
+        std::vector<const char *> msg_producer;
+        std::vector<const int *> msg_d_count;
+        bool dirty = false;
+        /* ... and increments of the monotonic counters */
+        long long d_migrations = 0, d_halo_bytes = 0, d_mig_bytes = 0;
+        std::vector<int> d_msg_seq, d_agent_seq;
+    };
+    std::map<std::vector<unsigned long long>, IterationGraph> slab_graphs;
     /* profiling */
     bool profiling = false;
     std::vector<ProfEntry> prof;
@@ -464,6 +483,9 @@ static void invalidate_graph(fgpu_sim *s) {
         cudaGraphExecDestroy(s->graph);
         s->graph = nullptr;
     }
+    for (auto &kv : s->slab_graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    s->slab_graphs.clear();
 }
 
 static int upload_columns(fgpu_sim *s, int agent, int state, int offset, int count, const void *const *columns) {
@@ -1081,6 +1103,8 @@ static void slab_release(fgpu_sim *s) {
     S.peer_lo = S.peer_hi = nullptr;
     if (S.xbuf) cudaFree(S.xbuf);
     if (S.d_done) cudaFree(S.d_done);
+    if (S.d_seq) cudaFree(S.d_seq);
+    S.d_seq = nullptr;
     S.xbuf = nullptr;
     S.d_done = nullptr;
     if (S.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(S.comm);
@@ -1219,6 +1243,8 @@ extern "C" int fgpu_sim_slab_init(fgpu_sim *s, int rank, int world, const void *
     S.agent_seq.assign(m->nagents, 0);
     CU(cudaMalloc(&S.d_done, sizeof(unsigned int) * 64));
     CU(cudaMemset(S.d_done, 0, sizeof(unsigned int) * 64));
+    CU(cudaMalloc(&S.d_seq, sizeof(int) * 64));
+    CU(cudaMemset(S.d_seq, 0, sizeof(int) * 64));
     if (s->opt_slab_p2p) {
         size_t off = 4096; /* flags */
         auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -1331,8 +1357,8 @@ static int slab_exchange_halo(fgpu_sim *s, int mi) {
                                                             S.peer_lo + S.msg_off[mi] + (2 + par) * A4,
                                                             S.peer_hi + S.msg_off[mi] + (0 + par) * A4, PLY, S.d_done + mi,
                                                             (int *)(S.peer_lo + 16 * mi) + 1, (int *)(S.peer_hi + 16 * mi) + 0,
-                                                            (const int *)(S.xbuf + 16 * mi), (const int *)(S.xbuf + 16 * mi) + 1, seq,
-                                                            S.d_status + 3);
+                                                            (const int *)(S.xbuf + 16 * mi), (const int *)(S.xbuf + 16 * mi) + 1,
+                                                            S.d_seq + mi, S.d_status + 3);
         LAUNCH_CHECK();
     } else {
         NC(g_nccl.GroupStart());
@@ -1377,6 +1403,16 @@ static void slab_mark_exact(fgpu_sim *s) {
     S.exact_mig = S.migrations;
 }
 
+static int slab_check_status(const SlabRT &S, const int *r) {
+    if (r[0] == 1 || r[1] || r[2])
+        return set_err(FGPU_ERR_OVERFLOW, "slab exchange: fixed-capacity buffer overflow (halo %d, migrants %d, status %d/%d/%d)",
+                       S.halo_cap, S.mig_cap, r[0], r[1], r[2]);
+    if (r[0] == 2) return set_err(FGPU_ERR_COMM, "slab exchange: an agent moved further than one slab in one step");
+    if (r[3]) return set_err(FGPU_ERR_COMM, "slab exchange: timed out waiting for a neighbour's data (peer-memory transport)");
+    if (r[4]) return set_err(FGPU_ERR_MODEL, "slab mode: a message was output outside the planes its rank owns (messages must be emitted at the agent's position)");
+    return FGPU_OK;
+}
+
 /* Collects finished read-backs of the asynchronous mode: newest exact populations + error flags.
  * `wait` blocks until everything enqueued so far has landed. */
 static int slab_poll(fgpu_sim *s, bool wait) {
@@ -1390,12 +1426,8 @@ static int slab_poll(fgpu_sim *s, bool wait) {
         if (wait) CU(cudaEventSynchronize(S.ring_ev[slot]));
         else if (cudaEventQuery(S.ring_ev[slot]) != cudaSuccess) continue;
         const int *r = S.h_ring + slot * SlabRT::RING_STRIDE;
-        if (r[0] == 1 || r[1] || r[2])
-            return set_err(FGPU_ERR_OVERFLOW, "slab exchange: fixed-capacity buffer overflow (halo %d, migrants %d, status %d/%d/%d)",
-                           S.halo_cap, S.mig_cap, r[0], r[1], r[2]);
-        if (r[0] == 2) return set_err(FGPU_ERR_COMM, "slab exchange: an agent moved further than one slab in one step");
-        if (r[3]) return set_err(FGPU_ERR_COMM, "slab exchange: timed out waiting for a neighbour's data (peer-memory transport)");
-        if (r[4]) return set_err(FGPU_ERR_MODEL, "slab mode: a message was output outside the planes its rank owns (messages must be emitted at the agent's position)");
+        int rc = slab_check_status(S, r);
+        if (rc) return rc;
         if (mig >= S.exact_mig) {
             S.exact.assign(r + 8, r + SlabRT::RING_STRIDE);
             S.exact_mig = mig + 1;
@@ -1427,7 +1459,9 @@ static int slab_migrate(fgpu_sim *s) {
     const fgpu_model *m = s->model;
     const int ring = (int)(S.migrations % SlabRT::RING);
     int *hdst = S.async ? S.h_ring + ring * SlabRT::RING_STRIDE : S.h_pinned;
-    if (S.async && S.ring_mig[ring] >= 0) CU(cudaEventSynchronize(S.ring_ev[ring])); /* RING migrations old: long done */
+    /* a captured iteration carries no read-back: populations and status are read when the stream is settled */
+    const bool ringed = S.async && !s->capturing && !S.graph_bounds;
+    if (ringed && S.ring_mig[ring] >= 0) CU(cudaEventSynchronize(S.ring_ev[ring])); /* RING migrations old: long done */
     int slot = 0;
     for (int a = 0; a < m->nagents; ++a) {
         AgentRT &A = s->agents[a];
@@ -1472,7 +1506,8 @@ static int slab_migrate(fgpu_sim *s) {
                                                                     (int *)(S.peer_lo + 2048 + 16 * a) + 1,
                                                                     (int *)(S.peer_hi + 2048 + 16 * a) + 0,
                                                                     (const int *)(S.xbuf + 2048 + 16 * a),
-                                                                    (const int *)(S.xbuf + 2048 + 16 * a) + 1, seq, S.d_status + 3);
+                                                                    (const int *)(S.xbuf + 2048 + 16 * a) + 1, S.d_seq + 32 + a,
+                                                                    S.d_status + 3);
                 LAUNCH_CHECK();
             } else {
                 NC(g_nccl.GroupStart());
@@ -1489,13 +1524,17 @@ static int slab_migrate(fgpu_sim *s) {
                                                                               A.d_state_count + st, A.d->buffer_size, S.d_status + 2);
             LAUNCH_CHECK();
             s->prof_end();
-            CU(cudaMemcpyAsync(hdst + 8 + slot, A.d_state_count + st, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+            if (ringed || !S.async) CU(cudaMemcpyAsync(hdst + 8 + slot, A.d_state_count + st, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
             std::swap(A.state[st], A.swap);
             s->touch(A.state[st]);
         }
     }
-    CU(cudaMemcpyAsync(hdst, S.d_status, sizeof(int) * 8, cudaMemcpyDeviceToHost, s->stream));
     S.dirty = false;
+    if (S.async && !ringed) {
+        S.migrations++;
+        return FGPU_OK;
+    }
+    CU(cudaMemcpyAsync(hdst, S.d_status, sizeof(int) * 8, cudaMemcpyDeviceToHost, s->stream));
     if (S.async) {
         CU(cudaEventRecord(S.ring_ev[ring], s->stream));
         S.ring_mig[ring] = S.migrations;
@@ -1504,12 +1543,10 @@ static int slab_migrate(fgpu_sim *s) {
     }
     S.migrations++;
     CU(cudaStreamSynchronize(s->stream));
-    if (hdst[0] == 1 || hdst[1] || hdst[2])
-        return set_err(FGPU_ERR_OVERFLOW, "slab exchange: fixed-capacity buffer overflow (halo %d, migrants %d, status %d/%d/%d)",
-                       S.halo_cap, S.mig_cap, hdst[0], hdst[1], hdst[2]);
-    if (hdst[0] == 2) return set_err(FGPU_ERR_COMM, "slab exchange: an agent moved further than one slab in one step");
-    if (hdst[3]) return set_err(FGPU_ERR_COMM, "slab exchange: timed out waiting for a neighbour's data (peer-memory transport)");
-    if (hdst[4]) return set_err(FGPU_ERR_MODEL, "slab mode: a message was output outside the planes its rank owns (messages must be emitted at the agent's position)");
+    {
+        int rc = slab_check_status(S, hdst);
+        if (rc) return rc;
+    }
     slot = 0;
     for (int a = 0; a < m->nagents; ++a) {
         if (S.agents[a].axis_var < 0) continue;
@@ -1526,10 +1563,21 @@ static int slab_migrate(fgpu_sim *s) {
 /* After the stream has drained: make the host-side populations exact again (asynchronous slab mode). */
 static int slab_settle(fgpu_sim *s) {
     if (!s->slab.on || !s->slab.async) return FGPU_OK;
-    int rc = slab_poll(s, true);
+    int rc = s->slab.graph_bounds ? FGPU_OK : slab_poll(s, true);
     if (rc) return rc;
-    for (AgentRT &A : s->agents)
+    CU(cudaStreamSynchronize(s->stream));
+    int status[8];
+    CU(cudaMemcpy(status, s->slab.d_status, sizeof(status), cudaMemcpyDeviceToHost));
+    rc = slab_check_status(s->slab, status);
+    if (rc) return rc;
+    for (size_t a = 0; a < s->agents.size(); ++a) {
+        AgentRT &A = s->agents[a];
         CU(cudaMemcpy(A.h_state_count.data(), A.d_state_count, sizeof(int) * (size_t)A.d->nstates, cudaMemcpyDeviceToHost));
+        for (int st = 0; st < A.d->nstates; ++st)
+            if (A.h_state_count[st] > A.d->buffer_size)
+                return set_err(FGPU_ERR_OVERFLOW, "slab migration: %d agents exceed the buffer of %s", A.h_state_count[st], A.d->name);
+    }
+    s->slab.graph_bounds = false;
     slab_mark_exact(s);
     return FGPU_OK;
 }
@@ -1821,12 +1869,141 @@ static std::vector<int> current_counts(fgpu_sim *s) {
     return c;
 }
 
+/* ---- slab mode: replay of captured iterations ------------------------------------------------------
+ * With device-side populations, device-side exchange numbers and peer-memory transport, an iteration of
+ * a static model in slab mode is a fixed sequence of launches -- except that migration swaps each state
+ * list with its swap buffer and the receive buffers alternate, so consecutive iterations start from
+ * (two to four) different host-side configurations.  Each configuration gets its own captured graph; the
+ * host bookkeeping an iteration performs (pointer swaps, counters) is recorded at capture and re-applied at
+ * replay.  Launch grids are sized for the buffer capacity (kernels read the exact populations on the
+ * device), and populations / error flags are read when the stream is settled. */
+static std::vector<unsigned long long> slab_graph_key(fgpu_sim *s) {
+    std::vector<unsigned long long> k;
+    for (AgentRT &A : s->agents) {
+        k.push_back((unsigned long long)(uintptr_t)A.work);
+        k.push_back((unsigned long long)(uintptr_t)A.swap);
+        for (char *p : A.state) k.push_back((unsigned long long)(uintptr_t)p);
+    }
+    for (int v : s->slab.msg_seq) k.push_back((unsigned long long)(v & 1));
+    for (int v : s->slab.agent_seq) k.push_back((unsigned long long)(v & 1));
+    k.push_back(s->slab.dirty ? 1ull : 0ull);
+    k.push_back((unsigned long long)s->opt_order);
+    k.push_back((unsigned long long)s->opt_radix_bits);
+    return k;
+}
+
+static void slab_graph_record_after(fgpu_sim *s, fgpu_sim::IterationGraph &G) {
+    G.agent_ptrs.clear();
+    G.agent_h_count.clear();
+    for (AgentRT &A : s->agents) {
+        G.agent_ptrs.push_back(A.work);
+        G.agent_ptrs.push_back(A.swap);
+        for (char *p : A.state) G.agent_ptrs.push_back(p);
+        G.agent_h_count.push_back(A.h_count);
+    }
+    G.msg_ints.clear();
+    G.msg_producer.clear();
+    G.msg_d_count.clear();
+    for (MsgRT &M : s->msgs) {
+        G.msg_ints.push_back(M.h_count);
+        G.msg_ints.push_back(M.producers);
+        G.msg_ints.push_back(M.sorted_in);
+        G.msg_ints.push_back(M.built ? 1 : 0);
+        G.msg_producer.push_back(M.producer_buf);
+        G.msg_d_count.push_back(M.d_count);
+    }
+    G.dirty = s->slab.dirty;
+}
+
+static void slab_graph_apply_after(fgpu_sim *s, const fgpu_sim::IterationGraph &G) {
+    size_t k = 0;
+    for (size_t a = 0; a < s->agents.size(); ++a) {
+        AgentRT &A = s->agents[a];
+        A.work = G.agent_ptrs[k++];
+        A.swap = G.agent_ptrs[k++];
+        for (char *&p : A.state) p = G.agent_ptrs[k++];
+        A.h_count = G.agent_h_count[a];
+        /* list contents changed: any producer/consumer pairing recorded before the replay is void */
+        s->touch(A.work);
+        for (char *p : A.state) s->touch(p);
+    }
+    for (size_t m = 0; m < s->msgs.size(); ++m) {
+        MsgRT &M = s->msgs[m];
+        M.h_count = G.msg_ints[4 * m + 0];
+        M.producers = G.msg_ints[4 * m + 1];
+        M.sorted_in = G.msg_ints[4 * m + 2];
+        M.built = G.msg_ints[4 * m + 3] != 0;
+        M.producer_buf = G.msg_producer[m];
+        M.producer_epoch = M.producer_buf ? s->epoch_of(M.producer_buf) : 0;
+        M.d_count = G.msg_d_count[m];
+    }
+    SlabRT &S = s->slab;
+    S.dirty = G.dirty;
+    S.migrations += G.d_migrations;
+    S.halo_bytes += G.d_halo_bytes;
+    S.mig_bytes += G.d_mig_bytes;
+    for (size_t i = 0; i < S.msg_seq.size(); ++i) S.msg_seq[i] += G.d_msg_seq[i];
+    for (size_t i = 0; i < S.agent_seq.size(); ++i) S.agent_seq[i] += G.d_agent_seq[i];
+    s->iteration++;
+    s->launches += G.launches;
+}
+
+static int slab_graph_step(fgpu_sim *s, int n) {
+    SlabRT &S = s->slab;
+    if (!S.graph_bounds) {
+        /* grids for the capacity; the exact populations are on the device (d_state_count) */
+        for (size_t a = 0; a < s->agents.size(); ++a) {
+            if (S.agents[a].axis_var < 0) continue;
+            for (int &c : s->agents[a].h_state_count) c = s->agents[a].d->buffer_size;
+        }
+        S.graph_bounds = true;
+    }
+    for (int i = 0; i < n; ++i) {
+        const std::vector<unsigned long long> key = slab_graph_key(s);
+        auto it = s->slab_graphs.find(key);
+        if (it != s->slab_graphs.end()) {
+            CU(cudaGraphLaunch(it->second.exec, s->stream));
+            slab_graph_apply_after(s, it->second);
+            continue;
+        }
+        fgpu_sim::IterationGraph G;
+        const long long launches0 = s->launches, mig0 = S.migrations, hb0 = S.halo_bytes, mb0 = S.mig_bytes;
+        const std::vector<int> ms0 = S.msg_seq, as0 = S.agent_seq;
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        s->capturing = true;
+        int rc = single_iteration(s); /* performs the host bookkeeping of the iteration; the work is only recorded */
+        s->capturing = false;
+        cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+        if (rc) {
+            if (g) cudaGraphDestroy(g);
+            return rc;
+        }
+        if (e != cudaSuccess) return set_err(FGPU_ERR_CUDA, "cudaStreamEndCapture -> %s", cudaGetErrorString(e));
+        CU(cudaGraphInstantiate(&G.exec, g, 0));
+        CU(cudaGraphDestroy(g));
+        G.launches = s->launches - launches0;
+        G.d_migrations = S.migrations - mig0;
+        G.d_halo_bytes = S.halo_bytes - hb0;
+        G.d_mig_bytes = S.mig_bytes - mb0;
+        for (size_t k = 0; k < ms0.size(); ++k) G.d_msg_seq.push_back(S.msg_seq[k] - ms0[k]);
+        for (size_t k = 0; k < as0.size(); ++k) G.d_agent_seq.push_back(S.agent_seq[k] - as0[k]);
+        slab_graph_record_after(s, G);
+        CU(cudaGraphLaunch(G.exec, s->stream)); /* the host state is already the one after this iteration */
+        s->slab_graphs.emplace(key, std::move(G));
+    }
+    return FGPU_OK;
+}
+
 static int step_async(fgpu_sim *s, int n) {
     if (n <= 0) return FGPU_OK;
     CU(cudaSetDevice(s->device));
     const bool use_graph = s->is_static && s->opt_graph && !s->profiling;
     CU(cudaEventRecord(s->ev0, s->stream));
-    if (use_graph) {
+    if (s->slab.on && s->slab.async && s->slab.p2p && s->opt_graph && !s->profiling && s->model->nstep_functions == 0) {
+        int rc = slab_graph_step(s, n);
+        if (rc) return rc;
+    } else if (use_graph) {
         if (!s->graph || s->graph_counts != current_counts(s)) {
             invalidate_graph(s);
             cudaGraph_t g = nullptr;

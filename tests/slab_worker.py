@@ -62,6 +62,9 @@ def main():
     cfg = W.BROWNIAN["c2_s2"]
     assert cfg.world == world
     sim = Simulation(build.model_path(cfg.name + "_exact"), device=local)
+    for kv in filter(None, os.environ.get("SLAB_OPTIONS", "").split(",")):   # e.g. "graph=0,slab_p2p=0"
+        k, v = kv.split("=")
+        sim.set_option(k, int(v))
     uid = torch.zeros(128, dtype=torch.uint8, device=device)
     if rank == 0:
         uid = torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8).to(device)
@@ -94,6 +97,14 @@ def main():
             pl = slabs.make_plan(m.dims, m.min_bounds, m.max_bounds, m.is_2d, r, world)
             assert (slabs.owner_of(after["z"][owner == r], pl) == r).all(), f"it {it}: misplaced agent on rank {r}"
     moved = int((after["z"] != state["z"][ids_a]).sum())
+    # a few more iterations in one call (replayed graphs in the default mode), then a digest of the global state in
+    # rank order: every transport / scheduling mode must produce the same bits
+    sim.step(7)
+    final, owner = gather_cols(sim, ("id", "x", "y", "z", "nbr"), device)
+    import hashlib
+    digest = hashlib.sha1(b"".join(final[k].astype(np.float64).tobytes() for k in ("id", "x", "y", "z", "nbr"))).hexdigest()
+    if rank == 0:
+        print(f"SLAB_DIGEST {digest} transport={'p2p' if sim.slab_info().get('p2p') else 'nccl'}")
     if rank == 0:
         print(f"SLAB_OK world={world} iters={iters} agents={cfg.n} mismatches={bad} moved={moved} "
               f"per_rank={[int((owner == r).sum()) for r in range(world)]}")

@@ -18,10 +18,27 @@ def _ngpus():
         return 0
 
 
-@pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs (run under `gpurun --gpus 2`)")
-def test_two_slabs_neighbour_counts_and_migration():
+def _run_worker(options, port):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29611", os.path.join(ROOT, "tests", "slab_worker.py")]
-    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+           "--master-port", str(port), os.path.join(ROOT, "tests", "slab_worker.py")]
+    env = dict(os.environ, SLAB_OPTIONS=options)
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
     assert proc.returncode == 0, proc.stdout[-4000:]
     assert "SLAB_OK" in proc.stdout and "mismatches=0" in proc.stdout, proc.stdout[-2000:]
+    line = [l for l in proc.stdout.splitlines() if l.startswith("SLAB_DIGEST")][0].split()
+    return line[1], line[2]
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs (run under `gpurun --gpus 2`)")
+def test_two_slabs_neighbour_counts_and_migration():
+    """Default mode: peer-memory transport, device-side populations, replayed iteration graphs.  The worker
+    checks every iteration against a brute-force neighbour count over the global positions."""
+    digest, transport = _run_worker("", 29611)
+    assert transport == "transport=p2p"
+    # Same run with each mechanism switched off in turn: stream-mode launches instead of graph replay, NCCL
+    # send/recv instead of peer stores, host round trip per migration instead of device-side populations.
+    # List order, rand48 streams and arithmetic are the same, so the final global state must be bit-identical.
+    for k, options in enumerate(("graph=0", "slab_p2p=0", "slab_async=0")):
+        d, t = _run_worker(options, 29612 + k)
+        assert d == digest, (options, d, digest)
+        assert t == ("transport=nccl" if options == "slab_p2p=0" else "transport=p2p")
