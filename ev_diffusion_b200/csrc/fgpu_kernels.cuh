@@ -592,16 +592,10 @@ __device__ __forceinline__ void push_bytes(const char *__restrict__ src, char *_
     for (size_t i = w0 + tid; i < w1; i += nthreads) ((unsigned int *)dst)[i] = ((const unsigned int *)src)[i];
 }
 
-__global__ void __launch_bounds__(256)
-k_push(const char *__restrict__ send_lo, const char *__restrict__ send_hi, char *__restrict__ peer_lo, char *__restrict__ peer_hi,
-       const PushLayout L, unsigned int *done_counter, int *peer_flag_lo, int *peer_flag_hi, const int *my_flag_a,
-       const int *my_flag_b, int *seq_counter, int *status) {
-    const char *src = blockIdx.y ? send_hi : send_lo;
-    char *dst = blockIdx.y ? peer_hi : peer_lo;
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-    const int cnt = ((const int *)src)[0];
-    push_bytes(src, dst, (size_t)L.fixed_bytes, tid, nthreads);
-    for (int k = 0; k < L.nseg; ++k) push_bytes(src + L.off[k], dst + L.off[k], (size_t)cnt * L.elem[k], tid, nthreads);
+/* End of a push kernel: every block fences its peer stores; the last block to arrive publishes the
+ * exchange number in both neighbours' memory and waits (bounded) until theirs have arrived here. */
+__device__ __forceinline__ void push_signal_and_wait(unsigned int *done_counter, int *peer_flag_lo, int *peer_flag_hi, const int *my_flag_a,
+                                                     const int *my_flag_b, int *seq_counter, int *status) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();
@@ -628,6 +622,19 @@ k_push(const char *__restrict__ send_lo, const char *__restrict__ send_hi, char 
     }
 }
 
+__global__ void __launch_bounds__(256)
+k_push(const char *__restrict__ send_lo, const char *__restrict__ send_hi, char *__restrict__ peer_lo, char *__restrict__ peer_hi,
+       const PushLayout L, unsigned int *done_counter, int *peer_flag_lo, int *peer_flag_hi, const int *my_flag_a,
+       const int *my_flag_b, int *seq_counter, int *status) {
+    const char *src = blockIdx.y ? send_hi : send_lo;
+    char *dst = blockIdx.y ? peer_hi : peer_lo;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    const int cnt = ((const int *)src)[0];
+    push_bytes(src, dst, (size_t)L.fixed_bytes, tid, nthreads);
+    for (int k = 0; k < L.nseg; ++k) push_bytes(src + L.off[k], dst + L.off[k], (size_t)cnt * L.elem[k], tid, nthreads);
+    push_signal_and_wait(done_counter, peer_flag_lo, peer_flag_hi, my_flag_a, my_flag_b, seq_counter, status);
+}
+
 /* plane -> send buffer: header | (plane_cells + 1) cell_start entries rebased to 0 | records */
 template <int NQ>
 __global__ void __launch_bounds__(256)
@@ -649,6 +656,28 @@ k_pack_planes(const uint4 *__restrict__ sorted_local, const unsigned int *__rest
     uint4 *recs = reinterpret_cast<uint4 *>(out + XHDR + ((plane_cells + 1 + 3) & ~3));
     const int quads = min(cnt, cap) * NQ;
     for (int i = tid; i < quads; i += stride) recs[i] = sorted_local[(size_t)lo * NQ + i];
+}
+
+/* Peer-memory transport of the two boundary planes in ONE kernel: what k_pack_planes writes into a local send
+ * buffer goes straight into the neighbours' receive buffers (same layout), followed by the signal/wait of
+ * k_push.  y = 0: my first owned plane -> the lower neighbour's HIGH halo; y = 1: my last -> the upper's LOW. */
+template <int NQ>
+__global__ void __launch_bounds__(256)
+k_push_planes(const uint4 *__restrict__ sorted_combined, const unsigned int *__restrict__ cell_start, int first_cell_lo, int first_cell_hi,
+              int plane_cells, int cap, int *__restrict__ peer_lo, int *__restrict__ peer_hi, unsigned int *done_counter,
+              int *peer_flag_lo, int *peer_flag_hi, const int *my_flag_a, const int *my_flag_b, int *seq_counter, int *status) {
+    const int first_cell = blockIdx.y ? first_cell_hi : first_cell_lo;
+    int *out = blockIdx.y ? peer_hi : peer_lo;
+    const int lo = (int)cell_start[first_cell], hi = (int)cell_start[first_cell + plane_cells];
+    const int cnt = hi - lo;
+    const int stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid == 0) *reinterpret_cast<int4 *>(out) = make_int4(min(cnt, cap), cnt > cap, 0, 0);
+    int *cs = out + XHDR;
+    for (int i = tid; i <= plane_cells; i += stride) cs[i] = min((int)cell_start[first_cell + i] - lo, cap);
+    uint4 *recs = reinterpret_cast<uint4 *>(out + XHDR + ((plane_cells + 1 + 3) & ~3));
+    const int quads = min(cnt, cap) * NQ;
+    for (int i = tid; i < quads; i += stride) recs[i] = sorted_combined[(size_t)lo * NQ + i];
+    push_signal_and_wait(done_counter, peer_flag_lo, peer_flag_hi, my_flag_a, my_flag_b, seq_counter, status);
 }
 
 /* Merge: shift the owned planes' cell_start by the position of the local block

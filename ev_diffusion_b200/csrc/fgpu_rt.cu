@@ -1330,37 +1330,41 @@ static int slab_exchange_halo(fgpu_sim *s, int mi) {
     const size_t A4 = (X.bytes + 255) & ~(size_t)255;
     const int seq = ++S.msg_seq[mi], par = seq & 1;
     const int *in_lo = X.recv_lo, *in_hi = X.recv_hi;  /* where the neighbours' planes arrive */
-    switch (Q) {
+    if (Q < 1 || Q > 8) return set_err(FGPU_ERR_MODEL, "record of %d quads unsupported", Q);
+    if (S.p2p) {
+        /* pack + push fused: my low plane is the lower neighbour's HIGH halo and vice versa */
+        in_lo = (const int *)(S.xbuf + S.msg_off[mi] + (0 + par) * A4);
+        in_hi = (const int *)(S.xbuf + S.msg_off[mi] + (2 + par) * A4);
+        const int gp = std::min(PUSH_BLOCKS * 2, g);
+        switch (Q) {
+#define PUSHP_CASE(QQ)                                                                                                              \
+    case QQ:                                                                                                                        \
+        k_push_planes<QQ><<<dim3(gp, 2), 256, 0, s->stream>>>(local, M.cell_start, S.p0 * PL, (S.p1 - 1) * PL, PL, S.halo_cap,     \
+                                                              (int *)(S.peer_lo + S.msg_off[mi] + (2 + par) * A4),                 \
+                                                              (int *)(S.peer_hi + S.msg_off[mi] + (0 + par) * A4), S.d_done + mi,  \
+                                                              (int *)(S.peer_lo + 16 * mi) + 1, (int *)(S.peer_hi + 16 * mi) + 0,  \
+                                                              (const int *)(S.xbuf + 16 * mi), (const int *)(S.xbuf + 16 * mi) + 1, \
+                                                              S.d_seq + mi, S.d_status + 3);                                        \
+        break;
+            PUSHP_CASE(1) PUSHP_CASE(2) PUSHP_CASE(3) PUSHP_CASE(4) PUSHP_CASE(5) PUSHP_CASE(6) PUSHP_CASE(7) PUSHP_CASE(8)
+#undef PUSHP_CASE
+        }
+        LAUNCH_CHECK();
+        s->prof_end();
+        s->prof_begin(std::string("halo_xfer:") + M.d->name);
+    } else {
+        switch (Q) {
 #define PACK_CASE(QQ)                                                                                                       \
     case QQ:                                                                                                                \
         k_pack_planes<QQ><<<dim3(g, 2), 256, 0, s->stream>>>(local, M.cell_start, S.p0 * PL, (S.p1 - 1) * PL, PL, S.halo_cap, \
                                                              X.send_lo, X.send_hi);                                         \
         break;
-        PACK_CASE(1) PACK_CASE(2) PACK_CASE(3) PACK_CASE(4) PACK_CASE(5) PACK_CASE(6) PACK_CASE(7) PACK_CASE(8)
+            PACK_CASE(1) PACK_CASE(2) PACK_CASE(3) PACK_CASE(4) PACK_CASE(5) PACK_CASE(6) PACK_CASE(7) PACK_CASE(8)
 #undef PACK_CASE
-        default:
-            return set_err(FGPU_ERR_MODEL, "record of %d quads unsupported", Q);
-    }
-    LAUNCH_CHECK();
-    s->prof_end();
-    s->prof_begin(std::string("halo_xfer:") + M.d->name);
-    if (S.p2p) {
-        /* my low plane is the lower neighbour's HIGH halo and vice versa */
-        PushLayout PLY;
-        PLY.fixed_bytes = (int)(sizeof(int) * (XHDR + ((PL + 1 + 3) & ~3)));
-        PLY.nseg = 1;
-        PLY.elem[0] = Q * 16;
-        PLY.off[0] = (unsigned long long)PLY.fixed_bytes;
-        in_lo = (const int *)(S.xbuf + S.msg_off[mi] + (0 + par) * A4);
-        in_hi = (const int *)(S.xbuf + S.msg_off[mi] + (2 + par) * A4);
-        k_push<<<dim3(PUSH_BLOCKS, 2), 256, 0, s->stream>>>((const char *)X.send_lo, (const char *)X.send_hi,
-                                                            S.peer_lo + S.msg_off[mi] + (2 + par) * A4,
-                                                            S.peer_hi + S.msg_off[mi] + (0 + par) * A4, PLY, S.d_done + mi,
-                                                            (int *)(S.peer_lo + 16 * mi) + 1, (int *)(S.peer_hi + 16 * mi) + 0,
-                                                            (const int *)(S.xbuf + 16 * mi), (const int *)(S.xbuf + 16 * mi) + 1,
-                                                            S.d_seq + mi, S.d_status + 3);
+        }
         LAUNCH_CHECK();
-    } else {
+        s->prof_end();
+        s->prof_begin(std::string("halo_xfer:") + M.d->name);
         NC(g_nccl.GroupStart());
         NC(g_nccl.Send(X.send_lo, X.bytes, NCCL_INT8, S.lo_rank, S.comm, s->stream));
         NC(g_nccl.Send(X.send_hi, X.bytes, NCCL_INT8, S.hi_rank, S.comm, s->stream));
