@@ -526,9 +526,8 @@ static int upload_columns(fgpu_sim *s, int agent, int state, int offset, int cou
     CU(cudaStreamSynchronize(s->stream));
     slab_mark_exact(s);
     s->touch(list);
-    /* a captured iteration depends on the list sizes, not on the values: new values of the same
-     * population keep it valid */
-    if (!same_count) invalidate_graph(s);
+    /* captured iterations stay valid: they depend on the list buffers, which an upload does not move, and --
+     * single-GPU graphs only -- on the list sizes, which step_async compares before every replay */
     return FGPU_OK;
 }
 
