@@ -62,9 +62,11 @@ BROWNIAN = {
     # tiny ragged case: count < bufferSize, few agents per tile, some empty cells
     "c2_tiny": BrownianConfig("Brownian_tiny", 4096, (16, 16, 16), 11),
     # weak scaling over z-slabs: 1M agents and 64 cell planes per GPU
-    "c2_w2": BrownianConfig("Brownian_w2", 2 << 20, (64, 64, 128), 42, buffer=1310720, world=2),
-    "c2_w4": BrownianConfig("Brownian_w4", 4 << 20, (64, 64, 256), 42, buffer=1310720, world=4),
-    "c2_w8": BrownianConfig("Brownian_w8", 8 << 20, (64, 64, 512), 42, buffer=1310720, world=8),
+    # weak-scaling variants: 1M agents and 64 cell planes per rank; per-rank buffers = population + 64K of
+    # headroom (replayed iterations launch for the buffer capacity, so slack costs empty blocks)
+    "c2_w2": BrownianConfig("Brownian_w2", 2 << 20, (64, 64, 128), 42, buffer=1114112, world=2),
+    "c2_w4": BrownianConfig("Brownian_w4", 4 << 20, (64, 64, 256), 42, buffer=1114112, world=4),
+    "c2_w8": BrownianConfig("Brownian_w8", 8 << 20, (64, 64, 512), 42, buffer=1114112, world=8),
     # small 2-slab parity case
     "c2_s2": BrownianConfig("Brownian_s2", 1 << 15, (16, 16, 32), 13, buffer=24576, world=2),
 }
