@@ -61,7 +61,7 @@ def peaks():
 class ClockSampler(threading.Thread):
     """SM clock / throttle reasons during the timed region (NVML)."""
 
-    def __init__(self, index=0, period=0.05):
+    def __init__(self, index=0, period=0.1):
         super().__init__(daemon=True)
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self.period, self.index, self._halt = period, index, threading.Event()
@@ -72,6 +72,14 @@ class ClockSampler(threading.Thread):
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            # first-call costs of the two queries are paid here, outside the timed region: an NVML query takes a
+            # driver lock and was seen to stall one timed iteration by ~2 ms now and then, so the thread samples
+            # sparsely (first sample 5 ms into the region, then every `period`)
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons"):
+                pynvml.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            else:
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
             self.ok = True
         except Exception:
             self.ok = False
@@ -82,6 +90,8 @@ class ClockSampler(threading.Thread):
         nv = self.nv
         names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
                  "hw_power_brake": 0x80, "sw_power_cap": 0x4}
+        if self._halt.wait(0.005):
+            return
         while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
@@ -92,7 +102,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(self.period)
+            self._halt.wait(self.period)
 
     def stop(self):
         self._halt.set()
@@ -235,12 +245,17 @@ def main():
     barrier()
     launches0 = sim.launch_count
     sampler = ClockSampler(local)
+    if os.environ.get("BENCH_NO_SAMPLER"):
+        sampler.ok = False
     sampler.start()
     ms_each = sim.step_timed(args.steps, FLUSH_BYTES)
     barrier()
     clocks = sampler.stop()
     launches = sim.launch_count - launches0
     total_ms = float(ms_each.sum())
+    if os.environ.get("BENCH_DEBUG_SPANS"):
+        q = np.percentile(ms_each, [0, 10, 50, 90, 99, 100])
+        print(f"rank {rank}: spans ms min/p10/p50/p90/p99/max = " + " ".join("%.3f" % v for v in q) + f" mean {ms_each.mean():.3f}", file=sys.stderr, flush=True)
     if dist is not None:
         import torch
         t = torch.tensor([total_ms], device="cuda")
@@ -324,7 +339,8 @@ def main():
                    "cells": list(cfg.dims),
                    "parallelism": "single GPU" if world == 1 else
                    f"{world} z-slabs of {cfg.dims[2] // world} cell planes, halo planes + migrating agents over NCCL send/recv",
-                   "l2": "flushed between timed iterations (256 MiB scratch rewrite, untimed)",
+                   "l2": "flushed between timed iterations (256 MiB scratch rewrite, untimed)" +
+                         ("; ranks re-aligned by an untimed neighbour flag exchange after each flush" if world > 1 else ""),
                    "options": args.option},
         "ms_per_step_warm_l2": warm_ms / args.steps,
         "value_warm_l2": n_global * args.steps / (warm_ms * 1e-3),

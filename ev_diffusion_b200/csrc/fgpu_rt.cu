@@ -1315,6 +1315,23 @@ extern "C" int fgpu_sim_slab_info(fgpu_sim *s, int *out8) {
     return FGPU_OK;
 }
 
+/* Flag-only exchange with both neighbours (peer-memory transport): the stream continues once they have reached
+ * the same point.  Used by the timed stepping to line the ranks up again after the untimed L2 flush, so that
+ * the jitter of the flush is not charged to the iteration that follows it. */
+static int slab_neighbour_barrier(fgpu_sim *s) {
+    SlabRT &S = s->slab;
+    if (!S.on || !S.p2p) return FGPU_OK;
+    PushLayout PLY;
+    PLY.fixed_bytes = 0;
+    PLY.nseg = 0;
+    const size_t flag_off = 4096 - 16; /* last slot of the flag page */
+    k_push<<<dim3(1, 2), 256, 0, s->stream>>>((const char *)S.d_status, (const char *)S.d_status, S.peer_lo, S.peer_hi, PLY, S.d_done + 63,
+                                              (int *)(S.peer_lo + flag_off) + 1, (int *)(S.peer_hi + flag_off) + 0,
+                                              (const int *)(S.xbuf + flag_off), (const int *)(S.xbuf + flag_off) + 1, S.d_seq + 63, S.d_status + 3);
+    LAUNCH_CHECK();
+    return FGPU_OK;
+}
+
 /* Halo exchange after a spatial message build: my two boundary planes go to the neighbours, theirs are
  * spliced around my local block (contiguous ranges of the SORTED list, so within-cell order is the owner's). */
 static int slab_exchange_halo(fgpu_sim *s, int mi) {
@@ -2087,6 +2104,8 @@ extern "C" int fgpu_sim_step_timed(fgpu_sim *s, int n, size_t flush_bytes, float
     clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int i = 0; i < n && rc == FGPU_OK; ++i) {
         if (flush_bytes) CU(cudaMemsetAsync(s->flush_buf, i & 0xff, flush_bytes, s->stream));
+        if (flush_bytes && s->slab.on) rc = slab_neighbour_barrier(s); /* untimed: ranks start the iteration together */
+        if (rc) break;
         CU(cudaEventRecord(ev[2 * i], s->stream));
         rc = step_async(s, 1);
         CU(cudaEventRecord(ev[2 * i + 1], s->stream));
