@@ -328,6 +328,9 @@ def main():
         t = torch.tensor([e2e_dt], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
+        b = torch.tensor([h2d, d2h], dtype=torch.int64, device="cuda")   # whole-job bytes: every rank moves its own slab
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        h2d, d2h = int(b[0].item()), int(b[1].item())
     e2e = {"value": n_global * e2e_steps / e2e_dt, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": e2e_steps}
 
