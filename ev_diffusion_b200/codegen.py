@@ -393,7 +393,51 @@ def _host_api_decls(model: Model) -> str:
                     if "vec" not in v.type:
                         out.append(f"{v.type} min_{a.name}_{s}_{v.name}_variable();")
                         out.append(f"{v.type} max_{a.name}_{s}_{v.name}_variable();")
+    # host-based agent creation (header.xslt:665-706)
+    for a in model.agents:
+        out.append(f"xmachine_memory_{a.name}* h_allocate_agent_{a.name}();")
+        out.append(f"void h_free_agent_{a.name}(xmachine_memory_{a.name}** agent);")
+        out.append(f"xmachine_memory_{a.name}** h_allocate_agent_{a.name}_array(unsigned int count);")
+        out.append(f"void h_free_agent_{a.name}_array(xmachine_memory_{a.name}*** agents, unsigned int count);")
+        for s in a.states:
+            out.append(f"void h_add_agent_{a.name}_{s}(xmachine_memory_{a.name}* agent);")
+            out.append(f"void h_add_agents_{a.name}_{s}(xmachine_memory_{a.name}** agents, unsigned int count);")
     return "\n".join(out)
+
+
+def _host_creation_defs(model: Model, add_call: str, count_call: str) -> List[str]:
+    """h_allocate_/h_free_/h_add_agent(s)_<A>_<S> (simulation.xslt:1192-1320): host structs with the XML default
+    values, unpacked AoS -> SoA columns and appended to the state list through
+    `add_call`(agent, state, count, const void* const* columns); `count_call`(agent, state) is the current
+    population for the reference's buffer-size guard (message + exit).  Agents with array variables get
+    the allocation helpers only (their h_add_ functions report the missing support)."""
+    out = []
+    for ai, a in enumerate(model.agents):
+        A = a.name
+        has_arrays = any(v.array_length for v in a.variables)
+        inits = "".join(f" agent->{v.name} = ({v.type}){v.default};" for v in a.variables if v.default is not None and not v.array_length)
+        arr_alloc = "".join(f" agent->{v.name} = ({v.type}*)calloc({v.array_length}, sizeof({v.type}));" for v in a.variables if v.array_length)
+        arr_free = "".join(f" free((*agent)->{v.name});" for v in a.variables if v.array_length)
+        out.append(f"xmachine_memory_{A}* h_allocate_agent_{A}(){{ xmachine_memory_{A}* agent = (xmachine_memory_{A}*)malloc(sizeof(xmachine_memory_{A})); "
+                   f"memset(agent, 0, sizeof(xmachine_memory_{A}));{inits}{arr_alloc} return agent; }}")
+        out.append(f"void h_free_agent_{A}(xmachine_memory_{A}** agent){{{arr_free} free(*agent); *agent = NULL; }}")
+        out.append(f"xmachine_memory_{A}** h_allocate_agent_{A}_array(unsigned int count){{ xmachine_memory_{A}** agents = "
+                   f"(xmachine_memory_{A}**)malloc(count * sizeof(xmachine_memory_{A}*)); for (unsigned int i = 0; i < count; i++) agents[i] = h_allocate_agent_{A}(); return agents; }}")
+        out.append(f"void h_free_agent_{A}_array(xmachine_memory_{A}*** agents, unsigned int count){{ for (unsigned int i = 0; i < count; i++) "
+                   f"h_free_agent_{A}(&((*agents)[i])); free(*agents); *agents = NULL; }}")
+        for si, st in enumerate(a.states):
+            if has_arrays:
+                body = (f'{{ (void)agents; (void)count; fprintf(stderr, "h_add_agents_{A}_{st}: agent array variables are not supported\\n"); exit(EXIT_FAILURE); }}')
+            else:
+                cols = "".join(f" std::vector<{v.type}> c_{v.name}(count); for (unsigned int i = 0; i < count; i++) c_{v.name}[i] = agents[i]->{v.name};"
+                               for v in a.variables)
+                ptrs = ", ".join(f"c_{v.name}.data()" for v in a.variables)
+                body = (f"{{ if (count == 0) return; if ({count_call}({ai}, {si}) + (int)count > xmachine_memory_{A}_MAX){{ "
+                        f'printf("Error: Buffer size of {A} agents in state {st} will be exceeded by h_add_agents_{A}_{st}\\n"); exit(EXIT_FAILURE); }}'
+                        f"{cols} const void* columns[] = {{{ptrs}}}; if ({add_call}({ai}, {si}, (int)count, columns) != 0) fgpu_die(); }}")
+            out.append(f"void h_add_agents_{A}_{st}(xmachine_memory_{A}** agents, unsigned int count){body}")
+            out.append(f"void h_add_agent_{A}_{st}(xmachine_memory_{A}* agent){{ h_add_agents_{A}_{st}(&agent, 1); }}")
+    return out
 
 
 def _reduction_defs(model: Model, call: str) -> List[str]:
@@ -673,6 +717,9 @@ void cleanup(){ fgpu_sim_run_exit_functions(fgpu_cur); fgpu_sim_destroy(fgpu_cur
                                f"if (fgpu_sim_read_agent_value(fgpu_cur, {ai}, {si}, {vi}, index, &t) != FGPU_OK) fgpu_die(); return t; }}")
     out.append("static int fgpu_reduce_cur(int a, int s, int v, int op, const void* cv, void* r){ return fgpu_sim_reduce_agent_var(fgpu_cur, a, s, v, op, cv, r); }")
     out += _reduction_defs(model, "fgpu_reduce_cur")
+    out.append("static int fgpu_add_cur(int a, int s, int n, const void* const* cols){ return fgpu_sim_add_agents(fgpu_cur, a, s, n, cols); }")
+    out.append("static int fgpu_count_cur(int a, int s){ return fgpu_sim_agent_count(fgpu_cur, a, s); }")
+    out += _host_creation_defs(model, "fgpu_add_cur", "fgpu_count_cur")
     return "\n".join(out) + "\n"
 
 
@@ -706,7 +753,7 @@ def emit_cuda_glue(model: Model, function_files: List[str], include_files: Optio
     actually compiled in their place (the loop-rewritten copies), default the scripts themselves."""
     sources = [open(p, "r", errors="replace").read() for p in function_files]
     out = ["/* generated by ev_diffusion_b200.codegen -- model plugin for sm_100a */",
-           "#include <cstddef>\n#include <cstring>\n#include <cstdio>\n#include <cmath>",
+           "#include <cstddef>\n#include <cstring>\n#include <cstdio>\n#include <cmath>\n#include <cstdlib>\n#include <vector>",
            '#include "header.h"',
            '#include "fgpu_model.h"']
     for p in (include_files or function_files):

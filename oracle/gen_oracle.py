@@ -397,6 +397,9 @@ template <int AGENT_TYPE> void add_{a.name}_agent(xmachine_memory_{a.name}_list*
         for si, st in enumerate(a.states):
             out.append(f"int get_agent_{a.name}_{st}_count(){{ return orc_sim_agent_count(orc_cur, {ai}, {si}); }}")
     out += codegen._reduction_defs(model, "orc_host_reduce")
+    out.append("static int orc_add_cur(int a, int s, int n, const void* const* cols){ return orc_sim_add_agents(orc_cur, a, s, n, cols); }")
+    out.append("static int orc_count_cur(int a, int s){ return orc_sim_agent_count(orc_cur, a, s); }")
+    out += codegen._host_creation_defs(model, "orc_add_cur", "orc_count_cur")
     out.append("const orc_message_hooks orc_hooks[] = {\n" + "\n".join(rows) + "\n    {0, 0, 0, nullptr, nullptr}\n};")
     return "\n".join(out) + "\n"
 

@@ -78,3 +78,37 @@ def test_analytics_step_function_runs_the_generated_names(capfd):
     assert "FLAME GPU Step function. Min circle position is (%f, %f, %f)" % (a["x"].min(), a["y"].min(), a["z"].min()) in out
     assert "FLAME GPU Step function. Max circle position is (%f, %f, %f)" % (a["x"].max(), a["y"].max(), a["z"].max()) in out
     sim.close()
+
+
+def test_host_agent_creation_from_init_and_step_functions():
+    """models/HostCreate: h_allocate_agent_<A>[_array], h_add_agent(s)_<A>_<S>, h_free_agent_<A>[_array]
+    (header.xslt:665-706) called from an init and a step function, XML default values, the buffer-size guard of
+    the step function, and max_<A>_<S>_<v>_variable() feeding back into the new agents -- bit for bit against
+    the oracle, which runs the same functions.c."""
+    from common import gen_oracle, OracleSimulation
+    xml = os.path.join(build.MODELS, "HostCreate", "src", "model", "XMLModelFile.xml")
+    p = build.model_path("HostCreate_exact")
+    if not os.path.exists(p):
+        p = build.build_model(xml, "HostCreate_exact", fmad=False)
+    so = gen_oracle.oracle_path("HostCreate")
+    if not os.path.exists(so):
+        so = gen_oracle.build_oracle(xml, "HostCreate")
+    gpu, orc = Simulation(p), OracleSimulation(so)
+    for s in (gpu, orc):
+        s.run_init_functions()
+    assert gpu.agent_count("Item", "default") == orc.agent_count("Item", "default") == 50
+    a = gpu.agents("Item")
+    assert np.all(a["y"] == np.float32(2.5)) and np.all(a["age"] == 7) and np.array_equal(a["id"], np.arange(50))
+    for it in range(1, 9):
+        gpu.step(1)
+        orc.step(1)
+        n = 50 + 3 * it
+        assert gpu.agent_count("Item", "default") == orc.agent_count("Item", "default") == n
+        a, b = gpu.agents("Item"), orc.agents("Item")
+        for k in a:
+            assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), (it, k)
+    # the newcomers of the last step: ids continue, x = oldest age + k, crowd = population before them
+    assert np.array_equal(a["id"][-3:], [71, 72, 73]) and np.array_equal(a["crowd"][-3:], [71, 71, 71])
+    assert np.array_equal(a["x"][-3:], np.float32([15, 16, 17]))
+    gpu.close()
+    orc.close()
