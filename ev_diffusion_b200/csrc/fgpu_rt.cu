@@ -20,6 +20,7 @@
  *     is the list that produced the messages (locality only, never semantics).
  */
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -178,6 +179,7 @@ struct fgpu_sim {
     unsigned long long epoch_counter = 1;
     /* options */
     int opt_order = 1;
+    int opt_nvtx = 0;
     int opt_graph = 1;
     int opt_radix_bits = 9;
     int opt_slab_async = 1;
@@ -232,7 +234,10 @@ struct fgpu_sim {
         }
         return ev_pool[ev_used++];
     }
+    /* Stage markers.  With option "nvtx" every stage is also an NVTX range on the host thread that enqueues it
+     * (PROFILE_SCOPED_RANGE of the reference, header.xslt:805-863): visible in Nsight Systems, free otherwise. */
     void prof_begin(const std::string &name) {
+        if (opt_nvtx) nvtxRangePushA(name.c_str());
         if (!profiling) return;
         ProfEntry e;
         e.name = name;
@@ -242,6 +247,7 @@ struct fgpu_sim {
         prof.push_back(e);
     }
     void prof_end() {
+        if (opt_nvtx) nvtxRangePop();
         if (!profiling) return;
         cudaEventRecord(prof.back().b, stream);
     }
@@ -2428,6 +2434,7 @@ extern "C" int fgpu_sim_reduce_agent_var(fgpu_sim *s, int agent, int state, int 
 extern "C" int fgpu_sim_set_option(fgpu_sim *s, const char *key, int value) {
     if (!s || !key) return set_err(FGPU_ERR_ARG, "bad argument");
     if (!strcmp(key, "order")) s->opt_order = value ? 1 : 0;
+    else if (!strcmp(key, "nvtx")) s->opt_nvtx = value ? 1 : 0;
     else if (!strcmp(key, "graph")) s->opt_graph = value ? 1 : 0;
     else if (!strcmp(key, "slab_p2p")) {
         if (s->slab.on) return set_err(FGPU_ERR_ARG, "slab_p2p must be set before fgpu_sim_slab_init");

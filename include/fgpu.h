@@ -146,7 +146,8 @@ long long fgpu_sim_launch_count(const fgpu_sim *sim);
  * simulation stream, like main.xslt:405-436). */
 float fgpu_sim_last_step_ms(const fgpu_sim *sim);
 /* Tuning knobs: "order" (0/1 cell-coherent processing of message consumers),
- * "graph" (0/1 CUDA-graph replay), "radix_bits" (4..11), "stage" (0/1). */
+ * "graph" (0/1 CUDA-graph replay), "radix_bits" (4..11), "nvtx" (0/1: every stage of an iteration
+ * is an NVTX range on the enqueueing thread, like PROFILE_SCOPED_RANGE of the reference), "slab_p2p", "slab_async". */
 int fgpu_sim_set_option(fgpu_sim *sim, const char *key, int value);
 /* Per-kernel-class device time of the most recent profiled iteration.
  * Writes up to `cap` (name,ms) pairs; returns the number written. */

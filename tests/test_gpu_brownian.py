@@ -221,3 +221,14 @@ def test_full_size_c2_properties():
     assert np.array_equal(gpu2.seeds(), orc.seeds())
     for s in (gpu, gpu2, orc):
         s.close()
+
+
+def test_nvtx_ranges_do_not_change_results():
+    """Option "nvtx": every stage of an iteration becomes an NVTX range on the enqueueing thread (the reference's
+    PROFILE_SCOPED_RANGE); without a tool attached the calls are no-ops and the run is unchanged."""
+    cfg, gpu, orc = _pair("c2_tiny", exact=True, nvtx=1, graph=0)
+    gpu.step(6)
+    orc.step(6)
+    _assert_same_state(gpu, orc, exact=True)
+    gpu.close()
+    orc.close()
