@@ -69,6 +69,9 @@ BROWNIAN = {
     "c2_w8": BrownianConfig("Brownian_w8", 8 << 20, (64, 64, 512), 42, buffer=1114112, world=8),
     # small 2-slab parity case
     "c2_s2": BrownianConfig("Brownian_s2", 1 << 15, (16, 16, 32), 13, buffer=24576, world=2),
+    # ... and with distinct lower / upper neighbours (4 and 8 slabs of 16 planes)
+    "c2_s4": BrownianConfig("Brownian_s4", 1 << 16, (16, 16, 64), 17, buffer=24576, world=4),
+    "c2_s8": BrownianConfig("Brownian_s8", 1 << 17, (16, 16, 128), 19, buffer=24576, world=8),
 }
 
 BROWNIAN_XML = os.path.join(build.MODELS, "Brownian", "src", "model", "XMLModelFile.xml")

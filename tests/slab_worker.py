@@ -1,5 +1,5 @@
-"""One rank of the 2-slab parity check (launched by tests/test_gpu_slabs.py through
-torch.distributed.run on a box with >= 2 GPUs).
+"""One rank of the slab parity check (launched by tests/test_gpu_slabs.py through
+torch.distributed.run on a box with 2, 4 or 8 GPUs; the workload is c2_s<world>).
 
 Property checked every iteration, with no oracle at this size: the neighbour count of
 every agent (keyed by id) equals a brute-force count over the GLOBAL positions at the
@@ -59,7 +59,7 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=device)
-    cfg = W.BROWNIAN["c2_s2"]
+    cfg = W.BROWNIAN[f"c2_s{world}"]
     assert cfg.world == world
     sim = Simulation(build.model_path(cfg.name + "_exact"), device=local)
     for kv in filter(None, os.environ.get("SLAB_OPTIONS", "").split(",")):   # e.g. "graph=0,slab_p2p=0"
@@ -77,6 +77,7 @@ def main():
     state = W.brownian_state(cfg)
     # a few agents exactly on faces / slab boundaries / the wrap boundary
     state["z"][:6] = [0.0, 15.999999, 16.0, 31.999998, 32.0, 16.000002]
+    state["z"][6:8] = [np.float32(cfg.dims[2]) - np.float32(1e-5), np.float32(cfg.dims[2])]   # the wrap face itself
     sim.set_agents("Particle", "default", slabs.partition_state(state, plan))
     iters = int(os.environ.get("SLAB_ITERS", "12"))
     bad = 0
