@@ -869,40 +869,5 @@ k_append_both(const char *__restrict__ rlo, const char *__restrict__ rhi, char *
     }
 }
 
-/* header of a migrant buffer := {count (clamped), overflow} from the compaction total */
-__global__ void k_set_header(int *hdr, const int *total, int cap) {
-    const int t = *total;
-    hdr[0] = min(t, cap);
-    hdr[1] = t > cap;
-    hdr[2] = 0;
-    hdr[3] = 0;
-}
-
-/* append received migrants: dst[dst_base + *off_a + *off_b + i] = src[i] for i < src_hdr[0] */
-__global__ void __launch_bounds__(256)
-k_append_received(const char *__restrict__ src, const int *__restrict__ src_hdr, char *__restrict__ dst, const ColSet scols,
-                  const ColSet dcols, const int *off_a, const int *off_b, int dst_cap, int *status) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int cnt = src_hdr[0];
-    if (i == 0 && src_hdr[1]) atomicExch(status, 3);
-    if (i >= cnt) return;
-    const size_t out = (size_t)(off_a ? *off_a : 0) + (size_t)(off_b ? *off_b : 0) + i;
-    if (out >= (size_t)dst_cap) {
-        atomicExch(status, 4);
-        return;
-    }
-    for (int c = 0; c < scols.ncols; ++c) {
-        if (scols.size[c] == 4)
-            ((unsigned int *)(dst + dcols.off[c]))[out] = ((const unsigned int *)(src + scols.off[c]))[i];
-        else
-            ((unsigned long long *)(dst + dcols.off[c]))[out] = ((const unsigned long long *)(src + scols.off[c]))[i];
-    }
-}
-
-/* result[0] = *a + hdr_b[0] + hdr_c[0] (new local population) */
-__global__ void k_sum_counts(int *result, const int *a, const int *hdr_b, const int *hdr_c) {
-    result[0] = *a + hdr_b[0] + hdr_c[0];
-}
-
 }  // namespace fgpu
 #endif
