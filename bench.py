@@ -144,7 +144,9 @@ def run_reference(args, cfg):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
         "config": {"workload": workload_name(args, cfg), "agents": cfg.n, "cells": list(cfg.dims)},
         "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} full iterations of the {cfg.n}-agent workload, OpenMP {cores} threads"},
+                         "sample": f"{args.steps} full iterations of the {cfg.n}-agent workload, OpenMP {cores} threads" +
+                                   (f" (one slab's worth of the {args.gpus}-GPU weak-scaling job: same density, same cells per slab)"
+                                    if args.gpus > 1 else "")},
         "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "the reference has no CPU path and its CUDA cannot be built here (no xsltproc; texture references "
