@@ -77,7 +77,7 @@ def model_path(name: str) -> str:
 
 def build_runtime(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB, exist_ok=True)
-    srcs = [os.path.join(CSRC, f) for f in ("fgpu_rt.cu", "fgpu_kernels.cuh")]
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.startswith("fgpu_rt") or f == "fgpu_kernels.cuh"]
     hdrs = [os.path.join(INCLUDE, f) for f in ("fgpu.h", "fgpu_model.h")]
     out = runtime_path()
     extra = []

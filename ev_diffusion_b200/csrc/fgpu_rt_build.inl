@@ -1,0 +1,161 @@
+/* fgpu_rt_build.inl -- building blocks: stream compaction, radix sort driver, spatial message build.
+ * Part of the single translation unit fgpu_rt.cu (textually included there, in this order, after the
+ * runtime objects it uses); not a standalone source file. */
+/* ------------------------------------------------------------------------- */
+/* building blocks                                                            */
+/* ------------------------------------------------------------------------- */
+#define LAUNCH_CHECK()                                                                       \
+    do {                                                                                     \
+        s->launches++;                                                                       \
+        cudaError_t e_ = cudaGetLastError();                                                 \
+        if (e_ != cudaSuccess)                                                               \
+            return set_err(FGPU_ERR_CUDA, "%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+
+/* Stable compaction of the flagged agents of `src` into `dst` at dst_offset.
+ * With count_out != nullptr the survivor count is read back (blocking, like
+ * the two 4-byte D2H copies after every cub scan, e.g. simulation.xslt:1476). */
+static int compact(fgpu_sim *s, AgentRT &A, const char *src, char *dst, int dst_offset, int n, const int *flags,
+                   bool scatter, int *count_out, int match = 1, const ColSet *dcols = nullptr, int dst_cap = 0x7fffffff,
+                   int *overflow = nullptr, const int *d_n = nullptr) {
+    if (n <= 0) {
+        if (count_out) *count_out = 0;
+        CU(cudaMemsetAsync(A.d_total, 0, sizeof(int), s->stream));
+        return FGPU_OK;
+    }
+    const int nb = (n + COMPACT_THREADS - 1) / COMPACT_THREADS;
+    k_flag_blocksum<<<nb, COMPACT_THREADS, 0, s->stream>>>(flags, n, d_n, A.block_sums, match);
+    LAUNCH_CHECK();
+    k_scan_blocksums<<<1, 1024, 0, s->stream>>>(A.block_sums, nb, A.d_total);
+    LAUNCH_CHECK();
+    if (count_out) {
+        CU(cudaMemcpyAsync(count_out, A.d_total, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    if (scatter) {
+        k_compact_scatter<<<nb, COMPACT_THREADS, 0, s->stream>>>(src, dst, A.cols, dcols ? *dcols : A.cols, flags, A.block_sums,
+                                                                 dst_offset, n, d_n, match, dst_cap, overflow);
+        LAUNCH_CHECK();
+        s->touch(dst);
+    }
+    return FGPU_OK;
+}
+
+static int choose_digit_bits(int radix_bits, int max_bits, int *passes_out) {
+    const int passes = std::max(1, sort_passes(radix_bits, max_bits));
+    *passes_out = passes;
+    return (radix_bits + passes - 1) / passes; /* balanced digits */
+}
+
+/* scratch layout (32-bit words): gap_count | pad[7] | totals[2048] | tile_hist[nbins][tiles] */
+constexpr int SCR_GAP = 0, SCR_TOTALS = 8, SCR_TILEHIST = 8 + SORT_MAX_BINS;
+
+static size_t sort_scratch_words(int n, int key_bits, int max_bits) {
+    int passes = 1;
+    const int digit_bits = choose_digit_bits(key_bits, max_bits, &passes);
+    const size_t tiles = ((size_t)n + SORT_TILE - 1) / SORT_TILE;
+    return (size_t)SCR_TILEHIST + tiles * ((size_t)1 << digit_bits);
+}
+
+template <int BITS>
+static cudaError_t launch_scatter(int tiles, cudaStream_t st, const unsigned int *kin, const unsigned int *vin, unsigned int *kout,
+                                  unsigned int *vout, int n, const int *d_n, int shift, int digit_bits, const unsigned int *tile_hist,
+                                  const unsigned int *totals, unsigned int key_base) {
+    static bool configured = false;
+    const size_t smem = sizeof(SortSmem<BITS>);
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_radix_scatter<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    k_radix_scatter<BITS><<<tiles, SORT_THREADS, smem, st>>>(kin, vin, kout, vout, n, d_n, shift, digit_bits, tile_hist, totals, tiles, key_base);
+    return cudaGetLastError();
+}
+
+/* The hand-written LSD radix sort of (keys_in[i], i): replaces cub::DeviceRadixSort::SortPairs (sim:1867).
+ * Returns the index (0/1) of the ping-pong pair holding the sorted result; counts launches. */
+static int radix_sort_pairs(cudaStream_t st, const unsigned int *keys_in, int n, int key_bits, int max_bits,
+                            unsigned int *keys[2], unsigned int *vals[2], unsigned int *scratch, int *sorted_in,
+                            long long *launches, const int *d_n = nullptr, unsigned int key_base = 0, unsigned int key_span = 0,
+                            int *range_error = nullptr) {
+    int passes = 1;
+    const int digit_bits = choose_digit_bits(key_bits, max_bits, &passes);
+    if (passes > SORT_MAX_PASSES) return set_err(FGPU_ERR_MODEL, "%d key bits need %d radix passes", key_bits, passes);
+    const int tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    const int nbins = 1 << digit_bits;
+    unsigned int *totals = scratch + SCR_TOTALS, *tile_hist = scratch + SCR_TILEHIST;
+    for (int p = 0; p < passes; ++p) {
+        const unsigned int *kin = p == 0 ? keys_in : keys[(p - 1) & 1];
+        const unsigned int *vin = p == 0 ? nullptr : vals[(p - 1) & 1];
+        const int shift = p * digit_bits;
+        k_tile_hist<<<tiles, SORT_THREADS, sizeof(unsigned int) * (size_t)nbins, st>>>(kin, n, d_n, shift, digit_bits, tile_hist, tiles, key_base,
+                                                                                       key_span, p == 0 ? range_error : nullptr);
+        k_row_scan<<<nbins, SORT_THREADS, 0, st>>>(tile_hist, tiles, totals);
+        cudaError_t e;
+        if (digit_bits <= 8) e = launch_scatter<8>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals, key_base);
+        else if (digit_bits == 9) e = launch_scatter<9>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals, key_base);
+        else if (digit_bits == 10) e = launch_scatter<10>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals, key_base);
+        else e = launch_scatter<11>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals, key_base);
+        if (e != cudaSuccess) return set_err(FGPU_ERR_CUDA, "radix pass launch -> %s", cudaGetErrorString(e));
+        (*launches) += 3;
+    }
+    *sorted_in = (passes - 1) & 1;
+    return FGPU_OK;
+}
+
+/* Spatial message build for h_count messages (simulation.xslt:1831-1892). */
+static int build_spatial(fgpu_sim *s, MsgRT &M) {
+    const int n = M.h_count;
+    M.built = true;
+    if (n <= 0) return FGPU_OK;
+    const int max_bits = std::min(std::max(s->opt_radix_bits, 4), SORT_MAXBITS);
+    unsigned int *gap_count = M.scratch + SCR_GAP;
+    s->prof_begin(std::string("sort:") + M.d->name);
+    CU(cudaMemsetAsync(gap_count, 0, 2 * sizeof(unsigned int), s->stream));
+    int in = 0;
+    int key_bits = M.d->radix_bits;
+    unsigned int key_base = 0, key_span = 0;
+    int *range_error = nullptr;
+    if (s->slab.on) {
+        /* every local message lies in an owned plane (agents migrate before they output): sort on the key
+         * relative to the first owned cell, which needs log2(owned cells) bits whatever the world size */
+        const SlabRT &S = s->slab;
+        key_base = (unsigned int)S.p0 * (unsigned int)S.plane_cells;
+        key_span = (unsigned int)S.ppr * (unsigned int)S.plane_cells;
+        key_bits = 1;
+        while (key_bits < 32 && (1u << key_bits) < key_span) ++key_bits;
+        key_bits = std::min(key_bits, M.d->radix_bits);
+        range_error = S.d_status + 4;
+    }
+    int rc = radix_sort_pairs(s->stream, M.keys_in, n, key_bits, max_bits, M.keys, M.vals, M.scratch, &in, &s->launches, M.d_count, key_base,
+                              key_span, range_error);
+    if (rc) return rc;
+    s->prof_end();
+    M.sorted_in = in;
+    s->prof_begin(std::string("pbm:") + M.d->name);
+    const int g = (n + 255) / 256;
+    switch (M.d->rec_quads) {
+#define GATHER_CASE(Q)                                                                                                   \
+    case Q:                                                                                                              \
+        k_gather_pbm<Q><<<g, 256, 0, s->stream>>>(M.keys[in], M.vals[in], M.unsorted, M.sorted + (size_t)M.local_at * Q, n, M.d_count, M.cell_start, \
+                                                  key_base, key_base + (key_span ? key_span : (unsigned int)M.d->grid_size),        \
+                                                  (unsigned int)M.local_at, M.gap_queue, gap_count);                           \
+        break;
+        GATHER_CASE(1)
+        GATHER_CASE(2)
+        GATHER_CASE(3)
+        GATHER_CASE(4)
+        GATHER_CASE(5)
+        GATHER_CASE(6)
+        GATHER_CASE(7)
+        GATHER_CASE(8)
+#undef GATHER_CASE
+        default:
+            return set_err(FGPU_ERR_MODEL, "message %s: record of %d quads is not supported", M.d->name, M.d->rec_quads);
+    }
+    LAUNCH_CHECK();
+    k_fill_gaps<<<148 * 2, 256, 0, s->stream>>>(M.cell_start, M.gap_queue, gap_count);
+    LAUNCH_CHECK();
+    s->prof_end();
+    return FGPU_OK;
+}

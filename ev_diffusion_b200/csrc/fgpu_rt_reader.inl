@@ -1,0 +1,161 @@
+/* fgpu_rt_reader.inl -- 0.xml reader (readInitialStates, io.xslt:211-621).
+ * Part of the single translation unit fgpu_rt.cu (textually included there, in this order, after the
+ * runtime objects it uses); not a standalone source file. */
+/* ------------------------------------------------------------------------- */
+/* 0.xml reader -- character stream, same tag rules as io.xslt:336-583        */
+/* ------------------------------------------------------------------------- */
+namespace {
+struct XmlAgentBuf {
+    std::vector<std::vector<char>> cols; /* per variable, raw bytes */
+    int count = 0;
+};
+
+void store_value(const fgpu_var &V, const char *text, char *dst) {
+    if (V.is_float) {
+        if (V.size == 4) *(float *)dst = (float)atof(text);      /* fgpu_atof */
+        else *(double *)dst = strtod(text, nullptr);             /* fpgu_strtod */
+    } else if (V.size == 4) {
+        if (!strcmp(V.ctype, "unsigned int")) *(unsigned int *)dst = (unsigned int)strtoul(text, nullptr, 0);
+        else *(int *)dst = (int)strtol(text, nullptr, 0);        /* fpgu_strtol(.., 0) */
+    } else {
+        if (!strncmp(V.ctype, "unsigned", 8)) *(unsigned long long *)dst = strtoull(text, nullptr, 0);
+        else *(long long *)dst = strtoll(text, nullptr, 0);
+    }
+}
+
+void default_value(const fgpu_var &V, char *dst) {
+    if (V.is_float) {
+        if (V.size == 4) *(float *)dst = (float)V.default_value;
+        else *(double *)dst = V.default_value;
+    } else if (V.size == 4) {
+        if (!strcmp(V.ctype, "unsigned int")) *(unsigned int *)dst = (unsigned int)V.default_value;
+        else *(int *)dst = (int)V.default_value;
+    } else {
+        *(long long *)dst = (long long)V.default_value;
+    }
+}
+}  // namespace
+
+extern "C" int fgpu_sim_load_states(fgpu_sim *s, const char *xml_path) {
+    if (!s || !xml_path) return set_err(FGPU_ERR_ARG, "bad argument");
+    const fgpu_model *m = s->model;
+    CU(cudaSetDevice(s->device));
+    if (m->init_constants) m->init_constants(); /* initEnvVars(), io.xslt:254-255 */
+    FILE *file = fopen(xml_path, "r");
+    if (!file) return set_err(FGPU_ERR_IO, "Could not open input file %s", xml_path);
+
+    std::vector<XmlAgentBuf> bufs(m->nagents);
+    /* current values per agent type per variable, reset to defaults after each </xagent> */
+    std::vector<std::vector<std::vector<char>>> cur(m->nagents);
+    auto reset_cur = [&]() {
+        for (int a = 0; a < m->nagents; ++a) {
+            cur[a].resize(m->agents[a].nvars);
+            for (int v = 0; v < m->agents[a].nvars; ++v) {
+                cur[a][v].assign(8, 0);
+                default_value(m->agents[a].vars[v], cur[a][v].data());
+            }
+        }
+    };
+    reset_cur();
+    for (int a = 0; a < m->nagents; ++a) bufs[a].cols.resize(m->agents[a].nvars);
+
+    std::string buffer, agentname;
+    bool in_tag = false, in_comment = false, in_itno = false, in_env = false, in_xagent = false, in_name = false;
+    bool reading = true;
+    std::string open_var; /* the variable tag we are inside of, matched by bare name (io.xslt:458-459) */
+    int rc = FGPU_OK;
+    int ch;
+    while (reading && (ch = fgetc(file)) != EOF) {
+        const char c = (char)ch;
+        if (buffer.size() >= 10000) {
+            rc = set_err(FGPU_ERR_IO, "Error: XML Parsing failed Tag name or content too long (> 10000 characters)");
+            break;
+        }
+        if (in_comment) {
+            if (c == '-') buffer.push_back(c);
+            else if (c == '>' && buffer.size() >= 2) { in_comment = false; buffer.clear(); }
+            else buffer.clear();
+        } else if (c == '>') {
+            const std::string &tag = buffer;
+            if (tag == "/states") reading = false;
+            if (tag == "itno") in_itno = true;
+            if (tag == "/itno") in_itno = false;
+            if (tag == "environment") in_env = true;
+            if (tag == "/environment") in_env = false;
+            if (tag == "name") in_name = true;
+            if (tag == "/name") in_name = false;
+            if (tag == "xagent") in_xagent = true;
+            if (tag == "/xagent") {
+                int a = -1;
+                for (int k = 0; k < m->nagents; ++k)
+                    if (agentname == m->agents[k].name) a = k;
+                if (a < 0) {
+                    fprintf(stdout, "Warning: agent name undefined - '%s'\n", agentname.c_str());
+                } else {
+                    if (bufs[a].count >= m->agents[a].buffer_size) {
+                        rc = set_err(FGPU_ERR_OVERFLOW, "ERROR: MAX Buffer size (%i) for agent %s exceeded whilst reading data",
+                                     m->agents[a].buffer_size, m->agents[a].name);
+                        break;
+                    }
+                    for (int v = 0; v < m->agents[a].nvars; ++v) {
+                        const int sz = m->agents[a].vars[v].size;
+                        bufs[a].cols[v].insert(bufs[a].cols[v].end(), cur[a][v].data(), cur[a][v].data() + sz);
+                    }
+                    bufs[a].count++;
+                }
+                reset_cur();
+                in_xagent = false;
+            }
+            if (!tag.empty() && tag[0] == '/') {
+                if (open_var == tag.substr(1)) open_var.clear();
+            } else {
+                open_var = tag;
+            }
+            in_tag = false;
+            buffer.clear();
+        } else if (c == '<') {
+            in_tag = true;
+            if (in_itno) { /* parsed into a dead local by the reference (io.xslt:478) */ }
+            if (in_name) {
+                agentname = buffer;
+            } else if (in_xagent) {
+                /* every agent type that has a variable of this name receives the value */
+                for (int a = 0; a < m->nagents; ++a)
+                    for (int v = 0; v < m->agents[a].nvars; ++v)
+                        if (open_var == m->agents[a].vars[v].name) store_value(m->agents[a].vars[v], buffer.c_str(), cur[a][v].data());
+            } else if (in_env) {
+                for (int k = 0; k < m->nconstants; ++k)
+                    if (open_var == m->constants[k].name && m->constants[k].length == 1) {
+                        fgpu_var V;
+                        V.ctype = m->constants[k].ctype;
+                        V.size = m->constants[k].size;
+                        V.is_float = (!strcmp(V.ctype, "float") || !strcmp(V.ctype, "double"));
+                        char tmp[8];
+                        store_value(V, buffer.c_str(), tmp);
+                        m->constants[k].set(tmp);
+                    }
+            }
+            buffer.clear();
+        } else if (in_tag) {
+            if (buffer.size() == 2 && c == '-' && buffer[1] == '-' && buffer[0] == '!') {
+                in_comment = true;
+                buffer.clear();
+            }
+            buffer.push_back(c);
+        } else {
+            buffer.push_back(c);
+        }
+    }
+    fclose(file);
+    if (rc != FGPU_OK) return rc;
+    for (int a = 0; a < m->nagents; ++a) {
+        std::vector<const void *> cols(m->agents[a].nvars);
+        for (int v = 0; v < m->agents[a].nvars; ++v) cols[v] = bufs[a].cols[v].data();
+        /* other states start empty */
+        for (int st = 0; st < m->agents[a].nstates; ++st) s->agents[a].h_state_count[st] = 0;
+        rc = upload_columns(s, a, m->agents[a].initial_state, 0, bufs[a].count, bufs[a].count ? cols.data() : nullptr);
+        if (rc != FGPU_OK) return rc;
+    }
+    CU(cudaDeviceSynchronize());
+    return FGPU_OK;
+}
