@@ -289,17 +289,21 @@ def main():
     n_kernel = sim.agent_count("Particle", "default")   # units one launch of the dominant kernel processes
     achieved = B_ALG[dom] * n_kernel / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     # DRAM bytes per launch of that kernel from the committed ncu capture (not measurable here without ncu)
-    traffic = None
+    traffic, issue = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
             rec = json.load(fh).get(args.workload, {}).get(dom)
         if rec and world == 1:
             traffic = rec["dram_read_bytes"] + rec["dram_write_bytes"]
+            issue = {k: rec[k] for k in ("warp_instructions", "issue_active_frac", "active_lanes_per_instruction",
+                                         "l1_sector_hit_rate", "l2_sector_hit_rate") if k in rec}
     except (OSError, ValueError, KeyError):
         traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_agent": B_ALG[dom], "kernel_ms": dom_ms,
+                # what actually bounds that kernel (same committed ncu capture): issue slots, not HBM
+                "ncu": issue,
                 "stage_ms": {k: round(v, 5) for k, v in stage.items()},
                 "iteration": {"alg_bytes_per_agent_step": B_ALG_ITERATION,
                               "achieved_per_gpu": B_ALG_ITERATION * n_global / world * args.steps / (total_ms * 1e-3) / 1e9,
