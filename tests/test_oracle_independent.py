@@ -1,0 +1,131 @@
+"""A second, independent statement of the Brownian iteration -- vectorised numpy, written from the reference's
+definitions (cell = floor((p-min)*dim/(max-min)) in float32, krn:860-871; jump-to-opposite-face hash,
+krn:877-889; stable sort by cell with ties by message index, sim:1860-1885; 27-cell neighbourhood; rand48 with
+one stream per list slot, sim:661-688 / krn:1488-1547) -- against the C++ oracle, which executes the same
+functions.c through a restatement of the reference's runtime.  Two implementations that share no code must
+agree bit for bit on cell keys, sorted order, partition matrix, neighbour counts, positions and rand48 seeds."""
+import numpy as np
+import pytest
+
+from common import W, brownian_oracle
+
+A48, C48, M24 = 0x5DEECE66D, 0xB, 0xFFFFFF
+
+
+def leapfrog_constants(N):
+    A, C = 1, 0
+    for _ in range(N):
+        C = (C + A * C48) & ((1 << 64) - 1)
+        A = (A * A48) & ((1 << 64) - 1)
+    return A & ((1 << 48) - 1), C & ((1 << 48) - 1)
+
+
+def initial_states(N):
+    x, out = (123 << 16) | 0x330E, np.zeros(N, dtype=np.uint64)
+    for i in range(N):
+        x = (A48 * x + C48) & ((1 << 48) - 1)
+        out[i] = x
+    return out
+
+
+def rand48_draw(state, A, C):
+    """rnd<>: top 31 bits of the 48-bit state as float32(r) / float32(2^31 - 1 rounded), then advance by the stride."""
+    lo, hi = state & np.uint64(M24), (state >> np.uint64(24)) & np.uint64(M24)
+    r = ((lo >> np.uint64(17)) | (hi << np.uint64(7))).astype(np.int64)
+    u = (r.astype(np.float32) / np.float32(2147483647)).astype(np.float32)
+    with np.errstate(over="ignore"):
+        nxt = (state * np.uint64(A) + np.uint64(C)) & np.uint64((1 << 48) - 1)
+    return u, nxt
+
+
+def cell_keys(x, y, z, dims):
+    g = []
+    for p, d in zip((x, y, z), dims):
+        num = (p.astype(np.float32) - np.float32(0.0)) * np.float32(d)
+        c = np.floor(num / np.float32(d - 0.0)).astype(np.int64)          # bounds are [0, dim) with radius 1
+        c = np.where(c < 0, d - 1, c)
+        c = np.where(c >= d, 0, c)
+        g.append(c)
+    return (g[2] * dims[1] + g[1]) * dims[0] + g[0], g
+
+
+def reflect(p, hi):
+    p = np.where(p < 0, -p, p).astype(np.float32)
+    return np.where(p > hi, (hi - (p - hi)).astype(np.float32), p).astype(np.float32)
+
+
+def numpy_iteration(st, seeds, dims, sigma, A, C):
+    x, y, z, ident = st["x"], st["y"], st["z"], st["id"]
+    n = len(x)
+    keys, (gx, gy, gz) = cell_keys(x, y, z, dims)
+    order = np.argsort(keys, kind="stable")
+    cells = dims[0] * dims[1] * dims[2]
+    count = np.bincount(keys, minlength=cells)
+    start = np.concatenate([[0], np.cumsum(count)[:-1]])
+    # neighbour count: every message of the 27 cells (wrap = opposite face), radius test in float32, script order
+    nbr = np.zeros(n, dtype=np.int32)
+    sx, sy, sz, sid = x[order], y[order], z[order], ident[order]
+    for i in range(n):
+        c = 0
+        for dz in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    cx, cy, cz = gx[i] + dx, gy[i] + dy, gz[i] + dz
+                    cx = dims[0] - 1 if cx < 0 else (0 if cx >= dims[0] else cx)
+                    cy = dims[1] - 1 if cy < 0 else (0 if cy >= dims[1] else cy)
+                    cz = dims[2] - 1 if cz < 0 else (0 if cz >= dims[2] else cz)
+                    h = (cz * dims[1] + cy) * dims[0] + cx
+                    lo, hi = start[h], start[h] + count[h]
+                    if hi > lo:
+                        ddx = x[i] - sx[lo:hi]
+                        ddy = y[i] - sy[lo:hi]
+                        ddz = z[i] - sz[lo:hi]
+                        d2 = ((ddx * ddx).astype(np.float32) + (ddy * ddy).astype(np.float32)).astype(np.float32)
+                        d2 = (d2 + (ddz * ddz).astype(np.float32)).astype(np.float32)
+                        c += int(np.count_nonzero((d2 < np.float32(1.0)) & (sid[lo:hi] != ident[i])))
+        nbr[i] = c
+    # move: three draws per agent from its own slot's stream, reflection at the walls
+    s = seeds.copy()
+    ux, s = rand48_draw(s, A, C)
+    uy, s = rand48_draw(s, A, C)
+    uz, s = rand48_draw(s, A, C)
+    sig = np.float32(sigma)
+    step = lambda u: (sig * (np.float32(2.0) * u - np.float32(1.0)).astype(np.float32)).astype(np.float32)
+    nx = reflect((x + step(ux)).astype(np.float32), np.float32(dims[0]))
+    ny = reflect((y + step(uy)).astype(np.float32), np.float32(dims[1]))
+    nz = reflect((z + step(uz)).astype(np.float32), np.float32(dims[2]))
+    return {"id": ident, "x": nx, "y": ny, "z": nz, "nbr": nbr}, s, keys, order, start, count
+
+
+@pytest.mark.parametrize("count", [700, 2048])
+def test_cpp_oracle_equals_numpy_restatement(count):
+    cfg = W.BROWNIAN["c2_tiny"]
+    orc = brownian_oracle("c2_tiny")
+    st = W.brownian_state(cfg, count)
+    # a few agents on faces and outside the box: wrap rule and reflection
+    st["x"][:4] = [0.0, 15.999999, -0.5, 16.25]
+    st["z"][4:7] = [16.0, -3.0, 47.0]
+    orc.set_agents("Particle", "default", st)
+    N = cfg.buffer_size                      # buffer_size_MAX of the model = leapfrog stride
+    A, C = leapfrog_constants(N)
+    seeds = initial_states(N)[:count]
+    sigma = float(orc.get_constant("SIGMA"))
+    cur = {k: v.copy() for k, v in st.items()}
+    for it in range(3):
+        want, seeds, keys, order, start, cnt = numpy_iteration(cur, seeds, cfg.dims, sigma, A, C)
+        orc.begin_iteration()
+        orc.run_function("output_location")
+        assert np.array_equal(orc.message_keys("location"), keys.astype(np.uint32)), it
+        assert np.array_equal(orc.message_order("location"), order.astype(np.uint32)), it
+        os_, oc = orc.pbm("location")
+        assert np.array_equal(oc, cnt) and np.array_equal(os_[cnt > 0], start[cnt > 0]), it
+        orc.run_function("count_neighbours")
+        orc.run_function("move")
+        got = orc.agents("Particle")
+        assert np.array_equal(got["nbr"], want["nbr"]), it
+        for k in "xyz":
+            assert np.array_equal(got[k].view(np.uint32), want[k].view(np.uint32)), (it, k)
+        so = orc.seeds()[:count]
+        assert np.array_equal(so[:, 0].astype(np.uint64) | (so[:, 1].astype(np.uint64) << np.uint64(24)), seeds), it
+        cur = want
+    orc.close()
