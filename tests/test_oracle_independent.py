@@ -43,10 +43,9 @@ def cell_keys(x, y, z, dims):
     for p, d in zip((x, y, z), dims):
         num = (p.astype(np.float32) - np.float32(0.0)) * np.float32(d)
         c = np.floor(num / np.float32(d - 0.0)).astype(np.int64)          # bounds are [0, dim) with radius 1
-        c = np.where(c < 0, d - 1, c)
-        c = np.where(c >= d, 0, c)
-        g.append(c)
-    return (g[2] * dims[1] + g[1]) * dims[0] + g[0], g
+        g.append(c)                                                        # unwrapped: the walk starts from this
+    w = [np.where(c < 0, d - 1, np.where(c >= d, 0, c)) for c, d in zip(g, dims)]
+    return (w[2] * dims[1] + w[1]) * dims[0] + w[0], g
 
 
 def reflect(p, hi):
@@ -62,7 +61,8 @@ def numpy_iteration(st, seeds, dims, sigma, A, C):
     cells = dims[0] * dims[1] * dims[2]
     count = np.bincount(keys, minlength=cells)
     start = np.concatenate([[0], np.cumsum(count)[:-1]])
-    # neighbour count: every message of the 27 cells (wrap = opposite face), radius test in float32, script order
+    # neighbour count: every message of the 27 cells around the UNWRAPPED cell, each neighbour wrapped on its own
+    # (opposite face, krn:1037-1160), radius test in float32, script order
     nbr = np.zeros(n, dtype=np.int32)
     sx, sy, sz, sid = x[order], y[order], z[order], ident[order]
     for i in range(n):
@@ -128,4 +128,73 @@ def test_cpp_oracle_equals_numpy_restatement(count):
         so = orc.seeds()[:count]
         assert np.array_equal(so[:, 0].astype(np.uint64) | (so[:, 1].astype(np.uint64) << np.uint64(24)), seeds), it
         cur = want
+    orc.close()
+
+
+def test_birth_death_list_discipline_against_numpy():
+    """BirthDeath (death compaction, birth into the function's own state, rand48): the list discipline restated in
+    numpy from simulation.xslt:1763-1829,1955 -- survivors keep their order (stable compaction), newborns take the
+    order of their parents, the new state list is [newborns..., survivors...], and a rand48 stream belongs to the
+    list SLOT, not to the agent that sits in it."""
+    import os
+    from common import build, gen_oracle, OracleSimulation
+    xml = os.path.join(build.MODELS, "BirthDeath", "src", "model", "XMLModelFile.xml")
+    so = gen_oracle.oracle_path("BirthDeath")
+    if not os.path.exists(so):
+        so = gen_oracle.build_oracle(xml, "BirthDeath")
+    orc = OracleSimulation(so)
+    n0, dims = 1500, (32, 32, 32)
+    u = W.uniform24(45, 3 * n0)
+    st = {"id": np.arange(n0, dtype=np.int32), "x": u[0::3] * np.float32(32), "y": u[1::3] * np.float32(32),
+          "z": u[2::3] * np.float32(32), "age": np.zeros(n0, np.int32), "crowd": np.zeros(n0, np.int32)}
+    orc.set_agents("Cell", "default", st)
+    for k, v in (("DEATH_P", 0.1), ("BIRTH_P", 0.15)):
+        orc.set_constant(k, np.float32(v))
+    death_p, birth_p = np.float32(0.1), np.float32(0.15)
+    N = orc.model.agents[0].buffer_size      # one agent type: buffer_size_MAX
+    A, C = leapfrog_constants(N)
+    seeds = initial_states(N)
+    cur = {k: v.copy() for k, v in st.items()}
+    for it in range(6):
+        n = len(cur["id"])
+        keys, _ = cell_keys(cur["x"], cur["y"], cur["z"], dims)
+        count = np.bincount(keys, minlength=dims[0] * dims[1] * dims[2]).reshape(dims[2], dims[1], dims[0])
+        # crowd = messages in the 27 cells around the agent's UNWRAPPED grid position (krn:1037-1160: the walk adds
+        # the relative cell first and wraps each neighbour on its own, so an agent outside the box visits the
+        # face cell twice -- a newborn can be jittered out of bounds)
+        raw = [np.floor((cur[a] * np.float32(d)) / np.float32(d)).astype(np.int64) for a, d in zip("xyz", dims)]
+        wrap = lambda c, d: np.where(c < 0, d - 1, np.where(c >= d, 0, c))
+        crowd_of = np.zeros(n, dtype=np.int32)
+        for dz in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    crowd_of += count[wrap(raw[2] + dz, dims[2]), wrap(raw[1] + dy, dims[1]), wrap(raw[0] + dx, dims[0])].astype(np.int32)
+        s = seeds[:n].copy()
+        uu, s = rand48_draw(s, A, C)
+        dies = uu < death_p
+        births = (~dies) & (uu > np.float32(1.0) - birth_p)
+        jit = []
+        for _ in range(3):                     # three more draws, only in the slots that give birth
+            d, s2 = rand48_draw(s, A, C)
+            s = np.where(births, s2, s)
+            jit.append((d - np.float32(0.5)).astype(np.float32))
+        seeds[:n] = s
+        age = cur["age"] + 1
+        newborn = {"id": cur["id"][births] ^ np.int32(0x40000000),
+                   "x": (cur["x"][births] + jit[0][births]).astype(np.float32),
+                   "y": (cur["y"][births] + jit[1][births]).astype(np.float32),
+                   "z": (cur["z"][births] + jit[2][births]).astype(np.float32),
+                   "age": np.zeros(int(births.sum()), np.int32), "crowd": np.zeros(int(births.sum()), np.int32)}
+        keep = ~dies
+        survivor = {"id": cur["id"][keep], "x": cur["x"][keep], "y": cur["y"][keep], "z": cur["z"][keep],
+                    "age": age[keep], "crowd": crowd_of[keep]}
+        cur = {k: np.concatenate([newborn[k], survivor[k]]) for k in cur}
+        orc.step(1)
+        got = orc.agents("Cell")
+        assert orc.agent_count("Cell", "default") == len(cur["id"]), it
+        for k in cur:
+            assert np.array_equal(got[k].view(np.uint32), cur[k].view(np.uint32)), (it, k)
+        so_ = orc.seeds()
+        assert np.array_equal(so_[:, 0].astype(np.uint64) | (so_[:, 1].astype(np.uint64) << np.uint64(24)), seeds), it
+    assert len(cur["id"]) != n0
     orc.close()
