@@ -164,6 +164,21 @@ def build_driver(source: str, model_name: str, out_name: str, force: bool = Fals
     return out
 
 
+def build_console(force: bool = False) -> str:
+    """The reference's console mode for any model plugin (csrc/fgpu_console.cpp): host code only, linked to
+    libfgpu_rt.so."""
+    build_runtime()
+    src = os.path.join(CSRC, "fgpu_console.cpp")
+    out = os.path.join(LIB, "fgpu_console")
+    cmd = ["g++", "-std=c++17", "-O2", "-I", INCLUDE, src, "-o", out, "-L", LIB, "-lfgpu_rt", "-Wl,-rpath,$ORIGIN", "-ldl"]
+    stamp = _stamp([src, os.path.join(INCLUDE, "fgpu.h"), runtime_path()], " ".join(cmd))
+    if not force and _fresh(out, stamp):
+        return out
+    _run(cmd, log=out + ".log")
+    _mark(out, stamp)
+    return out
+
+
 def write_scaled_xml(src_xml: str, dst_xml: str, replacements: dict) -> str:
     """XML-only scaling of a model (bufferSize, bounds, radius, constants): plain
     text substitution of ``<tag>old</tag>`` pairs, the functions.c is untouched."""

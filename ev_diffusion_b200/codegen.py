@@ -376,7 +376,8 @@ def _host_api_decls(model: Model) -> str:
            "extern void cleanup();",
            "extern void singleIteration();",
            "extern void set_exit_early();",
-           "extern bool get_exit_early();"]
+           "extern bool get_exit_early();",
+           "extern const char* getOutputDir();"]
     for a in model.agents:
         out.append(f"extern int get_agent_{a.name}_MAX_count();")
         for s in a.states:
@@ -689,12 +690,13 @@ def _face2_shim(model: Model, cuda: bool) -> str:
         return "static void fgpu_plugin_bind(void*){}\n"
     out = ['#include "fgpu.h"',
            "static fgpu_sim* fgpu_cur = nullptr;",
-           "static bool fgpu_exit_early = false;",
+
            "static void fgpu_plugin_bind(void* sim){ fgpu_cur = (fgpu_sim*)sim; }",
            'static void fgpu_die(){ fprintf(stderr, "%s\\n", fgpu_last_error()); fflush(stderr); exit(EXIT_FAILURE); }',
            "unsigned int getIterationNumber(){ return fgpu_sim_iteration(fgpu_cur); }",
-           "void set_exit_early(){ fgpu_exit_early = true; }",
-           "bool get_exit_early(){ return fgpu_exit_early; }",
+           "void set_exit_early(){ fgpu_set_exit_early(1); }",
+           "bool get_exit_early(){ return fgpu_get_exit_early() != 0; }",
+           "const char* getOutputDir(){ return fgpu_get_output_dir(); }",
            """void initialise(char * inputfile){
     /* simulation.xslt:472-747: allocate, read the initial states, seed rand48, run init functions */
     const char* dev = getenv("FGPU_DEVICE");

@@ -69,6 +69,14 @@ extern "C" const char *fgpu_last_error(void) { return g_err; }
             return set_err(FGPU_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
     } while (0)
 
+/* driver state of the reference's main.cu that step functions may use (process-wide there too) */
+static std::string g_output_dir;
+static int g_exit_early = 0;
+extern "C" void fgpu_set_output_dir(const char *path) { g_output_dir = path ? path : ""; }
+extern "C" const char *fgpu_get_output_dir(void) { return g_output_dir.c_str(); }
+extern "C" void fgpu_set_exit_early(int flag) { g_exit_early = flag ? 1 : 0; }
+extern "C" int fgpu_get_exit_early(void) { return g_exit_early; }
+
 /* ------------------------------------------------------------------------- */
 /* runtime objects                                                            */
 /* ------------------------------------------------------------------------- */

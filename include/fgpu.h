@@ -55,6 +55,14 @@ void fgpu_sim_destroy(fgpu_sim *sim);
  * lists, apply <environment> constants, upload. */
 int fgpu_sim_load_states(fgpu_sim *sim, const char *xml_path);
 
+/* Process-wide driver state of the reference's main.cu that step functions may use: getOutputDir()
+ * (main.xslt:139-141: where iteration files and custom outputs go) and set_exit_early()/get_exit_early()
+ * (header.xslt:569-576: a step function asks the driver loop to stop).  The plugin shim forwards to these. */
+void fgpu_set_output_dir(const char *path);
+const char *fgpu_get_output_dir(void);
+void fgpu_set_exit_early(int flag);
+int fgpu_get_exit_early(void);
+
 /* saveIterationData() (io.xslt:124-200): writes <outputpath><iteration_number>.xml in the reference's
  * format -- <states><itno/><environment/> then one <xagent> per agent, per agent type and state in model
  * order, every value through the reference's format specifier (%f for float/double: lossy, like the

@@ -392,6 +392,8 @@ template <int AGENT_TYPE> void add_{a.name}_agent(xmachine_memory_{a.name}_list*
     # host API the scripts' init/step/exit functions may call (header.xslt:588-596, 729-751), on the oracle's lists
     out.append('static void fgpu_die(){ fprintf(stderr, "%s\\n", orc_last_error()); exit(EXIT_FAILURE); }')
     out.append("unsigned int getIterationNumber(){ return orc_cur ? orc_cur->iteration : 0u; }")
+    out.append('static bool orc_exit_early = false;\nvoid set_exit_early(){ orc_exit_early = true; }\nbool get_exit_early(){ return orc_exit_early; }')
+    out.append('const char* getOutputDir(){ const char* d = getenv("ORACLE_OUTPUT_DIR"); return d ? d : ""; }')
     for ai, a in enumerate(model.agents):
         out.append(f"int get_agent_{a.name}_MAX_count(){{ return xmachine_memory_{a.name}_MAX; }}")
         for si, st in enumerate(a.states):

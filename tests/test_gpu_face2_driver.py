@@ -41,3 +41,40 @@ def test_console_driver_matches_c_abi(tmp_path):
     # error behaviour of the reference: message + exit(EXIT_FAILURE) (simulation.xslt:198-206)
     bad = subprocess.run([exe, str(tmp_path / "missing.xml"), "1"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert bad.returncode != 0 and "Could not open" in bad.stdout
+
+
+def test_model_agnostic_console_mode(tmp_path):
+    """csrc/fgpu_console.cpp: the reference's console mode (main.xslt:60-448) for any plugin -- arguments,
+    messages, iteration files every XML_output_frequency iterations plus the last one, in the directory of the
+    input file -- against the same run through the Python mirror of the C ABI."""
+    exe = os.path.join(build.LIB, "fgpu_console")
+    if not os.path.exists(exe):
+        pytest.skip("console driver not prebuilt")
+    cfg = W.BROWNIAN["c2_tiny"]
+    st = W.brownian_state(cfg, 500)
+    d = tmp_path / "run"
+    d.mkdir()
+    xml = W.write_states_xml(str(d / "0.xml"), "Particle", st)
+    plugin = brownian_plugin("c2_tiny", exact=True)
+    out = subprocess.run([exe, plugin, xml, "7", "0", "3"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout
+    lines = out.stdout.splitlines()
+    assert lines[0] == "FLAMEGPU Console mode"
+    assert [l for l in lines if l.startswith("Processing Simulation Step")] == [f"Processing Simulation Step {i}" for i in range(1, 8)]
+    assert [l for l in lines if l.endswith("Saved to XML")] == [f"Iteration {i} Saved to XML" for i in (3, 6, 7)]
+    assert any(l.startswith("Total Processing time:") for l in lines)
+    assert sorted(p.name for p in d.iterdir()) == ["0.xml", "3.xml", "6.xml", "7.xml"]
+    sim = Simulation(plugin)
+    sim.load_states(xml)
+    sim.step(7)
+    ref = sim.save_states(str(tmp_path / "ref_"), 7)
+    assert open(ref, "rb").read() == (d / "7.xml").read_bytes()
+    sim.close()
+    # no XML output, usage and argument errors
+    out = subprocess.run([exe, plugin, xml, "2", "0", "0"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert out.returncode == 0 and "Saved to XML" not in out.stdout
+    assert subprocess.run([exe, plugin, xml], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).returncode != 0
+    bad = subprocess.run([exe, plugin, xml, "-4"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert bad.returncode != 0 and "positive integer" in bad.stdout
+    bad = subprocess.run([exe, str(tmp_path / "nope.so"), xml, "1"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert bad.returncode != 0 and "nope.so" in bad.stdout
