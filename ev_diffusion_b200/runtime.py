@@ -495,6 +495,12 @@ class Simulation(SimBase):
         self._check(self._lib.fgpu_sim_read_agents(self._h, agent, state, count, ptrs))
         return count
 
+    def run_exit_functions(self) -> None:
+        """The model's exit functions (simulation.xslt:779-790; cleanup() runs them before freeing)."""
+        self._lib.fgpu_sim_run_exit_functions.restype = C.c_int
+        self._lib.fgpu_sim_run_exit_functions.argtypes = [C.c_void_p]
+        self._check(self._lib.fgpu_sim_run_exit_functions(self._h))
+
     def save_states(self, outputpath: str, iteration_number: int) -> str:
         """saveIterationData(): writes <outputpath><iteration_number>.xml in the reference's format."""
         self._check(self._lib.fgpu_sim_save_states(self._h, os.fsencode(outputpath), int(iteration_number)))
@@ -551,6 +557,14 @@ class Simulation(SimBase):
         ms = (C.c_float * cap)()
         n = self._check(self._lib.fgpu_sim_profile_iterations(self._h, int(iters), names, ms, cap))
         return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
+
+def set_output_dir(path: str) -> None:
+    """getOutputDir() of step/exit functions (process-wide, like the reference's main.cu)."""
+    lib = load_runtime()
+    lib.fgpu_set_output_dir.argtypes = [C.c_char_p]
+    lib.fgpu_set_output_dir.restype = None
+    lib.fgpu_set_output_dir(os.fsencode(path))
 
 
 def nccl_unique_id() -> bytes:

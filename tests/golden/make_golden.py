@@ -34,7 +34,9 @@ CASES = [("CirclesPartitioning_float", 100), ("Boids_Partitioning", 50), ("Kerat
          ("CirclesBruteForce_float", 20), ("CirclesBruteForce_double", 20), ("CirclesPartitioning_double", 50),
          ("SocialParticleSimulation", 20), ("EmptyExample", 5),
          # init/step/exit functions calling the host analytics API (reduce_/min_/max_)
-         ("Analytics", 10)]
+         ("Analytics", 10),
+         # brute-force messages + rand48 + death compaction + powf (float state compared with a tolerance on the GPU)
+         ("MonteCarlo_MSMPR", 5)]
 
 
 def snapshot(sim):

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 CASES = {"CirclesPartitioning_float": 100, "Boids_Partitioning": 50, "Keratinocyte": 200,
          "CirclesBruteForce_float": 20, "CirclesBruteForce_double": 20, "CirclesPartitioning_double": 50,
-         "SocialParticleSimulation": 20, "EmptyExample": 5, "Analytics": 10}
+         "SocialParticleSimulation": 20, "EmptyExample": 5, "Analytics": 10, "MonteCarlo_MSMPR": 5}
 
 
 def _plugin(name, exact):
@@ -162,3 +162,35 @@ def test_keratinocyte_integer_state_and_order():
     assert diverged is None or diverged >= 50, f"id order diverged at iteration {diverged}"
     sim.close()
     orc.close()
+
+
+def test_montecarlo_msmpr_bruteforce_rng_and_exit_histogram(tmp_path):
+    """examples/MonteCarlo_MSMPR: 10 000 crystals, non-partitioned messages read by everyone (10^8 message visits
+    per iteration), rand48 ranks, powf growth, and an exit function that writes a histogram through
+    getOutputDir() + count_crystal_default_bin_variable().  Ranks and seeds are exact; lengths go through powf
+    (libdevice vs glibc), so they carry a relative tolerance and the integer bin may flip for a length that sits
+    on a bin edge."""
+    from ev_diffusion_b200 import runtime
+    name, iters = "MonteCarlo_MSMPR", CASES.get("MonteCarlo_MSMPR", 5)
+    sim = Simulation(_plugin(name, exact=True))
+    _start(sim, name)
+    sim.step(iters)
+    want = np.load(os.path.join(GOLDEN, f"{name}_iter{iters}.npz"))
+    n = int(want["count/crystal/default"])
+    assert sim.agent_count("crystal", "default") == n == 10000
+    got = sim.agents("crystal")
+    assert np.array_equal(got["rank"].view(np.uint32), want["agent/crystal/default/rank"].view(np.uint32))
+    assert np.array_equal(sim.seeds(), want["seeds"])
+    assert np.allclose(got["l"], want["agent/crystal/default/l"], rtol=2e-5, atol=1e-7)
+    assert (got["bin"] != want["agent/crystal/default/bin"]).mean() < 2e-3
+    # exit function: histogram file in the output directory, one "<bin> <count>"-like row per bin from count_()
+    runtime.set_output_dir(str(tmp_path) + os.sep)
+    sim.run_exit_functions()
+    path = tmp_path / "histogram_c2.dat"
+    assert path.exists()
+    rows = [r.split() for r in path.read_text().splitlines() if r.strip()]
+    counts = np.array([int(float(r[-1])) for r in rows])
+    assert 0 < counts.sum() <= n                                   # bins beyond the histogram range are not listed
+    ref = np.bincount(np.clip(got["bin"], 0, None), minlength=len(counts))[:len(counts)]
+    assert np.array_equal(counts, ref)
+    sim.close()

@@ -13,7 +13,7 @@ from common import REFERENCE, ROOT, OracleSimulation, gen_oracle
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 CASES = {"CirclesPartitioning_float": 100, "Boids_Partitioning": 50, "Keratinocyte": 200,
          "CirclesBruteForce_float": 20, "CirclesBruteForce_double": 20, "CirclesPartitioning_double": 50,
-         "SocialParticleSimulation": 20, "EmptyExample": 5, "Analytics": 10}
+         "SocialParticleSimulation": 20, "EmptyExample": 5, "Analytics": 10, "MonteCarlo_MSMPR": 5}
 
 
 def _oracle(name):
