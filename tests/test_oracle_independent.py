@@ -198,3 +198,58 @@ def test_birth_death_list_discipline_against_numpy():
         assert np.array_equal(so_[:, 0].astype(np.uint64) | (so_[:, 1].astype(np.uint64) << np.uint64(24)), seeds), it
     assert len(cur["id"]) != n0
     orc.close()
+
+
+def test_function_conditions_and_state_lists_against_numpy():
+    """models/TwoStage: function conditions and moves between state lists, restated from simulation.xslt:1439-1528
+    (the agents that meet the condition leave the current list in order, the others close ranks),
+    :1590-1601/:1936-1972 (an in-place function swaps its list back; a function into another state appends its
+    agents behind those already there) and krn:1320-1387 (a rand48 stream belongs to the slot of the WORKING list)."""
+    import os
+    from common import build, gen_oracle, OracleSimulation
+    xml = os.path.join(build.MODELS, "TwoStage", "src", "model", "XMLModelFile.xml")
+    so = gen_oracle.oracle_path("TwoStage")
+    if not os.path.exists(so):
+        so = gen_oracle.build_oracle(xml, "TwoStage")
+    orc = OracleSimulation(so)
+    n = 1500
+    cols = {"id": np.arange(n, dtype=np.int32), "energy": (np.arange(n, dtype=np.int32) * 7) % 5,
+            "fired": np.zeros(n, np.int32), "heat": np.zeros(n, np.float32)}
+    orc.set_agents("Unit", "idle", cols)
+    N = orc.model.agents[0].buffer_size
+    A, C = leapfrog_constants(N)
+    seeds = initial_states(N)
+    idle = {k: v.copy() for k, v in cols.items()}
+    active = {k: v[:0].copy() for k, v in cols.items()}
+    take = lambda d, m: {k: v[m] for k, v in d.items()}
+    cat = lambda a, b: {k: np.concatenate([a[k], b[k]]) for k in a}
+    for it in range(12):
+        # charge: idle -> idle, every idle unit, one draw from the stream of its slot
+        k = len(idle["id"])
+        u, nxt = rand48_draw(seeds[:k].copy(), A, C)
+        seeds[:k] = nxt
+        idle["energy"] = idle["energy"] + np.where(u < np.float32(0.5), 2, 1).astype(np.int32)
+        # fire: idle units with energy >= 5 move behind the units already active
+        m = idle["energy"] >= 5
+        firing = take(idle, m)
+        firing["fired"] = firing["fired"] + 1
+        firing["heat"] = firing["energy"].astype(np.float32)
+        firing["energy"] = np.zeros_like(firing["energy"])
+        idle, active = take(idle, ~m), cat(active, firing)
+        # burn: active -> active, in place
+        active["heat"] = (active["heat"] * np.float32(0.5)).astype(np.float32)
+        # cool: active units with heat < 1.5 move behind the idle ones
+        m = active["heat"] < np.float32(1.5)
+        cooled = take(active, m)
+        cooled["heat"] = np.zeros_like(cooled["heat"])
+        active, idle = take(active, ~m), cat(idle, cooled)
+        orc.step(1)
+        for state, want in (("idle", idle), ("active", active)):
+            assert orc.agent_count("Unit", state) == len(want["id"]), (it, state)
+            got = orc.agents("Unit", state)
+            for key in want:
+                assert np.array_equal(got[key].view(np.uint32), want[key].view(np.uint32)), (it, state, key)
+        so_ = orc.seeds()
+        assert np.array_equal(so_[:, 0].astype(np.uint64) | (so_[:, 1].astype(np.uint64) << np.uint64(24)), seeds), it
+    assert len(active["id"]) > 0 and len(idle["id"]) > 0 and not np.array_equal(idle["id"], np.sort(idle["id"]))
+    orc.close()
