@@ -137,3 +137,26 @@ def test_splitmix_generator_is_stable():
     assert u.dtype == np.float32 and ((u >= 0) & (u < 1)).all()
     st = W.brownian_state(W.BROWNIAN["c2_tiny"], 10)
     assert st["x"].max() < 16 and st["id"].tolist() == list(range(10))
+
+
+def test_product_path_fails_loudly_without_its_cuda_parts(tmp_path, monkeypatch):
+    """No CPU fallback: a missing runtime library, a missing plugin and a box without a GPU are errors with a
+    message, never a silent detour through the oracle."""
+    from ev_diffusion_b200 import runtime
+    from ev_diffusion_b200.runtime import FgpuError
+    # 1. missing model plugin
+    with pytest.raises(FgpuError, match="missing|dlopen"):
+        runtime.Simulation(str(tmp_path / "no_such_model.so"))
+    # 2. no CUDA device in this container: creating a simulation must fail with the CUDA error, not fall back
+    import torch
+    if not torch.cuda.is_available():
+        plugin = build.model_path("Brownian_tiny")
+        if os.path.exists(plugin):
+            with pytest.raises(FgpuError) as err:
+                runtime.Simulation(plugin)
+            assert "cuda" in str(err.value).lower() or "device" in str(err.value).lower()
+    # 3. missing runtime library
+    monkeypatch.setattr(runtime, "_RT", None)
+    monkeypatch.setattr(build, "runtime_path", lambda: str(tmp_path / "libfgpu_rt.so"))
+    with pytest.raises(FgpuError, match="no CPU fallback"):
+        runtime.load_runtime()
