@@ -1,5 +1,5 @@
 """Host-side logic of the N>1 path on CPU: slab plan, ownership rule and the
-fixed-capacity exchange protocol, run as 2 ranks over gloo.  Each rank holds the
+fixed-capacity exchange protocol, run as 2 and as 4 ranks over gloo.  Each rank holds the
 particles it owns, exchanges its two boundary planes with its neighbours (for
 world_size 2 both neighbours are the same peer, and plane 0 <-> plane nplanes-1 is
 the wrap pair) and counts neighbours from local + halo particles; the result must
@@ -43,7 +43,10 @@ def _worker(rank, world, port, results):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         plan = slabs.make_plan(DIMS, (0, 0, 0), DIMS, False, rank, world)
-        assert plan.lo_rank == plan.hi_rank == 1 - rank
+        if world == 2:
+            assert plan.lo_rank == plan.hi_rank == 1 - rank
+        else:
+            assert plan.lo_rank == (rank - 1) % world and plan.hi_rank == (rank + 1) % world
         st = slabs.partition_state(_global_state(), plan)
         planes = slabs.plane_of(st["z"], plan)
         assert ((planes >= plan.p0) & (planes < plan.p1)).all()
@@ -52,11 +55,11 @@ def _worker(rank, world, port, results):
         rows = lambda sel: np.stack([st["x"][sel], st["y"][sel], st["z"][sel]], 1)  # noqa: E731
         sends = [torch.from_numpy(slabs.pack_fixed(rows(planes == p), CAP)) for p, _ in slabs.halo_planes_to_send(plan)]
         recv_hi, recv_lo = torch.zeros_like(sends[0]), torch.zeros_like(sends[0])
-        peer = 1 - rank
-        if rank == 0:
-            dist.send(sends[0], peer); dist.send(sends[1], peer); dist.recv(recv_hi, peer); dist.recv(recv_lo, peer)
-        else:
-            dist.recv(recv_hi, peer); dist.recv(recv_lo, peer); dist.send(sends[0], peer); dist.send(sends[1], peer)
+        # tag 0: a low plane travelling to the lower neighbour (its HIGH halo); tag 1: a high plane to the upper one
+        ops = [dist.isend(sends[0], plan.lo_rank, tag=0), dist.isend(sends[1], plan.hi_rank, tag=1),
+               dist.irecv(recv_hi, plan.hi_rank, tag=0), dist.irecv(recv_lo, plan.lo_rank, tag=1)]
+        for op in ops:
+            op.wait()
         halo = np.concatenate([slabs.unpack_fixed(recv_lo.numpy()), slabs.unpack_fixed(recv_hi.numpy())])
         # the received planes are exactly my two halo planes
         hp = slabs.plane_of(halo[:, 2], plan)
@@ -76,13 +79,15 @@ def _worker(rank, world, port, results):
         dist.destroy_process_group()
 
 
-def test_two_rank_halo_exchange_over_gloo():
+@pytest.mark.parametrize("world", [2, 4])
+def test_halo_exchange_over_gloo(world):
+    """world 2: both neighbours are the same peer; world 4: distinct lower / upper neighbours, wrap pair at the ends."""
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_worker, args=(2, 29633, results), nprocs=2, join=True)
-    assert results[0][0] == 0 and results[1][0] == 0, dict(results)
-    assert results[0][1] + results[1][1] == N
-    assert results[0][2] > 0 and results[1][2] > 0
+    mp.spawn(_worker, args=(world, 29633 + world, results), nprocs=world, join=True)
+    assert all(results[r][0] == 0 for r in range(world)), dict(results)
+    assert sum(results[r][1] for r in range(world)) == N
+    assert all(results[r][2] > 0 for r in range(world))
 
 
 def test_plan_and_ownership_rules():
