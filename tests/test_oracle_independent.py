@@ -253,3 +253,35 @@ def test_function_conditions_and_state_lists_against_numpy():
         assert np.array_equal(so_[:, 0].astype(np.uint64) | (so_[:, 1].astype(np.uint64) << np.uint64(24)), seeds), it
     assert len(active["id"]) > 0 and len(idle["id"]) > 0 and not np.array_equal(idle["id"], np.sort(idle["id"]))
     orc.close()
+
+
+def test_global_condition_against_numpy():
+    """tests/models/GlobalGate: a function with a globalCondition (simulation.xslt:1530-1588) runs for EVERY agent of
+    its state, and only in an iteration where all of them meet the condition (mustEvaluateTo = true) -- or once the
+    condition has failed maxItterations times in a row, after which the counter starts again."""
+    import os
+    from common import ROOT, gen_oracle, OracleSimulation
+    xml = os.path.join(ROOT, "tests", "models", "GlobalGate", "XMLModelFile.xml")
+    orc = OracleSimulation(gen_oracle.build_oracle(xml, "GlobalGate"))
+    n = 300
+    ident = np.arange(n, dtype=np.int32)
+    level, rounds = (ident * 5 % 4).astype(np.int32), np.zeros(n, np.int32)
+    level[0] = -20                                        # one straggler: the first release comes from the limit
+    orc.set_agents("Node", "default", {"id": ident, "level": level.copy(), "rounds": rounds.copy()})
+    failed, ran = 0, []
+    for it in range(40):
+        level = level + 1 + ident % 3
+        all_true = bool((level >= 3).all())
+        if not all_true and failed < 4:
+            failed += 1                                   # skipped this iteration
+        else:
+            failed = 0
+            level, rounds = (ident % 2).astype(np.int32), rounds + 1
+            ran.append((it, all_true))
+        orc.step(1)
+        got = orc.agents("Node")
+        assert np.array_equal(got["level"], level) and np.array_equal(got["rounds"], rounds), it
+        assert np.array_equal(got["id"], ident)
+    # both ways of getting through the gate occurred: everybody ready, and the iteration limit
+    assert any(t for _, t in ran) and any(not t for _, t in ran), ran
+    orc.close()
