@@ -160,3 +160,18 @@ def test_product_path_fails_loudly_without_its_cuda_parts(tmp_path, monkeypatch)
     monkeypatch.setattr(build, "runtime_path", lambda: str(tmp_path / "libfgpu_rt.so"))
     with pytest.raises(FgpuError, match="no CPU fallback"):
         runtime.load_runtime()
+
+
+def test_every_prebuilt_plugin_matches_the_runtime_abi():
+    """The in-tree plugins travel to the GPU box as built: a plugin left over from an older plugin ABI would only
+    fail there.  dlopen + descriptor check needs no GPU."""
+    import glob
+    from ev_diffusion_b200 import runtime
+    lib = runtime.load_runtime()
+    plugins = sorted(glob.glob(os.path.join(build.LIB, "models", "*.so")))
+    assert plugins, "no model plugin built: run __graft_entry__.build()"
+    stale = []
+    for p in plugins:
+        if not lib.fgpu_model_load(os.fsencode(p)):
+            stale.append((os.path.basename(p), lib.fgpu_last_error().decode()))
+    assert not stale, stale
