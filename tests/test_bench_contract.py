@@ -1,0 +1,40 @@
+"""The CPU arm of bench.py (`--impl reference`: the host-C oracle on all host cores) prints one JSON line with the
+keys the driver reads; under torchrun only rank 0 prints.  The GPU arm needs a B200 and is exercised by the
+driver itself."""
+import json
+import os
+import subprocess
+import sys
+
+from common import ROOT
+
+REQUIRED = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+            "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"}
+
+
+def _run(extra_env=None, gpus=1):
+    env = dict(os.environ, **(extra_env or {}))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", str(gpus), "--steps", "1",
+                          "--warmup", "1", "--workload", "c2_tiny"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                         timeout=600, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return [l for l in out.stdout.splitlines() if l.strip()]
+
+
+def test_reference_arm_prints_the_contract_line():
+    lines = _run()
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert REQUIRED <= set(d), REQUIRED - set(d)
+    assert d["impl"] == "reference" and d["metric"] == "agent-steps/sec" and d["unit"] == "agent-steps/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["value"] > 0
+    assert d["warmup"] >= 3                                  # the timing rules ask for at least three warm-up steps
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_under_torchrun_only_rank0_prints():
+    assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, gpus=2) == []
+    lines = _run({"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"}, gpus=2)
+    assert len(lines) == 1 and json.loads(lines[0])["n_gpus"] == 2
