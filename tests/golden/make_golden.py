@@ -51,7 +51,22 @@ def snapshot(sim):
     return out
 
 
+def brownian_fixture():
+    """The flagship workload at parity size (c2_small: 16384 particles, 16^3 cells): state after 10 iterations of
+    the oracle from the seeded synthetic input of ev_diffusion_b200.workloads (no 0.xml involved)."""
+    from ev_diffusion_b200 import workloads as W
+    cfg = W.BROWNIAN["c2_small"]
+    so = gen_oracle.build_oracle(W.brownian_xml(cfg), cfg.name, function_files=W.brownian_function_files())
+    sim = OracleSimulation(so)
+    sim.set_agents("Particle", "default", W.brownian_state(cfg))
+    sim.step(10)
+    np.savez_compressed(os.path.join(HERE, "Brownian_small_iter10.npz"), **snapshot(sim))
+    print("Brownian_small: 10 iterations,", sim.agent_count("Particle", "default"), "particles")
+    sim.close()
+
+
 def main():
+    brownian_fixture()
     for name, iters in CASES:
         xml = f"{REF}/{name}/src/model/XMLModelFile.xml"
         model = xmml.parse_model(xml)

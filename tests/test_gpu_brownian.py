@@ -81,6 +81,24 @@ def test_many_iterations_exact(order, graph):
     orc.close()
 
 
+def test_exact_build_reproduces_the_committed_fixture():
+    """tests/golden/Brownian_small_iter10.npz (written by the oracle, tests/golden/make_golden.py): the CUDA path must
+    land on the same bytes without the oracle in the loop."""
+    import os
+    from common import ROOT
+    want = np.load(os.path.join(ROOT, "tests", "golden", "Brownian_small_iter10.npz"))
+    gpu = Simulation(brownian_plugin("c2_small", exact=True))
+    gpu.set_agents("Particle", "default", W.brownian_state(W.BROWNIAN["c2_small"]))
+    gpu.step(10)
+    assert gpu.agent_count("Particle", "default") == int(want["count/Particle/default"])
+    got = gpu.agents("Particle")
+    for v in ("id", "x", "y", "z", "nbr"):
+        ref = want[f"agent/Particle/default/{v}"]
+        assert got[v].dtype == ref.dtype and np.array_equal(got[v].view(np.uint8), ref.view(np.uint8)), v
+    assert np.array_equal(gpu.seeds(), want["seeds"])
+    gpu.close()
+
+
 def test_generic_get_next_build_is_bit_identical():
     """The same functions.c compiled byte for byte (flat get_first/get_next cursor, looprewrite off): the
     loop-restructured build every other test uses and this one must both match the oracle exactly."""

@@ -56,6 +56,22 @@ def test_oracle_reproduces_golden_fixture(name):
     sim.close()
 
 
+def test_oracle_reproduces_the_brownian_fixture():
+    """The flagship workload (C2 at parity size): seeded synthetic input from workloads.py, 10 iterations."""
+    from common import W, brownian_oracle
+    want = np.load(os.path.join(GOLDEN, "Brownian_small_iter10.npz"))
+    sim = brownian_oracle("c2_small")
+    sim.set_agents("Particle", "default", W.brownian_state(W.BROWNIAN["c2_small"]))
+    sim.step(10)
+    n = int(want["count/Particle/default"])
+    assert sim.agent_count("Particle", "default") == n
+    for v in ("id", "x", "y", "z", "nbr"):
+        got, ref = sim.agent_var("Particle", "default", v, n), want[f"agent/Particle/default/{v}"]
+        assert got.dtype == ref.dtype and np.array_equal(got.view(np.uint8), ref.view(np.uint8)), v
+    assert np.array_equal(sim.seeds(), want["seeds"])
+    sim.close()
+
+
 @pytest.mark.parametrize("name", ["Boids_Partitioning", "CirclesBruteForce_float", "SocialParticleSimulation"])
 def test_openmp_oracle_equals_sequential_oracle(name):
     """bench.py's CPU legs run the oracle with OpenMP over agents; per-agent work is independent, so the
