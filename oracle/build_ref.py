@@ -132,7 +132,7 @@ def functions_reaching_barrier(sources: List[str], defined: Set[str] = frozenset
     for s in sources:
         for k, v in function_bodies(s, defined).items():
             bodies[k] = bodies.get(k, "") + v
-    calls = {k: set(re.findall(r"\b([A-Za-z_]\w*)\s*(?:<[^;(){}]*>)?\s*\(", v)) & set(bodies) for k, v in bodies.items()}
+    calls = {k: set(re.findall(r"\b([A-Za-z_]\w*)\s*(?:<(?!<)[^;(){}]*>)?\s*\(", v)) & set(bodies) for k, v in bodies.items()}
     reach = {k for k, v in bodies.items() if re.search(r"\b__syncthreads\s*\(", v)}
     changed = True
     while changed:

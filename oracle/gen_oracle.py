@@ -75,8 +75,9 @@ def _message_api(m: Message) -> str:
         out.append(f"    messages->{v.name}[index] = {v.name};")
     out.append("}")
     if m.partitioning != "spatial":
-        # brute force: every message in list order (krn:445-520 visits all messages; the tile
-        # staging through shared memory does not change the order)
+        # brute force: every message, in list order 0..N-1.  krn:445-520 visits all messages starting at the calling
+        # block's own tile and wrapping round, so the reference's order is 0..N-1 exactly when one block holds the
+        # whole list; with smaller blocks it is a per-block rotation of it (tests/test_oracle_vs_reference.py)
         out.append(f"""static thread_local {S} orc_sm_{n};
 static {S}* orc_load_{n}({S}_list* messages, int i){{
     if (i >= d_message_{n}_count) return nullptr;

@@ -9,15 +9,27 @@
  *
  * The reference has no CPU path, no tests and no golden vectors (SURVEY.md 4,
  * 8c), and its generator (xsltproc) and its texture-reference CUDA cannot be
- * built in this image, so this oracle cannot be checked against a run of the
- * reference itself.  What pins it:
+ * built by this image's toolchain as shipped.  What pins this restatement:
+ *   - THE REFERENCE ITSELF, run here: oracle/build_ref.py expands the
+ *     reference's own templates (oracle/xslt_subset.py stands in for xsltproc),
+ *     rewrites only the <<<>>> launch syntax and compiles the generated
+ *     simulation.cu / FLAMEGPU_kernals.cu / io.cu plus the model's functions.c
+ *     against oracle/cuda_on_host/ (every CUDA thread run on the CPU) into
+ *     oracle/_ref/.  tests/test_oracle_vs_reference.py steps that build and
+ *     this oracle side by side -- eleven of the reference's example models
+ *     from their shipped inputs, the authored fixtures (death, births,
+ *     optional messages, conditions, globalCondition, host-side creation) and
+ *     the Brownian workload -- and requires identical bytes in every variable
+ *     of every state, identical counts and identical rand48 seeds;
  *   - the rand48 known-answer vectors derived from simulation.xslt:661-688 and
  *     cross-checked against glibc srand48(123)/lrand48();
  *   - partition dims / radix-bit vectors;
  *   - it executes the reference's OWN agent scripts (functions.c) unchanged.
- * Everything else (list discipline, message build, iteration order) is a
- * line-by-line reading of the templates cited at each function: parity for
- * those parts is "unpinned" in the sense of the task statement.
+ * One thing the reference leaves to the device: the order in which an agent
+ * meets NON-partitioned messages starts at its block's own tile
+ * (FLAMEGPU_kernals.xslt:445-520), so it depends on the block size the
+ * occupancy API picks.  This oracle (and the CUDA path) use 0..N-1 for every
+ * agent, the reference's order when one block holds the list.
  *
  * Every function cites the template lines it follows:
  *   sim = FLAMEGPU/templates/simulation.xslt, krn = FLAMEGPU_kernals.xslt,
