@@ -377,13 +377,23 @@ def _host_api_decls(model: Model) -> str:
            "extern void singleIteration();",
            "extern void set_exit_early();",
            "extern bool get_exit_early();",
-           "extern const char* getOutputDir();"]
+           "extern const char* getOutputDir();",
+           "/* bounds of the agents read by the last initialise()/readInitialStates(): start at 0, grow with every x, y, z (io.xslt:256-261,418-439,623-629) */",
+           "extern glm::vec3 getMaximumBounds();",
+           "extern glm::vec3 getMinimumBounds();"]
+    # io.xslt:124,211: one (host list, device list, count) triple per agent state / one (host list, count) pair per agent
+    save_args = "".join(f", xmachine_memory_{a.name}_list* h_{a.name}s_{s}, xmachine_memory_{a.name}_list* d_{a.name}s_{s}, int h_xmachine_memory_{a.name}_{s}_count"
+                        for a in model.agents for s in a.states)
+    read_args = "".join(f", xmachine_memory_{a.name}_list* h_{a.name}s, int* h_xmachine_memory_{a.name}_count" for a in model.agents)
+    out.append(f"extern void saveIterationData(char* outputpath, int iteration_number{save_args});")
+    out.append(f"extern void readInitialStates(char* inputpath{read_args});")
     for a in model.agents:
         out.append(f"extern int get_agent_{a.name}_MAX_count();")
         for s in a.states:
             out.append(f"extern int get_agent_{a.name}_{s}_count();")
             out.append(f"extern void reset_{a.name}_{s}_count();")
             out.append(f"extern xmachine_memory_{a.name}_list* get_device_{a.name}_{s}_agents();")
+            out.append(f"extern xmachine_memory_{a.name}_list* get_host_{a.name}_{s}_agents();")
             for v in a.variables:
                 if not v.array_length:
                     out.append(f"{v.type} get_{a.name}_{s}_variable_{v.name}(unsigned int index);")
@@ -404,6 +414,77 @@ def _host_api_decls(model: Model) -> str:
             out.append(f"void h_add_agent_{a.name}_{s}(xmachine_memory_{a.name}* agent);")
             out.append(f"void h_add_agents_{a.name}_{s}(xmachine_memory_{a.name}** agents, unsigned int count);")
     return "\n".join(out)
+
+
+def _host_list_defs(model: Model) -> List[str]:
+    """get_host_<A>_<S>_agents (header.xslt:605-613), readInitialStates / saveIterationData with the reference's
+    parameter lists (io.xslt:124,211) and getMaximum/MinimumBounds (io.xslt:623-629), all on top of the C ABI.
+
+    The reference keeps one host copy of every state list and refreshes it only when it writes an XML file; here the
+    host copy is filled from the device every time it is asked for, which is what a caller of the reference has to
+    arrange by hand (cudaMemcpy from get_device_*) before the pointer means anything."""
+    out = ["/* the reader accumulates the bounds while it parses; here they are folded on the device the first time they are",
+           "   asked for after a read (callers -- the visualisation -- ask right after initialise()) */",
+           "static glm::vec3 fgpu_agent_maximum(0.0f, 0.0f, 0.0f), fgpu_agent_minimum(0.0f, 0.0f, 0.0f);",
+           "static bool fgpu_bounds_stale = false;",
+           "static void fgpu_fold_bounds();",
+           "static void fgpu_update_bounds(){ fgpu_bounds_stale = true; }",
+           "glm::vec3 getMaximumBounds(){ if (fgpu_bounds_stale) fgpu_fold_bounds(); return fgpu_agent_maximum; }",
+           "glm::vec3 getMinimumBounds(){ if (fgpu_bounds_stale) fgpu_fold_bounds(); return fgpu_agent_minimum; }"]
+    fill: List[str] = []
+    for ai, a in enumerate(model.agents):
+        cols = ", ".join(("nullptr" if v.array_length else f"(void*)h->{v.name}") for v in a.variables)
+        out.append(f"""static void fgpu_fill_host_{a.name}(xmachine_memory_{a.name}_list* h, int state, int count){{
+    void* const columns[] = {{{cols}}};
+    if (count > 0 && fgpu_sim_read_agents(fgpu_cur, {ai}, state, count, columns) != FGPU_OK) fgpu_die();
+}}""")
+        for si, st in enumerate(a.states):
+            out.append(f"""xmachine_memory_{a.name}_list* get_host_{a.name}_{st}_agents(){{
+    static xmachine_memory_{a.name}_list* h = nullptr;
+    if (!h) h = (xmachine_memory_{a.name}_list*)calloc(1, sizeof(xmachine_memory_{a.name}_list));
+    if (!h) {{ fprintf(stderr, "get_host_{a.name}_{st}_agents: out of host memory\\n"); exit(EXIT_FAILURE); }}
+    fgpu_fill_host_{a.name}(h, {si}, fgpu_sim_agent_count(fgpu_cur, {ai}, {si}));
+    return h;
+}}""")
+        # bounds over the variables called x, y, z of the initial state list, as the reader accumulates them
+        init = a.states.index(a.initial_state)
+        for axis in "xyz":
+            for vi, v in enumerate(a.variables):
+                if v.name == axis and not v.array_length:
+                    fill.append(f"    if (fgpu_sim_agent_count(fgpu_cur, {ai}, {init}) > 0) {{ {v.type} lo = 0, hi = 0;\n"
+                                f"        if (fgpu_sim_reduce_agent_var(fgpu_cur, {ai}, {init}, {vi}, FGPU_REDUCE_MIN, nullptr, &lo) != FGPU_OK) fgpu_die();\n"
+                                f"        if (fgpu_sim_reduce_agent_var(fgpu_cur, {ai}, {init}, {vi}, FGPU_REDUCE_MAX, nullptr, &hi) != FGPU_OK) fgpu_die();\n"
+                                f"        if (fgpu_agent_minimum.{axis} > (float)lo) fgpu_agent_minimum.{axis} = (float)lo;\n"
+                                f"        if (fgpu_agent_maximum.{axis} < (float)hi) fgpu_agent_maximum.{axis} = (float)hi; }}")
+    out.append("static void fgpu_fold_bounds(){\n    fgpu_bounds_stale = false;\n    fgpu_agent_maximum = glm::vec3(0.0f, 0.0f, 0.0f); fgpu_agent_minimum = glm::vec3(0.0f, 0.0f, 0.0f);\n"
+               + "\n".join(fill) + "\n}")
+    save_args = "".join(f", xmachine_memory_{a.name}_list* h_{a.name}s_{s}, xmachine_memory_{a.name}_list* d_{a.name}s_{s}, int h_xmachine_memory_{a.name}_{s}_count"
+                        for a in model.agents for s in a.states)
+    read_args = "".join(f", xmachine_memory_{a.name}_list* h_{a.name}s, int* h_xmachine_memory_{a.name}_count" for a in model.agents)
+    body = []
+    for ai, a in enumerate(model.agents):
+        for si, st in enumerate(a.states):
+            body.append(f"    if (h_{a.name}s_{st}) fgpu_fill_host_{a.name}(h_{a.name}s_{st}, {si}, fgpu_sim_agent_count(fgpu_cur, {ai}, {si}));")
+            body.append(f"    (void)d_{a.name}s_{st}; (void)h_xmachine_memory_{a.name}_{st}_count;")
+    out.append(f"""void saveIterationData(char* outputpath, int iteration_number{save_args}){{
+    /* io.xslt:124-200: device lists -> host lists -> <outputpath><iteration_number>.xml.  The lists written are the
+       simulation's own (the device pointers a caller can pass are the ones get_device_* returned). */
+{chr(10).join(body)}
+    if (fgpu_sim_save_states(fgpu_cur, outputpath, iteration_number) != FGPU_OK) fgpu_die();
+}}""")
+    body = []
+    for ai, a in enumerate(model.agents):
+        init = a.states.index(a.initial_state)
+        body.append(f"    {{ int n = fgpu_sim_agent_count(fgpu_cur, {ai}, {init}); if (h_xmachine_memory_{a.name}_count) *h_xmachine_memory_{a.name}_count = n;")
+        body.append(f"      if (h_{a.name}s) fgpu_fill_host_{a.name}(h_{a.name}s, {init}, n); }}")
+    out.append(f"""void readInitialStates(char* inputpath{read_args}){{
+    /* io.xslt:211-621: parse the file into the initial state lists (and the environment constants).  Here the lists
+       live on the device, so the file is loaded into the simulation and the caller's host lists are filled from it. */
+    if (fgpu_sim_load_states(fgpu_cur, inputpath) != FGPU_OK) fgpu_die();
+    fgpu_update_bounds();
+{chr(10).join(body)}
+}}""")
+    return out
 
 
 def _host_creation_defs(model: Model, add_call: str, count_call: str) -> List[str]:
@@ -692,6 +773,7 @@ def _face2_shim(model: Model, cuda: bool) -> str:
            "static fgpu_sim* fgpu_cur = nullptr;",
 
            "static void fgpu_plugin_bind(void* sim){ fgpu_cur = (fgpu_sim*)sim; }",
+           "static void fgpu_update_bounds();",
            'static void fgpu_die(){ fprintf(stderr, "%s\\n", fgpu_last_error()); fflush(stderr); exit(EXIT_FAILURE); }',
            "unsigned int getIterationNumber(){ return fgpu_sim_iteration(fgpu_cur); }",
            "void set_exit_early(){ fgpu_set_exit_early(1); }",
@@ -703,6 +785,7 @@ def _face2_shim(model: Model, cuda: bool) -> str:
     fgpu_cur = fgpu_sim_create(fgpu_model_get(), dev ? atoi(dev) : 0);
     if (!fgpu_cur) fgpu_die();
     if (fgpu_sim_load_states(fgpu_cur, inputfile) != FGPU_OK) fgpu_die();
+    fgpu_update_bounds();
     if (fgpu_sim_run_init_functions(fgpu_cur) != FGPU_OK) fgpu_die();
 }
 void singleIteration(){ if (fgpu_sim_step(fgpu_cur, 1) != FGPU_OK) fgpu_die(); }
@@ -717,6 +800,7 @@ void cleanup(){ fgpu_sim_run_exit_functions(fgpu_cur); fgpu_sim_destroy(fgpu_cur
                 if not v.array_length:
                     out.append(f"{v.type} get_{a.name}_{st}_variable_{v.name}(unsigned int index){{ {v.type} t = 0; "
                                f"if (fgpu_sim_read_agent_value(fgpu_cur, {ai}, {si}, {vi}, index, &t) != FGPU_OK) fgpu_die(); return t; }}")
+    out += _host_list_defs(model)
     out.append("static int fgpu_reduce_cur(int a, int s, int v, int op, const void* cv, void* r){ return fgpu_sim_reduce_agent_var(fgpu_cur, a, s, v, op, cv, r); }")
     out += _reduction_defs(model, "fgpu_reduce_cur")
     out.append("static int fgpu_add_cur(int a, int s, int n, const void* const* cols){ return fgpu_sim_add_agents(fgpu_cur, a, s, n, cols); }")

@@ -69,7 +69,7 @@ def _matching(text: str, pos: int, open_c: str, close_c: str) -> int:
 def _active_branches_only(masked: str, defined: Set[str]) -> str:
     """Blank the inactive branches of preprocessor conditionals (same length, newlines kept): the expanded sources open
     a brace in both branches of an #ifdef and close it once, so only one branch may be seen when matching.  #ifdef and
-    #ifndef are decided against `defined`; any other #if keeps its first branch."""
+    #ifndef and a lone `#if [!]defined(X)` are decided against `defined`; any other #if keeps its first branch."""
     out, live = [], []                      # live[k]: the current branch of conditional k is compiled
     for line in masked.split("\n"):
         d = re.match(r"\s*#\s*(ifdef|ifndef|if|else|elif|endif)\b\s*(\w*)", line)
@@ -80,7 +80,8 @@ def _active_branches_only(masked: str, defined: Set[str]) -> str:
             elif kind == "ifndef":
                 live.append(d.group(2) not in defined)
             elif kind == "if":
-                live.append(True)
+                single = re.match(r"\s*#\s*if\s+(!?)\s*defined\s*\(?\s*(\w+)\s*\)?\s*$", line)
+                live.append(((single.group(2) in defined) != (single.group(1) == "!")) if single else True)
             elif kind in ("else", "elif") and live:
                 live[-1] = not live[-1]
             elif kind == "endif" and live:
@@ -281,11 +282,93 @@ def build_ref(xml_path: str, name: str, function_dir: Optional[str] = None, fast
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# device build: the reference's generated CUDA compiled for sm_100a (timing baseline on the GPU box)
+# ---------------------------------------------------------------------------------------------------------------------
+
+DEVICE_PRELUDE = r"""
+// ---- prelude written by oracle/build_ref.py (not reference text) ----------------------------------------------------
+// CUDA 12 removed texture REFERENCES (texture<T,1,cudaReadModeElementType> + cudaBindTexture + tex1Dfetch(ref, i)).  The
+// generated sources use them for one thing only: cached reads of a linear device array.  build_ref.py rewrites each
+// `texture<T, 1, cudaReadModeElementType> NAME;` into `__device__ const T* NAME;`; the three calls keep their spelling:
+#include <cuda_runtime.h>
+// thrust entry points the sources call but, with today's thrust, no longer receive through their own includes
+#include <thrust/count.h>
+#include <thrust/reduce.h>
+template <class T> static __device__ __forceinline__ T tex1Dfetch(const T* p, int i) { return __ldg(p + i); }
+template <class T> static cudaError_t fgpu_ref_bind(size_t* offset, T*& symbol, const void* p) {
+    if (offset) *offset = 0;
+    return cudaMemcpyToSymbol(symbol, &p, sizeof(p));
+}
+#define cudaBindTexture(offset, tex, ptr, size) fgpu_ref_bind(offset, tex, (const void*)(ptr))
+#define cudaUnbindTexture(tex) cudaSuccess
+// ---------------------------------------------------------------------------------------------------------------------
+"""
+
+
+def patch_texture_references(src: str) -> str:
+    return re.sub(r"\btexture\s*<\s*([\w:\s]+?)\s*,\s*1\s*,\s*cudaReadModeElementType\s*>\s*(\w+)\s*;",
+                  r"__device__ const \1* \2;", src)
+
+
+def ref_device_path(name: str) -> str:
+    return os.path.join(OUT, name, f"ref_gpu_{name}")
+
+
+def build_ref_device(xml_path: str, name: str, function_dir: Optional[str] = None, fast_atomic: bool = True,
+                     force: bool = False) -> str:
+    """The reference's console program for a model (its own main.cu, simulation.cu, kernels, io.cu and the model's
+    functions.c) compiled by nvcc for sm_100a: ``ref_gpu_<name> <0.xml> <iterations>`` prints the reference's own
+    "Total Processing time".  Edits: texture references (see DEVICE_PRELUDE) -- nothing else.  Default build options are
+    the reference's (FAST_ATOMIC_SORTING on, -use_fast_math off, Release -O3)."""
+    if not reference_available():
+        raise RuntimeError("the reference tree is not mounted (%s)" % REFERENCE)
+    model = xmml.parse_model(xml_path)
+    mdir = function_dir or os.path.dirname(os.path.abspath(xml_path))
+    out = ref_device_path(name)
+    dyn = os.path.join(OUT, name, "dynamic_device")
+    os.makedirs(dyn, exist_ok=True)
+    sources = dict(EXPANDED)
+    sources["main.xslt"] = "main.cu"
+    deps = [xml_path, os.path.abspath(__file__), os.path.join(HERE, "xslt_subset.py")]
+    deps += [os.path.join(mdir, f) for f in model.function_files] + [os.path.join(TEMPLATES, x) for x in sources]
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps if os.path.exists(d)):
+        return out
+    for xslt, target in sources.items():
+        text = xslt_subset.Stylesheet(os.path.join(TEMPLATES, xslt)).transform(xml_path)
+        if target.endswith(".cu"):
+            text = patch_texture_references(text)
+        with open(os.path.join(dyn, target), "w") as f:
+            f.write(text)
+    with open(os.path.join(dyn, "texture_prelude.h"), "w") as f:
+        f.write(DEVICE_PRELUDE)
+    # the reference vendors glm AND a 2016 cub under include/; only glm may be seen (cub and thrust are the toolkit's)
+    inc = os.path.join(dyn, "include")
+    os.makedirs(inc, exist_ok=True)
+    if not os.path.islink(os.path.join(inc, "glm")):
+        os.symlink(os.path.join(REFERENCE, "include", "glm"), os.path.join(inc, "glm"))
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-w",
+           "-include", os.path.join(dyn, "texture_prelude.h"), "-I", dyn, "-I", mdir, "-I", inc, "-DGLM_FORCE_PURE"]
+    if not fast_atomic:
+        cmd.append("-UFAST_ATOMIC_SORTING")
+    cmd += [os.path.join(dyn, "main.cu"), os.path.join(dyn, "simulation.cu"), os.path.join(dyn, "io.cu"), "-o", out]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    with open(out + ".log", "w") as f:
+        f.write(" ".join(cmd) + "\n" + proc.stdout)
+    if proc.returncode != 0:
+        raise RuntimeError("reference device build failed (%s):\n%s" % (name, proc.stdout[-8000:]))
+    return out
+
+
 if __name__ == "__main__":
     import argparse
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
     ap.add_argument("xml")
     ap.add_argument("name")
     ap.add_argument("--fast-atomic", action="store_true")
+    ap.add_argument("--device", action="store_true", help="nvcc build of the reference's console program for sm_100a")
     a = ap.parse_args()
-    print(build_ref(a.xml, a.name, fast_atomic=a.fast_atomic, force=True))
+    if a.device:
+        print(build_ref_device(a.xml, a.name, force=True))
+    else:
+        print(build_ref(a.xml, a.name, fast_atomic=a.fast_atomic, force=True))

@@ -1,0 +1,103 @@
+"""The drop-in boundary, name by name: every function the reference's OWN generated header.h declares for a model
+(header.xslt expanded over the model by oracle/xslt_subset.py) must be declared by the header this repository generates
+for the same model, with the same return type and parameter types -- agent scripts and drivers are compiled against one
+or the other and must not notice.  The exceptions are listed here, each with its reason; anything else missing or
+different fails."""
+import os
+import re
+
+import pytest
+
+from common import REFERENCE
+from ev_diffusion_b200 import codegen, xmml
+from ev_diffusion_b200.looprewrite import mask_comments_and_strings
+from oracle import build_ref, xslt_subset
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(f"{REFERENCE}/FLAMEGPU/templates"), reason="the reference tree is not mounted")
+
+# per-model name patterns the reference declares (console build: no -DVISUALISATION, no -DPROFILE) and this repository
+# does not provide yet
+NOT_PROVIDED = {
+    r"generate_\w+_id|set_initial_\w+_id": "device-side id generation (an atomic counter synchronised around every layer): DESIGN.md section 8, next round",
+    r"sort_\w+s_\w+": "agent sort by a user key/value kernel (simulation.xslt:750-776): DESIGN.md section 8, next round",
+}
+MODELS = ["CirclesPartitioning_float", "CirclesBruteForce_double", "Boids_Partitioning", "SmoothedParticleHydrodynamics",
+          "Keratinocyte", "SocialParticleSimulation", "MonteCarlo_MSMPR", "Analytics", "EmptyExample"]
+QUALIFIERS = ("extern", "__FLAME_GPU_HOST_FUNC__", "__FLAME_GPU_FUNC__", "__host__", "__device__", "FGPU_DEV", "FGPU_HD", "inline",
+              "static", "__forceinline__")
+
+
+def _strip_names(args: str):
+    out = []
+    depth, cur = 0, ""
+    for ch in args + ",":
+        if ch == "," and depth == 0:
+            a = re.sub(r"\s*=.*$", "", " ".join(cur.split()))
+            if a and a != "void":
+                fp = re.match(r"(.*)\(\s*\*\s*\w*\s*\)\s*\((.*)\)$", a)          # function pointer parameter
+                if fp:
+                    a = fp.group(1).strip() + "(*)(" + ",".join(_strip_names(fp.group(2))) + ")"
+                else:
+                    m = re.match(r"(.*?[\s\*&])([A-Za-z_]\w*)$", a)
+                    a = m.group(1) if m else a
+                out.append(a.replace(" ", ""))
+            cur = ""
+            continue
+        depth += ch in "(<"
+        depth -= ch in ")>"
+        cur += ch
+    return out
+
+
+def declarations(text: str):
+    """{name: (return type, [parameter types])} of every function declared or defined at namespace scope."""
+    masked = mask_comments_and_strings(text).replace("\\\n", " ")          # macro continuation lines
+    masked = build_ref._active_branches_only(masked, set())                  # no -DPROFILE, no -DVISUALISATION ...
+    masked = "\n".join("" if line.lstrip().startswith("#") else line for line in masked.split("\n"))
+    # drop bodies so that calls inside inline definitions are not mistaken for declarations
+    flat, depth = [], 0
+    for ch in masked:
+        if ch == "{":
+            depth += 1
+            flat.append(";" if depth == 1 else "")
+        elif ch == "}":
+            depth -= 1
+        elif depth == 0:
+            flat.append(ch)
+    found = {}
+    for stmt in "".join(flat).split(";"):
+        stmt = " ".join(stmt.split())
+        m = re.match(r"^(?:template\s*<[^>]*>\s*)?(.*?)\b([A-Za-z_]\w*)\s*\((.*)\)$", stmt)
+        if not m or not m.group(1).strip():
+            continue
+        ret = " ".join(w for w in m.group(1).split() if w not in QUALIFIERS and w != '"C"')
+        if not ret or ret.split()[0] in ("struct", "enum", "typedef", "class", "return", "public:"):
+            continue
+        found[m.group(2)] = (ret.replace(" ", ""), _strip_names(m.group(3)))
+    return found
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_every_reference_declaration_is_provided(name):
+    xml = f"{REFERENCE}/examples/{name}/src/model/XMLModelFile.xml"
+    ref = declarations(xslt_subset.Stylesheet(f"{REFERENCE}/FLAMEGPU/templates/header.xslt").transform(xml))
+    ours = declarations(codegen.emit_cuda_header(xmml.parse_model(xml)))
+    assert len(ref) > 40 and "singleIteration" in ref and "initialise" in ref
+    excused = re.compile("|".join(f"(?:{p})" for p in NOT_PROVIDED))
+    missing = sorted(k for k in ref if k not in ours and not excused.fullmatch(k))
+    assert not missing, f"{name}: declared by the reference's header.h, absent from ours: {missing}"
+    different = {k: (ref[k], ours[k]) for k in ref if k in ours and ref[k] != ours[k]}
+    assert not different, f"{name}: signatures differ from the reference's: {different}"
+    # the exceptions are real: each pattern matches something the reference declares for this model or another one
+    assert any(excused.fullmatch(k) for k in ref)
+
+
+def test_exception_list_is_not_stale():
+    """Every excuse pattern still matches a name the reference declares somewhere (a pattern that matches nothing has
+    been fixed and must be deleted)."""
+    seen = set()
+    for name in MODELS:
+        xml = f"{REFERENCE}/examples/{name}/src/model/XMLModelFile.xml"
+        seen |= set(declarations(xslt_subset.Stylesheet(f"{REFERENCE}/FLAMEGPU/templates/header.xslt").transform(xml)))
+    for pattern in NOT_PROVIDED:
+        assert any(re.fullmatch(pattern, k) for k in seen), pattern
