@@ -183,6 +183,12 @@ def emit_shim(model) -> str:
                     "    initialise(const_cast<char*>(input));",
                     "}",
                     "void ref_step(int n) { for (int i = 0; i < n; ++i) singleIteration(); }",
+                    "// the reference's own iteration-file writer, called the way its main.cu calls it (main.xslt:367)",
+                    "void ref_save_iteration(const char* outputpath, int iteration) {",
+                    "    saveIterationData(const_cast<char*>(outputpath), iteration, " + ", ".join(
+                        f"get_host_{a.name}_{s}_agents(), get_device_{a.name}_{s}_agents(), get_agent_{a.name}_{s}_count()"
+                        for a in model.agents for s in a.states) + ");",
+                    "}",
                     "void ref_cleanup() { cleanup(); }",
                     "unsigned ref_iteration() { return getIterationNumber(); }",
                     "int ref_buffer_size_max() { return buffer_size_MAX; }",

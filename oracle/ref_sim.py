@@ -104,6 +104,13 @@ class RefSimulation:
             raise KeyError(message)
         return start, end
 
+    def save_iteration(self, outputpath: str, iteration: int) -> str:
+        """The reference's saveIterationData (io.xslt:124-200): writes <outputpath><iteration>.xml; returns the path."""
+        self.lib.ref_save_iteration.argtypes = [ctypes.c_char_p, ctypes.c_int]
+        with _silenced(self.quiet):
+            self.lib.ref_save_iteration(outputpath.encode(), int(iteration))
+        return "%s%d.xml" % (outputpath, iteration)
+
     def seeds(self) -> np.ndarray:
         out = np.empty((int(self.lib.ref_buffer_size_max()), 2), dtype=np.uint32)
         self.lib.ref_seeds(out.ctypes.data)

@@ -216,3 +216,42 @@ def test_brute_force_order_depends_on_block_size(tmp_path):
         assert np.allclose(a, b, rtol=0, atol=2e-3), v
         moved += int((a != b).sum())
     assert moved > 0
+
+
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="the reference tree is not mounted")
+@pytest.mark.parametrize("name,iters", [("Keratinocyte", 3), ("CirclesPartitioning_double", 2), ("Boids_Partitioning", 2)])
+def test_iteration_file_writer_and_reader_against_the_reference(name, iters, tmp_path):
+    """SURVEY.md 8(f) row 1.  The reference's OWN saveIterationData (io.xslt:124-200, compiled into the reference
+    build) writes an iteration file; oracle/xml_states.py::write_states -- the restatement the CUDA path's writer is
+    compared with byte for byte in tests/test_gpu_state_io.py -- must produce the same bytes from the same state
+    (environment constants, several states, %f floats and doubles, ints).  Then the file goes back through the
+    reference's OWN reader in a second process and through xml_states.read_states: same lists."""
+    from oracle.xml_states import read_states, write_states
+    xml = f"{REFERENCE}/examples/{name}/src/model/XMLModelFile.xml"
+    ref = RefSimulation(_ref_library(name, xml), xml, f"{REFERENCE}/examples/{name}/iterations/0.xml")
+    orc = _replay(name, 1, iters)
+    ref.step(iters)
+    theirs = ref.save_iteration(str(tmp_path) + os.sep, iters)
+    model = ref.model                                       # the parsed XMML (names, C types, defaults)
+    agents = [(a.name, [(s, [(v.name, v.type) for v in a.variables]) for s in a.states]) for a in model.agents]
+    states = {(a.name, s): {v.name: orc.agent_var(a.name, s, v.name, orc.agent_count(a.name, s)) for v in a.variables}
+              for a in model.agents for s in a.states}
+    consts = [(c.name, c.type, orc.get_constant(c.name)) for c in model.constants]
+    mine = tmp_path / "mine.xml"
+    write_states(str(mine), iters, agents, states, consts)
+    assert open(theirs, "rb").read() == mine.read_bytes()
+    # read back: every agent returns in its initial state (the file does not record states), %f precision
+    spec = [(a.name, [(v.name, v.type, float(v.default or 0)) for v in a.variables]) for a in model.agents]
+    back, env = read_states(theirs, spec, [(c.name, c.type) for c in model.constants if not c.array_length])
+    worker = ("import sys, numpy as np\nsys.path.insert(0, sys.argv[1])\nfrom oracle.ref_sim import RefSimulation\n"
+              "sim = RefSimulation(sys.argv[2], sys.argv[3], sys.argv[4])\n"
+              "np.savez(sys.argv[5], **{f'{a.name}/{v.name}': sim.agent_var(a.name, a.states.index(a.initial_state), v.name)"
+              " for a in sim.model.agents for v in a.variables if not v.array_length})\n")
+    out = tmp_path / "reread.npz"
+    subprocess.run([sys.executable, "-c", worker, ROOT, build_ref.ref_path(name), xml, theirs, str(out)], check=True, stdout=subprocess.DEVNULL)
+    reread = np.load(out)
+    for a in model.agents:
+        for v in a.variables:
+            assert np.array_equal(reread[f"{a.name}/{v.name}"].view(np.uint8), back[a.name][v.name].view(np.uint8)), (a.name, v.name)
+    ref.close()
+    orc.close()
