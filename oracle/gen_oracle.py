@@ -85,8 +85,25 @@ static {S}* orc_load_{n}({S}_list* messages, int i){{
         for v in m.variables:
             out.append(f"    orc_sm_{n}.{v.name} = messages->{v.name}[i];")
         out.append(f"    return &orc_sm_{n};\n}}")
-        out.append(f"{S}* get_first_{n}_message({S}_list* messages){{ return orc_load_{n}(messages, 0); }}")
-        out.append(f"{S}* get_next_{n}_message({S}* current, {S}_list* messages){{ return orc_load_{n}(messages, current->_position + 1); }}")
+        out.append(f"""/* get_first / get_next, krn:445-520.  The reference starts at the calling block's own tile and walks round:
+ * block b of B threads meets messages (b*B) % wrap ... count-1, 0 ... start-1, with wrap = ceil(count / B) * B (computed
+ * in float, as there).  B is the launch's block size: orc_brute_force_block, capped by the number of agents launched
+ * like the occupancy call's limit (sim:1601-1606); 0 = one block holds everything = plain list order. */
+static thread_local int orc_bf_start_{n}, orc_bf_wrap_{n};
+{S}* get_first_{n}_message({S}_list* messages){{
+    if (d_message_{n}_count == 0) return nullptr;
+    int B = orc_brute_force_block;
+    if (B <= 0 || B > orc_launch_threads) B = orc_launch_threads > 0 ? orc_launch_threads : 1;
+    orc_bf_wrap_{n} = (int)(ceil((float)d_message_{n}_count / B) * B);
+    orc_bf_start_{n} = ((orc_tid / B) * B) % orc_bf_wrap_{n};
+    return orc_load_{n}(messages, orc_bf_start_{n});
+}}
+{S}* get_next_{n}_message({S}* current, {S}_list* messages){{
+    int i = (current->_position + 1) % orc_bf_wrap_{n};
+    if (i >= d_message_{n}_count) i = 0;
+    if (i == orc_bf_start_{n}) return nullptr;
+    return orc_load_{n}(messages, i);
+}}""")
         return "\n".join(out) + "\n"
     dx, dy, dz = m.partition_dims()
     mn = ", ".join(f"(float){x}" for x in m.min_literals)
@@ -193,6 +210,7 @@ def emit_header(model: Model) -> str:
     out.append(_message_structs(model))
     out.append("struct RNG_rand48\n{\n    glm::uvec2 A, C;\n    glm::uvec2 seeds[buffer_size_MAX];\n};")
     out.append("extern thread_local int orc_tid;")
+    out.append("extern int orc_launch_threads, orc_brute_force_block;")
     out.append("template <int AGENT_TYPE> float rnd(RNG_rand48* rand48);\nfloat rnd(RNG_rand48* rand48);")
     for m in model.messages:
         S = f"xmachine_message_{m.name}"
@@ -241,6 +259,7 @@ def _thunk(model: Model, f: Function) -> str:
         call.append(f"(xmachine_message_{M}_list*)L->out_recs")
     if f.rng:
         call.append("(RNG_rand48*)L->seeds")
+    out.append("    orc_launch_threads = L->n;")
     out.append("    #pragma omp parallel for schedule(static)")
     out.append("    for (int index = 0; index < L->n; ++index){")
     out.append("        orc_tid = index;")
@@ -305,6 +324,9 @@ def emit_glue(model: Model, function_files: List[str]) -> str:
            '#include "header.h"',
            '#include "fgpu_model.h"',
            "thread_local int orc_tid = 0;",
+           "int orc_launch_threads = 0;          /* threads of the agent function being run (L->n) */",
+           "int orc_brute_force_block = 0;       /* block size assumed for non-partitioned message walks; 0 = one block */",
+           'extern "C" void orc_set_brute_force_block(int threads_per_block){ orc_brute_force_block = threads_per_block; }',
            """/* next_cell3D / next_cell2D, krn:105-154 */
 static bool orc_next_cell3D(glm::ivec3* relative_cell)
 {

@@ -36,3 +36,8 @@ class OracleSimulation(SimBase):
 
     def set_threads(self, n: int) -> None:
         self._lib.orc_sim_set_threads(self._h, int(n))
+
+    def set_brute_force_block(self, threads_per_block: int) -> None:
+        """Block size assumed for walks over non-partitioned messages (the reference starts each block at its own
+        tile, FLAMEGPU_kernals.xslt:445-520); 0 = one block holds the whole list = plain list order (default)."""
+        self._lib.orc_set_brute_force_block(int(threads_per_block))

@@ -188,12 +188,26 @@ import sys, numpy as np
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
 from oracle.ref_sim import RefSimulation
 from oracle import build_ref
-name, ref_root = "CirclesBruteForce_float", sys.argv[2]
+name, ref_root, iters = sys.argv[2], sys.argv[3], int(sys.argv[4])
 xml = f"{ref_root}/examples/{name}/src/model/XMLModelFile.xml"
 sim = RefSimulation(build_ref.ref_path(name), xml, f"{ref_root}/examples/{name}/iterations/0.xml")
-sim.step(20)
-np.savez(sys.argv[3], **{v: sim.agent_var("Circle", "default", v) for v in ("id", "x", "y", "z", "fx", "fy")})
+sim.step(iters)
+out = {"seeds": sim.seeds()}
+for a in sim.model.agents:
+    for s in a.states:
+        out[f"count/{a.name}/{s}"] = np.int32(sim.agent_count(a.name, s))
+        for v in a.variables:
+            out[f"agent/{a.name}/{s}/{v.name}"] = sim.agent_var(a.name, s, v.name)
+np.savez(sys.argv[5], **out)
 """
+
+
+def _reference_run_with_block(name, iters, block, out):
+    _ref_library(name, f"{REFERENCE}/examples/{name}/src/model/XMLModelFile.xml")
+    env = dict(os.environ, CUDA_ON_HOST_BLOCK=str(block))
+    subprocess.run([sys.executable, "-c", _WORKER, ROOT, name, REFERENCE, str(iters), str(out)], check=True, env=env,
+                   stdout=subprocess.DEVNULL)
+    return np.load(out)
 
 
 @pytest.mark.skipif(not HAVE_REFERENCE, reason="the reference tree is not mounted")
@@ -204,18 +218,37 @@ def test_brute_force_order_depends_on_block_size(tmp_path):
     bit-level agreement of float sums over non-partitioned messages is not defined by the reference; the parity tests
     of the CUDA path state a tolerance for them (tests/test_gpu_reference_models.py)."""
     name = "CirclesBruteForce_float"
-    _ref_library(name, f"{REFERENCE}/examples/{name}/src/model/XMLModelFile.xml")
-    out = tmp_path / "b128.npz"
-    env = dict(os.environ, CUDA_ON_HOST_BLOCK="128")
-    subprocess.run([sys.executable, "-c", _WORKER, ROOT, REFERENCE, str(out)], check=True, env=env, stdout=subprocess.DEVNULL)
-    got, want = np.load(out), np.load(os.path.join(GOLDEN, f"{name}_iter20.npz"))
-    assert np.array_equal(got["id"], want["agent/Circle/default/id"])
+    got, want = _reference_run_with_block(name, 20, 128, tmp_path / "b128.npz"), np.load(os.path.join(GOLDEN, f"{name}_iter20.npz"))
+    assert np.array_equal(got["agent/Circle/default/id"], want["agent/Circle/default/id"])
     moved = 0
     for v in ("x", "y", "fx", "fy"):
-        a, b = got[v], want[f"agent/Circle/default/{v}"]
+        a, b = got[f"agent/Circle/default/{v}"], want[f"agent/Circle/default/{v}"]
         assert np.allclose(a, b, rtol=0, atol=2e-3), v
         moved += int((a != b).sum())
     assert moved > 0
+
+
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="the reference tree is not mounted")
+@pytest.mark.parametrize("name,iters,block", [("CirclesBruteForce_float", 20, 128), ("CirclesBruteForce_double", 5, 96),
+                                             ("Analytics", 10, 256), ("MonteCarlo_MSMPR", 1, 512)])
+def test_oracle_restates_the_block_rotated_walk(name, iters, block, tmp_path):
+    """The rotation itself is restated too (oracle option brute_force_block: block b of B threads starts at message
+    (b*B) mod wrap and walks round, krn:445-520): with the same block size on both sides the reference build and the
+    oracle agree bit for bit again -- including block sizes that do not divide the population (96) and populations
+    of several blocks with deaths in the list (MonteCarlo_MSMPR)."""
+    want = _reference_run_with_block(name, iters, block, tmp_path / "ref.npz")
+    orc = _replay(name, 1, 0)
+    orc.set_brute_force_block(block)
+    orc.step(iters)
+    for a in orc.model.agents:
+        for s in a.states:
+            n = int(want[f"count/{a.name}/{s}"])
+            assert orc.agent_count(a.name, s) == n
+            for v in a.vars:
+                assert np.array_equal(orc.agent_var(a.name, s, v.name, n).view(np.uint8), want[f"agent/{a.name}/{s}/{v.name}"].view(np.uint8)), (a.name, s, v.name)
+    assert np.array_equal(orc.seeds(), want["seeds"])
+    orc.set_brute_force_block(0)
+    orc.close()
 
 
 @pytest.mark.skipif(not HAVE_REFERENCE, reason="the reference tree is not mounted")
