@@ -4,7 +4,8 @@ TEST INFRASTRUCTURE.  Pins the CPU oracle (oracle_rt.hpp + gen_oracle.py, a rest
 
   1. expand the reference's templates -- ``FLAMEGPU/templates/{header,FLAMEGPU_kernals,simulation,io}.xslt``, read where
      they lie under /root/reference -- over the model's XMLModelFile.xml with oracle/xslt_subset.py (this image has no
-     xsltproc), into ``oracle/_ref/<name>/dynamic/`` (git-ignored; reference text never enters the repository);
+     xsltproc), into ``oracle/_ref/<name>/dynamic/`` (git-ignored, and deleted again once the compile has succeeded:
+     reference text never enters the repository);
   2. rewrite the ``kernel<<<grid, block, smem, stream>>>(args);`` launch statements of the expanded simulation.cu into
      ``cuda_on_host::Launch(grid, block, smem, stream).run(barriers, [&]{ kernel(args); });`` -- the only edit;
   3. compile simulation.cu (which includes FLAMEGPU_kernals.cu, which includes the model's own functions.c) and io.cu
@@ -22,6 +23,7 @@ from __future__ import annotations
 
 import os
 import re
+import shutil
 import subprocess
 import sys
 from typing import Dict, List, Optional, Set
@@ -246,6 +248,13 @@ def expand(xml_path: str, outdir: str) -> Dict[str, str]:
     return written
 
 
+def _discard_expansion(directory: str) -> None:
+    """The expanded sources are the reference's text: they exist only for the duration of the compile (kept after a
+    failed one, and with FGPU_KEEP_REF_SOURCES=1, for reading)."""
+    if os.environ.get("FGPU_KEEP_REF_SOURCES") != "1":
+        shutil.rmtree(directory, ignore_errors=True)
+
+
 def build_ref(xml_path: str, name: str, function_dir: Optional[str] = None, fast_atomic: bool = False, force: bool = False,
               opt: str = "-O2") -> str:
     """Expand, rewrite and compile; returns the library path.  Needs /root/reference (templates + glm)."""
@@ -285,6 +294,7 @@ def build_ref(xml_path: str, name: str, function_dir: Optional[str] = None, fast
         f.write(" ".join(cmd) + "\n" + proc.stdout)
     if proc.returncode != 0:
         raise RuntimeError("reference host build failed (%s):\n%s" % (name, proc.stdout[-8000:]))
+    _discard_expansion(dyn)
     return out
 
 
@@ -363,6 +373,7 @@ def build_ref_device(xml_path: str, name: str, function_dir: Optional[str] = Non
         f.write(" ".join(cmd) + "\n" + proc.stdout)
     if proc.returncode != 0:
         raise RuntimeError("reference device build failed (%s):\n%s" % (name, proc.stdout[-8000:]))
+    _discard_expansion(dyn)
     return out
 
 
