@@ -95,6 +95,37 @@ def test_reference_example_matches_oracle(name):
     orc.close()
 
 
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="the reference tree is not mounted")
+@pytest.mark.parametrize("name,iters", [("Boids_BruteForce", 10)])
+def test_further_reference_examples_without_fixtures(name, iters):
+    """A shipped example outside the GPU suite and without a golden fixture: oracle and reference build are both made on
+    demand and both start from the example's own 0.xml (the oracle through oracle/xml_states.py).  2048 boids walk a
+    non-partitioned list in two 1024-thread blocks, so the oracle is told the block size (module docstring)."""
+    from ev_diffusion_b200 import xmml
+    from oracle.xml_states import read_states
+    xml = f"{REFERENCE}/examples/{name}/src/model/XMLModelFile.xml"
+    inp = f"{REFERENCE}/examples/{name}/iterations/0.xml"
+    model = xmml.parse_model(xml)
+    ref = RefSimulation(_ref_library(name, xml), xml, inp)
+    orc = OracleSimulation(gen_oracle.build_oracle(xml, name))
+    spec = [(a.name, [(v.name, v.type, float(v.default or 0)) for v in a.variables]) for a in model.agents]
+    states, env = read_states(inp, spec, [(c.name, c.type) for c in model.constants if not c.array_length])
+    for k, v in env.items():
+        orc.set_constant(k, v)
+    for a in model.agents:
+        orc.set_agents(a.name, a.initial_state, states[a.name])
+    orc.run_init_functions()
+    orc.set_brute_force_block(int(os.environ["CUDA_ON_HOST_BLOCK"]))
+    _assert_same(ref, orc, "after reading 0.xml")
+    for it in range(iters):
+        ref.step(1)
+        orc.step(1)
+        _assert_same(ref, orc, f"iteration {it + 1}")
+    orc.set_brute_force_block(0)
+    ref.close()
+    orc.close()
+
+
 def _write_input(path, states):
     """0.xml in the reference's layout with round-trippable %.9g floats (atof gives the same float back)."""
     with open(path, "w") as fh:
