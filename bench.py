@@ -18,9 +18,10 @@ rand48, wall reflection).  Prints ONE JSON line (rank 0).
  roofline   dominant kernel, algorithmic bytes / CUDA-event time
  cpu_baseline  the CPU oracle (host-C execution of the same functions.c, OpenMP) on a
             bounded sample of the same workload
- --impl reference  the reference has no CPU path and its CUDA cannot be generated or
-            compiled in this image (no xsltproc; texture references); the arm times
-            the host-C oracle on all host cores, as the task statement prescribes.
+ reference_cuda  (N=1) the reference's own generated CUDA, built for sm_100a by
+            oracle/build_ref.py --device, run on the same workload in its own process
+ --impl reference  the reference has no CPU path; the arm times the host-C oracle on
+            all host cores, as the task statement prescribes for this tier.
 """
 import argparse
 import json
@@ -178,6 +179,40 @@ def cpu_baseline(cfg, budget_s=12.0):
     sim.close()
     return {"value": cfg.n * iters / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
             "sample": f"{iters} full iterations of the {cfg.n}-agent workload ({dt:.1f} s), OpenMP {cores} threads"}
+
+
+def reference_cuda(cfg, iterations=100, timeout_s=300.0):
+    """north_star: "the reference's own CUDA build on one B200 ... timed in the same run".  oracle/build_ref.py --device
+    expands the reference's templates and compiles its console program for sm_100a (texture references rewritten to
+    cached loads, nothing else; built in the build container, it travels in oracle/_ref/).  Here it is run as its own
+    process on the workload's 0.xml, XML output off, and its own "Total Processing time" is reported.  A baseline, never
+    part of the product path; any failure is recorded in the JSON and changes nothing else."""
+    import re
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", cfg.name, f"ref_gpu_{cfg.name}")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/%s/ref_gpu_%s is not built (python oracle/build_ref.py --device, needs /root/reference)" % (cfg.name, cfg.name)}
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            inp = W.write_states_xml(os.path.join(tmp, "0.xml"), "Particle", W.brownian_state(cfg))
+            best = None
+            for _ in range(2):                                   # first run also warms the driver's caches
+                proc = subprocess.run([exe, inp, str(iterations), "0", "0"], cwd=tmp, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True, timeout=timeout_s)
+                m = re.search(r"Total Processing time: ([0-9.eE+-]+) \(ms\)", proc.stdout)
+                if proc.returncode != 0 or not m:
+                    lines = [x for x in proc.stdout.strip().splitlines() if x.strip()]
+                    why = next((x for x in lines if "rror" in x), lines[-1] if lines else "")
+                    return {"unavailable": "exit %d: %s" % (proc.returncode, why[:200])}
+                ms = float(m.group(1))
+                best = ms if best is None else min(best, ms)
+        return {"value": cfg.n * iterations / (best * 1e-3), "unit": "agent-steps/s", "ms_per_step": best / iterations,
+                "steps": iterations, "kind": "reference templates expanded, nvcc sm_100a, FAST_ATOMIC_SORTING (its default)",
+                "timing": "the program's own cudaEvent pair around its iteration loop (main.xslt:415-446), best of 2 runs, warm L2, "
+                          "per-iteration printf to a pipe"}
+    except Exception as e:                                       # a baseline must never take the bench down
+        return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
 
 
 def main():
@@ -357,6 +392,7 @@ def main():
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg)
+        line["reference_cuda"] = reference_cuda(cfg)       # its own process; this one idles meanwhile
     if rank == 0:
         print(json.dumps(line))
     sim.close()
