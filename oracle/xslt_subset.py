@@ -633,6 +633,13 @@ def _f_name(c, *a, local=False):
     return ""
 
 
+def _f_namespace_uri(c, *a):
+    nodes = _nodeset(a[0](c)) if a else [c.node]
+    if not nodes or nodes[0].nodeType not in (nodes[0].ELEMENT_NODE, nodes[0].ATTRIBUTE_NODE):
+        return ""
+    return nodes[0].namespaceURI or ""
+
+
 def _f_sum(c, ns):
     return float(sum(to_number(string_value(n)) for n in _nodeset(ns(c))))
 
@@ -643,8 +650,7 @@ _FUNCTIONS: Dict[str, Callable] = {
     "count": lambda c, ns: float(len(_nodeset(ns(c)))),
     "local-name": lambda c, *a: _f_name(c, *a, local=True),
     "name": lambda c, *a: _f_name(c, *a),
-    "namespace-uri": lambda c, *a: ((_nodeset(a[0](c)) if a else [c.node]) or [None])[0] and (
-        ((_nodeset(a[0](c)) if a else [c.node])[0].namespaceURI) or ""),
+    "namespace-uri": lambda c, *a: _f_namespace_uri(c, *a),
     "string": _f_string,
     "concat": lambda c, *a: "".join(to_string(x(c)) for x in a),
     "starts-with": lambda c, a, b: to_string(a(c)).startswith(to_string(b(c))),
@@ -1003,10 +1009,7 @@ class Stylesheet:
                     x = to_number(v)
                     return (0, 0.0) if math.isnan(x) else (1, x)     # NaN sorts first in ascending order
                 return to_string(v)
-            decorated.sort(key=key, reverse=descending)
-            if descending:
-                # list.sort(reverse=True) keeps equal items in their original order, as XSLT requires
-                pass
+            decorated.sort(key=key, reverse=descending)     # reverse=True keeps equal items in document order too
         return [n for _, n in decorated]
 
 

@@ -64,6 +64,10 @@ def test_string_functions(tmp_path):
                          '<xsl:value-of select="substring-after($t, \'::\')"/>,<xsl:value-of select="concat(\'a\', 1, true())"/>,'
                          '<xsl:value-of select="normalize-space(\'  a   b \')"/>,<xsl:value-of select="starts-with($t, \'glm\')"/>,'
                          '<xsl:value-of select="local-name(m:model/m:agent)"/>') == "vec3,234,12,123,AB,true,glm,fvec3,a1true,a b,true,agent"
+    assert run(tmp_path, '<xsl:value-of select="namespace-uri(m:model)"/>,<xsl:value-of select="name(m:model/m:agent)"/>,'
+                         '<xsl:value-of select="namespace-uri(//p:name)"/>,<xsl:value-of select="namespace-uri(//m:agent/@kind)"/>;'
+                         '<xsl:value-of select="string(//m:agent[3]/@kind)"/>,<xsl:value-of select="string-length(//p:nothing)"/>') \
+        == "urn:model,m:agent,urn:plain,;a,0"
 
 
 def test_sort_choose_and_whitespace_rules(tmp_path):
