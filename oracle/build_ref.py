@@ -256,19 +256,31 @@ def _discard_expansion(directory: str) -> None:
 
 
 def build_ref(xml_path: str, name: str, function_dir: Optional[str] = None, fast_atomic: bool = False, force: bool = False,
-              opt: str = "-O2") -> str:
-    """Expand, rewrite and compile; returns the library path.  Needs /root/reference (templates + glm)."""
+              opt: str = "-O2", device_patch: bool = False) -> str:
+    """Expand, rewrite and compile; returns the library path.  Needs /root/reference (templates + glm).
+    `device_patch` applies the texture-reference rewrite of the sm_100a build (build_ref_device) first, so that the
+    very sources nvcc compiles for the GPU can be checked on the CPU (library name gets a `_patched` suffix)."""
     if not reference_available():
         raise RuntimeError("the reference tree is not mounted (%s): oracle/_ref can only be built where it is" % REFERENCE)
     model = xmml.parse_model(xml_path)
     mdir = function_dir or os.path.dirname(os.path.abspath(xml_path))
-    out = ref_path(name)
+    out = ref_path(name + "_patched") if device_patch else ref_path(name)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
     deps = [xml_path, os.path.abspath(__file__), os.path.join(HERE, "xslt_subset.py"), os.path.join(HERE, "cuda_on_host", "cuda_on_host.h")]
     deps += [os.path.join(mdir, f) for f in model.function_files] + [os.path.join(TEMPLATES, x) for x in EXPANDED]
     if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps if os.path.exists(d)):
         return out
-    dyn = os.path.join(OUT, name, "dynamic")
+    dyn = os.path.join(os.path.dirname(out), "dynamic")
     files = expand(xml_path, dyn)
+    prelude = []
+    if device_patch:
+        for target in ("FLAMEGPU_kernals.cu", "simulation.cu", "io.cu"):
+            text = patch_texture_references(open(files[target]).read())
+            with open(files[target], "w") as f:
+                f.write(text)
+        with open(os.path.join(dyn, "texture_prelude.h"), "w") as f:
+            f.write(DEVICE_PRELUDE)
+        prelude = ["-include", os.path.join(dyn, "texture_prelude.h")]
     kernels = open(files["FLAMEGPU_kernals.cu"]).read()
     scripts = [open(os.path.join(mdir, f)).read() for f in model.function_files]
     reach = functions_reaching_barrier([kernels] + scripts, {"FAST_ATOMIC_SORTING"} if fast_atomic else set())
@@ -280,7 +292,7 @@ def build_ref(xml_path: str, name: str, function_dir: Optional[str] = None, fast
     with open(os.path.join(dyn, "barriers.txt"), "w") as f:
         f.write("\n".join(sorted(reach)) + "\n")
     cmd = ["g++", "-std=c++17", opt, "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-fpermissive",
-           "-x", "c++", "-include", os.path.join(HERE, "cuda_on_host", "cuda_on_host.h"),
+           "-x", "c++", "-include", os.path.join(HERE, "cuda_on_host", "cuda_on_host.h")] + prelude + [
            "-I", os.path.join(HERE, "cuda_on_host"), "-I", dyn, "-I", mdir, "-I", os.path.join(REFERENCE, "include"),
            "-DGLM_FORCE_PURE",
            # header.h defines `__device__` variables; nvcc gives every translation unit its own copy, only the simulation
@@ -323,8 +335,9 @@ template <class T> static cudaError_t fgpu_ref_bind(size_t* offset, T*& symbol, 
 
 
 def patch_texture_references(src: str) -> str:
-    return re.sub(r"\btexture\s*<\s*([\w:\s]+?)\s*,\s*1\s*,\s*cudaReadModeElementType\s*>\s*(\w+)\s*;",
-                  r"__device__ const \1* \2;", src)
+    tex = r"\btexture\s*<\s*([\w:\s]+?)\s*,\s*1\s*,\s*cudaReadModeElementType\s*>"
+    src = re.sub(tex + r"\s*(\w+)\s*;", r"__device__ const \1* \2;", src)        # the references themselves (file scope)
+    return re.sub(tex, r"const \1*", src)                                        # helpers that take one by value
 
 
 def ref_device_path(name: str) -> str:

@@ -178,6 +178,7 @@ template <class T> static inline T atomicExch(T* p, T v) { T o = *p; *p = v; ret
 template <class T> static inline T atomicMin(T* p, T v) { T o = *p; *p = std::min(o, v); return o; }
 template <class T> static inline T atomicMax(T* p, T v) { T o = *p; *p = std::max(o, v); return o; }
 template <class T> static inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
+template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 

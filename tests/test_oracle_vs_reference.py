@@ -126,6 +126,23 @@ def test_further_reference_examples_without_fixtures(name, iters):
     orc.close()
 
 
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="the reference tree is not mounted")
+@pytest.mark.parametrize("name,iters", [("CirclesPartitioning_float", 100), ("CirclesPartitioning_double", 10), ("Keratinocyte", 50)])
+def test_device_patched_sources_compute_the_same(name, iters):
+    """The sm_100a build of the reference (build_ref_device, bench.py's reference_cuda leg) differs from the reference's
+    text in one thing: texture references become `__device__ const T*` read through __ldg, bound by cudaMemcpyToSymbol.
+    The SAME patched sources run on the CPU must still reproduce the golden fixtures (float, int2-as-double and PBM
+    textures; several messages), so the GPU baseline times the reference's computation and not a broken variant."""
+    xml = f"{REFERENCE}/examples/{name}/src/model/XMLModelFile.xml"
+    lib = build_ref.build_ref(xml, name, device_patch=True)
+    ref = RefSimulation(lib, xml, f"{REFERENCE}/examples/{name}/iterations/0.xml")
+    orc = _replay(name, 1, iters)
+    ref.step(iters)
+    _assert_same(ref, orc, f"iteration {iters}")
+    ref.close()
+    orc.close()
+
+
 def _write_input(path, states):
     """0.xml in the reference's layout with round-trippable %.9g floats (atof gives the same float back)."""
     with open(path, "w") as fh:
