@@ -12,6 +12,11 @@ REQUIRED = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step
             "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"}
 
 
+def _cuda_device_present():
+    import conftest
+    return conftest._has_gpu()
+
+
 def _run(extra_env=None, gpus=1):
     env = dict(os.environ, **(extra_env or {}))
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", str(gpus), "--steps", "1",
@@ -38,3 +43,17 @@ def test_reference_arm_under_torchrun_only_rank0_prints():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, gpus=2) == []
     lines = _run({"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"}, gpus=2)
     assert len(lines) == 1 and json.loads(lines[0])["n_gpus"] == 2
+
+
+def test_reference_cuda_leg_never_raises():
+    """bench.py's reference_cuda leg (the reference's own sm_100a build, run as a separate process) reports a reason
+    instead of a number when the binary is missing or cannot run -- here: no binary for the tiny workload, and no CUDA
+    device in this container for the real one -- and never raises into the bench."""
+    import bench
+    from ev_diffusion_b200 import workloads as W
+    missing = bench.reference_cuda(W.BROWNIAN["c2_tiny"])
+    assert set(missing) == {"unavailable"} and "not built" in missing["unavailable"]
+    exe = os.path.join(ROOT, "oracle", "_ref", "Brownian", "ref_gpu_Brownian")
+    if os.path.exists(exe) and not _cuda_device_present():
+        failed = bench.reference_cuda(W.BROWNIAN["c2"], iterations=1, timeout_s=120)
+        assert set(failed) == {"unavailable"} and "CUDA" in failed["unavailable"]
