@@ -168,21 +168,22 @@ def cpu_baseline(cfg, budget_s=12.0):
     from oracle.oracle import OracleSimulation
     cores = os.cpu_count() or 1
 
-    def timed(threads, budget, most):
+    def timed(threads, budget, most, least, warm):
         sim = OracleSimulation(gen_oracle.oracle_path(cfg.name), threads=threads)
         sim.set_agents("Particle", "default", W.brownian_state(cfg))
-        sim.step(1)
+        if warm:
+            sim.step(1)
         t0 = time.perf_counter()
         iters = 0
-        while iters < most and (iters < 2 or time.perf_counter() - t0 < budget):
+        while iters < most and (iters < least or time.perf_counter() - t0 < budget):
             sim.step(1)
             iters += 1
         dt = time.perf_counter() - t0
         sim.close()
         return iters, dt
 
-    iters, dt = timed(cores, budget_s, 20)
-    it1, dt1 = timed(1, budget_s / 2, 4)
+    iters, dt = timed(cores, budget_s, 20, 2, True)
+    it1, dt1 = timed(1, budget_s / 2, 4, 1, False)        # one thread: bounded even at 16M agents (one iteration)
     return {"value": cfg.n * iters / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
             "sample": f"{iters} full iterations of the {cfg.n}-agent workload ({dt:.1f} s), OpenMP {cores} threads",
             "single_thread": {"value": cfg.n * it1 / dt1, "unit": "agent-steps/s", "cores": 1,
