@@ -101,3 +101,31 @@ def test_exception_list_is_not_stale():
         seen |= set(declarations(xslt_subset.Stylesheet(f"{REFERENCE}/FLAMEGPU/templates/header.xslt").transform(xml)))
     for pattern in NOT_PROVIDED:
         assert any(re.fullmatch(pattern, k) for k in seen), pattern
+
+
+def _structs(text: str):
+    masked = mask_comments_and_strings(text)
+    return {m.group(1): [" ".join(x.split()) for x in m.group(2).split(";") if x.strip()]
+            for m in re.finditer(r"struct\s+(?:__align__\(\d+\)\s*)?(\w+)\s*\{([^{}]*)\}\s*;", masked)}
+
+
+@pytest.mark.parametrize("name", ["CirclesPartitioning_float", "Keratinocyte", "SmoothedParticleHydrodynamics", "CirclesBruteForce_double"])
+def test_struct_layouts_seen_by_scripts_and_drivers(name):
+    """What user code can touch has the reference's layout: the agent struct handed to every agent function and the
+    SoA agent list a driver gets from get_device_/get_host_<A>_<S>_agents() are member for member the reference's
+    (header.xslt:151-194).  A message struct keeps the model's variables in XML order; the reference's four hidden cursor
+    fields in front of them (header.xslt:170-173) are not reproduced -- scripts never name them, and the walk keeps its
+    cursor in the list proxy instead.  Message lists, partition matrices and RNG_rand48 are opaque handles on both
+    sides (scripts only pass the pointers back to the message / rnd functions)."""
+    xml = f"{REFERENCE}/examples/{name}/src/model/XMLModelFile.xml"
+    model = xmml.parse_model(xml)
+    ref = _structs(xslt_subset.Stylesheet(f"{REFERENCE}/FLAMEGPU/templates/header.xslt").transform(xml))
+    ours = _structs(codegen.emit_cuda_header(model))
+    for a in model.agents:
+        for s in (f"xmachine_memory_{a.name}", f"xmachine_memory_{a.name}_list"):
+            assert ours[s] == ref[s], s
+    hidden = ["glm::ivec3 _relative_cell", "int _cell_index_max", "glm::ivec3 _agent_grid_cell", "int _cell_index"]
+    for m in model.messages:
+        s = f"xmachine_message_{m.name}"
+        theirs = [x for x in ref[s] if x not in hidden and x != "int _position"]
+        assert ours[s] == theirs and len(theirs) == len(m.variables), s
