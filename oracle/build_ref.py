@@ -14,10 +14,11 @@ TEST INFRASTRUCTURE.  Pins the CPU oracle (oracle_rt.hpp + gen_oracle.py, a rest
      step, read any agent variable / the rand48 seeds / the sorted message list and PBM).
 
 The result executes the reference's own host orchestration, kernels and agent scripts, thread by thread on the CPU
-(-ffp-contract=off, as the oracle).  By default FAST_ATOMIC_SORTING is NOT defined: the reference's deterministic
-variant (hash + radix sort + reorder, ``FLAMEGPU_kernals.xslt:944-1021``), the one SURVEY.md section 8c names as
-comparable bit for bit.  ``fast_atomic=True`` builds the default variant; on one host thread its atomics resolve in
-thread order, so it is deterministic here too and must give the same states.
+(-ffp-contract=off, as the oracle).  The generated header.h defines FAST_ATOMIC_SORTING (``header.xslt:35``): the default
+message build is a counting sort with global atomics (``FLAMEGPU_kernals.xslt:899-934``); on one host thread its atomics
+resolve in thread order, so it is deterministic here.  ``fast_atomic=False`` removes that one #define and builds the
+deterministic variant (hash + radix sort + reorder,
+``FLAMEGPU_kernals.xslt:944-1021``) -- the one the oracle restates.  Both must give the same states.
 """
 from __future__ import annotations
 
@@ -255,7 +256,19 @@ def _discard_expansion(directory: str) -> None:
         shutil.rmtree(directory, ignore_errors=True)
 
 
-def build_ref(xml_path: str, name: str, function_dir: Optional[str] = None, fast_atomic: bool = False, force: bool = False,
+def _select_sort_variant(header_path: str, fast_atomic: bool) -> None:
+    if fast_atomic:
+        return
+    text = open(header_path).read()
+    patched = re.sub(r"^[ \t]*#define[ \t]+FAST_ATOMIC_SORTING[ \t]*$", "/* #define FAST_ATOMIC_SORTING  (removed by oracle/build_ref.py) */",
+                     text, count=1, flags=re.M)
+    if patched == text:
+        raise RuntimeError("header.h does not define FAST_ATOMIC_SORTING where expected")
+    with open(header_path, "w") as f:
+        f.write(patched)
+
+
+def build_ref(xml_path: str, name: str, function_dir: Optional[str] = None, fast_atomic: bool = True, force: bool = False,
               opt: str = "-O2", device_patch: bool = False) -> str:
     """Expand, rewrite and compile; returns the library path.  Needs /root/reference (templates + glm).
     `device_patch` applies the texture-reference rewrite of the sm_100a build (build_ref_device) first, so that the
@@ -264,7 +277,7 @@ def build_ref(xml_path: str, name: str, function_dir: Optional[str] = None, fast
         raise RuntimeError("the reference tree is not mounted (%s): oracle/_ref can only be built where it is" % REFERENCE)
     model = xmml.parse_model(xml_path)
     mdir = function_dir or os.path.dirname(os.path.abspath(xml_path))
-    out = ref_path(name + "_patched") if device_patch else ref_path(name)
+    out = ref_path(name + ("_patched" if device_patch else "") + ("" if fast_atomic else "_radix"))
     os.makedirs(os.path.dirname(out), exist_ok=True)
     deps = [xml_path, os.path.abspath(__file__), os.path.join(HERE, "xslt_subset.py"), os.path.join(HERE, "cuda_on_host", "cuda_on_host.h")]
     deps += [os.path.join(mdir, f) for f in model.function_files] + [os.path.join(TEMPLATES, x) for x in EXPANDED]
@@ -272,6 +285,7 @@ def build_ref(xml_path: str, name: str, function_dir: Optional[str] = None, fast
         return out
     dyn = os.path.join(os.path.dirname(out), "dynamic")
     files = expand(xml_path, dyn)
+    _select_sort_variant(files["header.h"], fast_atomic)
     prelude = []
     if device_patch:
         for target in ("FLAMEGPU_kernals.cu", "simulation.cu", "io.cu"):
@@ -298,8 +312,6 @@ def build_ref(xml_path: str, name: str, function_dir: Optional[str] = None, fast
            # header.h defines `__device__` variables; nvcc gives every translation unit its own copy, only the simulation
            # unit's is ever used -- on the host the two definitions may simply be merged
            "-Wl,--allow-multiple-definition"]
-    if fast_atomic:
-        cmd.append("-DFAST_ATOMIC_SORTING")
     cmd += [os.path.join(dyn, "simulation_host.cpp"), os.path.join(dyn, "io_host.cpp"), "-o", out]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     with open(out + ".log", "w") as f:
@@ -369,6 +381,7 @@ def build_ref_device(xml_path: str, name: str, function_dir: Optional[str] = Non
             text = patch_texture_references(text)
         with open(os.path.join(dyn, target), "w") as f:
             f.write(text)
+    _select_sort_variant(os.path.join(dyn, "header.h"), fast_atomic)
     with open(os.path.join(dyn, "texture_prelude.h"), "w") as f:
         f.write(DEVICE_PRELUDE)
     # the reference vendors glm AND a 2016 cub under include/; only glm may be seen (cub and thrust are the toolkit's)
@@ -378,8 +391,6 @@ def build_ref_device(xml_path: str, name: str, function_dir: Optional[str] = Non
         os.symlink(os.path.join(REFERENCE, "include", "glm"), os.path.join(inc, "glm"))
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-w",
            "-include", os.path.join(dyn, "texture_prelude.h"), "-I", dyn, "-I", mdir, "-I", inc, "-DGLM_FORCE_PURE"]
-    if not fast_atomic:
-        cmd.append("-UFAST_ATOMIC_SORTING")
     cmd += [os.path.join(dyn, "main.cu"), os.path.join(dyn, "simulation.cu"), os.path.join(dyn, "io.cu"), "-o", out]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     with open(out + ".log", "w") as f:
@@ -395,10 +406,10 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
     ap.add_argument("xml")
     ap.add_argument("name")
-    ap.add_argument("--fast-atomic", action="store_true")
+    ap.add_argument("--radix", action="store_true", help="the deterministic message build (FAST_ATOMIC_SORTING removed)")
     ap.add_argument("--device", action="store_true", help="nvcc build of the reference's console program for sm_100a")
     a = ap.parse_args()
     if a.device:
-        print(build_ref_device(a.xml, a.name, force=True))
+        print(build_ref_device(a.xml, a.name, fast_atomic=not a.radix, force=True))
     else:
-        print(build_ref(a.xml, a.name, fast_atomic=a.fast_atomic, force=True))
+        print(build_ref(a.xml, a.name, fast_atomic=not a.radix, force=True))

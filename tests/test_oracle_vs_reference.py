@@ -143,6 +143,43 @@ def test_device_patched_sources_compute_the_same(name, iters):
     orc.close()
 
 
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="the reference tree is not mounted")
+@pytest.mark.parametrize("fast_atomic", [True, False])
+@pytest.mark.parametrize("name,iters", [("CirclesPartitioning_float", 7), ("Boids_Partitioning", 5), ("Keratinocyte", 9)])
+def test_message_build_order_and_partition_matrix(name, iters, fast_atomic):
+    """SURVEY.md 8(a) rows a5/a6, 8(c) "comparable bit-exactly": after the last message build of an iteration the sorted
+    message list (every variable, in order) and the partition matrix equal the oracle's, for BOTH builds of the
+    reference -- its default counting sort with atomics (start[] = exclusive scan, end_or_count[] = count; one host thread
+    makes the atomics resolve in thread order) and the radix-sort variant with FAST_ATOMIC_SORTING removed (start[] =
+    first index or 0xffffffff for an empty cell, end_or_count[] = one past the last) -- compared in normalised form:
+    count per cell, start of every non-empty cell."""
+    xml = f"{REFERENCE}/examples/{name}/src/model/XMLModelFile.xml"
+    lib = build_ref.build_ref(xml, name, fast_atomic=fast_atomic)
+    ref = RefSimulation(lib, xml, f"{REFERENCE}/examples/{name}/iterations/0.xml")
+    orc = _replay(name, 1, iters)
+    ref.step(iters)
+    _assert_same(ref, orc, f"iteration {iters}")
+    checked = 0
+    for m in ref.model.messages:
+        n = orc.message_count(m.name)
+        assert ref.message_count(m.name) == n, m.name
+        if n == 0 or m.partitioning != "spatial":
+            continue
+        om = orc.messages(m.name)
+        for v in m.variables:
+            assert np.array_equal(ref.message_var(m.name, v.name).view(np.uint8), om[v.name][:n].view(np.uint8)), (m.name, v.name)
+        start, second = ref.pbm(m.name)
+        count = second if fast_atomic else np.where(start.view(np.uint32) == 0xFFFFFFFF, 0, second - start)
+        o_start, o_count = orc.pbm(m.name)
+        assert np.array_equal(count, o_count), m.name
+        assert np.array_equal(start[count > 0], o_start[o_count > 0]), m.name
+        assert int(count.sum()) == n
+        checked += 1
+    assert checked > 0
+    ref.close()
+    orc.close()
+
+
 def _write_input(path, states):
     """0.xml in the reference's layout with round-trippable %.9g floats (atof gives the same float back)."""
     with open(path, "w") as fh:
