@@ -28,7 +28,8 @@ _libc.strtoul.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int]
 def _parse(ctype: str, text: str):
     b = text.encode("latin-1", "replace")
     if ctype == "float":
-        return np.float32(_libc.atof(b))
+        with np.errstate(over="ignore"):          # (float)atof("1e39") is +inf in C, silently
+            return np.float32(_libc.atof(b))
     if ctype == "double":
         return np.float64(_libc.atof(b))
     if ctype == "int":

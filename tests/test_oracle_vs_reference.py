@@ -373,3 +373,72 @@ def test_iteration_file_writer_and_reader_against_the_reference(name, iters, tmp
             assert np.array_equal(reread[f"{a.name}/{v.name}"].view(np.uint8), back[a.name][v.name].view(np.uint8)), (a.name, v.name)
     ref.close()
     orc.close()
+
+
+_NASTY_INPUT = """<states>
+<itno>7</itno>
+<!-- a comment with <xagent> inside -->
+<environment>
+</environment>
+<xagent>
+<name>Circle</name>
+<id>0x1F</id>
+<x>1.5e1</x>
+<y> -2.25 </y>
+<z>.5</z>
+<fx>1e-3</fx>
+<fy>7</fy>
+</xagent>
+<xagent>
+<name>Circle</name>
+<id>-12</id>
+<unknown_tag>99</unknown_tag>
+<x>3.999999999999</x>
+<y>abc</y>
+</xagent>
+<xagent>
+<name>NoSuchAgent</name>
+<id>5</id>
+<x>1</x>
+</xagent>
+<xagent>
+<name>Circle</name>
+<id>017</id>
+<x>0.1</x><y>0.2</y><z>0.30000001192092896</z>
+<fx>-0.0</fx>
+<fy>123456789.123</fy>
+</xagent>
+<xagent><name>Circle</name><id>2147483647</id><x>1e39</x><y>-1e-46</y></xagent>
+</states>
+<xagent>
+<name>Circle</name>
+<id>1</id>
+</xagent>
+"""
+
+
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="the reference tree is not mounted")
+def test_reader_restatement_on_awkward_input(tmp_path):
+    """the reference's readInitialStates (io.xslt:211-621) and oracle/xml_states.py -- the
+    restatement the CUDA path's reader is compared with in tests/test_gpu_state_io.py -- on a file that exercises
+    strtol base 0 (hex, octal, negative), atof (exponents, surrounding blanks, garbage = 0, overflow to inf, underflow),
+    unknown tags, a comment containing tags, an agent of an unknown type, variables left out (defaults), several tags
+    on a line, and agents after </states> (ignored)."""
+    from oracle.xml_states import read_states
+    name = "CirclesPartitioning_float"
+    xml = f"{REFERENCE}/examples/{name}/src/model/XMLModelFile.xml"
+    inp = tmp_path / "0.xml"
+    inp.write_text(_NASTY_INPUT)
+    worker = ("import sys, numpy as np\nsys.path.insert(0, sys.argv[1])\nfrom oracle.ref_sim import RefSimulation\n"
+              "sim = RefSimulation(sys.argv[2], sys.argv[3], sys.argv[4])\n"
+              "np.savez(sys.argv[5], **{v.name: sim.agent_var('Circle', 'default', v.name) for v in sim.model.agents[0].variables})\n")
+    out = tmp_path / "read.npz"
+    subprocess.run([sys.executable, "-c", worker, ROOT, _ref_library(name, xml), xml, str(inp), str(out)], check=True, stdout=subprocess.DEVNULL)
+    theirs = np.load(out)
+    model = __import__("ev_diffusion_b200.xmml", fromlist=["x"]).parse_model(xml)
+    spec = [(a.name, [(v.name, v.type, float(v.default or 0)) for v in a.variables]) for a in model.agents]
+    mine, _ = read_states(str(inp), spec, [])
+    assert len(theirs["id"]) == 4
+    assert theirs["id"].tolist() == [31, -12, 15, 2147483647]
+    for v in model.agents[0].variables:
+        assert np.array_equal(theirs[v.name].view(np.uint8), mine["Circle"][v.name].view(np.uint8)), (v.name, theirs[v.name], mine["Circle"][v.name])
