@@ -67,10 +67,12 @@ def do_run(cfg, iterations: int, repeats: int) -> None:
     out = {"workload": cfg.name, "agents": n, "iterations": iterations}
     with tempfile.TemporaryDirectory() as tmp:
         sides = {"reference": [ref_bin], "ours": [console, plugin]}
+        shared = W.write_states_xml(os.path.join(tmp, "input.xml"), "Particle", W.brownian_state(cfg))   # 2 GB at 16M agents
         for side, head in sides.items():
             d = os.path.join(tmp, side)
             os.makedirs(d)
-            inp = W.write_states_xml(os.path.join(d, "0.xml"), "Particle", W.brownian_state(cfg))
+            inp = os.path.join(d, "0.xml")           # both programs write their iteration files beside their input
+            os.symlink(shared, inp)
             times = [_processing_ms(head + [inp, str(iterations), "0", "0"], d) for _ in range(repeats)]
             out[side] = {"processing_ms": times, "best_ms_per_iteration": min(times) / iterations,
                          "agent_steps_per_s": n * iterations / (min(times) * 1e-3)}
