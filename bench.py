@@ -190,7 +190,7 @@ def cpu_baseline(cfg, budget_s=12.0):
                               "sample": f"{it1} full iterations ({dt1:.1f} s), one thread"}}
 
 
-def reference_cuda(cfg, iterations=100, timeout_s=300.0):
+def reference_cuda(cfg, iterations=100, timeout_s=120.0):
     """north_star: "the reference's own CUDA build on one B200 ... timed in the same run".  oracle/build_ref.py --device
     expands the reference's templates and compiles its console program for sm_100a (texture references rewritten to
     cached loads, nothing else; built in the build container, it travels in oracle/_ref/).  Here it is run as its own
