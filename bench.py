@@ -150,8 +150,11 @@ def run_reference(args, cfg):
                                     if args.gpus > 1 else "")},
         "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "the reference has no CPU path and its CUDA cannot be built here (no xsltproc; texture references "
-                "rejected by CUDA 12.9): this arm is the host-C oracle executing the same functions.c",
+        "note": "the reference has no CPU path: this arm is the host-C oracle (port) executing the same functions.c with OpenMP. "
+                "The reference's own generated code also runs on the CPU here (oracle/build_ref.py, one host thread, "
+                "0.16 M agent-steps/s on this workload) and computes the same bytes (tests/test_oracle_vs_reference.py); "
+                "the port is timed because it is the faster CPU arm.  The reference's CUDA build for sm_100a is the "
+                "reference_cuda object of the GPU arm's line.",
     }
     print(json.dumps(line))
 
