@@ -10,9 +10,11 @@ For each reference example on the hot path:
                         the reference's own functions.c (compiled where it lies under
                         /root/reference; no reference source is copied into the repo)
 
-The reference ships no expected outputs, so these fixtures pin the
-oracle against ITSELF over time and give the GPU parity tests a reference-input
-case that travels; they are not an independent second opinion.
+The reference ships no expected outputs, so these fixtures keep the
+oracle fixed over time and give the GPU parity tests a reference-input case that
+travels.  The independent check is tests/test_oracle_vs_reference.py: the reference's
+own generated code, built by oracle/build_ref.py and run on the CPU, reproduces
+every one of these files bit for bit.
 """
 import os
 import sys
