@@ -34,17 +34,14 @@ void default_value(const fgpu_var &V, char *dst) {
         *(long long *)dst = (long long)V.default_value;
     }
 }
-}  // namespace
-
-extern "C" int fgpu_sim_load_states(fgpu_sim *s, const char *xml_path) {
-    if (!s || !xml_path) return set_err(FGPU_ERR_ARG, "bad argument");
-    const fgpu_model *m = s->model;
-    CU(cudaSetDevice(s->device));
-    if (m->init_constants) m->init_constants(); /* initEnvVars(), io.xslt:254-255 */
+/* The parser proper: host code only.  Fills one column buffer per agent variable with the agents of the file (each
+ * under the agent type named by its <name>); <environment> values go to the model's constant setters when
+ * `apply_environment` is set (fgpu_sim_load_states) and are skipped otherwise (fgpu_states_file_*: no device). */
+int parse_states_file(const fgpu_model *m, const char *xml_path, std::vector<XmlAgentBuf> &bufs, bool apply_environment) {
     FILE *file = fopen(xml_path, "r");
     if (!file) return set_err(FGPU_ERR_IO, "Could not open input file %s", xml_path);
 
-    std::vector<XmlAgentBuf> bufs(m->nagents);
+    bufs.assign(m->nagents, XmlAgentBuf());
     /* current values per agent type per variable, reset to defaults after each </xagent> */
     std::vector<std::vector<std::vector<char>>> cur(m->nagents);
     auto reset_cur = [&]() {
@@ -123,7 +120,7 @@ extern "C" int fgpu_sim_load_states(fgpu_sim *s, const char *xml_path) {
                 for (int a = 0; a < m->nagents; ++a)
                     for (int v = 0; v < m->agents[a].nvars; ++v)
                         if (open_var == m->agents[a].vars[v].name) store_value(m->agents[a].vars[v], buffer.c_str(), cur[a][v].data());
-            } else if (in_env) {
+            } else if (in_env && apply_environment) {
                 for (int k = 0; k < m->nconstants; ++k)
                     if (open_var == m->constants[k].name && m->constants[k].length == 1) {
                         fgpu_var V;
@@ -147,6 +144,17 @@ extern "C" int fgpu_sim_load_states(fgpu_sim *s, const char *xml_path) {
         }
     }
     fclose(file);
+    return rc;
+}
+}  // namespace
+
+extern "C" int fgpu_sim_load_states(fgpu_sim *s, const char *xml_path) {
+    if (!s || !xml_path) return set_err(FGPU_ERR_ARG, "bad argument");
+    const fgpu_model *m = s->model;
+    CU(cudaSetDevice(s->device));
+    if (m->init_constants) m->init_constants(); /* initEnvVars(), io.xslt:254-255 */
+    std::vector<XmlAgentBuf> bufs;
+    int rc = parse_states_file(m, xml_path, bufs, true);
     if (rc != FGPU_OK) return rc;
     for (int a = 0; a < m->nagents; ++a) {
         std::vector<const void *> cols(m->agents[a].nvars);
@@ -157,5 +165,24 @@ extern "C" int fgpu_sim_load_states(fgpu_sim *s, const char *xml_path) {
         if (rc != FGPU_OK) return rc;
     }
     CU(cudaDeviceSynchronize());
+    return FGPU_OK;
+}
+
+/* ---- a states file without a device: how many agents of a type it holds, and their columns ------------------------ */
+extern "C" int fgpu_states_file_count(const fgpu_model *model, const char *xml_path, int agent) {
+    if (!model || !xml_path || agent < 0 || agent >= model->nagents) return set_err(FGPU_ERR_ARG, "bad argument");
+    std::vector<XmlAgentBuf> bufs;
+    const int rc = parse_states_file(model, xml_path, bufs, false);
+    return rc != FGPU_OK ? rc : bufs[agent].count;
+}
+
+extern "C" int fgpu_states_file_read_var(const fgpu_model *model, const char *xml_path, int agent, int var, void *dst, int count) {
+    if (!model || !xml_path || !dst || agent < 0 || agent >= model->nagents || var < 0 || var >= model->agents[agent].nvars)
+        return set_err(FGPU_ERR_ARG, "bad argument");
+    std::vector<XmlAgentBuf> bufs;
+    const int rc = parse_states_file(model, xml_path, bufs, false);
+    if (rc != FGPU_OK) return rc;
+    if (count < 0 || count > bufs[agent].count) return set_err(FGPU_ERR_ARG, "the file holds %d agents of type %s", bufs[agent].count, model->agents[agent].name);
+    memcpy(dst, bufs[agent].cols[var].data(), (size_t)count * model->agents[agent].vars[var].size);
     return FGPU_OK;
 }

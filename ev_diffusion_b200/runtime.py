@@ -442,6 +442,10 @@ def load_runtime() -> C.CDLL:
     lib.fgpu_sim_slab_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
     lib.fgpu_sim_slab_info.restype = C.c_int
     lib.fgpu_sim_slab_info.argtypes = [C.c_void_p, C.c_void_p]
+    lib.fgpu_states_file_count.restype = C.c_int
+    lib.fgpu_states_file_count.argtypes = [C.POINTER(_Model), C.c_char_p, C.c_int]
+    lib.fgpu_states_file_read_var.restype = C.c_int
+    lib.fgpu_states_file_read_var.argtypes = [C.POINTER(_Model), C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
     lib.fgpu_debug_sort_pairs.restype = C.c_int
     lib.fgpu_debug_sort_pairs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.fgpu_debug_compact.restype = C.c_int
@@ -458,6 +462,26 @@ def load_model(plugin_path: str):
     if not m:
         raise FgpuError(lib.fgpu_last_error().decode())
     return m
+
+
+def read_states_file(plugin_path: str, xml_path: str) -> Dict[str, Dict[str, np.ndarray]]:
+    """{agent: {variable: array}} of a states file (0.xml), parsed by the runtime's own reader -- the one
+    ``Simulation.load_states`` uses (readInitialStates, io.xslt:211-621) -- without a device: host code only."""
+    lib = load_runtime()
+    model = load_model(plugin_path)
+    info = ModelInfo(model.contents)
+    out: Dict[str, Dict[str, np.ndarray]] = {}
+    for ai, a in enumerate(info.agents):
+        n = lib.fgpu_states_file_count(model, os.fsencode(xml_path), ai)
+        if n < 0:
+            raise FgpuError(lib.fgpu_last_error().decode())
+        out[a.name] = {}
+        for vi, v in enumerate(a.vars):
+            col = np.empty(n, dtype=v.dtype)
+            if lib.fgpu_states_file_read_var(model, os.fsencode(xml_path), ai, vi, col.ctypes.data, n) != 0:
+                raise FgpuError(lib.fgpu_last_error().decode())
+            out[a.name][v.name] = col
+    return out
 
 
 class Simulation(SimBase):

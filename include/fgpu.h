@@ -54,6 +54,11 @@ void fgpu_sim_destroy(fgpu_sim *sim);
 /* readInitialStates() (io.xslt:211-621): parse a 0.xml into the initial state
  * lists, apply <environment> constants, upload. */
 int fgpu_sim_load_states(fgpu_sim *sim, const char *xml_path);
+/* The same reader without a device (host code only): how many agents of type `agent` a states file holds -- e.g. to
+ * choose bufferSize before generating a model -- and variable `var` of the first `count` of them, in file order.
+ * <environment> values are not applied.  Returns the count / FGPU_OK, or a negative error code. */
+int fgpu_states_file_count(const fgpu_model *model, const char *xml_path, int agent);
+int fgpu_states_file_read_var(const fgpu_model *model, const char *xml_path, int agent, int var, void *dst, int count);
 
 /* Process-wide driver state of the reference's main.cu that step functions may use: getOutputDir()
  * (main.xslt:139-141: where iteration files and custom outputs go) and set_exit_early()/get_exit_early()
