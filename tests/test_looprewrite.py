@@ -97,7 +97,7 @@ def test_shipped_models_every_loop_is_rewritten():
         assert out.count("\n") == src.count("\n")
 
 
-@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference tree not mounted")
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "examples")), reason="reference tree not mounted")
 def test_reference_examples_every_loop_is_rewritten():
     """All message loops of the reference's continuous-agent examples have the canonical shape."""
     seen = 0
