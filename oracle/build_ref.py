@@ -249,6 +249,47 @@ def expand(xml_path: str, outdir: str) -> Dict[str, str]:
     return written
 
 
+def ref_console_path(name: str) -> str:
+    return os.path.join(OUT, name, f"ref_console_{name}")
+
+
+def build_ref_console(xml_path: str, name: str, function_dir: Optional[str] = None, force: bool = False) -> str:
+    """The reference's console PROGRAM on the host: its own main.cu (argument handling, messages, output paths,
+    iteration loop, XML output frequency) linked with the host build of simulation.cu / io.cu.  Used to check the
+    behaviour of this repository's console program (csrc/fgpu_console.cpp) where no device is involved."""
+    if not reference_available():
+        raise RuntimeError("the reference tree is not mounted (%s)" % REFERENCE)
+    model = xmml.parse_model(xml_path)
+    mdir = function_dir or os.path.dirname(os.path.abspath(xml_path))
+    out = ref_console_path(name)
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(os.path.abspath(__file__)), os.path.getmtime(xml_path)):
+        return out
+    dyn = os.path.join(OUT, name, "dynamic_console")
+    files = expand(xml_path, dyn)
+    main = xslt_subset.Stylesheet(os.path.join(TEMPLATES, "main.xslt")).transform(xml_path)
+    kernels = open(files["FLAMEGPU_kernals.cu"]).read()
+    scripts = [open(os.path.join(mdir, f)).read() for f in model.function_files]
+    reach = functions_reaching_barrier([kernels] + scripts, {"FAST_ATOMIC_SORTING"})
+    with open(os.path.join(dyn, "simulation_host.cpp"), "w") as f:
+        f.write("CUDA_ON_HOST_SHARED_MEMORY_DEFINITION\n" + rewrite_launches(open(files["simulation.cu"]).read(), reach))
+    with open(os.path.join(dyn, "io_host.cpp"), "w") as f:
+        f.write(rewrite_launches(open(files["io.cu"]).read(), reach))
+    with open(os.path.join(dyn, "main_host.cpp"), "w") as f:
+        f.write(rewrite_launches(main, reach))
+    cmd = ["g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-w", "-fpermissive",
+           "-x", "c++", "-include", os.path.join(HERE, "cuda_on_host", "cuda_on_host.h"),
+           "-I", os.path.join(HERE, "cuda_on_host"), "-I", dyn, "-I", mdir, "-I", os.path.join(REFERENCE, "include"),
+           "-DGLM_FORCE_PURE", "-Wl,--allow-multiple-definition",
+           os.path.join(dyn, "main_host.cpp"), os.path.join(dyn, "simulation_host.cpp"), os.path.join(dyn, "io_host.cpp"), "-o", out]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    with open(out + ".log", "w") as f:
+        f.write(" ".join(cmd) + "\n" + proc.stdout)
+    if proc.returncode != 0:
+        raise RuntimeError("reference console build failed (%s):\n%s" % (name, proc.stdout[-8000:]))
+    _discard_expansion(dyn)
+    return out
+
+
 def _discard_expansion(directory: str) -> None:
     """The expanded sources are the reference's text: they exist only for the duration of the compile (kept after a
     failed one, and with FGPU_KEEP_REF_SOURCES=1, for reading)."""

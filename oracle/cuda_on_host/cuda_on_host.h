@@ -92,7 +92,7 @@ static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 struct cudaDeviceProp {
     char name[256];
-    int major, minor, multiProcessorCount, maxThreadsPerBlock, warpSize;
+    int major, minor, multiProcessorCount, maxThreadsPerBlock, warpSize, pciBusID, pciDeviceID, tccDriver, computeMode;
     size_t totalGlobalMem, sharedMemPerBlock;
     int maxGridSize[3], maxThreadsDim[3];
 };
