@@ -16,7 +16,7 @@
  *     simulation.cu / FLAMEGPU_kernals.cu / io.cu plus the model's functions.c
  *     against oracle/cuda_on_host/ (every CUDA thread run on the CPU) into
  *     oracle/_ref/.  tests/test_oracle_vs_reference.py steps that build and
- *     this oracle side by side -- eleven of the reference's example models
+ *     this oracle side by side -- twelve of the reference's example models
  *     from their shipped inputs, the authored fixtures (death, births,
  *     optional messages, conditions, globalCondition, host-side creation) and
  *     the Brownian workload -- and requires identical bytes in every variable
