@@ -180,6 +180,27 @@ def test_message_build_order_and_partition_matrix(name, iters, fast_atomic):
     orc.close()
 
 
+def test_full_size_c2_against_the_reference_build(tmp_path):
+    """BASELINE config C2 at its full size -- 1 048 576 particles, 64^3 cells -- for two iterations: the reference's own
+    generated code (reading the 130 MB 0.xml with its own reader) and the oracle end in the same bytes and the same
+    1 048 576 rand48 seeds.  (The CUDA path is compared with the oracle at this size in
+    tests/test_gpu_brownian.py::test_full_size_c2_properties.)"""
+    cfg = W.BROWNIAN["c2"]
+    fdir = os.path.dirname(W.brownian_function_files()[0])
+    st = W.brownian_state(cfg)
+    ref = RefSimulation(_ref_library(cfg.name, W.brownian_xml(cfg), fdir), W.brownian_xml(cfg),
+                        W.write_states_xml(str(tmp_path / "0.xml"), "Particle", st))
+    orc = OracleSimulation(gen_oracle.oracle_path(cfg.name), threads=os.cpu_count() or 1)
+    orc.set_agents("Particle", "default", st)
+    _assert_same(ref, orc, "after reading 0.xml")
+    ref.step(2)
+    orc.step(2)
+    _assert_same(ref, orc, "iteration 2")
+    assert int(orc.agent_var("Particle", "default", "nbr", cfg.n).max()) > 0
+    ref.close()
+    orc.close()
+
+
 def _write_input(path, states):
     """0.xml in the reference's layout with round-trippable %.9g floats (atof gives the same float back)."""
     with open(path, "w") as fh:
