@@ -129,3 +129,46 @@ def test_struct_layouts_seen_by_scripts_and_drivers(name):
         s = f"xmachine_message_{m.name}"
         theirs = [x for x in ref[s] if x not in hidden and x != "int _position"]
         assert ours[s] == theirs and len(theirs) == len(m.variables), s
+
+
+@pytest.mark.parametrize("name", ["Keratinocyte", "CirclesBruteForce_float", "SmoothedParticleHydrodynamics", "MonteCarlo_MSMPR",
+                                  "Boids_Partitioning"])
+def test_reference_function_skeletons_compile_against_the_generated_header(name, tmp_path):
+    """functions.xslt is the reference's own statement of Face 1: for a model it writes a functions.c with one stub per
+    init/step/exit/agent function -- the exact signature the generated wrapper will call (agent, agent-output list,
+    input message list [+ partition matrix], output message list, rand48, in that order) -- and, in comments, the usage
+    template of every API call that function may make (add_<M>_message with all variables, the get_first/get_next loop,
+    add_<A>_agent, rnd).  The stubs with those templates switched on must compile as a model of this repository: the
+    plugin for sm_100a (nvcc, wrappers calling the stubs) and the oracle (g++)."""
+    import glob
+    import shutil
+    from ev_diffusion_b200 import build
+    from oracle import gen_oracle
+    xml = f"{REFERENCE}/examples/{name}/src/model/XMLModelFile.xml"
+    skeleton = xslt_subset.Stylesheet(f"{REFERENCE}/FLAMEGPU/templates/functions.xslt").transform(xml)
+    switched_on = [0]
+
+    def activate(m):
+        if "//Template" not in m.group(1):
+            return m.group(0)
+        switched_on[0] += 1
+        return "{" + m.group(1) + "}"
+
+    source = re.sub(r"/\*(?!\*)(.*?)\*/", activate, skeleton, flags=re.S)
+    model = xmml.parse_model(xml)
+    assert switched_on[0] >= sum(1 for f in model.all_functions() if f.input_message or f.output_message or f.xagent_output)
+    for f in model.all_functions():
+        assert re.search(r"__FLAME_GPU_FUNC__ int %s\(" % re.escape(f.name), source), f.name
+    path = tmp_path / "functions.c"
+    path.write_text(source)
+    tag = f"{name}_skeleton_check"
+    try:
+        gen_oracle.build_oracle(xml, tag, function_files=[str(path)], force=True)
+        plugin = build.build_model(xml, tag, fmad=True, function_files=[str(path)], force=True)
+        assert os.path.getsize(plugin) > 10000
+    finally:
+        for p in glob.glob(os.path.join(build.LIB, "models", tag + "*")) + [gen_oracle.oracle_path(tag)]:
+            if os.path.exists(p):
+                os.remove(p)
+        shutil.rmtree(os.path.join(build.GEN, tag), ignore_errors=True)
+        shutil.rmtree(os.path.join(gen_oracle.OUT, tag), ignore_errors=True)
