@@ -1,12 +1,14 @@
 #!/usr/bin/env python
 """bench.py -- agent-steps/s of the FLAME GPU 1.5 simulation step (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2_16m] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2_16m|c2] [--impl ours|reference]
 
 One "step" = one simulation iteration (singleIteration(), simulation.xslt:878-975) of
-the Brownian random-walk model over its whole population.  The default workload is
-BASELINE config C2 (1 048 576 float agents, 64^3 spatially partitioned cells,
-rand48, wall reflection).  Prints ONE JSON line (rank 0).
+the Brownian random-walk model over its whole population.  The default workload is the
+north-star configuration C2-16M (16 777 216 float agents, 128 x 128 x 256 spatially
+partitioned cells, rand48, wall reflection); with N GPUs the SAME population is cut into
+N z-slabs (strong scaling).  `--workload c2` is BASELINE config C2 (1 048 576 agents,
+64^3 cells; N GPUs: 1M agents per GPU, weak scaling).  Prints ONE JSON line (rank 0).
 
  value      whole-job agent-steps/s, inputs resident in HBM, device time from CUDA
             events on the simulation stream, max over ranks; every timed iteration
@@ -20,6 +22,10 @@ rand48, wall reflection).  Prints ONE JSON line (rank 0).
             sample of the same workload: OpenMP on all cores (`value`) and one thread
  reference_cuda  (N=1) the reference's own generated CUDA, built for sm_100a by
             oracle/build_ref.py --device, run on the same workload in its own process
+ parity     untimed, after the measurement: N=1 -- one iteration of the bit-exact build of the same
+            model against one oracle iteration on the same input (message order, every variable, seeds),
+            and the timed (FMA-contracted) build against the same oracle iteration; N>1 -- id multiset
+            conserved, every agent on its owner, brute-force neighbour count on a 64K sample
  --impl reference  the reference has no CPU path; the arm times the host-C oracle on
             all host cores, as the task statement prescribes for this tier.
 """
@@ -120,8 +126,16 @@ def dist_env():
     return rank, world, local
 
 
+def slab_key(workload, world):
+    return workload if world == 1 else f"{workload}_w{world}"
+
+
+def scaling_of(workload):
+    return "strong" if workload == "c2_16m" else "weak"
+
+
 def run_reference(args, cfg):
-    """CPU arm: the host-C oracle (OpenMP, all host cores) on the same workload."""
+    """CPU arm: the host-C oracle (OpenMP, all host cores) on the same workload (whole-job population)."""
     rank, world, _ = dist_env()
     if rank != 0:
         return
@@ -139,20 +153,23 @@ def run_reference(args, cfg):
     sim.step(args.steps)
     dt = time.perf_counter() - t0
     value = cfg.n * args.steps / dt
+    same = scaling_of(args.workload) == "strong" or args.gpus == 1
     line = {
         "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": scaling_of(args.workload),
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": workload_name(args, cfg), "agents": cfg.n, "cells": list(cfg.dims)},
+        "config": {"workload": workload_name(args, cfg), "agents": cfg.n, "cells": list(cfg.dims),
+                   "population_of_gpu_arm": cfg.n if same else cfg.n * args.gpus,
+                   "same_population_as_gpu_arm": same},
         "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} full iterations of the {cfg.n}-agent workload, OpenMP {cores} threads" +
-                                   (f" (one slab's worth of the {args.gpus}-GPU weak-scaling job: same density, same cells per slab)"
-                                    if args.gpus > 1 else "")},
+                                   ("" if same else f" (one slab's worth of the {args.gpus}-GPU weak-scaling job: same density, "
+                                                    "same cells per slab; agent-steps/s normalises)")},
         "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "the reference has no CPU path: this arm is the host-C oracle (port) executing the same functions.c with OpenMP. "
                 "The reference's own generated code also runs on the CPU here (oracle/build_ref.py, one host thread, "
-                "0.16 M agent-steps/s on this workload) and computes the same bytes (tests/test_oracle_vs_reference.py); "
+                "0.16 M agent-steps/s on C2) and computes the same bytes (tests/test_oracle_vs_reference.py); "
                 "the port is timed because it is the faster CPU arm.  The reference's CUDA build for sm_100a is the "
                 "reference_cuda object of the GPU arm's line.",
     }
@@ -161,19 +178,22 @@ def run_reference(args, cfg):
 
 def workload_name(args, cfg):
     return {"c2": "C2 Brownian random walk, 1M float agents, 64^3 spatially partitioned cells, rand48, wall reflection",
-            "c2_16m": "C2-16M Brownian random walk, 16M float agents, 128x128x256 cells"}.get(args.workload, cfg.name)
+            "c2_16m": "C2-16M Brownian random walk (north-star config), 16 777 216 float agents, 128x128x256 spatially "
+                      "partitioned cells, rand48, wall reflection"}.get(args.workload, cfg.name)
 
 
 def cpu_baseline(cfg, budget_s=12.0):
     """north_star: "a straightforward single-threaded and OpenMP host-C execution of the same functions.c on the box's
-    host cores, with the core count stated".  `value` is the OpenMP figure (the stronger baseline)."""
+    host cores, with the core count stated".  `value` is the OpenMP figure (the stronger baseline).  The one-thread
+    figure is taken on the 1M-agent C2 population (same model, same density) when the workload is larger, so that the
+    leg stays bounded: one thread needs ~28 s per 16M-agent iteration."""
     from oracle import gen_oracle
     from oracle.oracle import OracleSimulation
     cores = os.cpu_count() or 1
 
-    def timed(threads, budget, most, least, warm):
-        sim = OracleSimulation(gen_oracle.oracle_path(cfg.name), threads=threads)
-        sim.set_agents("Particle", "default", W.brownian_state(cfg))
+    def timed(c, threads, budget, most, least, warm):
+        sim = OracleSimulation(gen_oracle.oracle_path(c.name), threads=threads)
+        sim.set_agents("Particle", "default", W.brownian_state(c))
         if warm:
             sim.step(1)
         t0 = time.perf_counter()
@@ -185,31 +205,44 @@ def cpu_baseline(cfg, budget_s=12.0):
         sim.close()
         return iters, dt
 
-    iters, dt = timed(cores, budget_s, 20, 2, True)
-    it1, dt1 = timed(1, budget_s / 2, 4, 1, False)        # one thread: bounded even at 16M agents (one iteration)
+    iters, dt = timed(cfg, cores, budget_s, 20, 2, True)
+    c1 = cfg if cfg.n <= (1 << 20) else W.BROWNIAN["c2"]
+    it1, dt1 = timed(c1, 1, budget_s / 2, 4, 1, False)
     return {"value": cfg.n * iters / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
             "sample": f"{iters} full iterations of the {cfg.n}-agent workload ({dt:.1f} s), OpenMP {cores} threads",
-            "single_thread": {"value": cfg.n * it1 / dt1, "unit": "agent-steps/s", "cores": 1,
-                              "sample": f"{it1} full iterations ({dt1:.1f} s), one thread"}}
+            "single_thread": {"value": c1.n * it1 / dt1, "unit": "agent-steps/s", "cores": 1,
+                              "sample": f"{it1} full iterations of the {c1.n}-agent {c1.name} population ({dt1:.1f} s), one thread"}}
 
 
-def reference_cuda(cfg, iterations=100, timeout_s=120.0):
+def reference_cuda(cfg, sim_for_xml=None, iterations=None, timeout_s=420.0):
     """north_star: "the reference's own CUDA build on one B200 ... timed in the same run".  oracle/build_ref.py --device
     expands the reference's templates and compiles its console program for sm_100a (texture references rewritten to
     cached loads, nothing else; built in the build container, it travels in oracle/_ref/).  Here it is run as its own
-    process on the workload's 0.xml, XML output off, and its own "Total Processing time" is reported.  A baseline, never
-    part of the product path; any failure is recorded in the JSON and changes nothing else."""
+    process on the workload's 0.xml (written by this repository's own state writer with round-trippable %.9g floats),
+    XML output off, and its own "Total Processing time" is reported.  A baseline, never part of the product path; any
+    failure is recorded in the JSON and changes nothing else."""
     import re
     import subprocess
     import tempfile
     exe = os.path.join(ROOT, "oracle", "_ref", cfg.name, f"ref_gpu_{cfg.name}")
     if not os.path.exists(exe):
         return {"unavailable": "oracle/_ref/%s/ref_gpu_%s is not built (python oracle/build_ref.py --device, needs /root/reference)" % (cfg.name, cfg.name)}
+    big = cfg.n > (1 << 21)
+    iterations = iterations or (30 if big else 100)
+    runs = 1 if big else 2          # the reference's reader takes most of a minute on a 2 GB 0.xml
     try:
         with tempfile.TemporaryDirectory() as tmp:
-            inp = W.write_states_xml(os.path.join(tmp, "0.xml"), "Particle", W.brownian_state(cfg))
+            t0 = time.perf_counter()
+            if sim_for_xml is not None:                          # the runtime's C writer: seconds instead of minutes at 16M agents
+                sim_for_xml.set_option("xml_float_digits", 9)
+                sim_for_xml.set_agents("Particle", "default", W.brownian_state(cfg))
+                inp = sim_for_xml.save_states(tmp + os.sep, 0)
+            else:
+                inp = W.write_states_xml(os.path.join(tmp, "0.xml"), "Particle", W.brownian_state(cfg))
+            t_xml = time.perf_counter() - t0
             best = None
-            for _ in range(2):                                   # first run also warms the driver's caches
+            t0 = time.perf_counter()
+            for _ in range(runs):                                # with two runs the first also warms the driver's caches
                 proc = subprocess.run([exe, inp, str(iterations), "0", "0"], cwd=tmp, stdout=subprocess.PIPE,
                                       stderr=subprocess.STDOUT, text=True, timeout=timeout_s)
                 m = re.search(r"Total Processing time: ([0-9.eE+-]+) \(ms\)", proc.stdout)
@@ -219,22 +252,146 @@ def reference_cuda(cfg, iterations=100, timeout_s=120.0):
                     return {"unavailable": "exit %d: %s" % (proc.returncode, why[:200])}
                 ms = float(m.group(1))
                 best = ms if best is None else min(best, ms)
+            t_run = time.perf_counter() - t0
         return {"value": cfg.n * iterations / (best * 1e-3), "unit": "agent-steps/s", "ms_per_step": best / iterations,
-                "steps": iterations, "kind": "reference templates expanded, nvcc sm_100a, FAST_ATOMIC_SORTING (its default)",
-                "timing": "the program's own cudaEvent pair around its iteration loop (main.xslt:415-446), best of 2 runs, warm L2, "
-                          "per-iteration printf to a pipe"}
+                "steps": iterations, "agents": cfg.n,
+                "kind": "reference templates expanded, nvcc sm_100a, FAST_ATOMIC_SORTING (its default)",
+                "timing": "the program's own cudaEvent pair around its iteration loop (main.xslt:415-446), best of %d run(s), "
+                          "warm L2, per-iteration printf to a pipe" % runs,
+                "wall_s": {"write_0xml": round(t_xml, 1), "reference_process": round(t_run, 1)}}
     except Exception as e:                                       # a baseline must never take the bench down
         return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+
+
+def parity_single_gpu(cfg, timed_plugin, device, oracle_threads):
+    """One iteration on the same seeded input: the bit-exact build (-fmad=false) against the CPU oracle -- message
+    order, every agent variable bit for bit, every rand48 seed -- and the timed build (-fmad=true, the reference's
+    own setting) against the same oracle iteration: integer outputs that do not pass through float rounding
+    (message order, seeds) equal, nbr equal except where a distance is within rounding of the radius, positions
+    within 1 ulp-scale of the FMA contraction."""
+    from ev_diffusion_b200 import check
+    from ev_diffusion_b200.runtime import Simulation
+    from oracle import gen_oracle
+    from oracle.oracle import OracleSimulation
+    out = {}
+    st = W.brownian_state(cfg)
+    orc = OracleSimulation(gen_oracle.oracle_path(cfg.name), threads=oracle_threads)
+    orc.set_agents("Particle", "default", st)
+    orc.step(1)
+    want = orc.agents("Particle")
+    want_seeds = orc.seeds()
+    want_order = orc.message_order("location")
+    orc.close()
+    exact = B.model_path(cfg.name + "_exact")
+    ok = True
+    if os.path.exists(exact):
+        g = Simulation(exact, device=device)
+        g.set_agents("Particle", "default", st)
+        g.step(1)
+        got = g.agents("Particle")
+        e = {"message_order": bool(np.array_equal(g.message_order("location"), want_order)),
+             "seeds": bool(np.array_equal(g.seeds(), want_seeds))}
+        for k in want:
+            e[k] = bool(np.array_equal(got[k].view(np.uint32), want[k].view(np.uint32)))
+        g.close()
+        out["exact_build_vs_oracle"] = e
+        ok = ok and all(e.values())
+    else:
+        out["exact_build_vs_oracle"] = {"unavailable": exact + " not built"}
+        ok = False
+    g = Simulation(timed_plugin, device=device)
+    g.set_agents("Particle", "default", st)
+    g.step(1)
+    got = g.agents("Particle")
+    t = {"message_order": bool(np.array_equal(g.message_order("location"), want_order)),
+         "seeds": bool(np.array_equal(g.seeds(), want_seeds)),
+         "id": bool(np.array_equal(got["id"], want["id"])),
+         "nbr_mismatch_fraction": float((got["nbr"] != want["nbr"]).mean())}
+    g.close()
+    err = max(float(np.abs(got[k].astype(np.float64) - want[k].astype(np.float64)).max()) for k in ("x", "y", "z"))
+    t["max_abs_position_error"] = err
+    t["position_tolerance"] = 2.0 ** -16      # one rounding of fma(SIGMA, 2u-1, p) at |p| < 256: half an ulp = 2^-17
+    out["timed_build_vs_oracle"] = t
+    ok = ok and t["message_order"] and t["seeds"] and t["id"] and t["nbr_mismatch_fraction"] < 1e-5 and err <= t["position_tolerance"]
+    # the neighbour counts of the timed build against plain geometry on a sample (the check used at N > 1)
+    smp = check.neighbour_sample_check(st, got, cfg.dims)
+    out["neighbour_sample"] = smp
+    ok = ok and smp["mismatches"] == 0
+    out["iterations"] = 1
+    out["agents"] = cfg.n
+    return ok, out
+
+
+def gather_population(sim, names, dist, device):
+    """All ranks' state lists on rank 0 (padded all_gather over NCCL; check plumbing, untimed)."""
+    import torch
+    a = sim.agents("Particle")
+    n = len(a["id"])
+    world = dist.get_world_size()
+    sizes = torch.zeros(world, dtype=torch.int64, device=device)
+    sizes[dist.get_rank()] = n
+    dist.all_reduce(sizes)
+    cap = int(sizes.max().item())
+    out = {}
+    for k in names:
+        src = a[k]
+        buf = torch.zeros(cap, dtype=torch.int32, device=device)
+        buf[:n] = torch.from_numpy(src.view(np.int32).copy()).to(device)
+        parts = [torch.zeros_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf)
+        if dist.get_rank() == 0:
+            out[k] = np.concatenate([p[:int(sizes[r])].cpu().numpy() for r, p in enumerate(parts)]).view(src.dtype)
+    owner = np.concatenate([np.full(int(sizes[r]), r, dtype=np.int32) for r in range(world)])
+    return out, owner
+
+
+def parity_slabs(cfg, sim, dist, device, world):
+    """N > 1 (no oracle at this size, and a P-rank run is not bit-comparable to a 1-rank run: list order defines
+    rand48 stream ownership): one more iteration, then on rank 0 -- id multiset conserved, every agent on the rank
+    that owns its cell plane, and nbr of a 64K sample equal to a brute-force float32 count over the GLOBAL positions
+    at the start of that iteration (needs halo planes incl. the wrap pair, migration and ownership to be right)."""
+    from ev_diffusion_b200 import check
+    before, _ = gather_population(sim, ("id", "x", "y", "z"), dist, device)
+    sim.step(1)
+    after, owner = gather_population(sim, ("id", "x", "y", "z", "nbr"), dist, device)
+    if dist.get_rank() != 0:
+        return True, {}
+    out = {"ids_conserved": check.ids_conserved(after["id"], cfg.n),
+           "agents_on_owner": check.owners_ok(after["z"], owner, cfg.dims, world),
+           "agents_per_rank": [int((owner == r).sum()) for r in range(world)]}
+    if out["ids_conserved"]:
+        out["neighbour_sample"] = check.neighbour_sample_check(before, after, cfg.dims)
+    ok = out["ids_conserved"] and out["agents_on_owner"] and out["neighbour_sample"]["mismatches"] == 0
+    return bool(ok), out
+
+
+def load_ncu_record(workload, kernel):
+    """Per-launch DRAM traffic and issue statistics of the dominant kernel from this round's committed ncu capture
+    (profiles/r02_traffic.json, written by tools/ncu_traffic.py from an `ncu --set full` raw page; it records the
+    commit and command it came from).  Not measurable inside bench.py without a profiler."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                rec = json.load(fh).get(workload, {}).get(kernel)
+            if rec:
+                rec = dict(rec)
+                rec["source"] = "profiles/" + name
+                return rec
+        except (OSError, ValueError, KeyError):
+            pass
+    return None
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c2", choices=sorted(W.BROWNIAN.keys()))
+    ap.add_argument("--workload", default="c2_16m", choices=sorted(k for k, c in W.BROWNIAN.items() if c.world == 1))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--option", action="append", default=[], help="runtime option key=value")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -255,12 +412,13 @@ def main():
 
     from ev_diffusion_b200 import slabs
     from ev_diffusion_b200.runtime import Simulation, nccl_unique_id
+    cfg1 = cfg
     if world > 1:
-        # weak scaling over z-slabs: 1M agents and 64 cell planes per GPU, halo + migration over NCCL
-        key = f"{args.workload}_w{world}"
+        key = slab_key(args.workload, world)
         if key not in W.BROWNIAN:
             raise SystemExit(f"no slab variant {key} of workload {args.workload}")
         cfg = W.BROWNIAN[key]
+    scaling = scaling_of(args.workload)
     plugin = B.model_path(cfg.name)
     if not os.path.exists(plugin):
         raise SystemExit(f"{plugin} missing: run `python -c 'import __graft_entry__ as g; g.build()'` first")
@@ -269,6 +427,7 @@ def main():
         k, v = kv.split("=")
         sim.set_option(k, int(v))
     state = W.brownian_state(cfg)
+    transport = None
     if world > 1:
         import torch
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -279,8 +438,9 @@ def main():
         m = sim.model.messages[0]
         plan = slabs.make_plan(m.dims, m.min_bounds, m.max_bounds, m.is_2d, rank, world)
         state = slabs.partition_state(state, plan)
+        transport = ("peer-memory stores over NVLink (CUDA IPC; k_push_planes / k_push) with release/acquire flags; NCCL only "
+                     "exchanges the IPC handles" if sim.slab_info().get("p2p") else "NCCL grouped send/recv of fixed-capacity buffers")
     sim.set_agents("Particle", "default", state)
-    n_local0 = len(state["id"])
 
     def barrier():
         if dist is not None:
@@ -310,10 +470,10 @@ def main():
         t = torch.tensor([total_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-    n_global = cfg.n if world > 1 else cfg.n   # cfg.n is the whole-job population in both cases
+    n_global = cfg.n                                   # cfg.n is the whole-job population at every N
     value = n_global * args.steps / (total_ms * 1e-3)
 
-    # warm-L2 variant: K back-to-back iterations (graph replays on one GPU), one event pair
+    # warm-L2 variant: K back-to-back iterations (graph replays), one event pair
     sim.step(args.steps)
     warm_ms = sim.last_step_ms
     if dist is not None:
@@ -335,22 +495,22 @@ def main():
     dom_ms = classes[dom]
     n_kernel = sim.agent_count("Particle", "default")   # units one launch of the dominant kernel processes
     achieved = B_ALG[dom] * n_kernel / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    # DRAM bytes per launch of that kernel from the committed ncu capture (not measurable here without ncu)
-    traffic, issue = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-            rec = json.load(fh).get(args.workload, {}).get(dom)
-        if rec and world == 1:
-            traffic = rec["dram_read_bytes"] + rec["dram_write_bytes"]
-            issue = {k: rec[k] for k in ("warp_instructions", "issue_active_frac", "active_lanes_per_instruction",
-                                         "l1_sector_hit_rate", "l2_sector_hit_rate") if k in rec}
-    except (OSError, ValueError, KeyError):
-        traffic = None
+    rec = load_ncu_record(args.workload, dom) if world == 1 else None
+    traffic = (rec["dram_read_bytes"] + rec["dram_write_bytes"]) if rec else None
+    issue = None
+    if rec and "warp_instructions" in rec and dom_ms > 0:
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        slots = 4 * 148 * sm_hz                          # warp instructions per second a B200 can issue
+        issue = {"bound": "issue slots (4 warp instructions / clock / SM x 148 SMs)", "warp_instructions": rec["warp_instructions"],
+                 "achieved": rec["warp_instructions"] / (dom_ms * 1e-3) / 1e9, "peak": slots / 1e9, "unit": "G warp-instr/s",
+                 "frac": rec["warp_instructions"] / (dom_ms * 1e-3) / slots,
+                 "ncu": {k: rec[k] for k in ("issue_active_frac", "active_lanes_per_instruction", "l1_sector_hit_rate",
+                                             "l2_sector_hit_rate", "source", "commit") if k in rec}}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "alg_bytes_per_agent": B_ALG[dom], "kernel_ms": dom_ms,
-                # what actually bounds that kernel (same committed ncu capture): issue slots, not HBM
-                "ncu": issue,
+                "alg_bytes_per_agent": B_ALG[dom], "kernel_ms": dom_ms, "agents_per_launch": n_kernel,
+                # the bound that actually limits this kernel (user script over ~115 messages per agent): issue slots
+                "issue": issue,
                 "stage_ms": {k: round(v, 5) for k, v in stage.items()},
                 "iteration": {"alg_bytes_per_agent_step": B_ALG_ITERATION,
                               "achieved_per_gpu": B_ALG_ITERATION * n_global / world * args.steps / (total_ms * 1e-3) / 1e9,
@@ -377,7 +537,6 @@ def main():
     e2e_dt = time.perf_counter() - t0
     d2h = sum(got * o.itemsize for o in out.values())
     if dist is not None:
-        import torch
         t = torch.tensor([e2e_dt], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
@@ -387,27 +546,51 @@ def main():
     e2e = {"value": n_global * e2e_steps / e2e_dt, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": e2e_steps}
 
+    # ---- parity (untimed) -----------------------------------------------------------
+    parity_ok, parity = None, None
+    if not args.no_parity:
+        try:
+            if world == 1:
+                sim.close()
+                sim = None
+                parity_ok, parity = parity_single_gpu(cfg, plugin, local, os.cpu_count() or 1)
+            else:
+                sim.set_agents("Particle", "default", state)
+                parity_ok, parity = parity_slabs(cfg, sim, dist, torch.device("cuda", local), world)
+        except Exception as e:                                   # reported, never hidden
+            parity_ok, parity = False, {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+    planes = cfg.dims[2] // world
     line = {
         "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args, cfg), "agents": n_global, "agents_per_gpu": n_global // world,
+        "config": {"workload": workload_name(args, cfg1), "agents": n_global, "agents_per_gpu": n_global // world,
                    "cells": list(cfg.dims),
                    "parallelism": "single GPU" if world == 1 else
-                   f"{world} z-slabs of {cfg.dims[2] // world} cell planes, halo planes + migrating agents over NCCL send/recv",
+                   f"{world} z-slabs of {planes} cell planes ({scaling} scaling); halo planes + migrating agents by {transport}",
                    "l2": "flushed between timed iterations (256 MiB scratch rewrite, untimed)" +
                          ("; ranks re-aligned by an untimed neighbour flag exchange after each flush" if world > 1 else ""),
                    "options": args.option},
         "ms_per_step_warm_l2": warm_ms / args.steps,
         "value_warm_l2": n_global * args.steps / (warm_ms * 1e-3),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "parity_checked": parity_ok, "parity": parity,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg)
-        line["reference_cuda"] = reference_cuda(cfg)       # its own process; this one idles meanwhile
+    if rank == 0 and world == 1 and not args.no_reference_cuda:
+        xsim = Simulation(plugin, device=local)
+        line["reference_cuda"] = reference_cuda(cfg, xsim)       # its own process; this one idles meanwhile
+        xsim.close()
+        if "value" in line["reference_cuda"]:
+            line["reference_cuda"]["ours_over_reference_cuda"] = value / line["reference_cuda"]["value"]
     if rank == 0:
+        if parity_ok is False:
+            print("bench.py: PARITY CHECK FAILED: %s" % json.dumps(parity), file=sys.stderr, flush=True)
         print(json.dumps(line))
-    sim.close()
+    if sim is not None:
+        sim.close()
     if dist is not None:
         dist.destroy_process_group()
 

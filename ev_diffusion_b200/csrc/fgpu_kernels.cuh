@@ -182,11 +182,12 @@ k_radix_scatter(const unsigned int *__restrict__ keys_in, const unsigned int *__
             const unsigned int bal = __ballot_sync(0xffffffffu, m != 0);
             peers &= ~(bal ^ (unsigned int)m);
         }
-        /* every lane of a group reads the group's counter (same address: broadcast), the first
-         * lane of the group then adds the group size; same-warp shared accesses stay in order */
+        /* every lane of a group reads the group's counter (same address: broadcast); after a warp barrier the
+         * first lane of the group adds the group size */
         const unsigned int before = __popc(peers & lt);
         unsigned int prev = 0;
         if (valid) prev = sm.warp_hist[warp][d];
+        __syncwarp();
         if (valid && before == 0) sm.warp_hist[warp][d] = (unsigned short)(prev + __popc(peers));
         rank[r] = (unsigned short)(prev + before);
         __syncwarp();

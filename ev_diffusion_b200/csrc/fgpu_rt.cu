@@ -200,6 +200,7 @@ struct fgpu_sim {
     int opt_radix_bits = 9;
     int opt_slab_async = 1;
     int opt_slab_p2p = 1;
+    int opt_xml_digits = 0; /* 0: the reference's "%f" iteration files; n: "%.<n>g" */
     /* CUDA graph of one iteration (static models) */
     bool is_static = false;
     bool static_kind = false; /* every function is an in-place pointer-swap function (regardless of slab mode) */
@@ -313,6 +314,7 @@ static int sort_passes(int radix_bits, int max_bits) {
     return p;
 }
 static size_t sort_scratch_words(int n, int key_bits, int max_bits);
+constexpr int SCR_GAP = 0, SCR_TOTALS = 8, SCR_TILEHIST = 8 + SORT_MAX_BINS; /* scratch layout, 32-bit words */
 
 static int sim_alloc(fgpu_sim *s) {
     const fgpu_model *m = s->model;
@@ -363,13 +365,9 @@ static int sim_alloc(fgpu_sim *s) {
             CU(cudaMalloc(&M.cell_start, sizeof(unsigned int) * ((size_t)M.d->grid_size + 1)));
             CU(cudaMemsetAsync(M.cell_start, 0, sizeof(unsigned int) * ((size_t)M.d->grid_size + 1), s->stream));
             M.max_tiles = (M.d->buffer_size + SORT_TILE - 1) / SORT_TILE;
-            /* scratch: hist[4][2048] | tickets[4] | gap_count[1] | pad | status[passes][tiles][2048]
-             * (a sort of radix_bits key bits never needs more than ceil(bits/4) <= 8... passes; the status
-             * area is sized for the worst legal digit choice of this grid) */
-            size_t words = 0;
-            for (int mb = 4; mb <= SORT_MAXBITS; ++mb)
-                if (sort_passes(M.d->radix_bits, mb) <= SORT_MAX_PASSES)
-                    words = std::max(words, sort_scratch_words(M.d->buffer_size, M.d->radix_bits, mb));
+            /* scratch: gap_count | totals[2048] | tile_hist[bins][tiles], sized for the widest digit any key width can
+             * select (slab mode sorts on a narrower, slab-relative key, which may choose wider digits than the full key) */
+            const size_t words = (size_t)SCR_TILEHIST + (size_t)M.max_tiles * SORT_MAX_BINS;
             M.scratch_bytes = sizeof(unsigned int) * words;
             CU(cudaMalloc(&M.scratch, M.scratch_bytes));
             CU(cudaMalloc(&M.gap_queue, sizeof(unsigned int) * 3 * ((size_t)GAP_LONG_MAX + (size_t)M.d->grid_size / GAP_INLINE + 8)));

@@ -47,8 +47,7 @@ static int choose_digit_bits(int radix_bits, int max_bits, int *passes_out) {
     return (radix_bits + passes - 1) / passes; /* balanced digits */
 }
 
-/* scratch layout (32-bit words): gap_count | pad[7] | totals[2048] | tile_hist[nbins][tiles] */
-constexpr int SCR_GAP = 0, SCR_TOTALS = 8, SCR_TILEHIST = 8 + SORT_MAX_BINS;
+/* scratch layout (32-bit words): gap_count | pad[7] | totals[2048] | tile_hist[nbins][tiles] (SCR_* in fgpu_rt.cu) */
 
 static size_t sort_scratch_words(int n, int key_bits, int max_bits) {
     int passes = 1;
@@ -61,12 +60,15 @@ template <int BITS>
 static cudaError_t launch_scatter(int tiles, cudaStream_t st, const unsigned int *kin, const unsigned int *vin, unsigned int *kout,
                                   unsigned int *vout, int n, const int *d_n, int shift, int digit_bits, const unsigned int *tile_hist,
                                   const unsigned int *totals, unsigned int key_base) {
-    static bool configured = false;
+    /* the opt-in above 48 KB is per device: one flag per device of the process */
+    static bool configured[64] = {};
     const size_t smem = sizeof(SortSmem<BITS>);
-    if (!configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_radix_scatter<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     k_radix_scatter<BITS><<<tiles, SORT_THREADS, smem, st>>>(kin, vin, kout, vout, n, d_n, shift, digit_bits, tile_hist, totals, tiles, key_base);
     return cudaGetLastError();
@@ -127,6 +129,8 @@ static int build_spatial(fgpu_sim *s, MsgRT &M) {
         key_bits = std::min(key_bits, M.d->radix_bits);
         range_error = S.d_status + 4;
     }
+    if (sizeof(unsigned int) * sort_scratch_words(n, key_bits, max_bits) > M.scratch_bytes)
+        return set_err(FGPU_ERR_MODEL, "message %s: sort scratch too small for %d keys of %d bits", M.d->name, n, key_bits);
     int rc = radix_sort_pairs(s->stream, M.keys_in, n, key_bits, max_bits, M.keys, M.vals, M.scratch, &in, &s->launches, M.d_count, key_base,
                               key_span, range_error);
     if (rc) return rc;

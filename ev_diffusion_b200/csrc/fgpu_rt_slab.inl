@@ -132,6 +132,8 @@ extern "C" int fgpu_sim_slab_init(fgpu_sim *s, int rank, int world, const void *
     S.plane_cells = (S.axis == 2) ? g->dims[0] * g->dims[1] : g->dims[0];
     if (S.nplanes % world != 0 || S.nplanes / world < 2)
         return set_err(FGPU_ERR_MODEL, "%d cell planes cannot be cut into %d slabs of >= 2 whole planes", S.nplanes, world);
+    if (world == 2 && S.nplanes == 4) /* the two halo planes would be adjacent in hash order and share a boundary entry */
+        return set_err(FGPU_ERR_MODEL, "2 slabs need more than 4 cell planes (the two halo planes of a rank must not be adjacent)");
     S.rank = rank;
     S.world = world;
     S.ppr = S.nplanes / world;

@@ -6,7 +6,9 @@
 /* ------------------------------------------------------------------------- */
 namespace {
 /* formatSpecifier, _common_templates.xslt:25-60: integers by width and sign, everything else "%f" */
-int write_value(FILE *f, const char *ctype, int size, bool is_float, const void *p) {
+int write_value(FILE *f, const char *ctype, int size, bool is_float, const void *p, int digits = 0) {
+    /* option xml_float_digits: "%.<digits>g" instead of the reference's lossy "%f" (9 digits round-trip a float) */
+    if (is_float && digits > 0) return size == 8 ? fprintf(f, "%.*g", digits, *(const double *)p) : fprintf(f, "%.*g", digits, (double)*(const float *)p);
     if (is_float) return size == 8 ? fprintf(f, "%f", *(const double *)p) : fprintf(f, "%f", *(const float *)p);
     const bool uns = strstr(ctype, "unsigned") != nullptr;
     switch (size) {
@@ -63,6 +65,8 @@ extern "C" int fgpu_sim_save_states(fgpu_sim *s, const char *outputpath, int ite
     const std::string path = std::string(outputpath) + std::to_string(iteration_number) + ".xml"; /* io.xslt:143 */
     FILE *f = fopen(path.c_str(), "w");
     if (!f) return set_err(FGPU_ERR_IO, "Error: Could not open file `%s` for output. Aborting.", path.c_str());
+    std::vector<char> iobuf(4u << 20);
+    setvbuf(f, iobuf.data(), _IOFBF, iobuf.size());
     fprintf(f, "<states>\n<itno>%i</itno>\n<environment>\n", iteration_number);
     for (int c = 0; c < m->nconstants; ++c) {
         const fgpu_constant &K = m->constants[c];
@@ -89,7 +93,7 @@ extern "C" int fgpu_sim_save_states(fgpu_sim *s, const char *outputpath, int ite
                 for (int v = 0; v < A.d->nvars; ++v) {
                     const fgpu_var &V = A.d->vars[v];
                     fprintf(f, "<%s>", V.name);
-                    write_value(f, V.ctype, V.size, V.is_float != 0, cols[st][v].data() + (size_t)i * V.size);
+                    write_value(f, V.ctype, V.size, V.is_float != 0, cols[st][v].data() + (size_t)i * V.size, s->opt_xml_digits);
                     fprintf(f, "</%s>\n", V.name);
                 }
                 fputs("</xagent>\n", f);
@@ -266,6 +270,11 @@ extern "C" int fgpu_sim_set_option(fgpu_sim *s, const char *key, int value) {
     if (!strcmp(key, "order")) s->opt_order = value ? 1 : 0;
     else if (!strcmp(key, "nvtx")) s->opt_nvtx = value ? 1 : 0;
     else if (!strcmp(key, "graph")) s->opt_graph = value ? 1 : 0;
+    else if (!strcmp(key, "xml_float_digits")) {
+        if (value < 0 || value > 17) return set_err(FGPU_ERR_ARG, "xml_float_digits must be in [0,17]");
+        s->opt_xml_digits = value;
+        return FGPU_OK;
+    }
     else if (!strcmp(key, "slab_p2p")) {
         if (s->slab.on) return set_err(FGPU_ERR_ARG, "slab_p2p must be set before fgpu_sim_slab_init");
         s->opt_slab_p2p = value ? 1 : 0;

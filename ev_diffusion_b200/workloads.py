@@ -57,6 +57,11 @@ BROWNIAN = {
     "c2": BrownianConfig("Brownian", 1 << 20, (64, 64, 64), 42),
     # north-star target: 16M agents, 128 x 128 x 256 cells
     "c2_16m": BrownianConfig("Brownian_16M", 1 << 24, (128, 128, 256), 46),
+    # strong scaling of the north-star population over z-slabs: 16M agents in total, 256 cell planes cut into
+    # 128 / 64 / 32 planes per rank; per-rank buffers = the rank's share + 64K of headroom
+    "c2_16m_w2": BrownianConfig("Brownian_16M_w2", 1 << 24, (128, 128, 256), 46, buffer=(1 << 23) + 65536, world=2),
+    "c2_16m_w4": BrownianConfig("Brownian_16M_w4", 1 << 24, (128, 128, 256), 46, buffer=(1 << 22) + 65536, world=4),
+    "c2_16m_w8": BrownianConfig("Brownian_16M_w8", 1 << 24, (128, 128, 256), 46, buffer=(1 << 21) + 65536, world=8),
     # small parity case (the oracle finishes in well under a second)
     "c2_small": BrownianConfig("Brownian_small", 1 << 14, (16, 16, 16), 7),
     # tiny ragged case: count < bufferSize, few agents per tile, some empty cells
