@@ -292,11 +292,13 @@ FGPU_DEV {S}* get_next_{name}_message({S}* current, {S}_list* messages, {S}_PBM*
 }}
 /* the two levels of the walk, for message loops rewritten by looprewrite.py */
 FGPU_DEV {S}* fgpu_range_end_{name}({S}_list* messages){{ return const_cast<{S}*>(messages->end); }}
+FGPU_DEV int fgpu_range_count_{name}({S}_list* messages){{ return messages->cnt; }}
 FGPU_DEV {S}* fgpu_next_range_{name}({S}_list* messages){{ return fgpu::open_next_range<{S}, {T}>(messages); }}""")
     else:
         out.append(f"""FGPU_DEV {S}* get_first_{name}_message({S}_list* messages){{
     if (messages->in_count == 0) return nullptr;
     messages->end = messages->in_recs + messages->in_count;
+    messages->cnt = messages->in_count;
     return const_cast<{S}*>(messages->in_recs);
 }}
 FGPU_DEV {S}* get_next_{name}_message({S}* current, {S}_list* messages){{
@@ -304,6 +306,7 @@ FGPU_DEV {S}* get_next_{name}_message({S}* current, {S}_list* messages){{
     return next != messages->end ? next : nullptr;
 }}
 FGPU_DEV {S}* fgpu_range_end_{name}({S}_list* messages){{ return const_cast<{S}*>(messages->end); }}
+FGPU_DEV int fgpu_range_count_{name}({S}_list* messages){{ return messages->cnt; }}
 FGPU_DEV {S}* fgpu_next_range_{name}({S}_list* messages){{ (void)messages; return nullptr; }}""")
     return "\n".join(out) + "\n"
 
@@ -567,7 +570,7 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
         out.append(f"    xmachine_message_{M}_list inp;")
         out.append(f"    inp.in_recs = (const xmachine_message_{M}*)L.in_recs; inp.cell_start = L.in_cell_start; inp.in_count = L.d_in_count ? *L.d_in_count : L.in_count;")
         out.append("    inp.out_recs = nullptr; inp.out_keys = nullptr; inp.out_flags = nullptr; inp.out_index = 0; inp.end = nullptr;")
-        out.append("    inp.step = 0; inp.cx = 0; inp.cy = 0; inp.cz = 0; inp.nrows = -1; inp.nlo = 0; inp.nhi = 0;")
+        out.append("    inp.step = 0; inp.cx = 0; inp.cy = 0; inp.cz = 0; inp.mode = fgpu::WALK_CELL; inp.cnt = 0; inp.nlo = 0; inp.nhi = 0;")
         call.append("&inp")
         if model.message(M).partitioning == "spatial":
             call.append(f"(xmachine_message_{M}_PBM*)nullptr")
@@ -577,7 +580,7 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
             raise ModelError(f"function '{f.name}' reads and writes message '{M}'")
         out.append(f"    xmachine_message_{M}_list outp;")
         out.append("    outp.in_recs = nullptr; outp.cell_start = nullptr; outp.in_count = 0; outp.end = nullptr;")
-        out.append("    outp.step = 0; outp.cx = 0; outp.cy = 0; outp.cz = 0; outp.nrows = -1; outp.nlo = 0; outp.nhi = 0;")
+        out.append("    outp.step = 0; outp.cx = 0; outp.cy = 0; outp.cz = 0; outp.mode = fgpu::WALK_CELL; outp.cnt = 0; outp.nlo = 0; outp.nhi = 0;")
         out.append(f"    outp.out_recs = (xmachine_message_{M}*)L.out_recs; outp.out_keys = L.out_keys; outp.out_flags = L.out_flags; outp.out_index = L.out_base + index;")
         call.append("&outp")
     if f.rng:

@@ -83,7 +83,8 @@ FGPU_DEV unsigned int cell_hash(int cx, int cy, int cz) {
  * take at a time.  Scripts whose message loops have the canonical shape are restructured at generation
  * time (looprewrite.py) so that the two levels are two nested loops: the inner one is a counted loop over
  * contiguous 16-byte records, and the whole warp switches rows together.  Threads in the first or last
- * x column (x wraps, rows are not contiguous) walk cell by cell. */
+ * x column (x wraps) see a row as two ranges and stay in the same loop nest; only an agent outside the
+ * grid in x walks cell by cell. */
 
 template <class Msg, class T>
 struct MessageProxy {
@@ -99,36 +100,71 @@ struct MessageProxy {
     /* cursor (replaces _relative_cell/_cell_index/_cell_index_max/_agent_grid_cell, hdr:170-173) */
     const Msg *end;   /* one past the last message of the open range; the cursor itself is the pointer
                          user code holds (get_next receives it back) */
-    int step;         /* row walk: next row (0..9 / 0..3); cell walk: next relative cell (0..26 / 0..8) */
-    int nrows;        /* 0: row walk; -1: cell walk */
-    unsigned int nlo, nhi; /* row walk: PBM entries of the next row, loaded one row ahead */
+    int cnt;          /* number of messages in the open range (restructured loops count instead of comparing pointers) */
+    int step;         /* ROW: next row (0..9 / 0..3); EDGE: next half-row (0..18 / 0..6); CELL: next relative cell (0..27 / 0..9) */
+    int mode;         /* WALK_ROW / WALK_EDGE / WALK_CELL */
+    unsigned int nlo, nhi; /* ROW: PBM entries of the next row, loaded one row ahead */
     int cx, cy, cz;   /* agent grid cell */
 };
 
-/* hash of the first cell (x-1) of row k = (ry, rz) of the neighbourhood of cell (cx,cy,cz), 1 <= cx < DIMX-1 */
+enum { WALK_ROW = 0, WALK_EDGE = 1, WALK_CELL = 2 };
+
+/* hash of cell x = 0 of row k = (ry, rz) of the neighbourhood of cell (.,cy,cz); y and z wrap like message_<M>_hash */
 template <class T>
-FGPU_DEV unsigned int row_hash(int cx, int cy, int cz, int k) {
-    const int ry = (k % 3) - 1;
-    const int rz = T::IS2D ? -1 : (k / 3) - 1;   /* 2-D: relative z stays -1 (krn:137-154) */
-    return cell_hash<T>(cx - 1, cy + ry, cz + rz);
+FGPU_DEV unsigned int row_base(int cy, int cz, int k) {
+    const int kz = T::IS2D ? 0 : (k * 11) >> 5;          /* k / 3 for 0 <= k < 9 */
+    const int ry = k - 3 * kz - 1;                       /* k % 3 - 1 */
+    int y = cy + ry;
+    int z = cz + (T::IS2D ? -1 : kz - 1);                /* 2-D: relative z stays -1 (krn:137-154) */
+    y = (y < 0) ? T::DIMY - 1 : y;
+    y = (y >= T::DIMY) ? 0 : y;
+    z = (z < 0) ? T::DIMZ - 1 : z;
+    z = (z >= T::DIMZ) ? 0 : z;
+    return (unsigned int)((z * T::DIMY + y) * T::DIMX);
 }
 
 /* Opens the next non-empty range of the neighbourhood and returns its first message; nullptr when
- * the neighbourhood is exhausted. */
+ * the neighbourhood is exhausted.
+ *   ROW   1 <= cx <= DIMX-2: the three x cells of a row are adjacent hashes, one range per row, the PBM entries
+ *         of row k+1 requested when row k is opened;
+ *   EDGE  cx == 0 or cx == DIMX-1: x wraps to the opposite face (krn:880-885), a row is two ranges visited in
+ *         the reference's order -- (DIMX-1) then (0,1), or (DIMX-2,DIMX-1) then (0) -- so that these lanes stay
+ *         inside the same two-level loop as the rest of their warp;
+ *   CELL  an agent outside the grid in x (cells repeat under the wrap rule): cell by cell, like the reference. */
 template <class Msg, class T>
 FGPU_DEV Msg *open_next_range(MessageProxy<Msg, T> *p) {
-    if (p->nrows >= 0) {
+    if (p->mode == WALK_ROW) {
         constexpr int NROWS = T::IS2D ? 3 : 9;
 #pragma unroll 1
         while (p->step < NROWS) {
             const unsigned int lo = p->nlo, hi = p->nhi;
             const int k = ++p->step;
             if (k < NROWS) { /* PBM entries of the row after this one: in flight while this row is iterated */
-                const unsigned int h = row_hash<T>(p->cx, p->cy, p->cz, k);
-                p->nlo = __ldg(p->cell_start + h);
-                p->nhi = __ldg(p->cell_start + h + 3);
+                const unsigned int *cs = p->cell_start + (row_base<T>(p->cy, p->cz, k) + (unsigned int)(p->cx - 1));
+                p->nlo = __ldg(cs);
+                p->nhi = __ldg(cs + 3);
             }
             if (lo < hi) {
+                p->cnt = (int)(hi - lo);
+                p->end = p->in_recs + hi;
+                return const_cast<Msg *>(p->in_recs + lo);
+            }
+        }
+        return nullptr;
+    }
+    if (p->mode == WALK_EDGE) {
+        constexpr int NHALF = T::IS2D ? 6 : 18;
+#pragma unroll 1
+        while (p->step < NHALF) {
+            const int s = p->step++;
+            const unsigned int *cs = p->cell_start + row_base<T>(p->cy, p->cz, s >> 1);
+            /* cx == 0:       first (DIMX-1), then (0, 1);   cx == DIMX-1: first (DIMX-2, DIMX-1), then (0) */
+            const bool first = (s & 1) == 0, left = p->cx == 0;
+            const int c0 = first ? (left ? T::DIMX - 1 : T::DIMX - 2) : 0;
+            const int nc = (first == left) ? 1 : 2;
+            const unsigned int lo = __ldg(cs + c0), hi = __ldg(cs + c0 + nc);
+            if (lo < hi) {
+                p->cnt = (int)(hi - lo);
                 p->end = p->in_recs + hi;
                 return const_cast<Msg *>(p->in_recs + lo);
             }
@@ -147,6 +183,7 @@ FGPU_DEV Msg *open_next_range(MessageProxy<Msg, T> *p) {
         const int lo = (int)__ldg(p->cell_start + h);
         const int hi = (int)__ldg(p->cell_start + h + 1);
         if (lo < hi) {
+            p->cnt = hi - lo;
             p->end = p->in_recs + hi;
             return const_cast<Msg *>(p->in_recs + lo);
         }
@@ -174,12 +211,14 @@ FGPU_DEV void begin_walk(MessageProxy<Msg, T> *p, float x, float y, float z) {
     p->cx = cx;
     p->cy = cy;
     p->cz = cz;
-    p->nrows = -1;
+    p->mode = WALK_CELL;
     if (cx >= 1 && cx + 1 < T::DIMX) {
-        const unsigned int h = row_hash<T>(cx, cy, cz, 0);
-        p->nlo = __ldg(p->cell_start + h);
-        p->nhi = __ldg(p->cell_start + h + 3);
-        p->nrows = 0;
+        const unsigned int *cs = p->cell_start + (row_base<T>(cy, cz, 0) + (unsigned int)(cx - 1));
+        p->nlo = __ldg(cs);
+        p->nhi = __ldg(cs + 3);
+        p->mode = WALK_ROW;
+    } else if (T::DIMX >= 3 && (cx == 0 || cx == T::DIMX - 1)) {
+        p->mode = WALK_EDGE;
     }
 }
 

@@ -27,6 +27,22 @@ Same messages, same order, same arithmetic per agent: results are bit-identical 
 runs both forms).  The inner loop is a plain counted loop the compiler unrolls and batches loads for
 (measured on C2: count_neighbours 219 -> 171 us).
 
+The default emission ("pair") goes one step further, because ptxas turns neither `unroll 2` nor a pointer
+compare into tight code (two copies of the 64-bit cursor, a 64-bit compare, a spill): the body text is
+instantiated three times -- once for the odd message of a range, twice in a counted loop that issues both
+16-byte loads up front::
+
+    while (msg) {
+        int n = fgpu_range_count_M(messages); const M* p = msg;
+        if (n & 1) { M c = fgpu::load_message(p); M* msg = &c; { BODY } ++p; }
+        for (n >>= 1; n > 0; --n) { M a = load(p), b = load(p + 1);
+            { M* msg = &a; { BODY } }  { M* msg = &b; { BODY } }  p += 2; }
+        msg = fgpu_next_range_M(messages);
+    }
+
+The copy of BODY that stays where the author wrote it keeps its line numbers; the other two are the same text
+with comments removed, folded onto the existing lines.
+
 A loop is rewritten only when it matches exactly; anything else -- ``break``/``continue``/``goto`` in the body,
 another assignment to the cursor, a different statement order -- is left alone and runs through the generic
 ``get_next`` (still correct, just slower).  Line numbers are preserved (all inserted text stays on existing
@@ -69,6 +85,35 @@ def mask_comments_and_strings(src: str) -> str:
                 if out[k] != "\n":
                     out[k] = " "
             i = j
+        else:
+            i += 1
+    return "".join(out)
+
+
+def strip_comments(src: str) -> str:
+    """Same-length copy of `src` with comments blanked; string and char literals are kept."""
+    out = list(src)
+    i, n = 0, len(src)
+    while i < n:
+        c = src[i]
+        if c == "/" and i + 1 < n and src[i + 1] == "/":
+            j = src.find("\n", i)
+            j = n if j < 0 else j
+            for k in range(i, j):
+                out[k] = " "
+            i = j
+        elif c == "/" and i + 1 < n and src[i + 1] == "*":
+            j = src.find("*/", i + 2)
+            j = n if j < 0 else j + 2
+            for k in range(i, j):
+                if out[k] != "\n":
+                    out[k] = " "
+            i = j
+        elif c == '"' or c == "'":
+            j = i + 1
+            while j < n and src[j] != c:
+                j += 2 if src[j] == "\\" else 1
+            i = min(j + 1, n)
         else:
             i += 1
     return "".join(out)
@@ -124,11 +169,16 @@ class LoopReport:
     reason: str = ""
 
 
-def rewrite_message_loops(src: str, message_names: List[str], unroll: Optional[int] = None) -> Tuple[str, List[LoopReport]]:
+def rewrite_message_loops(src: str, message_names: List[str], unroll: Optional[int] = None,
+                          style: str = "pair") -> Tuple[str, List[LoopReport]]:
     """Rewrite every canonical message loop of `src`; returns the new text and one report per get_next call.
-    `unroll` puts an unroll pragma on the inner loop (tuning knob; default: the compiler decides)."""
+    `style` "pair": three instances of the body (odd message + a counted loop over pairs); "single": one
+    instance in a do-while over the range, with `unroll` as an unroll pragma on it (tuning knob; default: the
+    compiler decides).  A body that cannot be duplicated safely (preprocessor lines, labels, static locals) is
+    emitted in the single style, and so is a loop whose body holds another message walk."""
     pragma = ('_Pragma("unroll %d") ' % unroll) if unroll else ""
     masked = mask_comments_and_strings(src)
+    nocomment = strip_comments(src)
     names = "|".join(re.escape(m) for m in sorted(message_names, key=len, reverse=True))
     if not names:
         return src, []
@@ -190,9 +240,23 @@ def rewrite_message_loops(src: str, message_names: List[str], unroll: Optional[i
         serial += 1
         S = f"xmachine_message_{msg}"
         k = serial
-        prologue = (f" {S}* const fgpu_end{k} = fgpu_range_end_{msg}({lst}); {S}* fgpu_cur{k} = {var}; {pragma}do {{ "
-                    f"{S} fgpu_msg{k} = fgpu::load_message(fgpu_cur{k}); {S}* {var} = &fgpu_msg{k}; {{")
-        epilogue = f"}} }} while (++fgpu_cur{k} != fgpu_end{k}); {var} = fgpu_next_range_{msg}({lst});"
+        copy = " ".join(nocomment[body_open + 1:stmt_start].split())
+        dup_ok = (style == "pair" and not re.search(r"(^|\n)\s*#", body) and not re.search(r"\bstatic\b", body)
+                  and not re.search(r"\bget_next_\w+_message\b", body)      # a nested walk: its own rewrite edits this text
+
+                  and not re.search(r"(?:^|[;{}])\s*(?!case\b|default\b)[A-Za-z_]\w*\s*:(?!:)", body))
+        if dup_ok:
+            prologue = (f" int fgpu_n{k} = fgpu_range_count_{msg}({lst}); const {S}* fgpu_p{k} = {var}; "
+                        f"if (fgpu_n{k} & 1) {{ {S} fgpu_m{k} = fgpu::load_message(fgpu_p{k}); {S}* {var} = &fgpu_m{k}; {{ {copy} }} ++fgpu_p{k}; }} "
+                        f'_Pragma("unroll 1") for (fgpu_n{k} >>= 1; fgpu_n{k} > 0; --fgpu_n{k}) {{ '
+                        f"{S} fgpu_a{k} = fgpu::load_message(fgpu_p{k}); {S} fgpu_b{k} = fgpu::load_message(fgpu_p{k} + 1); "
+                        f"{{ {S}* {var} = &fgpu_a{k}; {{")
+            epilogue = (f"}} }} {{ {S}* {var} = &fgpu_b{k}; {{ {copy} }} }} fgpu_p{k} += 2; }} "
+                        f"{var} = fgpu_next_range_{msg}({lst});")
+        else:
+            prologue = (f" {S}* const fgpu_end{k} = fgpu_range_end_{msg}({lst}); {S}* fgpu_cur{k} = {var}; {pragma}do {{ "
+                        f"{S} fgpu_msg{k} = fgpu::load_message(fgpu_cur{k}); {S}* {var} = &fgpu_msg{k}; {{")
+            epilogue = f"}} }} while (++fgpu_cur{k} != fgpu_end{k}); {var} = fgpu_next_range_{msg}({lst});"
         edits.append((body_open + 1, body_open + 1, prologue))
         # replace exactly the statement (from the cursor name to its `;`), keeping any line breaks inside
         # it, so that neither line numbers nor the author's comments move

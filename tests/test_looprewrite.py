@@ -23,12 +23,20 @@ __FLAME_GPU_FUNC__ int f(xmachine_memory_A* agent, xmachine_message_loc_list* lo
 """
 
 
-def test_canonical_loop_is_rewritten_and_lines_stay():
-    out, rep = rewrite_message_loops(CANON, ["loc"])
+@pytest.mark.parametrize("style", ["pair", "single"])
+def test_canonical_loop_is_rewritten_and_lines_stay(style):
+    out, rep = rewrite_message_loops(CANON, ["loc"], style=style)
     assert [r.rewritten for r in rep] == [True]
     assert out.count("\n") == CANON.count("\n")
     assert "get_next_loc_message" not in mask_comments_and_strings(out)
-    assert "fgpu_next_range_loc(loc_messages)" in out and "fgpu::load_message(fgpu_cur1)" in out
+    assert "fgpu_next_range_loc(loc_messages)" in out
+    if style == "single":
+        assert "fgpu::load_message(fgpu_cur1)" in out
+    else:
+        # three instances of the body: the odd message, and a pair per trip of the counted loop; the two copies carry
+        # no comments (a `//` comment folded onto one line would swallow the rest of it)
+        assert out.count("agent->n++;") == 3 and out.count("another one") == 1
+        assert "fgpu_range_count_loc(loc_messages)" in out and "fgpu::load_message(fgpu_p1 + 1)" in out
     # every original line other than the two edited ones is untouched
     a, b = CANON.split("\n"), out.split("\n")
     changed = [i for i, (x, y) in enumerate(zip(a, b)) if x != y]
@@ -63,7 +71,7 @@ def test_two_loops_and_a_nested_pair():
     two = CANON + CANON.replace("int f(", "int g(")
     out, rep = rewrite_message_loops(two, ["loc"])
     assert [r.rewritten for r in rep] == [True, True]
-    assert "fgpu_cur1" in out and "fgpu_cur2" in out
+    assert "fgpu_p1" in out and "fgpu_p2" in out
     nested = """
     xmachine_message_a* m = get_first_a_message(a_messages);
     while (m) {
@@ -78,7 +86,15 @@ def test_two_loops_and_a_nested_pair():
     out, rep = rewrite_message_loops(nested, ["a", "b"])
     assert sorted((r.message, r.rewritten) for r in rep) == [("a", True), ("b", True)]
     assert out.count("\n") == nested.count("\n")
-    assert out.count("do {") == 2 and out.count("} while (++fgpu_cur") == 2
+    # the inner loop takes the pair form; the outer one, whose body holds another walk, the single form
+    assert out.count("do {") == 1 and out.count("} while (++fgpu_cur") == 1 and out.count("s += q->v * m->v;") == 3
+
+
+def test_bodies_that_cannot_be_duplicated_take_the_single_form():
+    for bad in ("static int seen = 0; seen++;", "again: agent->n++;", "#ifdef X\n agent->n++;\n#endif\n"):
+        src = CANON.replace("agent->n++; }", bad + " }")
+        out, rep = rewrite_message_loops(src, ["loc"])
+        assert rep[0].rewritten and "fgpu_cur1" in out and out.count("\n") == src.count("\n"), bad
 
 
 def test_message_name_that_prefixes_another():
