@@ -545,10 +545,32 @@ def _reduction_defs(model: Model, call: str) -> List[str]:
     return out
 
 
+def _carry_vars(a: Agent) -> List[Variable]:
+    """Variables of the carried agent record: every scalar variable (none if the agent has array variables)."""
+    if any(v.array_length for v in a.variables):
+        return []
+    return list(a.variables)
+
+
+def _cuda_carry_struct(a: Agent) -> str:
+    """The packed record a message producer stores beside its message (fgpu_launch.carry_out): the build moves it with
+    the message, so the consumer that runs in cell order reads its agents' variables with coalesced 16-byte loads
+    instead of one random 4-byte read per variable (each of which costs a 64-byte DRAM burst at 16M agents)."""
+    vs = _carry_vars(a)
+    if not vs:
+        return ""
+    out = [f"struct __align__(16) fgpu_carry_{a.name}\n{{"]
+    for v in vs:
+        out.append(f"    {v.type} {v.name};")
+    out.append("};")
+    return "\n".join(out) + "\n"
+
+
 def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
     a = model.agent(f.agent)
     A = a.name
     bs = 128 if f.input_message else 256
+    carry = _carry_vars(a)
     out = [f"/* GPUFLAME_{f.name} (krn:1320-1387) */",
            f"__global__ void __launch_bounds__({bs}) fgpu_k_{f.name}(const fgpu_launch L)\n{{",
            "    const int t = blockIdx.x * blockDim.x + threadIdx.x;"]
@@ -556,11 +578,23 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
             "    const int index = L.order ? (int)__ldg(L.order + t) : t;",
             f"    xmachine_memory_{A}_list* __restrict__ agents = (xmachine_memory_{A}_list*)L.agents;",
             f"    xmachine_memory_{A} agent;"]
-    for v in a.variables:
-        if v.array_length:
-            out.append(f"    agent.{v.name} = &(agents->{v.name}[index]);")
-        else:
-            out.append(f"    agent.{v.name} = agents->{v.name}[index];")
+    if carry and f.input_message:
+        out.append(f"    if (L.carry_in) {{   /* cell order: the producer's packed records, moved by the message build */")
+        out.append(f"        constexpr int CQ = (int)(sizeof(fgpu_carry_{A}) / 16);")
+        out.append(f"        union {{ fgpu_carry_{A} c; uint4 q[CQ]; }} r;")
+        out.append(f"        for (int _q = 0; _q < CQ; ++_q) r.q[_q] = __ldg((const uint4*)L.carry_in + (size_t)t * CQ + _q);")
+        for v in carry:
+            out.append(f"        agent.{v.name} = r.c.{v.name};")
+        out.append("    } else {")
+        for v in a.variables:
+            out.append(f"        agent.{v.name} = agents->{v.name}[index];")
+        out.append("    }")
+    else:
+        for v in a.variables:
+            if v.array_length:
+                out.append(f"    agent.{v.name} = &(agents->{v.name}[index]);")
+            else:
+                out.append(f"    agent.{v.name} = agents->{v.name}[index];")
     call = ["&agent"]
     if f.xagent_output:
         out.append("    fgpu::NewAgentProxy newp; newp.list = L.new_agents; newp.index = index;")
@@ -597,6 +631,15 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
             out.append(f"    agents->{v.name}[index] = agent.{v.name};")
     if f.rng:
         out.append("    ((uint2*)L.seeds)[index] = make_uint2(rng.sx, rng.sy);")
+    if carry and f.output_message:
+        out.append(f"    if (L.carry_out) {{   /* the variables as this function leaves them, for the consumer of its message */")
+        out.append(f"        constexpr int CQ = (int)(sizeof(fgpu_carry_{A}) / 16);")
+        out.append(f"        union {{ fgpu_carry_{A} c; uint4 q[CQ]; }} r;")
+        out.append(f"        r.q[CQ - 1] = make_uint4(0u, 0u, 0u, 0u);")
+        for v in carry:
+            out.append(f"        r.c.{v.name} = agent.{v.name};")
+        out.append(f"        for (int _q = 0; _q < CQ; ++_q) ((uint4*)L.carry_out)[(size_t)index * CQ + _q] = r.q[_q];")
+        out.append("    }")
     out.append("}")
     out.append(f"""static void fgpu_launch_{f.name}(const fgpu_launch* a, void* stream){{
     if (a->n <= 0) return;
@@ -684,7 +727,8 @@ def _descriptor_tables(model: Model, mode: str, launch_prefix: str, sources: Opt
     for a in model.agents:
         rows.append(f'    {{"{a.name}", {a.buffer_size}, {len(a.variables)}, fgpu_vars_agent_{a.name}, {len(a.states)}, '
                     f'fgpu_states_{a.name}, {a.states.index(a.initial_state)}, sizeof(xmachine_memory_{a.name}_list), '
-                    f'offsetof(xmachine_memory_{a.name}_list, _position), offsetof(xmachine_memory_{a.name}_list, _scan_input)}},')
+                    f'offsetof(xmachine_memory_{a.name}_list, _position), offsetof(xmachine_memory_{a.name}_list, _scan_input), '
+                    + (f'(int)(sizeof(fgpu_carry_{a.name}) / 16)' if mode == "cuda" and _carry_vars(a) else '0') + '},')
     out.append("static const fgpu_agent fgpu_agents[] = {\n" + "\n".join(rows) + "\n};")
     rows = []
     for m in model.messages:
@@ -847,6 +891,8 @@ def emit_cuda_glue(model: Model, function_files: List[str], include_files: Optio
            '#include "fgpu_model.h"']
     for p in (include_files or function_files):
         out.append(f'#include "{os.path.abspath(p)}"')
+    for a in model.agents:
+        out.append(_cuda_carry_struct(a))
     for f in model.all_functions():
         a = model.agent(f.agent)
         out.append(_cuda_kernel(model, f, written_variables(f, a, sources)))

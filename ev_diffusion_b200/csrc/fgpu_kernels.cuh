@@ -297,7 +297,8 @@ __global__ void __launch_bounds__(256)
 k_gather_pbm(const unsigned int *__restrict__ skeys, const unsigned int *__restrict__ svals,
              const uint4 *__restrict__ in_recs, uint4 *__restrict__ out_recs, int n_host, const int *__restrict__ d_n,
              unsigned int *__restrict__ cell_start, unsigned int first_cell, unsigned int cells, unsigned int value_offset,
-             unsigned int *gap_queue, unsigned int *gap_count) {
+             unsigned int *gap_queue, unsigned int *gap_count, const uint4 *__restrict__ carry_in, uint4 *__restrict__ carry_out,
+             int carry_quads) {
     /* boundaries are written for the cells [first_cell, cells] only (slab mode: the owned planes) and hold
      * value_offset + sorted index (slab mode: the local block sits behind the low halo in the combined list) */
     const int n = d_n ? *d_n : n_host;
@@ -310,6 +311,8 @@ k_gather_pbm(const unsigned int *__restrict__ skeys, const unsigned int *__restr
      * whole 16/32-byte record of the random-access side */
 #pragma unroll
     for (int q = 0; q < NQ; ++q) out_recs[(size_t)i * NQ + q] = __ldg(in_recs + (size_t)v * NQ + q);
+    /* the producer's carried agent records take the same route (message v is the message of list index v) */
+    for (int q = 0; q < carry_quads; ++q) carry_out[(size_t)i * carry_quads + q] = __ldg(carry_in + (size_t)v * carry_quads + q);
     if (i == 0) {
         fill_cells(cell_start, first_cell, key, value_offset, gap_queue, gap_count);
     } else {

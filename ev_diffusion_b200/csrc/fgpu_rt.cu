@@ -118,6 +118,13 @@ struct MsgRT {
     int sorted_in = 0; /* index of keys/vals buffer holding the final sorted pairs */
     bool built = false;
     int local_at = 0;  /* record index of the local block inside `sorted` (slab mode: halo_cap) */
+    /* carried agent records (fgpu_launch.carry_out / carry_in): written by the producer in list order, moved to cell
+     * order by the build together with the message records */
+    uint4 *carry_unsorted = nullptr, *carry_sorted = nullptr;
+    int carry_quads = 0;          /* record size of the buffers above (allocated for the first producer's agent type) */
+    bool carry_pending = false;   /* the producer of this iteration wrote carry_unsorted */
+    bool carry_valid = false;     /* carry_sorted matches the sorted list */
+    unsigned long long carry_content = 0; /* content epoch of the producer list when the records were written */
     const int *d_count = nullptr; /* slab mode: exact message count on the device (h_count is an upper bound) */
 };
 
@@ -193,6 +200,9 @@ struct fgpu_sim {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::map<const char *, unsigned long long> epoch; /* last structural modification per list buffer */
     unsigned long long epoch_counter = 1;
+    std::map<const char *, unsigned long long> content; /* bumped by every function launched on a list buffer */
+    std::vector<char> emits_carry; /* per function: its message has a cell-order consumer right behind it (static) */
+    int opt_carry = 1;
     /* options */
     int opt_order = 1;
     int opt_nvtx = 0;
@@ -374,6 +384,31 @@ static int sim_alloc(fgpu_sim *s) {
         }
     }
     s->gc_count.assign(m->nfunctions, 0);
+    /* A producer writes carried agent records when the next function executed on the same agent type consumes its
+     * spatial message from the very list the producer worked on (in place, no condition): that consumer runs in
+     * cell order and would otherwise gather every variable it reads with random 4-byte loads. */
+    s->emits_carry.assign(m->nfunctions, 0);
+    {
+        std::vector<int> seq;
+        for (int l = 0; l < m->nlayers; ++l)
+            for (int k = 0; k < m->layers[l].nfunctions; ++k) seq.push_back(m->layers[l].functions[k]);
+        for (size_t i = 0; i < seq.size(); ++i) {
+            const fgpu_function &P = m->functions[seq[i]];
+            if (P.output_message < 0 || P.output_type != FGPU_OUT_SINGLE || !P.swappable) continue;
+            if (m->messages[P.output_message].partitioning != FGPU_PART_SPATIAL || m->agents[P.agent].carry_quads <= 0) continue;
+            bool other_producer = false;
+            for (size_t j = 0; j < seq.size(); ++j)
+                if (j != i && m->functions[seq[j]].output_message == P.output_message) other_producer = true;
+            if (other_producer) continue;
+            for (size_t j = i + 1; j < seq.size(); ++j) {
+                const fgpu_function &G = m->functions[seq[j]];
+                if (G.agent != P.agent) continue;
+                if (G.input_message == P.output_message && G.condition == FGPU_COND_NONE && G.current_state == P.next_state)
+                    s->emits_carry[seq[i]] = 1;
+                break; /* only the next function on this agent type sees the variables unchanged */
+            }
+        }
+    }
 
     /* rand48 seeding, simulation.xslt:661-688 */
     const unsigned int N = (unsigned int)m->buffer_size_max;
@@ -458,6 +493,8 @@ extern "C" void fgpu_sim_destroy(fgpu_sim *s) {
         cudaFree(M.opt_recs);
         cudaFree(M.opt_keys);
         cudaFree(M.opt_flags);
+        cudaFree(M.carry_unsorted);
+        cudaFree(M.carry_sorted);
         for (int k = 0; k < 2; ++k) {
             cudaFree(M.keys[k]);
             cudaFree(M.vals[k]);
@@ -861,12 +898,30 @@ static int run_function(fgpu_sim *s, int fi) {
             Min->producer_buf == A.work && Min->producer_epoch == s->epoch_of(A.work) && Min->h_count == A.h_count &&
             Min->built) {
             L.order = Min->vals[Min->sorted_in];
+            /* ... and the variables themselves in cell order, if the producer left them and nothing ran on the list since */
+            if (s->opt_carry && Min->carry_valid && Min->carry_quads == A.d->carry_quads && Min->carry_content == s->content[A.work])
+                L.carry_in = Min->carry_sorted;
         }
     }
     if (Mout) {
         L.out_recs = Mout->unsorted;
         L.out_keys = Mout->keys_in;
         L.out_base = Mout->h_count; /* a second producer appends; the whole list is re-binned (sim:1836-1837) */
+        if (s->opt_carry && s->emits_carry[fi] && !optional_out && Mout->h_count == 0) {
+            const int cq = A.d->carry_quads;
+            if (Mout->carry_unsorted && Mout->carry_quads != cq) {
+                cudaFree(Mout->carry_unsorted);
+                cudaFree(Mout->carry_sorted);
+                Mout->carry_unsorted = Mout->carry_sorted = nullptr;
+            }
+            if (!Mout->carry_unsorted) {
+                const size_t bytes = (size_t)cq * 16 * (size_t)Mout->d->buffer_size;
+                CU(cudaMalloc(&Mout->carry_unsorted, bytes));
+                CU(cudaMalloc(&Mout->carry_sorted, bytes));
+                Mout->carry_quads = cq;
+            }
+            L.carry_out = Mout->carry_unsorted;
+        }
         if (optional_out) {
             /* reset_<M>_swaps (sim:1666-1672), then every agent that calls add_<M>_message flags its own slot */
             CU(cudaMemsetAsync(Mout->opt_flags, 0, sizeof(int) * (size_t)std::max(A.h_count, 1), s->stream));
@@ -887,6 +942,11 @@ static int run_function(fgpu_sim *s, int fi) {
     F.launch(&L, s->stream);
     LAUNCH_CHECK();
     s->prof_end();
+    s->content[A.work]++;
+    if (Mout && L.carry_out) {
+        Mout->carry_pending = true;
+        Mout->carry_content = s->content[A.work];
+    }
 
     if (optional_out) {
         /* exclusive scan of the flags + scatter_optional_<M>_messages + the count read-back the reference also
@@ -997,6 +1057,8 @@ static int begin_iteration(fgpu_sim *s) {
         M.producer_buf = nullptr;
         M.built = false;
         M.d_count = nullptr;
+        M.carry_pending = false;
+        M.carry_valid = false;
     }
     return FGPU_OK;
 }
@@ -1028,6 +1090,7 @@ static std::vector<int> current_counts(fgpu_sim *s) {
         for (int v : A.h_state_count) c.push_back(v);
     c.push_back(s->opt_order);
     c.push_back(s->opt_radix_bits);
+    c.push_back(s->opt_carry);
     return c;
 }
 

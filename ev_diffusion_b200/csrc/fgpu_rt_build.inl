@@ -138,12 +138,15 @@ static int build_spatial(fgpu_sim *s, MsgRT &M) {
     M.sorted_in = in;
     s->prof_begin(std::string("pbm:") + M.d->name);
     const int g = (n + 255) / 256;
+    const bool carry = M.carry_pending && M.producers == 1;
+    M.carry_valid = carry;
     switch (M.d->rec_quads) {
 #define GATHER_CASE(Q)                                                                                                   \
     case Q:                                                                                                              \
         k_gather_pbm<Q><<<g, 256, 0, s->stream>>>(M.keys[in], M.vals[in], M.unsorted, M.sorted + (size_t)M.local_at * Q, n, M.d_count, M.cell_start, \
                                                   key_base, key_base + (key_span ? key_span : (unsigned int)M.d->grid_size),        \
-                                                  (unsigned int)M.local_at, M.gap_queue, gap_count);                           \
+                                                  (unsigned int)M.local_at, M.gap_queue, gap_count,                            \
+                                                  carry ? M.carry_unsorted : nullptr, M.carry_sorted, carry ? M.carry_quads : 0); \
         break;
         GATHER_CASE(1)
         GATHER_CASE(2)

@@ -21,6 +21,7 @@ static std::vector<unsigned long long> slab_graph_key(fgpu_sim *s) {
     k.push_back(s->slab.dirty ? 1ull : 0ull);
     k.push_back((unsigned long long)s->opt_order);
     k.push_back((unsigned long long)s->opt_radix_bits);
+    k.push_back((unsigned long long)s->opt_carry);
     return k;
 }
 

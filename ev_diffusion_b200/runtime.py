@@ -39,7 +39,8 @@ class _Var(C.Structure):
 class _Agent(C.Structure):
     _fields_ = [("name", C.c_char_p), ("buffer_size", C.c_int), ("nvars", C.c_int), ("vars", C.POINTER(_Var)),
                 ("nstates", C.c_int), ("states", C.POINTER(C.c_char_p)), ("initial_state", C.c_int),
-                ("list_bytes", C.c_size_t), ("position_offset", C.c_size_t), ("scan_offset", C.c_size_t)]
+                ("list_bytes", C.c_size_t), ("position_offset", C.c_size_t), ("scan_offset", C.c_size_t),
+                ("carry_quads", C.c_int)]
 
 
 class _Message(C.Structure):

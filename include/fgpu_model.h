@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FGPU_MODEL_ABI_VERSION 9
+#define FGPU_MODEL_ABI_VERSION 10
 
 /* One agent or message variable.  Agent lists keep the reference's SoA struct
  * layout (header.xslt:187-194): int _position[MAX]; int _scan_input[MAX];
@@ -46,6 +46,9 @@ typedef struct fgpu_agent {
     size_t list_bytes;       /* sizeof(xmachine_memory_<A>_list) */
     size_t position_offset;  /* offsetof(_position)  (= 0) */
     size_t scan_offset;      /* offsetof(_scan_input) */
+    int carry_quads;         /* sizeof(packed record of all scalar variables) / 16: the record a message producer writes
+                                beside its message so that the build can deliver the agents' variables in cell order
+                                (fgpu_launch.carry_out / carry_in); 0 = the plugin does not support it */
 } fgpu_agent;
 
 enum { FGPU_PART_NONE = 0, FGPU_PART_SPATIAL = 1 };
@@ -91,6 +94,10 @@ typedef struct fgpu_launch {
     /* rand48 (simulation.xslt:661-688) */
     void *seeds;                  /* uint2[buffer_size_MAX], .x low 24 bits, .y high 24 bits */
     unsigned int Ax, Ay, Cx, Cy;
+    /* carried agent records (16 * carry_quads bytes each: every scalar variable, XML order, natural alignment) */
+    const void *carry_in;         /* consumer: record t = the variables of list index order[t], i.e. in cell order, as the
+                                     producer of the input message left them; NULL = read the SoA list at order[t] */
+    void *carry_out;              /* producer: the wrapper stores record `index` after the script returns; NULL = no */
 } fgpu_launch;
 
 typedef void (*fgpu_launch_fn)(const fgpu_launch *args, void *cuda_stream);

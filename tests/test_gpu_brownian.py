@@ -68,10 +68,12 @@ def test_function_by_function_exact(key, count):
     orc.close()
 
 
-@pytest.mark.parametrize("order", [0, 1])
+@pytest.mark.parametrize("order,carry", [(0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("graph", [0, 1])
-def test_many_iterations_exact(order, graph):
-    cfg, gpu, orc = _pair("c2_small", exact=True, order=order, graph=graph)
+def test_many_iterations_exact(order, carry, graph):
+    """Processing order (list order / cell order) and the source of a consumer's agent variables (the SoA list at
+    order[t] / the producer's carried records moved into cell order by the build) never change a result."""
+    cfg, gpu, orc = _pair("c2_small", exact=True, order=order, graph=graph, carry=carry)
     gpu.step(50)
     orc.step(50)
     _assert_same_state(gpu, orc, exact=True)
