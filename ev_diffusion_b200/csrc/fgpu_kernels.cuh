@@ -137,7 +137,8 @@ __global__ void __launch_bounds__(SORT_THREADS)
 k_radix_scatter(const unsigned int *__restrict__ keys_in, const unsigned int *__restrict__ vals_in,
                 unsigned int *__restrict__ keys_out, unsigned int *__restrict__ vals_out, int n_host,
                 const int *__restrict__ d_n, int shift, int digit_bits, const unsigned int *__restrict__ tile_hist,
-                const unsigned int *__restrict__ totals, int tiles, unsigned int key_base) {
+                const unsigned int *__restrict__ totals, int tiles, unsigned int key_base,
+                const uint4 *__restrict__ pay_in, uint4 *__restrict__ pay_out, int pay_quads) {
     constexpr int BINS = 1 << BITS;
     const int n = d_n ? *d_n : n_host;
     constexpr int BPT = BINS / SORT_THREADS; /* bins per thread: 1, 2, 4 or 8 */
@@ -248,7 +249,170 @@ k_radix_scatter(const unsigned int *__restrict__ keys_in, const unsigned int *__
         const unsigned int k = sm.keys[i];
         const int dst = sm.goff[((k - key_base) >> shift) & mask] + i;
         keys_out[dst] = k;
-        vals_out[dst] = sm.vals[i];
+        const unsigned int v = sm.vals[i];
+        vals_out[dst] = v;
+        /* MSD build: the 16-byte message records move with their key.  In a first pass v is the record's own
+         * index, so these reads stay inside the tile's contiguous 64 KB of records (sequential DRAM traffic), and
+         * records of one digit leave as a contiguous run. */
+        for (int q = 0; q < pay_quads; ++q) pay_out[(size_t)dst * pay_quads + q] = __ldg(pay_in + (size_t)v * pay_quads + q);
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* MSD build: bucket finish                                                   */
+/* ------------------------------------------------------------------------- */
+/* After ONE stable pass on the high digit (k_tile_hist + k_row_scan + k_radix_scatter with the records as
+ * payload) the list is partitioned into buckets of 2^low_bits consecutive cells, each still in message-index
+ * order.  One block per bucket finishes the job inside the bucket's own window of memory:
+ *   - histogram of the low digit over the bucket, exclusive scan = the bucket's slice of the partition
+ *     boundary matrix (cell_start), written for EVERY cell of the bucket, empty or not -- no boundary
+ *     detection, no gap filling;
+ *   - stable placement in chunks of 4096 messages (one ballot per digit bit inside a warp, per-warp counters,
+ *     running per-digit offsets across chunks): message index -> order_out, record -> sorted_out.
+ * All random accesses stay inside the bucket's window (a few tens of KB), so DRAM only sees sequential
+ * traffic; the LSD build's final gather reads one 64-byte DRAM burst per 16-byte record instead
+ * (profiles/r01_notes.md: 107 B per record at 16M messages).  Any bucket size works (more chunks). */
+template <int BITS>
+struct BucketSmem {
+    static constexpr int BINS = 1 << BITS;
+    unsigned short warp_hist[SORT_WARPS][BINS];
+    unsigned int excl[BINS];
+    unsigned int scan[SORT_WARPS];
+    unsigned int base;
+};
+
+template <int BITS>
+__global__ void __launch_bounds__(SORT_THREADS)
+k_bucket_finish(const unsigned int *__restrict__ keys_a, const unsigned int *__restrict__ vals_a, const uint4 *__restrict__ pay_a,
+                int pay_quads, unsigned int *__restrict__ order_out, uint4 *__restrict__ sorted_out,
+                const unsigned int *__restrict__ totals, int nbuckets, int low_bits, unsigned int key_base,
+                unsigned int *__restrict__ cell_start, unsigned int first_cell, unsigned int cells_end, unsigned int value_offset) {
+    constexpr int BINS = 1 << BITS;
+    constexpr int BPT = BINS / SORT_THREADS;
+    extern __shared__ __align__(16) unsigned char bucket_smem_raw[];
+    BucketSmem<BITS> &sm = *reinterpret_cast<BucketSmem<BITS> *>(bucket_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x;
+    const int nbins = 1 << low_bits;
+    const unsigned int mask = (unsigned int)nbins - 1u;
+    const unsigned int lt = (1u << lane) - 1u;
+
+    /* position of the bucket in the list = messages in the buckets before it */
+    {
+        unsigned int part = 0;
+        for (int j = tid; j < b; j += SORT_THREADS) part += totals[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) sm.scan[warp] = part;
+        for (int i = tid; i < BINS; i += SORT_THREADS) sm.excl[i] = 0;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int t = 0;
+#pragma unroll
+            for (int w = 0; w < SORT_WARPS; ++w) t += sm.scan[w];
+            sm.base = t;
+        }
+        __syncthreads();
+    }
+    const unsigned int base = sm.base;
+    const int cnt = (int)totals[b];
+    const unsigned int *bk = keys_a + base;
+
+    /* low-digit histogram of the bucket */
+    for (int i = tid; i < cnt; i += SORT_THREADS) atomicAdd(&sm.excl[(bk[i] - key_base) & mask], 1u);
+    __syncthreads();
+    {
+        unsigned int c[BPT], csum = 0;
+#pragma unroll
+        for (int k = 0; k < BPT; ++k) {
+            const int d = tid * BPT + k;
+            c[k] = (d < nbins) ? sm.excl[d] : 0u;
+            csum += c[k];
+        }
+        unsigned int run = block_exclusive_scan_256(csum, sm.scan);
+#pragma unroll
+        for (int k = 0; k < BPT; ++k) {
+            const int d = tid * BPT + k;
+            if (d < nbins) {
+                sm.excl[d] = run;
+                const unsigned int cell = key_base + ((unsigned int)b << low_bits) + (unsigned int)d;
+                if (cell >= first_cell && cell < cells_end) cell_start[cell] = value_offset + base + run;
+            }
+            run += c[k];
+        }
+        if (b == nbuckets - 1 && tid == 0) cell_start[cells_end] = value_offset + base + (unsigned int)cnt;
+    }
+
+    /* stable placement, a chunk of 4096 messages at a time */
+    for (int c0 = 0; c0 < cnt; c0 += SORT_TILE) {
+        {
+            unsigned int *z = reinterpret_cast<unsigned int *>(&sm.warp_hist[0][0]);
+            for (int i = tid; i < SORT_WARPS * BINS / 2; i += SORT_THREADS) z[i] = 0;
+        }
+        __syncthreads();
+        unsigned int key[SORT_ITEMS];
+        unsigned short rank[SORT_ITEMS];
+#pragma unroll
+        for (int r = 0; r < SORT_ITEMS; ++r) {
+            const int idx = c0 + warp * (SORT_ITEMS * 32) + r * 32 + lane;
+            key[r] = (idx < cnt) ? bk[idx] : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < SORT_ITEMS; ++r) {
+            const int idx = c0 + warp * (SORT_ITEMS * 32) + r * 32 + lane;
+            const bool valid = idx < cnt;
+            const unsigned int d = (key[r] - key_base) & mask;
+            unsigned int peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+            for (int bit = 0; bit < BITS; ++bit) {
+                const int m = ((int)(d << (31 - bit))) >> 31;
+                const unsigned int bal = __ballot_sync(0xffffffffu, m != 0);
+                peers &= ~(bal ^ (unsigned int)m);
+            }
+            const unsigned int before = __popc(peers & lt);
+            unsigned int prev = 0;
+            if (valid) prev = sm.warp_hist[warp][d];
+            __syncwarp();
+            if (valid && before == 0) sm.warp_hist[warp][d] = (unsigned short)(prev + __popc(peers));
+            rank[r] = (unsigned short)(prev + before);
+            __syncwarp();
+        }
+        __syncthreads();
+        /* per digit: exclusive offsets across the warps of this chunk */
+        unsigned int chunk_cnt[BPT];
+#pragma unroll
+        for (int k = 0; k < BPT; ++k) {
+            const int d = tid * BPT + k;
+            unsigned int run = 0;
+            if (d < nbins) {
+#pragma unroll
+                for (int w = 0; w < SORT_WARPS; ++w) {
+                    const unsigned int t = sm.warp_hist[w][d];
+                    sm.warp_hist[w][d] = (unsigned short)run;
+                    run += t;
+                }
+            }
+            chunk_cnt[k] = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < SORT_ITEMS; ++r) {
+            const int idx = c0 + warp * (SORT_ITEMS * 32) + r * 32 + lane;
+            if (idx < cnt) {
+                const unsigned int d = (key[r] - key_base) & mask;
+                const size_t dst = (size_t)base + sm.excl[d] + sm.warp_hist[warp][d] + rank[r];
+                const size_t src = (size_t)base + idx;
+                order_out[dst] = vals_a[src];
+                for (int q = 0; q < pay_quads; ++q) sorted_out[dst * pay_quads + q] = pay_a[src * pay_quads + q];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BPT; ++k) {
+            const int d = tid * BPT + k;
+            if (d < nbins) sm.excl[d] += chunk_cnt[k];
+        }
+        /* the barrier at the top of the next chunk orders these updates before their next use */
     }
 }
 

@@ -98,6 +98,7 @@ struct MsgRT {
     const fgpu_message *d = nullptr;
     uint4 *unsorted = nullptr; /* staging written by add_<M>_message */
     uint4 *sorted = nullptr;   /* cell-ordered list read by get_first/next */
+    uint4 *pay_a = nullptr;    /* MSD build: the records after the pass on the high digit (bucket-major) */
     unsigned int *keys_in = nullptr; /* cell key of each unsorted message (written by add_<M>_message) */
     /* optional_message producers write a sparse staging list first (allocated on first use) */
     uint4 *opt_recs = nullptr;
@@ -202,7 +203,8 @@ struct fgpu_sim {
     unsigned long long epoch_counter = 1;
     std::map<const char *, unsigned long long> content; /* bumped by every function launched on a list buffer */
     std::vector<char> emits_carry; /* per function: its message has a cell-order consumer right behind it (static) */
-    int opt_carry = 1;
+    int opt_msd = 1;   /* spatial message build: MSD pass + bucket finish where the key width allows, else LSD + gather */
+    int opt_carry = 0; /* off by default: measured at 16M agents it trades 0.10 ms of the consumer for 0.55 ms of build (profiles/r02_notes.md) */
     /* options */
     int opt_order = 1;
     int opt_nvtx = 0;
@@ -326,6 +328,22 @@ static int sort_passes(int radix_bits, int max_bits) {
 static size_t sort_scratch_words(int n, int key_bits, int max_bits);
 constexpr int SCR_GAP = 0, SCR_TOTALS = 8, SCR_TILEHIST = 8 + SORT_MAX_BINS; /* scratch layout, 32-bit words */
 
+/* Buffers of the carried agent records (option "carry"): allocated with the option, never inside a captured iteration. */
+static int alloc_carry(fgpu_sim *s) {
+    const fgpu_model *m = s->model;
+    for (int f = 0; f < m->nfunctions; ++f) {
+        if (!s->emits_carry[f]) continue;
+        const fgpu_function &P = m->functions[f];
+        MsgRT &M = s->msgs[P.output_message];
+        if (M.carry_unsorted) continue;
+        M.carry_quads = m->agents[P.agent].carry_quads;
+        const size_t bytes = (size_t)M.carry_quads * 16 * (size_t)M.d->buffer_size;
+        CU(cudaMalloc(&M.carry_unsorted, bytes));
+        CU(cudaMalloc(&M.carry_sorted, bytes));
+    }
+    return FGPU_OK;
+}
+
 static int sim_alloc(fgpu_sim *s) {
     const fgpu_model *m = s->model;
     CU(cudaSetDevice(s->device));
@@ -367,6 +385,7 @@ static int sim_alloc(fgpu_sim *s) {
         CU(cudaMalloc(&M.unsorted, msg_plane_bytes(M.d)));
         if (M.d->partitioning == FGPU_PART_SPATIAL) {
             CU(cudaMalloc(&M.sorted, msg_plane_bytes(M.d)));
+            CU(cudaMalloc(&M.pay_a, msg_plane_bytes(M.d)));
             CU(cudaMalloc(&M.keys_in, sizeof(unsigned int) * (size_t)M.d->buffer_size));
             for (int k = 0; k < 2; ++k) {
                 CU(cudaMalloc(&M.keys[k], sizeof(unsigned int) * (size_t)M.d->buffer_size));
@@ -408,6 +427,10 @@ static int sim_alloc(fgpu_sim *s) {
                 break; /* only the next function on this agent type sees the variables unchanged */
             }
         }
+    }
+    if (s->opt_carry) {
+        int rc = alloc_carry(s);
+        if (rc) return rc;
     }
 
     /* rand48 seeding, simulation.xslt:661-688 */
@@ -489,6 +512,7 @@ extern "C" void fgpu_sim_destroy(fgpu_sim *s) {
     for (MsgRT &M : s->msgs) {
         cudaFree(M.unsorted);
         cudaFree(M.sorted);
+        cudaFree(M.pay_a);
         cudaFree(M.keys_in);
         cudaFree(M.opt_recs);
         cudaFree(M.opt_keys);
@@ -908,18 +932,8 @@ static int run_function(fgpu_sim *s, int fi) {
         L.out_keys = Mout->keys_in;
         L.out_base = Mout->h_count; /* a second producer appends; the whole list is re-binned (sim:1836-1837) */
         if (s->opt_carry && s->emits_carry[fi] && !optional_out && Mout->h_count == 0) {
-            const int cq = A.d->carry_quads;
-            if (Mout->carry_unsorted && Mout->carry_quads != cq) {
-                cudaFree(Mout->carry_unsorted);
-                cudaFree(Mout->carry_sorted);
-                Mout->carry_unsorted = Mout->carry_sorted = nullptr;
-            }
-            if (!Mout->carry_unsorted) {
-                const size_t bytes = (size_t)cq * 16 * (size_t)Mout->d->buffer_size;
-                CU(cudaMalloc(&Mout->carry_unsorted, bytes));
-                CU(cudaMalloc(&Mout->carry_sorted, bytes));
-                Mout->carry_quads = cq;
-            }
+            /* buffers were allocated with the simulation (no allocation inside a captured iteration) */
+            if (Mout->carry_unsorted && Mout->carry_quads == A.d->carry_quads)
             L.carry_out = Mout->carry_unsorted;
         }
         if (optional_out) {
@@ -1091,6 +1105,7 @@ static std::vector<int> current_counts(fgpu_sim *s) {
     c.push_back(s->opt_order);
     c.push_back(s->opt_radix_bits);
     c.push_back(s->opt_carry);
+    c.push_back(s->opt_msd);
     return c;
 }
 

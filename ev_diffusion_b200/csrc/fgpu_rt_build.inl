@@ -59,7 +59,8 @@ static size_t sort_scratch_words(int n, int key_bits, int max_bits) {
 template <int BITS>
 static cudaError_t launch_scatter(int tiles, cudaStream_t st, const unsigned int *kin, const unsigned int *vin, unsigned int *kout,
                                   unsigned int *vout, int n, const int *d_n, int shift, int digit_bits, const unsigned int *tile_hist,
-                                  const unsigned int *totals, unsigned int key_base) {
+                                  const unsigned int *totals, unsigned int key_base, const uint4 *pay_in = nullptr, uint4 *pay_out = nullptr,
+                                  int pay_quads = 0) {
     /* the opt-in above 48 KB is per device: one flag per device of the process */
     static bool configured[64] = {};
     const size_t smem = sizeof(SortSmem<BITS>);
@@ -70,9 +71,98 @@ static cudaError_t launch_scatter(int tiles, cudaStream_t st, const unsigned int
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    k_radix_scatter<BITS><<<tiles, SORT_THREADS, smem, st>>>(kin, vin, kout, vout, n, d_n, shift, digit_bits, tile_hist, totals, tiles, key_base);
+    k_radix_scatter<BITS><<<tiles, SORT_THREADS, smem, st>>>(kin, vin, kout, vout, n, d_n, shift, digit_bits, tile_hist, totals, tiles, key_base,
+                                                             pay_in, pay_out, pay_quads);
     return cudaGetLastError();
 }
+
+template <int BITS>
+static cudaError_t launch_bucket(int nbuckets, cudaStream_t st, const unsigned int *ka, const unsigned int *va, const uint4 *pa, int pq,
+                                 unsigned int *order_out, uint4 *sorted_out, const unsigned int *totals, int low_bits, unsigned int key_base,
+                                 unsigned int *cell_start, unsigned int first_cell, unsigned int cells_end, unsigned int value_offset) {
+    static bool configured[64] = {};
+    const size_t smem = sizeof(BucketSmem<BITS>);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_bucket_finish<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    k_bucket_finish<BITS><<<nbuckets, SORT_THREADS, smem, st>>>(ka, va, pa, pq, order_out, sorted_out, totals, nbuckets, low_bits, key_base,
+                                                                cell_start, first_cell, cells_end, value_offset);
+    return cudaGetLastError();
+}
+
+template <class F8, class F9, class F10, class F11>
+static cudaError_t by_bits(int bits, F8 f8, F9 f9, F10 f10, F11 f11) {
+    if (bits <= 8) return f8();
+    if (bits == 9) return f9();
+    if (bits == 10) return f10();
+    return f11();
+}
+
+/* Split of a key of key_bits into a high digit (one stable MSD pass over the whole list) and a low digit (finished
+ * bucket by bucket): balanced, so that the pass writes runs of several records per digit and there are enough
+ * buckets to fill the machine.  Keys of fewer than 12 or more than 22 bits take the LSD build. */
+static bool msd_split(int key_bits, int *high_bits, int *low_bits) {
+    if (key_bits < 12 || key_bits > 2 * SORT_MAXBITS) return false;
+    *low_bits = key_bits / 2;
+    *high_bits = key_bits - *low_bits;
+    return true;
+}
+
+/* MSD build of a spatially partitioned message list (4 launches whatever the grid size):
+ *   k_tile_hist + k_row_scan + k_radix_scatter on the HIGH digit, the message records travelling as payload
+ *   k_bucket_finish: per bucket of 2^low cells -- low-digit order, records, message order and the bucket's slice
+ *   of the partition boundary matrix. */
+static int build_spatial_msd(fgpu_sim *s, MsgRT &M, int n, int key_bits, unsigned int key_base, unsigned int key_span, int *range_error) {
+    int H = 0, L = 0;
+    msd_split(key_bits, &H, &L);
+    const int tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    const int nbins = 1 << H;
+    const unsigned int span = key_span ? key_span : (unsigned int)M.d->grid_size;
+    const int nbuckets = (int)((span + (1u << L) - 1u) >> L);
+    unsigned int *totals = M.scratch + SCR_TOTALS, *tile_hist = M.scratch + SCR_TILEHIST;
+    const int Q = M.d->rec_quads;
+    cudaStream_t st = s->stream;
+    s->prof_begin(std::string("sort:") + M.d->name);
+    k_tile_hist<<<tiles, SORT_THREADS, sizeof(unsigned int) * (size_t)nbins, st>>>(M.keys_in, n, M.d_count, L, H, tile_hist, tiles, key_base, key_span,
+                                                                                   range_error);
+    LAUNCH_CHECK();
+    k_row_scan<<<nbins, SORT_THREADS, 0, st>>>(tile_hist, tiles, totals);
+    LAUNCH_CHECK();
+    unsigned int *k0 = M.keys[0], *v0 = M.vals[0];
+    const unsigned int *kin = M.keys_in;
+    const int *dn = M.d_count;
+    const uint4 *pin = M.unsorted;
+    uint4 *pa = M.pay_a;
+    cudaError_t e = by_bits(
+        H, [&] { return launch_scatter<8>(tiles, st, kin, nullptr, k0, v0, n, dn, L, H, tile_hist, totals, key_base, pin, pa, Q); },
+        [&] { return launch_scatter<9>(tiles, st, kin, nullptr, k0, v0, n, dn, L, H, tile_hist, totals, key_base, pin, pa, Q); },
+        [&] { return launch_scatter<10>(tiles, st, kin, nullptr, k0, v0, n, dn, L, H, tile_hist, totals, key_base, pin, pa, Q); },
+        [&] { return launch_scatter<11>(tiles, st, kin, nullptr, k0, v0, n, dn, L, H, tile_hist, totals, key_base, pin, pa, Q); });
+    if (e != cudaSuccess) return set_err(FGPU_ERR_CUDA, "MSD pass launch -> %s", cudaGetErrorString(e));
+    s->launches++;
+    s->prof_end();
+    s->prof_begin(std::string("pbm:") + M.d->name);
+    unsigned int *order = M.vals[1];
+    uint4 *sorted = M.sorted + (size_t)M.local_at * Q;
+    unsigned int *cs = M.cell_start;
+    const unsigned int cells_end = key_base + span, off = (unsigned int)M.local_at;
+    e = by_bits(
+        L, [&] { return launch_bucket<8>(nbuckets, st, k0, v0, pa, Q, order, sorted, totals, L, key_base, cs, key_base, cells_end, off); },
+        [&] { return launch_bucket<9>(nbuckets, st, k0, v0, pa, Q, order, sorted, totals, L, key_base, cs, key_base, cells_end, off); },
+        [&] { return launch_bucket<10>(nbuckets, st, k0, v0, pa, Q, order, sorted, totals, L, key_base, cs, key_base, cells_end, off); },
+        [&] { return launch_bucket<11>(nbuckets, st, k0, v0, pa, Q, order, sorted, totals, L, key_base, cs, key_base, cells_end, off); });
+    if (e != cudaSuccess) return set_err(FGPU_ERR_CUDA, "bucket finish launch -> %s", cudaGetErrorString(e));
+    s->launches++;
+    s->prof_end();
+    M.sorted_in = 1;
+    M.carry_valid = false;
+    return FGPU_OK;
+}
+
 
 /* The hand-written LSD radix sort of (keys_in[i], i): replaces cub::DeviceRadixSort::SortPairs (sim:1867).
  * Returns the index (0/1) of the ping-pong pair holding the sorted result; counts launches. */
@@ -112,8 +202,6 @@ static int build_spatial(fgpu_sim *s, MsgRT &M) {
     if (n <= 0) return FGPU_OK;
     const int max_bits = std::min(std::max(s->opt_radix_bits, 4), SORT_MAXBITS);
     unsigned int *gap_count = M.scratch + SCR_GAP;
-    s->prof_begin(std::string("sort:") + M.d->name);
-    CU(cudaMemsetAsync(gap_count, 0, 2 * sizeof(unsigned int), s->stream));
     int in = 0;
     int key_bits = M.d->radix_bits;
     unsigned int key_base = 0, key_span = 0;
@@ -129,6 +217,16 @@ static int build_spatial(fgpu_sim *s, MsgRT &M) {
         key_bits = std::min(key_bits, M.d->radix_bits);
         range_error = S.d_status + 4;
     }
+    {
+        int H = 0, L = 0;
+        const bool carry = s->opt_carry && M.carry_pending && M.producers == 1; /* carried records take the LSD build */
+        if (s->opt_msd && !carry && M.pay_a && msd_split(key_bits, &H, &L) &&
+            sizeof(unsigned int) * ((size_t)SCR_TILEHIST + (size_t)((n + SORT_TILE - 1) / SORT_TILE) * ((size_t)1 << H)) <= M.scratch_bytes) {
+            return build_spatial_msd(s, M, n, key_bits, key_base, key_span, range_error);
+        }
+    }
+    s->prof_begin(std::string("sort:") + M.d->name);
+    CU(cudaMemsetAsync(gap_count, 0, 2 * sizeof(unsigned int), s->stream));
     if (sizeof(unsigned int) * sort_scratch_words(n, key_bits, max_bits) > M.scratch_bytes)
         return set_err(FGPU_ERR_MODEL, "message %s: sort scratch too small for %d keys of %d bits", M.d->name, n, key_bits);
     int rc = radix_sort_pairs(s->stream, M.keys_in, n, key_bits, max_bits, M.keys, M.vals, M.scratch, &in, &s->launches, M.d_count, key_base,

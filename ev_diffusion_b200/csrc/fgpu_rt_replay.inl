@@ -22,6 +22,7 @@ static std::vector<unsigned long long> slab_graph_key(fgpu_sim *s) {
     k.push_back((unsigned long long)s->opt_order);
     k.push_back((unsigned long long)s->opt_radix_bits);
     k.push_back((unsigned long long)s->opt_carry);
+    k.push_back((unsigned long long)s->opt_msd);
     return k;
 }
 

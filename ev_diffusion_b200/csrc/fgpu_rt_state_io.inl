@@ -270,7 +270,15 @@ extern "C" int fgpu_sim_set_option(fgpu_sim *s, const char *key, int value) {
     if (!strcmp(key, "order")) s->opt_order = value ? 1 : 0;
     else if (!strcmp(key, "nvtx")) s->opt_nvtx = value ? 1 : 0;
     else if (!strcmp(key, "graph")) s->opt_graph = value ? 1 : 0;
-    else if (!strcmp(key, "carry")) s->opt_carry = value ? 1 : 0;
+    else if (!strcmp(key, "msd")) s->opt_msd = value ? 1 : 0;
+    else if (!strcmp(key, "carry")) {
+        s->opt_carry = value ? 1 : 0;
+        if (s->opt_carry) {
+            CU(cudaSetDevice(s->device));
+            int rc = alloc_carry(s);
+            if (rc) return rc;
+        }
+    }
     else if (!strcmp(key, "xml_float_digits")) {
         if (value < 0 || value > 17) return set_err(FGPU_ERR_ARG, "xml_float_digits must be in [0,17]");
         s->opt_xml_digits = value;

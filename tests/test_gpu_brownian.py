@@ -51,9 +51,12 @@ def _assert_same_messages(gpu, orc):
         assert np.array_equal(gm[k].view(np.uint32), om[k].view(np.uint32)), k
 
 
+@pytest.mark.parametrize("msd", [0, 1])
 @pytest.mark.parametrize("key,count", [("c2_tiny", 1000), ("c2_tiny", 4096), ("c2_small", None)])
-def test_function_by_function_exact(key, count):
-    cfg, gpu, orc = _pair(key, exact=True, count=count)
+def test_function_by_function_exact(key, count, msd):
+    """Both message builds -- LSD radix sort + gather, and the MSD pass + bucket finish -- must produce the oracle's
+    sorted order, records and partition boundary matrix."""
+    cfg, gpu, orc = _pair(key, exact=True, count=count, msd=msd)
     for it in range(5):
         gpu.begin_iteration()
         orc.begin_iteration()
@@ -68,7 +71,7 @@ def test_function_by_function_exact(key, count):
     orc.close()
 
 
-@pytest.mark.parametrize("order,carry", [(0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("order,carry", [(0, 0), (1, 0), (1, 1)])
 @pytest.mark.parametrize("graph", [0, 1])
 def test_many_iterations_exact(order, carry, graph):
     """Processing order (list order / cell order) and the source of a consumer's agent variables (the SoA list at
@@ -241,6 +244,38 @@ def test_full_size_c2_properties():
     assert np.array_equal(gpu2.seeds(), orc.seeds())
     for s in (gpu, gpu2, orc):
         s.close()
+
+
+def test_north_star_16m_one_iteration_exact():
+    """The north-star configuration itself (16 777 216 agents, 128 x 128 x 256 cells), one iteration of the bit-exact
+    build against one oracle iteration on the same input: what no smaller case reaches -- 22-bit keys (an 11 + 11 bit
+    MSD split; three 8-bit passes in the LSD build), a 4M-cell partition boundary matrix, 4096 sort tiles.  Message
+    order, partition boundary matrix (normalised), every agent variable and every rand48 seed must be equal."""
+    import os
+    from common import build
+    cfg = W.BROWNIAN["c2_16m"]
+    plugin = build.model_path(cfg.name + "_exact")
+    if not os.path.exists(plugin):
+        pytest.skip("Brownian_16M_exact is not built")
+    orc = brownian_oracle("c2_16m", threads=os.cpu_count() or 1)
+    st = W.brownian_state(cfg)
+    orc.set_agents("Particle", "default", st)
+    orc.step(1)
+    want_order, (os_, oc), b, want_seeds = orc.message_order("location"), orc.pbm("location"), orc.agents("Particle"), orc.seeds()
+    orc.close()
+    for msd in (1, 0):
+        gpu = Simulation(plugin)
+        gpu.set_option("msd", msd)
+        gpu.set_agents("Particle", "default", st)
+        gpu.step(1)
+        assert np.array_equal(gpu.message_order("location"), want_order), msd
+        gs, gc = gpu.pbm("location")
+        assert np.array_equal(gc, oc) and np.array_equal(gs[oc > 0], os_[oc > 0]), msd
+        a = gpu.agents("Particle")
+        for k in a:
+            assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), (msd, k)
+        assert np.array_equal(gpu.seeds(), want_seeds), msd
+        gpu.close()
 
 
 def test_nvtx_ranges_do_not_change_results():
