@@ -543,9 +543,41 @@ def main():
         b = torch.tensor([h2d, d2h], dtype=torch.int64, device="cuda")   # whole-job bytes: every rank moves its own slab
         dist.all_reduce(b, op=dist.ReduceOp.SUM)
         h2d, d2h = int(b[0].item()), int(b[1].item())
-    e2e = {"value": n_global * e2e_steps / e2e_dt, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "steps": e2e_steps}
-
+    e2e_serial = {"value": n_global * e2e_steps / e2e_dt, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+                  "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                  "mode": "serial: set_agents (H2D) -> step -> read_agents (D2H), one simulation, each call synchronous"}
+    e2e = e2e_serial
+    if world == 1 and not os.environ.get("BENCH_NO_PIPELINE"):
+        # the same per-step work -- upload of the step's population from pinned host memory, one iteration, read-back of
+        # x, y, z, nbr -- with two simulations driven in alternation through the asynchronous calls of the C ABI, so that
+        # one's copies overlap the other's iteration and both PCIe directions are busy at once
+        sim2 = Simulation(plugin, device=local)
+        for kv in args.option:
+            k, v = kv.split("=")
+            sim2.set_option(k, int(v))
+        out2 = {k: torch.empty_like(torch.from_numpy(v)).pin_memory().numpy() for k, v in out.items()}
+        pair = [(sim, out), (sim2, out2)]
+        n_agents = len(state["id"])
+        for s_, o_ in pair:                                          # untimed: graph capture, first touch
+            s_.set_agents("Particle", "default", pin)
+            s_.step(1)
+            s_.read_agents("Particle", "default", o_)
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            s_, o_ = pair[k & 1]
+            s_.sync()                                                # its previous step's results have landed in o_
+            s_.set_agents_async("Particle", "default", pin)          # H2D
+            s_.step_async(1)                                         # one iteration
+            s_.read_agents_async("Particle", "default", o_, n_agents)   # D2H
+        for s_, _ in pair:
+            s_.sync()
+        dt2 = time.perf_counter() - t0
+        sim2.close()
+        e2e = {"value": n_global * e2e_steps / dt2, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": e2e_steps,
+               "mode": "pipelined: two simulations alternate, fgpu_sim_set_agents_async / step_async / read_agents_async per step "
+                       "(every step still uploads its whole population and reads its results back)",
+               "serial": e2e_serial}
     # ---- parity (untimed) -----------------------------------------------------------
     parity_ok, parity = None, None
     if not args.no_parity:

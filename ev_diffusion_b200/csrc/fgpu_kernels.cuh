@@ -133,7 +133,7 @@ struct SortSmem {
  * ascending input index; tiles are in input order.  BITS is the compile-time digit
  * capacity (bins per thread = 2^BITS / 256); digit_bits <= BITS is the width in use. */
 template <int BITS>
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, (BITS <= 9 ? 3 : 2))
 k_radix_scatter(const unsigned int *__restrict__ keys_in, const unsigned int *__restrict__ vals_in,
                 unsigned int *__restrict__ keys_out, unsigned int *__restrict__ vals_out, int n_host,
                 const int *__restrict__ d_n, int shift, int digit_bits, const unsigned int *__restrict__ tile_hist,
@@ -183,13 +183,16 @@ k_radix_scatter(const unsigned int *__restrict__ keys_in, const unsigned int *__
             const unsigned int bal = __ballot_sync(0xffffffffu, m != 0);
             peers &= ~(bal ^ (unsigned int)m);
         }
-        /* every lane of a group reads the group's counter (same address: broadcast); after a warp barrier the
-         * first lane of the group adds the group size */
+        /* the first lane of a group reads the group's counter and adds the group size; the others get the old
+         * value from it by shuffle (one lane touches the counter per round: no race inside a round, and the
+         * warp barrier below orders this round's update before the next round's read by another lane) */
         const unsigned int before = __popc(peers & lt);
         unsigned int prev = 0;
-        if (valid) prev = sm.warp_hist[warp][d];
-        __syncwarp();
-        if (valid && before == 0) sm.warp_hist[warp][d] = (unsigned short)(prev + __popc(peers));
+        if (valid && before == 0) {
+            prev = sm.warp_hist[warp][d];
+            sm.warp_hist[warp][d] = (unsigned short)(prev + __popc(peers));
+        }
+        prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
         rank[r] = (unsigned short)(prev + before);
         __syncwarp();
     }
@@ -371,9 +374,11 @@ k_bucket_finish(const unsigned int *__restrict__ keys_a, const unsigned int *__r
             }
             const unsigned int before = __popc(peers & lt);
             unsigned int prev = 0;
-            if (valid) prev = sm.warp_hist[warp][d];
-            __syncwarp();
-            if (valid && before == 0) sm.warp_hist[warp][d] = (unsigned short)(prev + __popc(peers));
+            if (valid && before == 0) {
+                prev = sm.warp_hist[warp][d];
+                sm.warp_hist[warp][d] = (unsigned short)(prev + __popc(peers));
+            }
+            prev = __shfl_sync(0xffffffffu, prev, __ffs(peers) - 1);
             rank[r] = (unsigned short)(prev + before);
             __syncwarp();
         }

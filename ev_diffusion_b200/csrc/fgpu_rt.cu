@@ -203,7 +203,8 @@ struct fgpu_sim {
     unsigned long long epoch_counter = 1;
     std::map<const char *, unsigned long long> content; /* bumped by every function launched on a list buffer */
     std::vector<char> emits_carry; /* per function: its message has a cell-order consumer right behind it (static) */
-    int opt_msd = 1;   /* spatial message build: MSD pass + bucket finish where the key width allows, else LSD + gather */
+    int opt_msd = 0;   /* spatial message build: 1 = MSD pass + bucket finish where the key width allows; 0 = LSD + gather.
+                          Measured slower at both 1M and 16M messages (wide-digit scatter), profiles/r02_notes.md: off */
     int opt_carry = 0; /* off by default: measured at 16M agents it trades 0.10 ms of the consumer for 0.55 ms of build (profiles/r02_notes.md) */
     /* options */
     int opt_order = 1;
@@ -569,7 +570,7 @@ static void invalidate_graph(fgpu_sim *s) {
     s->slab_graphs.clear();
 }
 
-static int upload_columns(fgpu_sim *s, int agent, int state, int offset, int count, const void *const *columns) {
+static int upload_columns(fgpu_sim *s, int agent, int state, int offset, int count, const void *const *columns, bool async = false) {
     if (agent < 0 || agent >= (int)s->agents.size()) return set_err(FGPU_ERR_ARG, "bad agent index %d", agent);
     AgentRT &A = s->agents[agent];
     if (state < 0 || state >= A.d->nstates) return set_err(FGPU_ERR_ARG, "bad state index %d", state);
@@ -604,7 +605,7 @@ static int upload_columns(fgpu_sim *s, int agent, int state, int offset, int cou
     A.h_state_count[state] = offset + count;
     if (!same_count || s->slab.on) /* d_state_count already holds this value otherwise */
         CU(cudaMemcpyAsync(A.d_state_count + state, &A.h_state_count[state], sizeof(int), cudaMemcpyHostToDevice, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
+    if (!async) CU(cudaStreamSynchronize(s->stream));
     slab_mark_exact(s);
     s->touch(list);
     /* captured iterations stay valid: they depend on the list buffers, which an upload does not move, and --
@@ -615,6 +616,12 @@ static int upload_columns(fgpu_sim *s, int agent, int state, int offset, int cou
 extern "C" int fgpu_sim_set_agents(fgpu_sim *s, int agent, int state, int count, const void *const *columns) {
     if (!s) return set_err(FGPU_ERR_ARG, "null sim");
     return upload_columns(s, agent, state, 0, count, columns);
+}
+
+extern "C" int fgpu_sim_set_agents_async(fgpu_sim *s, int agent, int state, int count, const void *const *columns) {
+    if (!s) return set_err(FGPU_ERR_ARG, "null sim");
+    if (s->slab.on) return set_err(FGPU_ERR_ARG, "fgpu_sim_set_agents_async is not available in slab mode");
+    return upload_columns(s, agent, state, 0, count, columns, true);
 }
 
 extern "C" int fgpu_sim_add_agents(fgpu_sim *s, int agent, int state, int count, const void *const *columns) {
@@ -643,7 +650,14 @@ extern "C" int fgpu_sim_read_agent_var(fgpu_sim *s, int agent, int state, int va
     return FGPU_OK;
 }
 
+static int read_agents(fgpu_sim *s, int agent, int state, int count, void *const *columns, bool async);
 extern "C" int fgpu_sim_read_agents(fgpu_sim *s, int agent, int state, int count, void *const *columns) {
+    return read_agents(s, agent, state, count, columns, false);
+}
+extern "C" int fgpu_sim_read_agents_async(fgpu_sim *s, int agent, int state, int count, void *const *columns) {
+    return read_agents(s, agent, state, count, columns, true);
+}
+static int read_agents(fgpu_sim *s, int agent, int state, int count, void *const *columns, bool async) {
     if (!s || !columns || agent < 0 || agent >= (int)s->agents.size()) return set_err(FGPU_ERR_ARG, "bad argument");
     AgentRT &A = s->agents[agent];
     if (state < 0 || state >= A.d->nstates) return set_err(FGPU_ERR_ARG, "bad index");
@@ -654,7 +668,7 @@ extern "C" int fgpu_sim_read_agents(fgpu_sim *s, int agent, int state, int count
         const fgpu_var &V = A.d->vars[v];
         CU(cudaMemcpyAsync(columns[v], A.state[state] + V.list_offset, (size_t)count * V.size, cudaMemcpyDeviceToHost, s->stream));
     }
-    CU(cudaStreamSynchronize(s->stream));
+    if (!async) CU(cudaStreamSynchronize(s->stream));
     return FGPU_OK;
 }
 

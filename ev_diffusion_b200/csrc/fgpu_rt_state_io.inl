@@ -271,6 +271,14 @@ extern "C" int fgpu_sim_set_option(fgpu_sim *s, const char *key, int value) {
     else if (!strcmp(key, "nvtx")) s->opt_nvtx = value ? 1 : 0;
     else if (!strcmp(key, "graph")) s->opt_graph = value ? 1 : 0;
     else if (!strcmp(key, "msd")) s->opt_msd = value ? 1 : 0;
+    else if (!strcmp(key, "l2_fetch")) {
+        /* device-wide hint: bytes the L2 fetches from HBM per miss (32, 64 or 128).  The random 16-byte record
+         * gather of the message build wastes most of a 64-byte fetch. */
+        if (value != 32 && value != 64 && value != 128) return set_err(FGPU_ERR_ARG, "l2_fetch must be 32, 64 or 128");
+        CU(cudaSetDevice(s->device));
+        CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+        return FGPU_OK;
+    }
     else if (!strcmp(key, "carry")) {
         s->opt_carry = value ? 1 : 0;
         if (s->opt_carry) {

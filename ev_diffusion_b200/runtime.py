@@ -503,7 +503,22 @@ class Simulation(SimBase):
     def step_async(self, n: int = 1) -> None:
         self._check(self._lib.fgpu_sim_step_async(self._h, int(n)))
 
-    def read_agents(self, agent, state, out: Dict[str, np.ndarray], count: Optional[int] = None) -> int:
+    def set_agents_async(self, agent, state, columns: Dict[str, np.ndarray], count: Optional[int] = None) -> None:
+        """set_agents without the final synchronisation (fgpu_sim_set_agents_async): every variable must be given,
+        ideally from pinned arrays, which must stay untouched until sync()."""
+        agent = self._agent(agent)
+        state = self._state(agent, state)
+        n, ptrs, keep = self._columns(agent, columns, count)
+        self._keep_async = keep
+        self._lib.fgpu_sim_set_agents_async.restype = C.c_int
+        self._lib.fgpu_sim_set_agents_async.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        self._check(self._lib.fgpu_sim_set_agents_async(self._h, agent, state, n, ptrs))
+
+    def read_agents_async(self, agent, state, out: Dict[str, np.ndarray], count: int) -> int:
+        """read_agents, enqueued only: `out` is complete after the next sync()."""
+        return self.read_agents(agent, state, out, count, _async=True)
+
+    def read_agents(self, agent, state, out: Dict[str, np.ndarray], count: Optional[int] = None, _async: bool = False) -> int:
         """Fill caller-owned arrays (ideally pinned) with the named variables of a state list: all copies
         are issued before one synchronisation (fgpu_sim_read_agents).  Returns the number of agents read."""
         agent = self._agent(agent)
@@ -517,7 +532,12 @@ class Simulation(SimBase):
             if arr.dtype != a.vars[vi].dtype or arr.size < count or not arr.flags["C_CONTIGUOUS"]:
                 raise ValueError(f"read_agents: bad destination for '{name}'")
             ptrs[vi] = arr.ctypes.data
-        self._check(self._lib.fgpu_sim_read_agents(self._h, agent, state, count, ptrs))
+        if _async:
+            self._lib.fgpu_sim_read_agents_async.restype = C.c_int
+            self._lib.fgpu_sim_read_agents_async.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+            self._check(self._lib.fgpu_sim_read_agents_async(self._h, agent, state, count, ptrs))
+        else:
+            self._check(self._lib.fgpu_sim_read_agents(self._h, agent, state, count, ptrs))
         return count
 
     def run_exit_functions(self) -> None:

@@ -84,6 +84,13 @@ int fgpu_sim_load_snapshot(fgpu_sim *sim, const char *path);
  * cudaMemcpy H2D of the whole list struct (simulation.xslt:568-581). */
 int fgpu_sim_set_agents(fgpu_sim *sim, int agent, int state, int count, const void *const *columns);
 
+/* The same upload without the final synchronisation: the copies are enqueued on the simulation stream and the call
+ * returns (every column must be given, from pinned host memory that stays untouched until fgpu_sim_sync, for the
+ * copies to be asynchronous).  With fgpu_sim_step_async and fgpu_sim_read_agents_async, two simulations can be
+ * driven in alternation so that one's upload and read-back overlap the other's iteration (both PCIe directions and
+ * the SMs busy at once); the reference's initialise / singleIteration / get_host_* sequence is strictly serial. */
+int fgpu_sim_set_agents_async(fgpu_sim *sim, int agent, int state, int count, const void *const *columns);
+
 /* Host-side mirror of h_add_agents_<A>_<S> (simulation.xslt:1275-1320): append. */
 int fgpu_sim_add_agents(fgpu_sim *sim, int agent, int state, int count, const void *const *columns);
 
@@ -121,6 +128,8 @@ int fgpu_sim_read_agent_var(fgpu_sim *sim, int agent, int state, int var, void *
  * agents of the state list, NULL entries are skipped.  All copies are issued before one synchronisation,
  * so pinned destinations are filled at bus speed. */
 int fgpu_sim_read_agents(fgpu_sim *sim, int agent, int state, int count, void *const *columns);
+/* ... enqueued only: the destination arrays are complete after the next fgpu_sim_sync */
+int fgpu_sim_read_agents_async(fgpu_sim *sim, int agent, int state, int count, void *const *columns);
 /* get_<A>_<S>_variable_<v>(index) (header.xslt:645): one element of a state list. */
 int fgpu_sim_read_agent_value(fgpu_sim *sim, int agent, int state, int var, unsigned int index, void *dst);
 /* reduce_/min_/max_/count_<A>_<S>_<v>_variable() (header.xslt:729-751, simulation.xslt:1325-1357): one scalar

@@ -278,6 +278,32 @@ def test_north_star_16m_one_iteration_exact():
         gpu.close()
 
 
+def test_async_upload_step_readback_two_simulations_in_alternation():
+    """fgpu_sim_set_agents_async / step_async / read_agents_async: two simulations driven in alternation (what
+    bench.py's pipelined end-to-end leg does) end in the bytes the synchronous calls give."""
+    cfg = W.BROWNIAN["c2_small"]
+    st = W.brownian_state(cfg)
+    ref = Simulation(brownian_plugin("c2_small", exact=True))
+    for _ in range(3):                       # the rand48 streams run on across uploads: same number of rounds on every side
+        ref.set_agents("Particle", "default", st)
+        ref.step(1)
+    want = ref.agents("Particle")
+    ref.close()
+    sims = [Simulation(brownian_plugin("c2_small", exact=True)) for _ in range(2)]
+    outs = [{k: np.zeros(cfg.n, dtype=st[k].dtype) for k in ("x", "y", "z", "nbr")} for _ in range(2)]
+    for k in range(6):
+        s_, o_ = sims[k & 1], outs[k & 1]
+        s_.sync()
+        s_.set_agents_async("Particle", "default", st)
+        s_.step_async(1)
+        s_.read_agents_async("Particle", "default", o_, cfg.n)
+    for s_, o_ in zip(sims, outs):
+        s_.sync()
+        for k in o_:
+            assert np.array_equal(o_[k].view(np.uint32), want[k].view(np.uint32)), k
+        s_.close()
+
+
 def test_nvtx_ranges_do_not_change_results():
     """Option "nvtx": every stage of an iteration becomes an NVTX range on the enqueueing thread (the reference's
     PROFILE_SCOPED_RANGE); without a tool attached the calls are no-ops and the run is unchanged."""
