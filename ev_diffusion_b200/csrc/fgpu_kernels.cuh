@@ -1017,6 +1017,246 @@ k_scatter3(const char *__restrict__ src, char *__restrict__ stay, char *__restri
     }
 }
 
+/* ---- in-place migration ------------------------------------------------------------------------------
+ * Leavers are a fraction of a percent of a slab per iteration, so the list is NOT re-compacted (k_scatter3 above
+ * copies every stayer, 40 bytes per agent per iteration at 5 variables): leavers are packed into the send
+ * buffers and their list slots recorded as holes; after the exchange arrival j takes hole j, surplus arrivals are
+ * appended, and surplus holes are filled with the live agents of the list's tail.  Every step is a function of
+ * list positions only, so the resulting order does not depend on timing, transport or launch mode.
+ *   k_mig_count   owner class of every agent, leavers (down / up) per block of 1024 agents
+ *   k_mig_scan    exclusive offsets of the blocks, totals -> send headers + hole count
+ *   k_mig_pack    leavers -> send buffers (stable), their slots -> holes[] (ascending)
+ *   (transport)
+ *   k_mig_fill    arrivals -> holes / end of the list;   k_mig_tail: surplus holes <- tail agents, new count */
+__device__ __forceinline__ int owner_class(float c, float minb, float range, float scale, int nplanes, int ppr, int rank, int world,
+                                           int lo_rank, int hi_rank) {
+    int p = (int)floorf(__fdiv_rn(__fmul_rn(__fsub_rn(c, minb), scale), range));
+    p = (p < 0) ? nplanes - 1 : p;
+    p = (p >= nplanes) ? 0 : p;
+    const int owner = min(p / ppr, world - 1);
+    if (owner == rank) return 1;
+    if (owner == lo_rank && owner == hi_rank) return (p < rank * ppr) ? 2 : 3; /* world == 2 */
+    if (owner == lo_rank) return 2;
+    if (owner == hi_rank) return 3;
+    return 4;
+}
+
+/* header of the migration bookkeeping (ints): {n_old, holes, arrivals_used, -} */
+constexpr int MIG_HDR = 4;
+
+__global__ void __launch_bounds__(256)
+k_mig_count(const float *__restrict__ coord, int n_host, const int *__restrict__ d_n, float minb, float maxb, int nplanes,
+            int ppr, int rank, int world, unsigned int *__restrict__ block_sums, int nb, int *status) {
+    __shared__ unsigned int s_cnt[2];
+    const int n = d_n ? *d_n : n_host;
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int lo_rank = (rank + world - 1) % world, hi_rank = (rank + 1) % world;
+    const float scale = (float)nplanes, range = __fsub_rn(maxb, minb);
+    unsigned int c2 = 0, c3 = 0;
+#pragma unroll
+    for (int r = 0; r < COMPACT_THREADS / 256; ++r) {
+        const int i = blockIdx.x * COMPACT_THREADS + r * 256 + threadIdx.x;
+        const int f = (i < n) ? owner_class(coord[i], minb, range, scale, nplanes, ppr, rank, world, lo_rank, hi_rank) : 0;
+        if (f == 4) atomicExch(status, 2);
+        c2 += __popc(__ballot_sync(0xffffffffu, f == 2));
+        c3 += __popc(__ballot_sync(0xffffffffu, f == 3));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (c2) atomicAdd(&s_cnt[0], c2);
+        if (c3) atomicAdd(&s_cnt[1], c3);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) block_sums[threadIdx.x * nb + blockIdx.x] = s_cnt[threadIdx.x];
+}
+
+/* one block: exclusive scan of block_sums[0][.] and block_sums[1][.] in place; totals -> headers */
+__global__ void __launch_bounds__(1024)
+k_mig_scan(unsigned int *__restrict__ block_sums, int nb, int n_host, const int *__restrict__ d_n, int cap, int *__restrict__ mig_hdr,
+           int *__restrict__ hdr_dn, int *__restrict__ hdr_up, int *overflow) {
+    __shared__ unsigned int s_warp[32];
+    __shared__ unsigned int s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int totals[2];
+    for (int a = 0; a < 2; ++a) {
+        unsigned int *arr = block_sums + (size_t)a * nb;
+        if (threadIdx.x == 0) s_carry = 0;
+        __syncthreads();
+        for (int base = 0; base < nb; base += 1024) {
+            const int i = base + threadIdx.x;
+            const unsigned int v = (i < nb) ? arr[i] : 0u;
+            unsigned int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane == 31) s_warp[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                unsigned int w = s_warp[lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int t = __shfl_up_sync(0xffffffffu, w, o);
+                    if (lane >= o) w += t;
+                }
+                s_warp[lane] = w;
+            }
+            __syncthreads();
+            const unsigned int wbase = warp ? s_warp[warp - 1] : 0u;
+            const unsigned int carry = s_carry;
+            if (i < nb) arr[i] = carry + wbase + inc - v;
+            __syncthreads();
+            if (threadIdx.x == 1023) s_carry = carry + wbase + inc;
+            __syncthreads();
+        }
+        totals[a] = s_carry;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int dn = (int)totals[0], up = (int)totals[1];
+        if (dn > cap || up > cap) atomicExch(overflow, 1);
+        const int sdn = min(dn, cap), sup = min(up, cap);
+        hdr_dn[0] = sdn; hdr_dn[1] = dn > cap; hdr_dn[2] = 0; hdr_dn[3] = 0;
+        hdr_up[0] = sup; hdr_up[1] = up > cap; hdr_up[2] = 0; hdr_up[3] = 0;
+        mig_hdr[0] = d_n ? *d_n : n_host;
+        mig_hdr[1] = dn + up;     /* on overflow the status flag aborts the run: the hole list is then not used */
+        mig_hdr[2] = 0;
+        mig_hdr[3] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(COMPACT_THREADS)
+k_mig_pack(const char *__restrict__ list, char *__restrict__ dn, char *__restrict__ up, const ColSet cols, const ColSet bcols,
+           const float *__restrict__ coord, int n_host, const int *__restrict__ d_n, float minb, float maxb, int nplanes, int ppr,
+           int rank, int world, const unsigned int *__restrict__ block_offs, int nb, int cap, unsigned int *__restrict__ holes) {
+    __shared__ unsigned int s_warp[2][32];
+    const int n = d_n ? *d_n : n_host;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lo_rank = (rank + world - 1) % world, hi_rank = (rank + 1) % world;
+    const int f = (i < n) ? owner_class(coord[i], minb, __fsub_rn(maxb, minb), (float)nplanes, nplanes, ppr, rank, world, lo_rank, hi_rank) : 0;
+    const unsigned int b2 = __ballot_sync(0xffffffffu, f == 2), b3 = __ballot_sync(0xffffffffu, f == 3);
+    if (__syncthreads_or(f == 2 || f == 3) == 0) return; /* most blocks hold no leaver */
+    if (lane == 0) {
+        s_warp[0][warp] = __popc(b2);
+        s_warp[1][warp] = __popc(b3);
+    }
+    __syncthreads();
+    if (warp < 2) {
+        const unsigned int v = s_warp[warp][lane];
+        unsigned int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        s_warp[warp][lane] = inc - v;
+    }
+    __syncthreads();
+    if (f != 2 && f != 3) return;
+    const unsigned int lt = (1u << lane) - 1u;
+    const unsigned int dn_before = block_offs[blockIdx.x] + s_warp[0][warp] + __popc(b2 & lt);
+    const unsigned int up_before = block_offs[nb + blockIdx.x] + s_warp[1][warp] + __popc(b3 & lt);
+    const unsigned int hole = dn_before + up_before;             /* leavers with a smaller list index */
+    if (hole < 2u * (unsigned int)cap) holes[hole] = (unsigned int)i;
+    const unsigned int out = (f == 2) ? dn_before : up_before;
+    if (out >= (unsigned int)cap) return;                        /* overflow was flagged by k_mig_scan */
+    char *dst = (f == 2) ? dn : up;
+    for (int c = 0; c < cols.ncols; ++c) {
+        if (cols.size[c] == 4)
+            ((unsigned int *)(dst + bcols.off[c]))[out] = ((const unsigned int *)(list + cols.off[c]))[i];
+        else
+            ((unsigned long long *)(dst + bcols.off[c]))[out] = ((const unsigned long long *)(list + cols.off[c]))[i];
+    }
+}
+
+__device__ __forceinline__ void copy_agent(const char *src, const ColSet &scols, size_t si, char *dst, const ColSet &dcols, size_t di) {
+    for (int c = 0; c < scols.ncols; ++c) {
+        if (scols.size[c] == 4)
+            ((unsigned int *)(dst + dcols.off[c]))[di] = ((const unsigned int *)(src + scols.off[c]))[si];
+        else
+            ((unsigned long long *)(dst + dcols.off[c]))[di] = ((const unsigned long long *)(src + scols.off[c]))[si];
+    }
+}
+
+/* arrivals (lower neighbour's first): arrival j takes hole j; those beyond the holes go to the end of the list */
+__global__ void __launch_bounds__(256)
+k_mig_fill(const char *__restrict__ rlo, const char *__restrict__ rhi, char *__restrict__ list, const ColSet scols, const ColSet dcols,
+           const int *__restrict__ mig_hdr, const unsigned int *__restrict__ holes, int dst_cap, int *status) {
+    const int *hlo = (const int *)rlo, *hhi = (const int *)rhi;
+    const int clo = hlo[0], chi = hhi[0], n_old = mig_hdr[0], nh = mig_hdr[1];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0 && (hlo[1] || hhi[1])) atomicExch(status, 3);
+    if (j >= clo + chi) return;
+    const char *src = (j < clo) ? rlo : rhi;
+    const int sj = (j < clo) ? j : j - clo;
+    const long long dst = (j < nh) ? (long long)holes[j] : (long long)n_old + (j - nh);
+    if (dst >= (long long)dst_cap) {
+        atomicExch(status, 4);
+        return;
+    }
+    copy_agent(src, scols, (size_t)sj, list, dcols, (size_t)dst);
+}
+
+/* one block: holes the arrivals did not fill are filled with the live agents of the tail (ascending hole <- ascending
+ * tail agent), and the new population is published */
+__global__ void __launch_bounds__(1024)
+k_mig_tail(const char *__restrict__ rlo, const char *__restrict__ rhi, char *__restrict__ list, const ColSet cols,
+           const int *__restrict__ mig_hdr, const unsigned int *__restrict__ holes, int *__restrict__ n_new_out, int dst_cap) {
+    __shared__ unsigned int s_warp[32];
+    __shared__ unsigned int s_carry;
+    const int arrivals = ((const int *)rlo)[0] + ((const int *)rhi)[0], n_old = mig_hdr[0], nh = mig_hdr[1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (arrivals >= nh) {
+        if (threadIdx.x == 0) *n_new_out = min(n_old + (arrivals - nh), dst_cap);
+        return;
+    }
+    const int T = nh - arrivals, n_new = n_old - T;
+    /* holes[arrivals .. nh) are the T largest holes, ascending; those below n_new need an agent, the others lie in the
+     * tail [n_new, n_old) that is cut off */
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < T; base += 1024) {
+        const int t = base + threadIdx.x;
+        const int pos = n_new + t;                    /* tail slot */
+        bool live = false;
+        if (t < T) {
+            /* is `pos` a hole?  binary search in the ascending hole list */
+            int lo = arrivals, hi = nh;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (holes[mid] < (unsigned int)pos) lo = mid + 1;
+                else hi = mid;
+            }
+            live = !(lo < nh && holes[lo] == (unsigned int)pos);
+        }
+        const unsigned int bal = __ballot_sync(0xffffffffu, live);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned int v = s_warp[lane];
+            unsigned int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += u;
+            }
+            s_warp[lane] = inc - v;
+        }
+        __syncthreads();
+        const unsigned int carry = s_carry;
+        if (live) {
+            const unsigned int r = carry + s_warp[warp] + __popc(bal & ((1u << lane) - 1u));
+            copy_agent(list, cols, (size_t)pos, list, cols, (size_t)holes[arrivals + r]);
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[31] + __popc(bal);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_new_out = n_new;
+}
+
 /* pass 4 (after the exchange): append both received buffers after the stayers and publish the new population */
 __global__ void __launch_bounds__(256)
 k_append_both(const char *__restrict__ rlo, const char *__restrict__ rhi, char *__restrict__ dst, const ColSet scols,

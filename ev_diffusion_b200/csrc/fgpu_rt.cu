@@ -140,6 +140,8 @@ struct SlabAgent {
     ColSet bufcols; /* column offsets inside a migrant buffer (after the 16-byte header) */
     int axis_var = -1;
     int *d_counts = nullptr; /* per state: {n_stay, n_new} */
+    unsigned int *holes = nullptr; /* in-place migration: list slots of the leavers, ascending (2 * mig_cap per state) */
+    int *mig_hdr = nullptr;        /* per state: {n_old, holes, -, -} */
 };
 struct SlabRT {
     bool on = false;
@@ -213,6 +215,7 @@ struct fgpu_sim {
     int opt_radix_bits = 9;
     int opt_slab_async = 1;
     int opt_slab_p2p = 1;
+    int opt_slab_inplace = 1; /* migration: 1 = leavers leave holes that arrivals / tail agents fill; 0 = stable three-way re-compaction */
     int opt_xml_digits = 0; /* 0: the reference's "%f" iteration files; n: "%.<n>g" */
     /* CUDA graph of one iteration (static models) */
     bool is_static = false;
@@ -540,6 +543,8 @@ extern "C" void fgpu_sim_destroy(fgpu_sim *s) {
         cudaFree(X.recv_lo);
         cudaFree(X.recv_hi);
         cudaFree(X.d_counts);
+        cudaFree(X.holes);
+        cudaFree(X.mig_hdr);
     }
     if (s->slab.d_status) cudaFree(s->slab.d_status);
     if (s->slab.h_pinned) cudaFreeHost(s->slab.h_pinned);

@@ -197,6 +197,9 @@ extern "C" int fgpu_sim_slab_init(fgpu_sim *s, int rank, int world, const void *
         CU(cudaMalloc(&X.recv_hi, X.bytes));
         CU(cudaMalloc(&X.d_counts, sizeof(int) * 4 * (size_t)A.d->nstates));
         CU(cudaMemset(X.d_counts, 0, sizeof(int) * 4 * (size_t)A.d->nstates));
+        CU(cudaMalloc(&X.holes, sizeof(unsigned int) * 2 * (size_t)S.mig_cap * (size_t)A.d->nstates));
+        CU(cudaMalloc(&X.mig_hdr, sizeof(int) * MIG_HDR * (size_t)A.d->nstates));
+        CU(cudaMemset(X.mig_hdr, 0, sizeof(int) * MIG_HDR * (size_t)A.d->nstates));
     }
     rc = seed_rand48(s, (unsigned long long)rank * (unsigned long long)m->buffer_size_max,
                      (unsigned long long)world * (unsigned long long)m->buffer_size_max);
@@ -461,20 +464,38 @@ static int slab_migrate(fgpu_sim *s) {
             int *flags = (int *)(list + A.d->scan_offset);
             int *cnt = X.d_counts + 4 * st; /* {n_stay, -, total down, total up} */
             const int nb = std::max(1, (n + COMPACT_THREADS - 1) / COMPACT_THREADS);
-            s->prof_begin("mig:flags");
-            k_owner_count<<<nb, 256, 0, s->stream>>>((const float *)(list + A.d->vars[X.axis_var].list_offset), n, d_n,
-                                                                 S.axis_min, S.axis_max, S.nplanes, S.ppr, S.rank, S.world, flags,
-                                                                 A.block_sums, nb, S.d_status);
-            LAUNCH_CHECK();
-            s->prof_end();
             const size_t A4 = (X.bytes + 255) & ~(size_t)255;
             const int seq = ++S.agent_seq[a], par = seq & 1;
             const char *in_lo = X.recv_lo, *in_hi = X.recv_hi;
-            s->prof_begin("mig:scatter");
-            k_scatter3<<<nb, COMPACT_THREADS, 0, s->stream>>>(list, A.swap, X.send_dn, X.send_up, A.cols, X.bufcols, flags, A.block_sums, nb, n,
-                                                              d_n, S.mig_cap, S.d_status + 1, cnt, (int *)X.send_dn, (int *)X.send_up);
-            LAUNCH_CHECK();
-            s->prof_end();
+            const float *coord = (const float *)(list + A.d->vars[X.axis_var].list_offset);
+            const bool inplace = s->opt_slab_inplace != 0;
+            unsigned int *holes = X.holes + 2 * (size_t)S.mig_cap * st;
+            int *mhdr = X.mig_hdr + MIG_HDR * st;
+            if (inplace) {
+                s->prof_begin("mig:flags");
+                k_mig_count<<<nb, 256, 0, s->stream>>>(coord, n, d_n, S.axis_min, S.axis_max, S.nplanes, S.ppr, S.rank, S.world, A.block_sums, nb,
+                                                       S.d_status);
+                LAUNCH_CHECK();
+                k_mig_scan<<<1, 1024, 0, s->stream>>>(A.block_sums, nb, n, d_n, S.mig_cap, mhdr, (int *)X.send_dn, (int *)X.send_up, S.d_status + 1);
+                LAUNCH_CHECK();
+                s->prof_end();
+                s->prof_begin("mig:scatter");
+                k_mig_pack<<<nb, COMPACT_THREADS, 0, s->stream>>>(list, X.send_dn, X.send_up, A.cols, X.bufcols, coord, n, d_n, S.axis_min, S.axis_max,
+                                                                  S.nplanes, S.ppr, S.rank, S.world, A.block_sums, nb, S.mig_cap, holes);
+                LAUNCH_CHECK();
+                s->prof_end();
+            } else {
+                s->prof_begin("mig:flags");
+                k_owner_count<<<nb, 256, 0, s->stream>>>(coord, n, d_n, S.axis_min, S.axis_max, S.nplanes, S.ppr, S.rank, S.world, flags,
+                                                         A.block_sums, nb, S.d_status);
+                LAUNCH_CHECK();
+                s->prof_end();
+                s->prof_begin("mig:scatter");
+                k_scatter3<<<nb, COMPACT_THREADS, 0, s->stream>>>(list, A.swap, X.send_dn, X.send_up, A.cols, X.bufcols, flags, A.block_sums, nb, n,
+                                                                  d_n, S.mig_cap, S.d_status + 1, cnt, (int *)X.send_dn, (int *)X.send_up);
+                LAUNCH_CHECK();
+                s->prof_end();
+            }
             s->prof_begin("mig:xfer");
             if (S.p2p) {
                 PushLayout PLY;
@@ -506,12 +527,20 @@ static int slab_migrate(fgpu_sim *s) {
             S.mig_bytes += 2 * (long long)X.bytes;
             s->prof_end();
             s->prof_begin("mig:append");
-            k_append_both<<<(2 * S.mig_cap + 255) / 256, 256, 0, s->stream>>>(in_lo, in_hi, A.swap, X.bufcols, A.cols, cnt,
-                                                                              A.d_state_count + st, A.d->buffer_size, S.d_status + 2);
-            LAUNCH_CHECK();
+            if (inplace) {
+                k_mig_fill<<<(2 * S.mig_cap + 255) / 256, 256, 0, s->stream>>>(in_lo, in_hi, list, X.bufcols, A.cols, mhdr, holes, A.d->buffer_size,
+                                                                               S.d_status + 2);
+                LAUNCH_CHECK();
+                k_mig_tail<<<1, 1024, 0, s->stream>>>(in_lo, in_hi, list, A.cols, mhdr, holes, A.d_state_count + st, A.d->buffer_size);
+                LAUNCH_CHECK();
+            } else {
+                k_append_both<<<(2 * S.mig_cap + 255) / 256, 256, 0, s->stream>>>(in_lo, in_hi, A.swap, X.bufcols, A.cols, cnt,
+                                                                                  A.d_state_count + st, A.d->buffer_size, S.d_status + 2);
+                LAUNCH_CHECK();
+            }
             s->prof_end();
             if (ringed || !S.async) CU(cudaMemcpyAsync(hdst + 8 + slot, A.d_state_count + st, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-            std::swap(A.state[st], A.swap);
+            if (!inplace) std::swap(A.state[st], A.swap);
             s->touch(A.state[st]);
         }
     }

@@ -295,6 +295,8 @@ extern "C" int fgpu_sim_set_option(fgpu_sim *s, const char *key, int value) {
     else if (!strcmp(key, "slab_p2p")) {
         if (s->slab.on) return set_err(FGPU_ERR_ARG, "slab_p2p must be set before fgpu_sim_slab_init");
         s->opt_slab_p2p = value ? 1 : 0;
+    } else if (!strcmp(key, "slab_inplace")) {
+        s->opt_slab_inplace = value ? 1 : 0;
     } else if (!strcmp(key, "slab_async")) {
         if (s->slab.on) return set_err(FGPU_ERR_ARG, "slab_async must be set before fgpu_sim_slab_init");
         s->opt_slab_async = value ? 1 : 0;
