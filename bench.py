@@ -382,12 +382,161 @@ def load_ncu_record(workload, kernel):
     return None
 
 
+# --------------------------------------------------------------------------------------------------
+# BASELINE configs C3 / C4 / C5' (`--workload c3|c4|c4_2m|c5p`): the dynamic path (function conditions, two
+# spatial messages, death compaction, births) at its BASELINE size.  Single GPU.
+# --------------------------------------------------------------------------------------------------
+def _population(sim):
+    return sum(sim.agent_count(a.name, st) for a in sim.model.agents for st in range(len(a.states)))
+
+
+def _all_states(sim):
+    out = {}
+    for a in sim.model.agents:
+        for si, st in enumerate(a.states):
+            if sim.agent_count(a.name, si) > 0:
+                out[(a.name, st)] = sim.agents(a.name, si)
+    return out
+
+
+def run_model_workload(args):
+    from oracle import gen_oracle
+    from oracle.oracle import OracleSimulation
+    w = W.MODEL_WORKLOADS[args.workload]
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    st = W.model_state(w)
+    base = {"metric": METRIC, "unit": "agent-steps/s", "n_gpus": 1, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w.label, "agents": w.n, "parallelism": "single GPU", "baseline_iterations": w.iterations}}
+
+    def cpu_run(steps, warm):
+        orc = OracleSimulation(gen_oracle.oracle_path(w.name), threads=cores)
+        orc.set_agents(w.agent, w.state, st)
+        if warm:
+            orc.step(warm)
+        n0 = _population(orc)
+        t0 = time.perf_counter()
+        orc.step(steps)
+        dt = time.perf_counter() - t0
+        n1 = _population(orc)
+        orc.close()
+        return 0.5 * (n0 + n1) * steps / dt, dt, steps
+
+    if args.impl == "reference":
+        steps = max(1, min(args.steps, 5))
+        v, dt, k = cpu_run(steps, 1)
+        line = dict(base, value=v, steps=k, warmup=1, ms_per_step=dt / k * 1e3, impl="reference", gpu_launches=0,
+                    cpu_baseline={"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+                                  "sample": f"{k} full iterations of the workload, OpenMP {cores} threads"},
+                    e2e={"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line))
+        return
+
+    from ev_diffusion_b200.runtime import Simulation
+    plugin = B.model_path(w.name)
+    if not os.path.exists(plugin):
+        raise SystemExit(f"{plugin} missing: run `python -c 'import __graft_entry__ as g; g.build()'` first (needs /root/reference)")
+    sim = Simulation(plugin, device=local)
+    for kv in args.option:
+        k, v = kv.split("=")
+        sim.set_option(k, int(v))
+    sim.set_agents(w.agent, w.state, st)
+    sim.step(args.warmup)
+    n0 = _population(sim)
+    launches0 = sim.launch_count
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_each = sim.step_timed(args.steps, FLUSH_BYTES)
+    clocks = sampler.stop()
+    launches = sim.launch_count - launches0
+    n1 = _population(sim)
+    total_ms = float(ms_each.sum())
+    agent_steps = 0.5 * (n0 + n1) * args.steps            # populations change by a few percent per iteration at most
+    value = agent_steps / (total_ms * 1e-3)
+    reps = min(args.steps, 10)
+    sim.profile_iterations(reps)
+    stage = dict(sim.profile_iterations(reps))
+    dom = max(stage, key=lambda k: stage[k])
+    peak, peak_src = peaks()
+    ach = w.b_alg * value / 1e9
+    roofline = {"bound": "hbm", "kernel": "whole iteration (sum of its kernels; dominant stage: %s)" % dom, "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src, "alg_bytes_per_agent_step": w.b_alg,
+                "stage_ms": {k: round(v, 5) for k, v in stage.items()}, "dominant_stage": dom, "dominant_stage_ms": stage[dom]}
+    # end to end: upload of the initial population, one iteration, read-back of every variable (host buffers)
+    import torch
+    pin = {k: torch.from_numpy(v.copy()).pin_memory().numpy() for k, v in st.items()}
+    h2d = sum(v.nbytes for v in pin.values())
+    e2e_steps = min(args.steps, 5)
+    sim2 = Simulation(plugin, device=local)
+    sim2.set_agents(w.agent, w.state, pin)
+    sim2.step(1)
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(e2e_steps):
+        sim2.set_agents(w.agent, w.state, pin)
+        sim2.step(1)
+        got = _all_states(sim2)
+        d2h = sum(v.nbytes for cols in got.values() for v in cols.values())
+    e2e_dt = time.perf_counter() - t0
+    sim2.close()
+    e2e = {"value": w.n * e2e_steps / e2e_dt, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps}
+    # parity: the bit-exact build against the oracle on the same input, where the oracle finishes in seconds
+    parity_ok, parity = None, None
+    exact = B.model_path(w.name + "_exact")
+    if not args.no_parity and os.path.exists(exact) and os.path.exists(gen_oracle.oracle_path(w.name)):
+        iters = 2
+        orc = OracleSimulation(gen_oracle.oracle_path(w.name), threads=cores)
+        g = Simulation(exact, device=local)
+        for s_ in (orc, g):
+            s_.set_agents(w.agent, w.state, st)
+            s_.step(iters)
+        a, b = _all_states(g), _all_states(orc)
+        parity = {"iterations": iters, "lists": {}}
+        parity_ok = set(a) == set(b)
+        for key in a:
+            if key not in b:
+                continue
+            same = {k: bool(a[key][k].shape == b[key][k].shape and np.array_equal(a[key][k].view(np.uint32), b[key][k].view(np.uint32)))
+                    for k in a[key]}
+            parity["lists"]["%s/%s" % key] = {"agents": int(len(next(iter(a[key].values())))), "bit_identical": all(same.values()),
+                                              "differing": [k for k, v in same.items() if not v]}
+            intcols = [k for k in a[key] if a[key][k].dtype.kind in "iu"]
+            parity_ok = parity_ok and all(same[k] for k in intcols)
+            if not all(same.values()):               # libm functions (powf, sinf ...) differ between libdevice and glibc
+                worst = 0.0
+                for k, v in same.items():
+                    if not v and a[key][k].dtype.kind == "f" and a[key][k].shape == b[key][k].shape:
+                        den = np.maximum(np.abs(b[key][k].astype(np.float64)), 1e-6)
+                        worst = max(worst, float(np.nanmax(np.abs(a[key][k].astype(np.float64) - b[key][k]) / den)))
+                parity["lists"]["%s/%s" % key]["max_rel_float_error"] = worst
+                parity["float_rtol"] = 1e-3
+                parity_ok = parity_ok and worst <= 1e-3
+        parity["seeds_equal"] = bool(np.array_equal(g.seeds(), orc.seeds()))
+        parity_ok = bool(parity_ok and parity["seeds_equal"])
+        g.close()
+        orc.close()
+    line = dict(base, value=value, steps=args.steps, warmup=args.warmup, ms_per_step=total_ms / args.steps, clocks=clocks, e2e=e2e,
+                gpu_launches=int(launches), roofline=roofline, parity_checked=parity_ok, parity=parity,
+                population={"start": n0, "end": n1})
+    line["config"]["l2"] = "flushed between timed iterations (256 MiB scratch rewrite, untimed)"
+    if not args.no_cpu_baseline:
+        v, dt, k = cpu_run(1 if w.n > (1 << 22) else 2, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+                                "sample": f"{k} full iteration(s) of the workload ({dt:.1f} s), OpenMP {cores} threads"}
+    print(json.dumps(line))
+    sim.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c2_16m", choices=sorted(k for k, c in W.BROWNIAN.items() if c.world == 1))
+    ap.add_argument("--workload", default="c2_16m",
+                    choices=sorted(k for k, c in W.BROWNIAN.items() if c.world == 1) + sorted(W.MODEL_WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-cuda", action="store_true")
@@ -395,6 +544,9 @@ def main():
     ap.add_argument("--option", action="append", default=[], help="runtime option key=value")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.workload in W.MODEL_WORKLOADS:
+        run_model_workload(args)
+        return
     cfg = W.BROWNIAN[args.workload]
 
     if args.impl == "reference":

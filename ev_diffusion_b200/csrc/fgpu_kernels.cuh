@@ -1033,9 +1033,10 @@ __device__ __forceinline__ int owner_class(float c, float minb, float range, flo
     int p = (int)floorf(__fdiv_rn(__fmul_rn(__fsub_rn(c, minb), scale), range));
     p = (p < 0) ? nplanes - 1 : p;
     p = (p >= nplanes) ? 0 : p;
+    const int p0 = rank * ppr;
+    if (p >= p0 && (p < p0 + ppr || rank == world - 1)) return 1;   /* the common case: no integer division */
     const int owner = min(p / ppr, world - 1);
-    if (owner == rank) return 1;
-    if (owner == lo_rank && owner == hi_rank) return (p < rank * ppr) ? 2 : 3; /* world == 2 */
+    if (owner == lo_rank && owner == hi_rank) return (p < p0) ? 2 : 3; /* world == 2 */
     if (owner == lo_rank) return 2;
     if (owner == hi_rank) return 3;
     return 4;
@@ -1186,17 +1187,17 @@ k_mig_fill(const char *__restrict__ rlo, const char *__restrict__ rhi, char *__r
            const int *__restrict__ mig_hdr, const unsigned int *__restrict__ holes, int dst_cap, int *status) {
     const int *hlo = (const int *)rlo, *hhi = (const int *)rhi;
     const int clo = hlo[0], chi = hhi[0], n_old = mig_hdr[0], nh = mig_hdr[1];
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j == 0 && (hlo[1] || hhi[1])) atomicExch(status, 3);
-    if (j >= clo + chi) return;
-    const char *src = (j < clo) ? rlo : rhi;
-    const int sj = (j < clo) ? j : j - clo;
-    const long long dst = (j < nh) ? (long long)holes[j] : (long long)n_old + (j - nh);
-    if (dst >= (long long)dst_cap) {
-        atomicExch(status, 4);
-        return;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (hlo[1] || hhi[1])) atomicExch(status, 3);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < clo + chi; j += gridDim.x * blockDim.x) {
+        const char *src = (j < clo) ? rlo : rhi;
+        const int sj = (j < clo) ? j : j - clo;
+        const long long dst = (j < nh) ? (long long)holes[j] : (long long)n_old + (j - nh);
+        if (dst >= (long long)dst_cap) {
+            atomicExch(status, 4);
+            continue;
+        }
+        copy_agent(src, scols, (size_t)sj, list, dcols, (size_t)dst);
     }
-    copy_agent(src, scols, (size_t)sj, list, dcols, (size_t)dst);
 }
 
 /* one block: holes the arrivals did not fill are filled with the live agents of the tail (ascending hole <- ascending

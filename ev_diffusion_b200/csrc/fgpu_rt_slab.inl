@@ -528,7 +528,7 @@ static int slab_migrate(fgpu_sim *s) {
             s->prof_end();
             s->prof_begin("mig:append");
             if (inplace) {
-                k_mig_fill<<<(2 * S.mig_cap + 255) / 256, 256, 0, s->stream>>>(in_lo, in_hi, list, X.bufcols, A.cols, mhdr, holes, A.d->buffer_size,
+                k_mig_fill<<<std::min(148, (2 * S.mig_cap + 255) / 256), 256, 0, s->stream>>>(in_lo, in_hi, list, X.bufcols, A.cols, mhdr, holes, A.d->buffer_size,
                                                                                S.d_status + 2);
                 LAUNCH_CHECK();
                 k_mig_tail<<<1, 1024, 0, s->stream>>>(in_lo, in_hi, list, A.cols, mhdr, holes, A.d_state_count + st, A.d->buffer_size);

@@ -141,3 +141,102 @@ def write_states_xml(path: str, agent_name: str, columns: Dict[str, np.ndarray],
             fh.write("".join(template % row for row in zip(*cols)))
         fh.write("</states>\n")
     return path
+
+
+# --------------------------------------------------------------------------------------------------
+# BASELINE configs C3 / C4 / C5' (SURVEY.md 8d): the reference's own example scripts, XML-only scaling
+# --------------------------------------------------------------------------------------------------
+REFERENCE_EXAMPLES = "/root/reference/examples"
+
+
+@dataclass
+class ModelWorkload:
+    key: str
+    name: str                 # plugin / oracle name
+    label: str
+    xml_source: str           # XMLModelFile.xml the variant is scaled from
+    replacements: Dict[str, str]
+    agent: str
+    state: str
+    n: int
+    b_alg: float              # algorithmic bytes per agent-step
+    iterations: int           # iterations the BASELINE row asks for
+    function_files: tuple = ()
+
+    def xml(self) -> str:
+        if not self.replacements:
+            return self.xml_source
+        dst = os.path.join(build.GEN, self.name, "src", "model", "XMLModelFile.xml")
+        return build.write_scaled_xml(self.xml_source, dst, self.replacements)
+
+    def functions(self):
+        if self.function_files:
+            return list(self.function_files)
+        return [os.path.join(os.path.dirname(self.xml_source), "functions.c")]
+
+
+def _boids_state(n: int, seed: int = 43) -> Dict[str, np.ndarray]:
+    u = uniform24(seed, 6 * n) - np.float32(0.5)
+    return {"id": np.arange(n, dtype=np.int32), "x": u[0::6].copy(), "y": u[1::6].copy(), "z": u[2::6].copy(),
+            "fx": u[3::6].copy(), "fy": u[4::6].copy(), "fz": u[5::6].copy()}
+
+
+def _sph_state(side: int, seed: int = 44) -> Dict[str, np.ndarray]:
+    """side^3 particles, one per partition cell of a side^3 grid over [-0.5, 0.5)^3, jittered inside the cell."""
+    n = side ** 3
+    i = np.arange(n, dtype=np.int64)
+    u = uniform24(seed, 3 * n)
+    h = np.float32(1.0 / side)
+    cols = {"id": i.astype(np.int32)}
+    for k, (name, idx) in enumerate((("x", i % side), ("y", (i // side) % side), ("z", i // (side * side)))):
+        cols[name] = ((idx.astype(np.float32) + np.float32(0.25) + np.float32(0.5) * u[k::3]) * h - np.float32(0.5)).astype(np.float32)
+    for name in ("dx", "dy", "dz", "fx", "fy", "fz", "density", "pressure"):
+        cols[name] = np.zeros(n, dtype=np.float32)
+    cols["isStatic"] = np.zeros(n, dtype=np.int32)
+    return cols
+
+
+def _birthdeath_state(n: int, seed: int = 45) -> Dict[str, np.ndarray]:
+    u = uniform24(seed, 3 * n) * np.float32(32.0)
+    return {"id": np.arange(n, dtype=np.int32), "x": u[0::3].copy(), "y": u[1::3].copy(), "z": u[2::3].copy(),
+            "age": np.zeros(n, dtype=np.int32), "crowd": np.zeros(n, dtype=np.int32)}
+
+
+_BOIDS_XML = os.path.join(REFERENCE_EXAMPLES, "Boids_Partitioning", "src", "model", "XMLModelFile.xml")
+_SPH_XML = os.path.join(REFERENCE_EXAMPLES, "SmoothedParticleHydrodynamics", "src", "model", "XMLModelFile.xml")
+_BD_XML = os.path.join(build.MODELS, "BirthDeath", "src", "model", "XMLModelFile.xml")
+
+MODEL_WORKLOADS = {
+    # C3: Boids_Partitioning functions.c unchanged; bufferSize 4 194 304, radius 1/128 -> 128^3 cells, ~2 agents / cell
+    "c3": ModelWorkload("c3", "Boids_4M", "C3 Boids_Partitioning (reference functions.c), 4 194 304 agents, 128^3 cells, 27-cell neighbour search",
+                        _BOIDS_XML, {"<gpu:bufferSize>2048</gpu:bufferSize>": "<gpu:bufferSize>4194304</gpu:bufferSize>",
+                                     "<gpu:radius>0.1</gpu:radius>": "<gpu:radius>0.0078125</gpu:radius>"},
+                        "Boid", "default", 1 << 22, 260.0, 100),
+    # C4: SmoothedParticleHydrodynamics functions.c unchanged; 16 777 216 particles, radius 1/256 -> 256^3 cells (a
+    # throughput case: the script's 1 m box cannot hold 16M particles at rest density, SURVEY.md 8d)
+    "c4": ModelWorkload("c4", "SPH_16M", "C4 SmoothedParticleHydrodynamics (reference functions.c), 16 777 216 particles, 256^3 cells, "
+                        "two spatial messages, function conditions",
+                        _SPH_XML, {"<gpu:bufferSize>131072</gpu:bufferSize>": "<gpu:bufferSize>16777216</gpu:bufferSize>",
+                                   "<gpu:radius>0.02</gpu:radius>": "<gpu:radius>0.00390625</gpu:radius>"},
+                        "FluidParticle", "default", 1 << 24, 556.0, 10),
+    # a 2M-particle variant of the same (128^3 cells) that the CPU oracle finishes in seconds: parity at scale
+    "c4_2m": ModelWorkload("c4_2m", "SPH_2M", "SmoothedParticleHydrodynamics, 2 097 152 particles, 128^3 cells",
+                           _SPH_XML, {"<gpu:bufferSize>131072</gpu:bufferSize>": "<gpu:bufferSize>2097152</gpu:bufferSize>",
+                                      "<gpu:radius>0.02</gpu:radius>": "<gpu:radius>0.0078125</gpu:radius>"},
+                           "FluidParticle", "default", 1 << 21, 556.0, 10),
+    # C5': BirthDeath (authored): death compaction + births + rand48 on the spatial path, 524 288 -> <= 2 097 152 agents
+    "c5p": ModelWorkload("c5p", "BirthDeath", "C5' BirthDeath (authored), 524 288 agents growing in a 2 097 152 buffer, 32^3 cells, "
+                         "death compaction + births + rand48", _BD_XML, {}, "Cell", "default", 1 << 19, 170.0, 200),
+}
+
+
+def model_state(w: ModelWorkload) -> Dict[str, np.ndarray]:
+    if w.key == "c3":
+        return _boids_state(w.n)
+    if w.key == "c4":
+        return _sph_state(256)
+    if w.key == "c4_2m":
+        return _sph_state(128)
+    if w.key == "c5p":
+        return _birthdeath_state(w.n)
+    raise KeyError(w.key)
