@@ -130,6 +130,11 @@ def written_variables(func: Function, agent: Agent, sources: List[str]) -> Set[s
             tail = body[use.end():use.end() + 8].lstrip()
             if not tail.startswith("->"):
                 return allv
+        # fail closed: a member name after `p->` that is not a variable of the agent is a macro (or a typo the compiler
+        # will report); its expansion is invisible here, so every variable counts as written
+        for member in re.finditer(r"\b" + re.escape(p) + r"\s*->\s*([A-Za-z_]\w*)", body):
+            if member.group(1) not in allv:
+                return allv
         written = set()
         assign = r"\s*(?:\[[^\]]*\])?\s*(?:=(?!=)|\+=|-=|\*=|/=|%=|&=|\|=|\^=|<<=|>>=|\+\+|--)"
         for v in agent.variables:
@@ -365,6 +370,8 @@ FGPU_DEV float rnd(RNG_rand48* rand48){ return fgpu::rand48_draw(rand48); }""")
         out.append(f"extern {c.type} h_env_{c.name}{dim};")
         out.append(f"void set_{c.name}({c.type}* h_{c.name});")
         out.append(f"const {c.type}* get_{c.name}();")
+    out.append("/* agent id generation (header.xslt:500-512) */")
+    out.append(_id_decls(model, cuda=True))
     out.append(_host_api_decls(model))
     out.append("#endif /* __HEADER */")
     return "\n".join(out) + "\n"
@@ -397,6 +404,7 @@ def _host_api_decls(model: Model) -> str:
             out.append(f"extern void reset_{a.name}_{s}_count();")
             out.append(f"extern xmachine_memory_{a.name}_list* get_device_{a.name}_{s}_agents();")
             out.append(f"extern xmachine_memory_{a.name}_list* get_host_{a.name}_{s}_agents();")
+            out.append(f"void sort_{a.name}s_{s}(void (*generate_key_value_pairs)(unsigned int* keys, unsigned int* values, xmachine_memory_{a.name}_list* agents));")
             for v in a.variables:
                 if not v.array_length:
                     out.append(f"{v.type} get_{a.name}_{s}_variable_{v.name}(unsigned int index);")
@@ -545,6 +553,82 @@ def _reduction_defs(model: Model, call: str) -> List[str]:
     return out
 
 
+_ID_TYPES = {"int": "2147483647", "unsigned int": "4294967295u", "unsigned long long": "18446744073709551615ull",
+             "unsigned long long int": "18446744073709551615ull"}
+
+
+def _id_agents(model: Model) -> List[Tuple[int, Agent, Variable]]:
+    """Agents that get generate_<A>_id(): an integer scalar variable called `id` (header.xslt:500-512).  atomicAdd
+    limits the types to the ones it supports."""
+    out = []
+    for ai, a in enumerate(model.agents):
+        for v in a.variables:
+            if v.name == "id" and not v.array_length and v.type in _ID_TYPES:
+                out.append((ai, a, v))
+    return out
+
+
+def _id_decls(model: Model, cuda: bool) -> str:
+    out = []
+    for _, a, v in _id_agents(model):
+        out.append(f"extern {v.type} h_current_value_generate_{a.name}_id;")
+        if cuda:
+            out.append(f"__device__ {v.type} d_current_value_generate_{a.name}_id;")
+        out.append(f"__FLAME_GPU_HOST_FUNC__ __FLAME_GPU_FUNC__ {v.type} generate_{a.name}_id();")
+        out.append(f"void set_initial_{a.name}_id({v.type} firstID);")
+    return "\n".join(out)
+
+
+def _id_defs(model: Model, cuda: bool) -> str:
+    """generate_<A>_id / set_initial_<A>_id (FLAMEGPU_kernals.xslt:1400-1411, simulation.xslt:336-356) and the three
+    hooks the runtime calls where the reference synchronises the counters."""
+    ids = _id_agents(model)
+    out = []
+    for ai, a, v in ids:
+        A, T = a.name, v.type
+        out.append(f"{T} h_current_value_generate_{A}_id = 0;")
+        out.append(f"static {T} h_last_value_generate_{A}_id = {_ID_TYPES[T]};")
+        if cuda:
+            out.append(f"""__FLAME_GPU_HOST_FUNC__ __FLAME_GPU_FUNC__ {T} generate_{A}_id(){{
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(&d_current_value_generate_{A}_id, ({T})1);
+#else
+    {T} new_id = h_current_value_generate_{A}_id;
+    h_current_value_generate_{A}_id++;
+    return new_id;
+#endif
+}}""")
+        else:
+            out.append(f"{T} generate_{A}_id(){{ {T} new_id = h_current_value_generate_{A}_id; h_current_value_generate_{A}_id++; return new_id; }}")
+        out.append(f"void set_initial_{A}_id({T} firstID){{ h_current_value_generate_{A}_id = firstID; }}")
+    if not cuda:
+        return "\n".join(out) + "\n"
+    if not ids:
+        out.append("static void (*const fgpu_ids_after_load)(void*) = nullptr;\nstatic void (*const fgpu_ids_to_host)(void) = nullptr;\n"
+                   "static void (*const fgpu_ids_to_device)(void) = nullptr;")
+        return "\n".join(out) + "\n"
+    out.append("static void fgpu_ids_to_device(void){")
+    for ai, a, v in ids:   # update_device_generate_<A>_id: only when the host value moved (simulation.xslt:346-350)
+        out.append(f"    if (h_current_value_generate_{a.name}_id != h_last_value_generate_{a.name}_id){{ "
+                   f"cudaMemcpyToSymbol(d_current_value_generate_{a.name}_id, &h_current_value_generate_{a.name}_id, sizeof({v.type})); "
+                   f"h_last_value_generate_{a.name}_id = h_current_value_generate_{a.name}_id; }}")
+    out.append("}")
+    out.append("static void fgpu_ids_to_host(void){")
+    for ai, a, v in ids:   # update_host_generate_<A>_id (simulation.xslt:352-356)
+        out.append(f"    cudaMemcpyFromSymbol(&h_current_value_generate_{a.name}_id, d_current_value_generate_{a.name}_id, sizeof({v.type})); "
+                   f"h_last_value_generate_{a.name}_id = h_current_value_generate_{a.name}_id;")
+    out.append("}")
+    out.append("static void fgpu_ids_after_load(void* sim){")
+    for ai, a, v in ids:   # io.xslt:599-616
+        init = a.states.index(a.initial_state)
+        vi = [x.name for x in a.variables].index("id")
+        out.append(f"    if (fgpu_sim_agent_count((fgpu_sim*)sim, {ai}, {init}) > 0){{ {v.type} mx = 0; "
+                   f"if (fgpu_sim_reduce_agent_var((fgpu_sim*)sim, {ai}, {init}, {vi}, FGPU_REDUCE_MAX, nullptr, &mx) != FGPU_OK) fgpu_die(); "
+                   f"set_initial_{a.name}_id(mx + 1); }} else set_initial_{a.name}_id(0);")
+    out.append("    fgpu_ids_to_device();\n}")
+    return "\n".join(out) + "\n"
+
+
 def _carry_vars(a: Agent) -> List[Variable]:
     """Variables of the carried agent record: every scalar variable (none if the agent has array variables)."""
     if any(v.array_length for v in a.variables):
@@ -573,7 +657,13 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
     carry = _carry_vars(a)
     out = [f"/* GPUFLAME_{f.name} (krn:1320-1387) */",
            f"__global__ void __launch_bounds__({bs}) fgpu_k_{f.name}(const fgpu_launch L)\n{{",
-           "    const int t = blockIdx.x * blockDim.x + threadIdx.x;"]
+           "    int t = blockIdx.x * blockDim.x + threadIdx.x;"]
+    if f.input_message and model.message(f.input_message).partitioning == "spatial":
+        out += ["    if (L.win_mode) {   /* slab mode: interior planes first, boundary planes once the halo has arrived */",
+                "        const int w0 = (int)(L.in_cell_start[L.win_cell_lo] - L.win_base), w1 = (int)(L.in_cell_start[L.win_cell_hi] - L.win_base);",
+                "        if (L.win_mode == 1) { t += w0; if (t >= w1) return; }",
+                "        else if (t >= w0) t = w1 + (t - w0);",
+                "    }"]
     out += ["    if (t >= (L.d_n ? *L.d_n : L.n)) return;",
             "    const int index = L.order ? (int)__ldg(L.order + t) : t;",
             f"    xmachine_memory_{A}_list* __restrict__ agents = (xmachine_memory_{A}_list*)L.agents;",
@@ -642,8 +732,9 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
         out.append("    }")
     out.append("}")
     out.append(f"""static void fgpu_launch_{f.name}(const fgpu_launch* a, void* stream){{
-    if (a->n <= 0) return;
-    const int grid = (a->n + {bs} - 1) / {bs};
+    const int threads = a->win_mode ? a->launch_n : a->n;
+    if (threads <= 0) return;
+    const int grid = (threads + {bs} - 1) / {bs};
     fgpu_k_{f.name}<<<grid, {bs}, 0, (cudaStream_t)stream>>>(*a);
 }}""")
     return "\n".join(out) + "\n"
@@ -843,6 +934,8 @@ void cleanup(){ fgpu_sim_run_exit_functions(fgpu_cur); fgpu_sim_destroy(fgpu_cur
             out.append(f"int get_agent_{a.name}_{st}_count(){{ return fgpu_sim_agent_count(fgpu_cur, {ai}, {si}); }}")
             out.append(f"void reset_{a.name}_{st}_count(){{ fgpu_sim_set_agents(fgpu_cur, {ai}, {si}, 0, nullptr); }}")
             out.append(f"xmachine_memory_{a.name}_list* get_device_{a.name}_{st}_agents(){{ return (xmachine_memory_{a.name}_list*)fgpu_sim_device_agents(fgpu_cur, {ai}, {si}); }}")
+            out.append(f"void sort_{a.name}s_{st}(void (*generate_key_value_pairs)(unsigned int* keys, unsigned int* values, xmachine_memory_{a.name}_list* agents)){{ "
+                       f"if (fgpu_sim_sort_agents(fgpu_cur, {ai}, {si}, (const void*)generate_key_value_pairs) != FGPU_OK) fgpu_die(); }}")
             for vi, v in enumerate(a.variables):
                 if not v.array_length:
                     out.append(f"{v.type} get_{a.name}_{st}_variable_{v.name}(unsigned int index){{ {v.type} t = 0; "
@@ -853,15 +946,21 @@ void cleanup(){ fgpu_sim_run_exit_functions(fgpu_cur); fgpu_sim_destroy(fgpu_cur
     out.append("static int fgpu_add_cur(int a, int s, int n, const void* const* cols){ return fgpu_sim_add_agents(fgpu_cur, a, s, n, cols); }")
     out.append("static int fgpu_count_cur(int a, int s){ return fgpu_sim_agent_count(fgpu_cur, a, s); }")
     out += _host_creation_defs(model, "fgpu_add_cur", "fgpu_count_cur")
+    out.append(_id_defs(model, cuda=True))
     return "\n".join(out) + "\n"
 
 
-def _model_struct(model: Model) -> str:
+def _model_struct(model: Model, cuda: bool = True) -> str:
     def fnlist(kind, names):
         if not names:
             return f"static void (*const *fgpu_{kind}_functions)(void) = nullptr;"
         return f"static void (*const fgpu_{kind}_functions[])(void) = {{{', '.join(names)}}};"
-    out = [fnlist("init", model.init_functions), fnlist("step", model.step_functions), fnlist("exit", model.exit_functions)]
+    def namelist(kind, names):
+        if not names:
+            return f"static const char* const* fgpu_{kind}_function_names = nullptr;"
+        return f"static const char* const fgpu_{kind}_function_names[] = {{{', '.join(chr(34) + n + chr(34) for n in names)}}};"
+    out = [fnlist("init", model.init_functions), fnlist("step", model.step_functions), fnlist("exit", model.exit_functions),
+           namelist("init", model.init_functions), namelist("step", model.step_functions), namelist("exit", model.exit_functions)]
     safe = model.name.replace('"', "'")
     out.append(f"""static const fgpu_model fgpu_the_model = {{
     FGPU_MODEL_ABI_VERSION, "{safe}", {model.buffer_size_max},
@@ -874,7 +973,9 @@ def _model_struct(model: Model) -> str:
     {len(model.init_functions)}, fgpu_init_functions,
     {len(model.step_functions)}, fgpu_step_functions,
     {len(model.exit_functions)}, fgpu_exit_functions,
-    fgpu_plugin_bind
+    fgpu_plugin_bind,
+    fgpu_init_function_names, fgpu_step_function_names, fgpu_exit_function_names,
+    {'fgpu_ids_after_load, fgpu_ids_to_host, fgpu_ids_to_device' if cuda else 'nullptr, nullptr, nullptr'}
 }};
 extern "C" const fgpu_model* fgpu_model_get(void){{ return &fgpu_the_model; }}
 """)

@@ -102,6 +102,14 @@ int main(int argc, char **argv) {
     fgpu_sim *sim = fgpu_sim_create(model, device);
     if (!sim) die();
     fgpu_set_output_dir(outputpath.c_str()); /* getOutputDir() of step functions */
+    /* The reference's -DINSTRUMENT_ITERATIONS / _AGENT_FUNCTIONS / _INIT_ / _STEP_ / _EXIT_FUNCTIONS are compile-time
+     * (simulation.xslt:370-377); a plugin is not recompiled for them, so the console takes the same switches from the
+     * environment: FGPU_INSTRUMENT=iterations,agent_functions,... */
+    if (const char *ins = getenv("FGPU_INSTRUMENT")) {
+        const std::string want(ins);
+        for (const char *k : {"iterations", "agent_functions", "init_functions", "step_functions", "exit_functions"})
+            if (want.find(k) != std::string::npos && fgpu_sim_set_option(sim, (std::string("instrument_") + k).c_str(), 1) != FGPU_OK) die();
+    }
     if (!inputfile.empty()) {
         printf("Initial states: %s\n", inputfile.c_str());
         if (fgpu_sim_load_states(sim, inputfile.c_str()) != FGPU_OK) die();

@@ -648,6 +648,21 @@ k_compact_records(const uint4 *__restrict__ src_recs, const unsigned int *__rest
     if (src_keys != nullptr) dst_keys[out] = src_keys[i];
 }
 
+/* reorder_<A>_agents (krn:322-333) after the pairs of sort_<A>s_<S> were sorted: new[i] = old[values[order[i]]] */
+__global__ void __launch_bounds__(256)
+k_reorder_agents(const char *__restrict__ src, char *__restrict__ dst, const ColSet cols, const unsigned int *__restrict__ order,
+                 const unsigned int *__restrict__ values, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t old_pos = values[order[i]];
+    for (int c = 0; c < cols.ncols; ++c) {
+        if (cols.size[c] == 4)
+            ((unsigned int *)(dst + cols.off[c]))[i] = ((const unsigned int *)(src + cols.off[c]))[old_pos];
+        else
+            ((unsigned long long *)(dst + cols.off[c]))[i] = ((const unsigned long long *)(src + cols.off[c]))[old_pos];
+    }
+}
+
 /* append_<A>_Agents (krn:265-280) */
 __global__ void __launch_bounds__(256)
 k_append(const char *__restrict__ src, char *__restrict__ dst, const ColSet cols, int dst_offset, int n) {

@@ -92,6 +92,8 @@ struct AgentRT {
     unsigned int *block_sums = nullptr;
     int *d_total = nullptr;
     int *d_state_count = nullptr; /* slab mode: exact population of each state list, on the device */
+    /* sort_<A>s_<S> (allocated on first use): the caller's pairs, the radix ping-pong, its scratch */
+    unsigned int *sort_keys = nullptr, *sort_vals = nullptr, *sort_k[2] = {nullptr, nullptr}, *sort_v[2] = {nullptr, nullptr}, *sort_scratch = nullptr;
 };
 
 struct MsgRT {
@@ -123,6 +125,7 @@ struct MsgRT {
      * order by the build together with the message records */
     uint4 *carry_unsorted = nullptr, *carry_sorted = nullptr;
     int carry_quads = 0;          /* record size of the buffers above (allocated for the first producer's agent type) */
+    bool halo_pending = false;    /* slab mode: the halo exchange of this build runs on the side stream; join before reading halo cells */
     bool carry_pending = false;   /* the producer of this iteration wrote carry_unsorted */
     bool carry_valid = false;     /* carry_sorted matches the sorted list */
     unsigned long long carry_content = 0; /* content epoch of the producer list when the records were written */
@@ -215,7 +218,15 @@ struct fgpu_sim {
     int opt_radix_bits = 9;
     int opt_slab_async = 1;
     int opt_slab_p2p = 1;
+    int opt_slab_overlap = 1; /* halo exchange on a side stream while the agents of the interior planes are processed */
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int opt_slab_inplace = 1; /* migration: 1 = leavers leave holes that arrivals / tail agents fill; 0 = stable three-way re-compaction */
+    /* the reference's compile-time -DINSTRUMENT_* switches (simulation.xslt:370-377), as run-time options: each prints
+     * the reference's own "Instrumentation: ... = %f (ms)" lines */
+    int opt_instr_iterations = 0, opt_instr_agent_functions = 0, opt_instr_init_functions = 0, opt_instr_step_functions = 0,
+        opt_instr_exit_functions = 0;
+    cudaEvent_t instr_a = nullptr, instr_b = nullptr, instr_it_a = nullptr, instr_it_b = nullptr;
     int opt_xml_digits = 0; /* 0: the reference's "%f" iteration files; n: "%.<n>g" */
     /* CUDA graph of one iteration (static models) */
     bool is_static = false;
@@ -287,6 +298,7 @@ struct fgpu_sim {
 };
 
 static void slab_release(fgpu_sim *s);
+static int join_pending_halos(fgpu_sim *s);
 static void slab_mark_exact(fgpu_sim *s);
 static size_t msg_plane_bytes(const fgpu_message *m) { return (size_t)m->rec_quads * m->buffer_size * sizeof(uint4); }
 
@@ -512,6 +524,13 @@ extern "C" void fgpu_sim_destroy(fgpu_sim *s) {
         cudaFree(A.block_sums);
         cudaFree(A.d_total);
         cudaFree(A.d_state_count);
+        cudaFree(A.sort_keys);
+        cudaFree(A.sort_vals);
+        for (int k = 0; k < 2; ++k) {
+            cudaFree(A.sort_k[k]);
+            cudaFree(A.sort_v[k]);
+        }
+        cudaFree(A.sort_scratch);
     }
     for (MsgRT &M : s->msgs) {
         cudaFree(M.unsorted);
@@ -558,6 +577,11 @@ extern "C" void fgpu_sim_destroy(fgpu_sim *s) {
     for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    for (cudaEvent_t e : {s->instr_a, s->instr_b, s->instr_it_a, s->instr_it_b})
+        if (e) cudaEventDestroy(e);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
+    if (s->stream2) cudaStreamDestroy(s->stream2);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -972,6 +996,23 @@ static int run_function(fgpu_sim *s, int fi) {
         L.Cy = s->Cy;
     }
     s->prof_begin(std::string("func:") + F.name);
+    if (Min && Min->halo_pending) {
+        const SlabRT &S = s->slab;
+        if (L.order && S.ppr > 2) {
+            /* agents of the interior planes need no halo cell: run them while the exchange is in flight */
+            L.win_mode = 1;
+            L.win_cell_lo = (unsigned int)(S.p0 + 1) * (unsigned int)S.plane_cells;
+            L.win_cell_hi = (unsigned int)(S.p1 - 1) * (unsigned int)S.plane_cells;
+            L.win_base = (unsigned int)Min->local_at;
+            L.launch_n = L.n;
+            F.launch(&L, s->stream);
+            LAUNCH_CHECK();
+            L.win_mode = 2;
+            L.launch_n = std::min(L.n, 2 * S.halo_cap); /* a plane never holds more than halo_cap messages (checked by the pack) */
+        }
+        CU(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+        Min->halo_pending = false;
+    }
     F.launch(&L, s->stream);
     LAUNCH_CHECK();
     s->prof_end();
@@ -1060,8 +1101,19 @@ static int run_function(fgpu_sim *s, int fi) {
         int rc = build_spatial(s, *Mout);
         if (rc) return rc;
         if (s->slab.on) {
-            rc = slab_exchange_halo(s, F.output_message);
-            if (rc) return rc;
+            const bool overlap = s->opt_slab_overlap && s->slab.p2p && !s->profiling && s->stream2 && Mout->producers == 1;
+            if (overlap) {
+                /* fork: pack + push + wait + merge on the side stream; the consumer joins before it touches halo cells */
+                CU(cudaEventRecord(s->ev_fork, s->stream));
+                CU(cudaStreamWaitEvent(s->stream2, s->ev_fork, 0));
+                rc = slab_exchange_halo(s, F.output_message, s->stream2);
+                if (rc) return rc;
+                CU(cudaEventRecord(s->ev_join, s->stream2));
+                Mout->halo_pending = true;
+            } else {
+                rc = slab_exchange_halo(s, F.output_message, s->stream);
+                if (rc) return rc;
+            }
         }
     }
     if (s->slab.on && (F.writes_position || F.xagent_output >= 0)) s->slab.dirty = true;
@@ -1096,24 +1148,94 @@ static int begin_iteration(fgpu_sim *s) {
     return FGPU_OK;
 }
 
+/* joins a halo exchange nobody consumed (every fork must be joined before the iteration ends or is captured) */
+static int join_pending_halos(fgpu_sim *s) {
+    for (MsgRT &M : s->msgs)
+        if (M.halo_pending) {
+            CU(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+            M.halo_pending = false;
+        }
+    return FGPU_OK;
+}
+
+/* cudaEvent pair + the reference's line, simulation.xslt:898-914 */
+static int instr_begin(fgpu_sim *s) {
+    if (!s->instr_a) {
+        CU(cudaEventCreate(&s->instr_a));
+        CU(cudaEventCreate(&s->instr_b));
+        CU(cudaEventCreate(&s->instr_it_a));
+        CU(cudaEventCreate(&s->instr_it_b));
+    }
+    CU(cudaEventRecord(s->instr_a, s->stream));
+    return FGPU_OK;
+}
+static int instr_end(fgpu_sim *s, const char *prefix, const char *name) {
+    float ms = 0.f;
+    CU(cudaEventRecord(s->instr_b, s->stream));
+    CU(cudaEventSynchronize(s->instr_b));
+    CU(cudaEventElapsedTime(&ms, s->instr_a, s->instr_b));
+    printf("Instrumentation: %s%s = %f (ms)\n", prefix, name, ms);
+    return FGPU_OK;
+}
+
 static int single_iteration(fgpu_sim *s) {
     const fgpu_model *m = s->model;
+    const bool it_timer = s->opt_instr_iterations && !s->capturing;
+    if (it_timer) {
+        int rc = instr_begin(s);
+        if (rc) return rc;
+        CU(cudaEventRecord(s->instr_it_a, s->stream));
+    }
     begin_iteration(s);
     for (int l = 0; l < m->nlayers; ++l)
         for (int k = 0; k < m->layers[l].nfunctions; ++k) {
-            int rc = run_function(s, m->layers[l].functions[k]);
+            const int fi = m->layers[l].functions[k];
+            const bool timed = s->opt_instr_agent_functions && !s->capturing;
+            if (timed) {
+                int rc = instr_begin(s);
+                if (rc) return rc;
+            }
+            int rc = run_function(s, fi);
             if (rc) return rc;
+            if (timed) { /* "<Agent>_<function>", simulation.xslt:913 */
+                const std::string name = std::string(m->agents[m->functions[fi].agent].name) + "_" + m->functions[fi].name;
+                rc = instr_end(s, "", name.c_str());
+                if (rc) return rc;
+            }
         }
+    {
+        int rc = join_pending_halos(s);
+        if (rc) return rc;
+    }
     if (s->slab.on && s->slab.dirty) {
         int rc = slab_migrate(s);
         if (rc) return rc;
     }
-    if (!s->capturing)
+    if (!s->capturing && m->nstep_functions > 0) {
+        CU(cudaStreamSynchronize(s->stream));
+        if (m->ids_to_host) m->ids_to_host(); /* simulation.xslt:918-930 */
         for (int k = 0; k < m->nstep_functions; ++k) {
-            CU(cudaStreamSynchronize(s->stream));
             if (m->bind) m->bind(s);
+            if (s->opt_instr_step_functions) {
+                int rc = instr_begin(s);
+                if (rc) return rc;
+            }
             m->step_functions[k]();
+            if (s->opt_instr_step_functions) {
+                int rc = instr_end(s, "", m->step_function_names ? m->step_function_names[k] : "step function");
+                if (rc) return rc;
+            }
+            CU(cudaStreamSynchronize(s->stream));
         }
+        if (m->ids_to_device) m->ids_to_device(); /* simulation.xslt:948-960 */
+    }
+    if (it_timer) {
+        float ms = 0.f;
+        CU(cudaEventRecord(s->instr_it_b, s->stream));
+        CU(cudaEventSynchronize(s->instr_it_b));
+        CU(cudaEventElapsedTime(&ms, s->instr_it_a, s->instr_it_b));
+        printf("Instrumentation: Iteration Time = %f (ms)\n", ms); /* simulation.xslt:973 */
+    }
     return FGPU_OK;
 }
 
@@ -1133,9 +1255,10 @@ static std::vector<int> current_counts(fgpu_sim *s) {
 static int step_async(fgpu_sim *s, int n) {
     if (n <= 0) return FGPU_OK;
     CU(cudaSetDevice(s->device));
-    const bool use_graph = s->is_static && s->opt_graph && !s->profiling;
+    const bool instrumented = s->opt_instr_iterations || s->opt_instr_agent_functions;
+    const bool use_graph = s->is_static && s->opt_graph && !s->profiling && !instrumented;
     CU(cudaEventRecord(s->ev0, s->stream));
-    if (s->slab.on && s->slab.async && s->slab.p2p && s->opt_graph && !s->profiling && s->model->nstep_functions == 0) {
+    if (s->slab.on && s->slab.async && s->slab.p2p && s->opt_graph && !s->profiling && !instrumented && s->model->nstep_functions == 0) {
         int rc = slab_graph_step(s, n);
         if (rc) return rc;
     } else if (use_graph) {
@@ -1266,8 +1389,19 @@ extern "C" int fgpu_sim_run_init_functions(fgpu_sim *s) {
     if (!s) return set_err(FGPU_ERR_ARG, "null sim");
     CU(cudaSetDevice(s->device));
     if (s->model->bind) s->model->bind(s);
-    for (int k = 0; k < s->model->ninit_functions; ++k) s->model->init_functions[k]();
+    for (int k = 0; k < s->model->ninit_functions; ++k) {
+        if (s->opt_instr_init_functions) {
+            int rc = instr_begin(s);
+            if (rc) return rc;
+        }
+        s->model->init_functions[k]();
+        if (s->opt_instr_init_functions) { /* simulation.xslt:714 */
+            int rc = instr_end(s, "", s->model->init_function_names ? s->model->init_function_names[k] : "init function");
+            if (rc) return rc;
+        }
+    }
     CU(cudaDeviceSynchronize());
+    if (s->model->ids_to_device) s->model->ids_to_device(); /* ids handed out by init functions on the host */
     return FGPU_OK;
 }
 
@@ -1276,7 +1410,55 @@ extern "C" int fgpu_sim_run_exit_functions(fgpu_sim *s) {
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->stream));
     if (s->model->bind) s->model->bind(s);
-    for (int k = 0; k < s->model->nexit_functions; ++k) s->model->exit_functions[k]();
+    if (s->model->ids_to_host) s->model->ids_to_host();
+    for (int k = 0; k < s->model->nexit_functions; ++k) {
+        if (s->opt_instr_exit_functions) {
+            int rc = instr_begin(s);
+            if (rc) return rc;
+        }
+        s->model->exit_functions[k]();
+        if (s->opt_instr_exit_functions) { /* simulation.xslt:796 */
+            int rc = instr_end(s, "", s->model->exit_function_names ? s->model->exit_function_names[k] : "exit function");
+            if (rc) return rc;
+        }
+    }
+    return FGPU_OK;
+}
+
+/* sort_<A>s_<S>(), simulation.xslt:750-776 */
+extern "C" int fgpu_sim_sort_agents(fgpu_sim *s, int agent, int state, const void *generate_key_value_pairs) {
+    if (!s || !generate_key_value_pairs || agent < 0 || agent >= (int)s->agents.size()) return set_err(FGPU_ERR_ARG, "bad argument");
+    AgentRT &A = s->agents[agent];
+    if (state < 0 || state >= A.d->nstates) return set_err(FGPU_ERR_ARG, "bad state index");
+    if (s->slab.on) return set_err(FGPU_ERR_MODEL, "sort_%ss_%s is not available in slab mode", A.d->name, A.d->states[state]);
+    CU(cudaSetDevice(s->device));
+    const int n = A.h_state_count[state];
+    if (n <= 0) return FGPU_OK;
+    const int cap = (A.d->buffer_size + 1023) & ~1023; /* the caller's kernel has no bounds check: whole blocks may write */
+    if (!A.sort_keys) {
+        CU(cudaMalloc(&A.sort_keys, sizeof(unsigned int) * (size_t)cap));
+        CU(cudaMalloc(&A.sort_vals, sizeof(unsigned int) * (size_t)cap));
+        for (int k = 0; k < 2; ++k) {
+            CU(cudaMalloc(&A.sort_k[k], sizeof(unsigned int) * (size_t)cap));
+            CU(cudaMalloc(&A.sort_v[k], sizeof(unsigned int) * (size_t)cap));
+        }
+        CU(cudaMalloc(&A.sort_scratch, sizeof(unsigned int) * sort_scratch_words(A.d->buffer_size, 32, 8)));
+    }
+    unsigned int *keys = A.sort_keys, *values = A.sort_vals;
+    void *list = A.state[state];
+    void *args[3] = {&keys, &values, &list};
+    const int block = 256;
+    CU(cudaLaunchKernel(generate_key_value_pairs, dim3((n + block - 1) / block), dim3(block), args, 0, s->stream));
+    s->launches++;
+    int in = 0;
+    int rc = radix_sort_pairs(s->stream, keys, n, 32, 8, A.sort_k, A.sort_v, A.sort_scratch, &in, &s->launches);
+    if (rc) return rc;
+    k_reorder_agents<<<(n + 255) / 256, 256, 0, s->stream>>>(A.state[state], A.swap, A.cols, A.sort_v[in], values, n);
+    LAUNCH_CHECK();
+    std::swap(A.state[state], A.swap);
+    s->touch(A.state[state]);
+    s->touch(A.swap);
+    CU(cudaStreamSynchronize(s->stream));
     return FGPU_OK;
 }
 

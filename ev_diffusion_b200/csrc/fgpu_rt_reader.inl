@@ -165,6 +165,10 @@ extern "C" int fgpu_sim_load_states(fgpu_sim *s, const char *xml_path) {
         if (rc != FGPU_OK) return rc;
     }
     CU(cudaDeviceSynchronize());
+    if (m->ids_after_load) { /* io.xslt:599-616: the first generated id = the largest id read + 1 */
+        if (m->bind) m->bind(s);
+        m->ids_after_load(s);
+    }
     return FGPU_OK;
 }
 

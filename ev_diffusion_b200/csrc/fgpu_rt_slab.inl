@@ -258,6 +258,13 @@ extern "C" int fgpu_sim_slab_init(fgpu_sim *s, int rank, int world, const void *
         }
     }
     S.async = s->static_kind && s->opt_slab_async;
+    if (!s->stream2) {
+        int lo_pri = 0, hi_pri = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+        CU(cudaStreamCreateWithPriority(&s->stream2, cudaStreamNonBlocking, hi_pri)); /* the exchange must not queue behind the interior agents */
+        CU(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+    }
     for (int i = 0; i < SlabRT::RING; ++i) CU(cudaEventCreateWithFlags(&S.ring_ev[i], cudaEventDisableTiming));
     CU(cudaMallocHost(&S.h_ring, sizeof(int) * SlabRT::RING * SlabRT::RING_STRIDE));
     for (int a = 0; a < m->nagents; ++a)
@@ -303,12 +310,12 @@ static int slab_neighbour_barrier(fgpu_sim *s) {
 
 /* Halo exchange after a spatial message build: my two boundary planes go to the neighbours, theirs are
  * spliced around my local block (contiguous ranges of the SORTED list, so within-cell order is the owner's). */
-static int slab_exchange_halo(fgpu_sim *s, int mi) {
+static int slab_exchange_halo(fgpu_sim *s, int mi, cudaStream_t st) {
     SlabRT &S = s->slab;
     MsgRT &M = s->msgs[mi];
     SlabMsg &X = S.msgs[mi];
     const int n = M.h_count, PL = S.plane_cells, Q = M.d->rec_quads;
-    if (n == 0) CU(cudaMemsetAsync(M.cell_start, 0, sizeof(unsigned int) * ((size_t)M.d->grid_size + 1), s->stream));
+    if (n == 0) CU(cudaMemsetAsync(M.cell_start, 0, sizeof(unsigned int) * ((size_t)M.d->grid_size + 1), st));
     const uint4 *local = M.sorted; /* cell_start of the owned planes already counts from the start of the combined list */
     s->prof_begin(std::string("halo_pack:") + M.d->name);
     const int g = std::min(148 * 4, (std::max(S.halo_cap * Q, PL) + 255) / 256);
@@ -324,7 +331,7 @@ static int slab_exchange_halo(fgpu_sim *s, int mi) {
         switch (Q) {
 #define PUSHP_CASE(QQ)                                                                                                              \
     case QQ:                                                                                                                        \
-        k_push_planes<QQ><<<dim3(gp, 2), 256, 0, s->stream>>>(local, M.cell_start, S.p0 * PL, (S.p1 - 1) * PL, PL, S.halo_cap,     \
+        k_push_planes<QQ><<<dim3(gp, 2), 256, 0, st>>>(local, M.cell_start, S.p0 * PL, (S.p1 - 1) * PL, PL, S.halo_cap,     \
                                                               (int *)(S.peer_lo + S.msg_off[mi] + (2 + par) * A4),                 \
                                                               (int *)(S.peer_hi + S.msg_off[mi] + (0 + par) * A4), S.d_done + mi,  \
                                                               (int *)(S.peer_lo + 16 * mi) + 1, (int *)(S.peer_hi + 16 * mi) + 0,  \
@@ -341,7 +348,7 @@ static int slab_exchange_halo(fgpu_sim *s, int mi) {
         switch (Q) {
 #define PACK_CASE(QQ)                                                                                                       \
     case QQ:                                                                                                                \
-        k_pack_planes<QQ><<<dim3(g, 2), 256, 0, s->stream>>>(local, M.cell_start, S.p0 * PL, (S.p1 - 1) * PL, PL, S.halo_cap, \
+        k_pack_planes<QQ><<<dim3(g, 2), 256, 0, st>>>(local, M.cell_start, S.p0 * PL, (S.p1 - 1) * PL, PL, S.halo_cap, \
                                                              X.send_lo, X.send_hi);                                         \
         break;
             PACK_CASE(1) PACK_CASE(2) PACK_CASE(3) PACK_CASE(4) PACK_CASE(5) PACK_CASE(6) PACK_CASE(7) PACK_CASE(8)
@@ -351,10 +358,10 @@ static int slab_exchange_halo(fgpu_sim *s, int mi) {
         s->prof_end();
         s->prof_begin(std::string("halo_xfer:") + M.d->name);
         NC(g_nccl.GroupStart());
-        NC(g_nccl.Send(X.send_lo, X.bytes, NCCL_INT8, S.lo_rank, S.comm, s->stream));
-        NC(g_nccl.Send(X.send_hi, X.bytes, NCCL_INT8, S.hi_rank, S.comm, s->stream));
-        NC(g_nccl.Recv(X.recv_hi, X.bytes, NCCL_INT8, S.hi_rank, S.comm, s->stream));
-        NC(g_nccl.Recv(X.recv_lo, X.bytes, NCCL_INT8, S.lo_rank, S.comm, s->stream));
+        NC(g_nccl.Send(X.send_lo, X.bytes, NCCL_INT8, S.lo_rank, S.comm, st));
+        NC(g_nccl.Send(X.send_hi, X.bytes, NCCL_INT8, S.hi_rank, S.comm, st));
+        NC(g_nccl.Recv(X.recv_hi, X.bytes, NCCL_INT8, S.hi_rank, S.comm, st));
+        NC(g_nccl.Recv(X.recv_lo, X.bytes, NCCL_INT8, S.lo_rank, S.comm, st));
         NC(g_nccl.GroupEnd());
     }
     S.halo_bytes += 2 * (long long)X.bytes;
@@ -364,7 +371,7 @@ static int slab_exchange_halo(fgpu_sim *s, int mi) {
     switch (Q) {
 #define MERGE_CASE(QQ)                                                                                                      \
     case QQ:                                                                                                                \
-        k_merge_halo<QQ><<<g, 256, 0, s->stream>>>(M.sorted, M.cell_start, M.local_at, n, M.d_count, S.p0 * PL, S.ppr * PL, in_lo, \
+        k_merge_halo<QQ><<<g, 256, 0, st>>>(M.sorted, M.cell_start, M.local_at, n, M.d_count, S.p0 * PL, S.ppr * PL, in_lo, \
                                                    lo_first, in_hi, hi_first, PL, S.d_status);                              \
         break;
         MERGE_CASE(1) MERGE_CASE(2) MERGE_CASE(3) MERGE_CASE(4) MERGE_CASE(5) MERGE_CASE(6) MERGE_CASE(7) MERGE_CASE(8)

@@ -270,6 +270,11 @@ extern "C" int fgpu_sim_set_option(fgpu_sim *s, const char *key, int value) {
     if (!strcmp(key, "order")) s->opt_order = value ? 1 : 0;
     else if (!strcmp(key, "nvtx")) s->opt_nvtx = value ? 1 : 0;
     else if (!strcmp(key, "graph")) s->opt_graph = value ? 1 : 0;
+    else if (!strcmp(key, "instrument_iterations")) s->opt_instr_iterations = value ? 1 : 0;
+    else if (!strcmp(key, "instrument_agent_functions")) s->opt_instr_agent_functions = value ? 1 : 0;
+    else if (!strcmp(key, "instrument_init_functions")) s->opt_instr_init_functions = value ? 1 : 0;
+    else if (!strcmp(key, "instrument_step_functions")) s->opt_instr_step_functions = value ? 1 : 0;
+    else if (!strcmp(key, "instrument_exit_functions")) s->opt_instr_exit_functions = value ? 1 : 0;
     else if (!strcmp(key, "msd")) s->opt_msd = value ? 1 : 0;
     else if (!strcmp(key, "l2_fetch")) {
         /* device-wide hint: bytes the L2 fetches from HBM per miss (32, 64 or 128).  The random 16-byte record
@@ -295,6 +300,8 @@ extern "C" int fgpu_sim_set_option(fgpu_sim *s, const char *key, int value) {
     else if (!strcmp(key, "slab_p2p")) {
         if (s->slab.on) return set_err(FGPU_ERR_ARG, "slab_p2p must be set before fgpu_sim_slab_init");
         s->opt_slab_p2p = value ? 1 : 0;
+    } else if (!strcmp(key, "slab_overlap")) {
+        s->opt_slab_overlap = value ? 1 : 0;
     } else if (!strcmp(key, "slab_inplace")) {
         s->opt_slab_inplace = value ? 1 : 0;
     } else if (!strcmp(key, "slab_async")) {

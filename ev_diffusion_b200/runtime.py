@@ -79,7 +79,9 @@ class _Model(C.Structure):
                 ("init_constants", C.c_void_p),
                 ("ninit_functions", C.c_int), ("init_functions", C.c_void_p),
                 ("nstep_functions", C.c_int), ("step_functions", C.c_void_p),
-                ("nexit_functions", C.c_int), ("exit_functions", C.c_void_p), ("bind", C.c_void_p)]
+                ("nexit_functions", C.c_int), ("exit_functions", C.c_void_p), ("bind", C.c_void_p),
+                ("init_function_names", C.c_void_p), ("step_function_names", C.c_void_p), ("exit_function_names", C.c_void_p),
+                ("ids_after_load", C.c_void_p), ("ids_to_host", C.c_void_p), ("ids_to_device", C.c_void_p)]
 
 
 # ---- description objects ----------------------------------------------------

@@ -91,6 +91,12 @@ int fgpu_sim_set_agents(fgpu_sim *sim, int agent, int state, int count, const vo
  * the SMs busy at once); the reference's initialise / singleIteration / get_host_* sequence is strictly serial. */
 int fgpu_sim_set_agents_async(fgpu_sim *sim, int agent, int state, int count, const void *const *columns);
 
+/* sort_<A>s_<S>() (simulation.xslt:750-776): `generate_key_value_pairs` is the caller's __global__ kernel
+ * (unsigned int* keys, unsigned int* values, xmachine_memory_<A>_list* agents), launched over the state list; the
+ * (key, value) pairs are sorted by key with the runtime's own LSD radix sort (stable, where the reference's
+ * thrust::sort_by_key promises no order among equal keys) and agent i of the new list is agent values[i] of the old. */
+int fgpu_sim_sort_agents(fgpu_sim *sim, int agent, int state, const void *generate_key_value_pairs);
+
 /* Host-side mirror of h_add_agents_<A>_<S> (simulation.xslt:1275-1320): append. */
 int fgpu_sim_add_agents(fgpu_sim *sim, int agent, int state, int count, const void *const *columns);
 

@@ -98,6 +98,13 @@ typedef struct fgpu_launch {
     const void *carry_in;         /* consumer: record t = the variables of list index order[t], i.e. in cell order, as the
                                      producer of the input message left them; NULL = read the SoA list at order[t] */
     void *carry_out;              /* producer: the wrapper stores record `index` after the script returns; NULL = no */
+    /* launch window over the cell-order positions (functions with a spatial input message, order != NULL): slab mode
+     * runs the agents of the interior planes while the halo planes are still in flight, the boundary planes after.
+     *   w0 = in_cell_start[win_cell_lo] - win_base,  w1 = in_cell_start[win_cell_hi] - win_base  (read on the device)
+     *   win_mode 0: every position;  1: positions [w0, w1);  2: positions [0, w0) and [w1, n) */
+    int win_mode;
+    unsigned int win_cell_lo, win_cell_hi, win_base;
+    int launch_n;                 /* win_mode != 0: number of threads to launch (a host-side upper bound) */
 } fgpu_launch;
 
 typedef void (*fgpu_launch_fn)(const fgpu_launch *args, void *cuda_stream);
@@ -174,6 +181,16 @@ typedef struct fgpu_model {
     /* Makes `sim` the simulation the plugin's Face-2 shim (initialise, singleIteration,
      * get_agent_<A>_<S>_count ... header.xslt:531-645) and its init/step/exit functions act on. */
     void (*bind)(void *sim);
+    /* Agent id generation (generate_<A>_id / set_initial_<A>_id, header.xslt:500-512).  The counters live in the
+     * plugin (a __device__ symbol and its host shadow); the runtime calls these where the reference synchronises
+     * them: after the initial states are read (io.xslt:599-616: first id = largest id read + 1), before and after
+     * the step / init / exit functions (simulation.xslt:918-960).  NULL when no agent has an integer `id`. */
+    const char *const *init_function_names;   /* for the "Instrumentation: <name> = ..." lines; may be NULL */
+    const char *const *step_function_names;
+    const char *const *exit_function_names;
+    void (*ids_after_load)(void *sim);
+    void (*ids_to_host)(void);
+    void (*ids_to_device)(void);
 } fgpu_model;
 
 /* The single symbol a model plugin exports. */

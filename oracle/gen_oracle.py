@@ -234,6 +234,7 @@ def emit_header(model: Model) -> str:
         out.append(f"const {c.type}* get_{c.name}();")
     # host API the scripts' init/step/exit functions may call; the oracle defines the counts and the analytics
     out.append(codegen._host_api_decls(model))
+    out.append(codegen._id_decls(model, cuda=False))
     out.append("#endif")
     return "\n".join(out) + "\n"
 
@@ -403,7 +404,12 @@ template <int AGENT_TYPE> void add_{a.name}_agent(xmachine_memory_{a.name}_list*
     out.append(codegen._constants_code(model, cuda=False))
     out.append(codegen._descriptor_tables(model, "oracle", "orc_thunk_").replace("orc_thunk_filter_", "orc_filter_"))
     out.append(codegen._face2_shim(model, cuda=False))
-    out.append(codegen._model_struct(model))
+    out.append(codegen._id_defs(model, cuda=False))
+    for a in model.agents:      # sort_<A>s_<S> takes a CUDA kernel: declared for the scripts, not executable on the host
+        for st in a.states:
+            out.append(f"void sort_{a.name}s_{st}(void (*)(unsigned int*, unsigned int*, xmachine_memory_{a.name}_list*)){{ "
+                       f'fprintf(stderr, "sort_{a.name}s_{st}: the oracle cannot launch a CUDA kernel\\n"); abort(); }}')
+    out.append(codegen._model_struct(model, cuda=False))
     rows = []
     for m in model.messages:
         S = f"xmachine_message_{m.name}"

@@ -93,6 +93,9 @@ def test_write_set_analysis():
     assert codegen.written_variables(m.function("move"), a, esc) == {"id", "x", "y", "z", "nbr"}
     mac = ["#define PX agent->x\n__FLAME_GPU_FUNC__ int move(xmachine_memory_Particle* agent, RNG_rand48* r){ PX = 1; return 0; }"]
     assert codegen.written_variables(m.function("move"), a, mac) == {"id", "x", "y", "z", "nbr"}
+    # ... and so does a macro standing for the member NAME (`agent->FIELD = ...` is a write of x the text does not show)
+    fld = ["#define FIELD x\n__FLAME_GPU_FUNC__ int move(xmachine_memory_Particle* agent, RNG_rand48* r){ agent->FIELD = 1; return 0; }"]
+    assert codegen.written_variables(m.function("move"), a, fld) == {"id", "x", "y", "z", "nbr"}
     inc = ["__FLAME_GPU_FUNC__ int move(xmachine_memory_Particle* a, RNG_rand48* r){ ++a->nbr; a->x *= 2; if (a->y == 3) return 1; return 0; }"]
     assert codegen.written_variables(m.function("move"), a, inc) == {"nbr", "x"}
 

@@ -16,11 +16,8 @@ from oracle import build_ref, xslt_subset
 pytestmark = pytest.mark.skipif(not os.path.isdir(f"{REFERENCE}/FLAMEGPU/templates"), reason="the reference tree is not mounted")
 
 # per-model name patterns the reference declares (console build: no -DVISUALISATION, no -DPROFILE) and this repository
-# does not provide yet
-NOT_PROVIDED = {
-    r"generate_\w+_id|set_initial_\w+_id": "device-side id generation (an atomic counter synchronised around every layer): DESIGN.md section 8, next round",
-    r"sort_\w+s_\w+": "agent sort by a user key/value kernel (simulation.xslt:750-776): DESIGN.md section 8, next round",
-}
+# does not provide: none since round 2 (generate_<A>_id / set_initial_<A>_id and sort_<A>s_<S> were the last two)
+NOT_PROVIDED = {}
 MODELS = ["CirclesPartitioning_float", "CirclesBruteForce_double", "Boids_Partitioning", "SmoothedParticleHydrodynamics",
           "Keratinocyte", "SocialParticleSimulation", "MonteCarlo_MSMPR", "Analytics", "EmptyExample"]
 QUALIFIERS = ("extern", "__FLAME_GPU_HOST_FUNC__", "__FLAME_GPU_FUNC__", "__host__", "__device__", "FGPU_DEV", "FGPU_HD", "inline",
@@ -83,13 +80,13 @@ def test_every_reference_declaration_is_provided(name):
     ref = declarations(xslt_subset.Stylesheet(f"{REFERENCE}/FLAMEGPU/templates/header.xslt").transform(xml))
     ours = declarations(codegen.emit_cuda_header(xmml.parse_model(xml)))
     assert len(ref) > 40 and "singleIteration" in ref and "initialise" in ref
-    excused = re.compile("|".join(f"(?:{p})" for p in NOT_PROVIDED))
+    excused = re.compile("|".join(f"(?:{p})" for p in NOT_PROVIDED) if NOT_PROVIDED else r"(?!)")
     missing = sorted(k for k in ref if k not in ours and not excused.fullmatch(k))
     assert not missing, f"{name}: declared by the reference's header.h, absent from ours: {missing}"
     different = {k: (ref[k], ours[k]) for k in ref if k in ours and ref[k] != ours[k]}
     assert not different, f"{name}: signatures differ from the reference's: {different}"
     # the exceptions are real: each pattern matches something the reference declares for this model or another one
-    assert any(excused.fullmatch(k) for k in ref)
+    assert not NOT_PROVIDED or any(excused.fullmatch(k) for k in ref)
 
 
 def test_exception_list_is_not_stale():

@@ -70,6 +70,14 @@ def test_model_agnostic_console_mode(tmp_path):
     ref = sim.save_states(str(tmp_path / "ref_"), 7)
     assert open(ref, "rb").read() == (d / "7.xml").read_bytes()
     sim.close()
+    # the reference's instrumentation lines (simulation.xslt:913,973), switched on from the environment
+    out = subprocess.run([exe, plugin, xml, "2", "0", "0"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120,
+                         env=dict(os.environ, FGPU_INSTRUMENT="iterations,agent_functions"))
+    assert out.returncode == 0, out.stdout
+    import re
+    ins = [l for l in out.stdout.splitlines() if l.startswith("Instrumentation: ")]
+    names = [re.match(r"Instrumentation: (.*) = [0-9.]+ \(ms\)$", l).group(1) for l in ins]
+    assert names == ["Particle_output_location", "Particle_count_neighbours", "Particle_move", "Iteration Time"] * 2, out.stdout
     # no XML output, usage and argument errors
     out = subprocess.run([exe, plugin, xml, "2", "0", "0"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
     assert out.returncode == 0 and "Saved to XML" not in out.stdout

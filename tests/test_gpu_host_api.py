@@ -112,3 +112,37 @@ def test_host_agent_creation_from_init_and_step_functions():
     assert np.array_equal(a["x"][-3:], np.float32([15, 16, 17]))
     gpu.close()
     orc.close()
+
+
+def test_generate_id_on_device_and_host_and_sort_agents(tmp_path):
+    """models/IdSort: generate_<A>_id() on the device (atomic counter) and in a step function on the host, the
+    counter initialised from the largest id of the 0.xml (io.xslt:599-616) and synchronised around the step
+    functions (simulation.xslt:918-960); sort_<A>s_<S> with the model's own key/value kernel, stable among equal
+    keys.  Device-side tickets arrive in no particular order, so the checks are on sets and on the sort."""
+    xml = os.path.join(build.MODELS, "IdSort", "src", "model", "XMLModelFile.xml")
+    p = build.model_path("IdSort_exact")
+    if not os.path.exists(p):
+        p = build.build_model(xml, "IdSort_exact", fmad=False)
+    n = 5000
+    st = {"id": np.arange(n, dtype=np.int32), "x": np.arange(n, dtype=np.float32), "ticket": np.zeros(n, dtype=np.int32)}
+    inp = W.write_states_xml(str(tmp_path / "0.xml"), "Item", st)
+    sim = Simulation(p)
+    sim.load_states(inp)
+    sim.step(1)
+    a = sim.agents("Item")
+    assert len(a["id"]) == n + 1
+    # every agent drew one ticket, the first being the largest id read + 1
+    assert np.array_equal(np.sort(a["ticket"][:n]), np.arange(n, 2 * n, dtype=np.int32))
+    # sorted by ticket % 7, and among equal keys in the order the list had before (ids ascending): stable
+    key = a["ticket"][:n] % 7
+    assert (np.diff(key) >= 0).all()
+    for k in range(7):
+        assert (np.diff(a["id"][:n][key == k]) > 0).all()
+    assert np.array_equal(a["x"][:n], a["id"][:n].astype(np.float32))      # whole agents moved, not single columns
+    # the host-created agent took the next value of the same counter
+    assert a["id"][n] == 2 * n and a["ticket"][n] == -1
+    sim.step(1)
+    b = sim.agents("Item")
+    assert len(b["id"]) == n + 2 and b["id"][-1] == 3 * n + 2
+    assert np.array_equal(np.sort(b["ticket"][:n + 1]), np.arange(2 * n + 1, 3 * n + 2, dtype=np.int32))
+    sim.close()
