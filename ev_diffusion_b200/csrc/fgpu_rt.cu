@@ -218,8 +218,10 @@ struct fgpu_sim {
     int opt_radix_bits = 9;
     int opt_slab_async = 1;
     int opt_slab_p2p = 1;
-    int opt_slab_overlap = 1; /* halo exchange on a side stream while the agents of the interior planes are processed */
+    int opt_slab_overlap = 0; /* 1: halo exchange on a side stream while the agents of the interior planes are processed.
+                                 Off: measured no gain at 2 ranks (1.601 vs 1.592 ms; the exchange is 32 us of the step) */
     cudaStream_t stream2 = nullptr;
+    int side_priority = 0;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int opt_slab_inplace = 1; /* migration: 1 = leavers leave holes that arrivals / tail agents fill; 0 = stable three-way re-compaction */
     /* the reference's compile-time -DINSTRUMENT_* switches (simulation.xslt:370-377), as run-time options: each prints

@@ -262,6 +262,7 @@ extern "C" int fgpu_sim_slab_init(fgpu_sim *s, int rank, int world, const void *
         int lo_pri = 0, hi_pri = 0;
         CU(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
         CU(cudaStreamCreateWithPriority(&s->stream2, cudaStreamNonBlocking, hi_pri)); /* the exchange must not queue behind the interior agents */
+        s->side_priority = hi_pri;
         CU(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
     }
@@ -323,15 +324,29 @@ static int slab_exchange_halo(fgpu_sim *s, int mi, cudaStream_t st) {
     const int seq = ++S.msg_seq[mi], par = seq & 1;
     const int *in_lo = X.recv_lo, *in_hi = X.recv_hi;  /* where the neighbours' planes arrive */
     if (Q < 1 || Q > 8) return set_err(FGPU_ERR_MODEL, "record of %d quads unsupported", Q);
+    /* on the side stream the exchange runs beside the interior agents' kernel: its blocks must be dispatched ahead of
+     * that kernel's remaining blocks, so the launches carry the priority explicitly (a captured kernel node keeps the
+     * attribute) */
+    const int gp = std::min(PUSH_BLOCKS * 2, g);
+    cudaLaunchAttribute pri_attr[1];
+    pri_attr[0].id = cudaLaunchAttributePriority;
+    pri_attr[0].val.priority = s->side_priority;
+    cudaLaunchConfig_t cfg_push = {}, cfg_merge = {};
+    cfg_push.gridDim = dim3(gp, 2);
+    cfg_push.blockDim = dim3(256);
+    cfg_push.stream = st;
+    cfg_push.attrs = pri_attr;
+    cfg_push.numAttrs = (st == s->stream2) ? 1 : 0;
+    cfg_merge = cfg_push;
+    cfg_merge.gridDim = dim3(g);
     if (S.p2p) {
         /* pack + push fused: my low plane is the lower neighbour's HIGH halo and vice versa */
         in_lo = (const int *)(S.xbuf + S.msg_off[mi] + (0 + par) * A4);
         in_hi = (const int *)(S.xbuf + S.msg_off[mi] + (2 + par) * A4);
-        const int gp = std::min(PUSH_BLOCKS * 2, g);
         switch (Q) {
 #define PUSHP_CASE(QQ)                                                                                                              \
     case QQ:                                                                                                                        \
-        k_push_planes<QQ><<<dim3(gp, 2), 256, 0, st>>>(local, M.cell_start, S.p0 * PL, (S.p1 - 1) * PL, PL, S.halo_cap,     \
+        cudaLaunchKernelEx(&cfg_push, k_push_planes<QQ>, local, (const unsigned int *)M.cell_start, S.p0 * PL, (S.p1 - 1) * PL, PL, S.halo_cap, \
                                                               (int *)(S.peer_lo + S.msg_off[mi] + (2 + par) * A4),                 \
                                                               (int *)(S.peer_hi + S.msg_off[mi] + (0 + par) * A4), S.d_done + mi,  \
                                                               (int *)(S.peer_lo + 16 * mi) + 1, (int *)(S.peer_hi + 16 * mi) + 0,  \
@@ -371,8 +386,8 @@ static int slab_exchange_halo(fgpu_sim *s, int mi, cudaStream_t st) {
     switch (Q) {
 #define MERGE_CASE(QQ)                                                                                                      \
     case QQ:                                                                                                                \
-        k_merge_halo<QQ><<<g, 256, 0, st>>>(M.sorted, M.cell_start, M.local_at, n, M.d_count, S.p0 * PL, S.ppr * PL, in_lo, \
-                                                   lo_first, in_hi, hi_first, PL, S.d_status);                              \
+        cudaLaunchKernelEx(&cfg_merge, k_merge_halo<QQ>, M.sorted, M.cell_start, M.local_at, n, M.d_count, S.p0 * PL, S.ppr * PL, in_lo, \
+                           lo_first, in_hi, hi_first, PL, S.d_status);                                                       \
         break;
         MERGE_CASE(1) MERGE_CASE(2) MERGE_CASE(3) MERGE_CASE(4) MERGE_CASE(5) MERGE_CASE(6) MERGE_CASE(7) MERGE_CASE(8)
 #undef MERGE_CASE
