@@ -657,6 +657,7 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
     carry = _carry_vars(a)
     out = [f"/* GPUFLAME_{f.name} (krn:1320-1387) */",
            f"__global__ void __launch_bounds__({bs}) fgpu_k_{f.name}(const fgpu_launch L)\n{{",
+           '    asm volatile("griddepcontrol.wait;" ::: "memory");   /* programmatic dependent launch: the previous kernel of the iteration has completed */',
            "    int t = blockIdx.x * blockDim.x + threadIdx.x;"]
     if f.input_message and model.message(f.input_message).partitioning == "spatial":
         out += ["    if (L.win_mode) {   /* slab mode: interior planes first, boundary planes once the halo has arrived */",
@@ -735,7 +736,12 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
     const int threads = a->win_mode ? a->launch_n : a->n;
     if (threads <= 0) return;
     const int grid = (threads + {bs} - 1) / {bs};
-    fgpu_k_{f.name}<<<grid, {bs}, 0, (cudaStream_t)stream>>>(*a);
+    cudaLaunchConfig_t cfg = {{}};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3({bs}); cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = a->pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, fgpu_k_{f.name}, *a);
 }}""")
     return "\n".join(out) + "\n"
 

@@ -24,6 +24,12 @@
 
 namespace fgpu {
 
+/* Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may
+ * be scheduled while its predecessor in the stream is still draining; it must not touch anything the predecessor
+ * wrote before this returns.  The iteration is a chain of 14-25 short dependent kernels, so the launch latency hidden
+ * per link adds up (profiles/r02_notes.md).  A no-op for an ordinary launch. */
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 /* ------------------------------------------------------------------------- */
 /* radix sort                                                                 */
 /* ------------------------------------------------------------------------- */
@@ -50,8 +56,11 @@ constexpr int SORT_MAX_BINS = 1 << SORT_MAXBITS;
 /* digit counts of one tile; tile_hist is bin-major so that k_row_scan reads rows contiguously */
 __global__ void __launch_bounds__(SORT_THREADS)
 k_tile_hist(const unsigned int *__restrict__ keys, int n_host, const int *__restrict__ d_n, int shift, int digit_bits,
-            unsigned int *__restrict__ tile_hist, int tiles, unsigned int key_base, unsigned int key_span, int *range_error) {
+            unsigned int *__restrict__ tile_hist, int tiles, unsigned int key_base, unsigned int key_span, int *range_error,
+            unsigned int *zero2) {
+    pdl_wait();
     extern __shared__ unsigned int sh[]; /* 1 << digit_bits */
+    if (zero2 != nullptr && blockIdx.x == 0 && threadIdx.x == 0) zero2[0] = zero2[1] = 0u; /* gap counters of the build this sort starts */
     const int n = d_n ? *d_n : n_host; /* slab mode: the exact count lives on the device, n_host is an upper bound */
     const int nbins = 1 << digit_bits;
     for (int i = threadIdx.x; i < nbins; i += SORT_THREADS) sh[i] = 0;
@@ -101,6 +110,7 @@ __device__ __forceinline__ unsigned int block_exclusive_scan_256(unsigned int v,
 /* one block per digit: exclusive scan of that digit's counts over the tiles, in place */
 __global__ void __launch_bounds__(SORT_THREADS)
 k_row_scan(unsigned int *__restrict__ tile_hist, int tiles, unsigned int *__restrict__ totals) {
+    pdl_wait();
     __shared__ unsigned int s_scan[SORT_WARPS];
     unsigned int *row = tile_hist + (size_t)blockIdx.x * tiles;
     const int per = (tiles + SORT_THREADS - 1) / SORT_THREADS;
@@ -139,6 +149,7 @@ k_radix_scatter(const unsigned int *__restrict__ keys_in, const unsigned int *__
                 const int *__restrict__ d_n, int shift, int digit_bits, const unsigned int *__restrict__ tile_hist,
                 const unsigned int *__restrict__ totals, int tiles, unsigned int key_base,
                 const uint4 *__restrict__ pay_in, uint4 *__restrict__ pay_out, int pay_quads) {
+    pdl_wait();
     constexpr int BINS = 1 << BITS;
     const int n = d_n ? *d_n : n_host;
     constexpr int BPT = BINS / SORT_THREADS; /* bins per thread: 1, 2, 4 or 8 */
@@ -468,6 +479,7 @@ k_gather_pbm(const unsigned int *__restrict__ skeys, const unsigned int *__restr
              unsigned int *__restrict__ cell_start, unsigned int first_cell, unsigned int cells, unsigned int value_offset,
              unsigned int *gap_queue, unsigned int *gap_count, const uint4 *__restrict__ carry_in, uint4 *__restrict__ carry_out,
              int carry_quads) {
+    pdl_wait();
     /* boundaries are written for the cells [first_cell, cells] only (slab mode: the owned planes) and hold
      * value_offset + sorted index (slab mode: the local block sits behind the low halo in the combined list) */
     const int n = d_n ? *d_n : n_host;
@@ -495,6 +507,7 @@ k_gather_pbm(const unsigned int *__restrict__ skeys, const unsigned int *__restr
 __global__ void __launch_bounds__(256)
 k_fill_gaps(unsigned int *__restrict__ cell_start, const unsigned int *__restrict__ gap_queue,
             const unsigned int *__restrict__ gap_count) {
+    pdl_wait();
     const unsigned int nlong = min(gap_count[1], (unsigned int)GAP_LONG_MAX);
     for (unsigned int e = 0; e < nlong; ++e) {
         const unsigned int lo = gap_queue[3 * e + 0], hi = gap_queue[3 * e + 1], value = gap_queue[3 * e + 2];
@@ -815,6 +828,7 @@ __global__ void __launch_bounds__(256)
 k_push(const char *__restrict__ send_lo, const char *__restrict__ send_hi, char *__restrict__ peer_lo, char *__restrict__ peer_hi,
        const PushLayout L, unsigned int *done_counter, int *peer_flag_lo, int *peer_flag_hi, const int *my_flag_a,
        const int *my_flag_b, int *seq_counter, int *status) {
+    pdl_wait();
     const char *src = blockIdx.y ? send_hi : send_lo;
     char *dst = blockIdx.y ? peer_hi : peer_lo;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
@@ -855,6 +869,7 @@ __global__ void __launch_bounds__(256)
 k_push_planes(const uint4 *__restrict__ sorted_combined, const unsigned int *__restrict__ cell_start, int first_cell_lo, int first_cell_hi,
               int plane_cells, int cap, int *__restrict__ peer_lo, int *__restrict__ peer_hi, unsigned int *done_counter,
               int *peer_flag_lo, int *peer_flag_hi, const int *my_flag_a, const int *my_flag_b, int *seq_counter, int *status) {
+    pdl_wait();
     const int first_cell = blockIdx.y ? first_cell_hi : first_cell_lo;
     int *out = blockIdx.y ? peer_hi : peer_lo;
     const int lo = (int)cell_start[first_cell], hi = (int)cell_start[first_cell + plane_cells];
@@ -877,6 +892,7 @@ __global__ void __launch_bounds__(256)
 k_merge_halo(uint4 *__restrict__ combined, unsigned int *__restrict__ cell_start, int local_at, int n_host,
              const int *__restrict__ d_n, int own_first_cell, int own_cells, const int *__restrict__ lo_buf,
              int lo_first_cell, const int *__restrict__ hi_buf, int hi_first_cell, int plane_cells, int *status) {
+    pdl_wait();
     const int n = d_n ? *d_n : n_host;
     const int stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int lo_cnt = lo_buf[0], hi_cnt = hi_buf[0];
@@ -1063,6 +1079,7 @@ constexpr int MIG_HDR = 4;
 __global__ void __launch_bounds__(256)
 k_mig_count(const float *__restrict__ coord, int n_host, const int *__restrict__ d_n, float minb, float maxb, int nplanes,
             int ppr, int rank, int world, unsigned int *__restrict__ block_sums, int nb, int *status) {
+    pdl_wait();
     __shared__ unsigned int s_cnt[2];
     const int n = d_n ? *d_n : n_host;
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
@@ -1086,104 +1103,100 @@ k_mig_count(const float *__restrict__ coord, int n_host, const int *__restrict__
     if (threadIdx.x < 2) block_sums[threadIdx.x * nb + blockIdx.x] = s_cnt[threadIdx.x];
 }
 
-/* one block: exclusive scan of block_sums[0][.] and block_sums[1][.] in place; totals -> headers */
-__global__ void __launch_bounds__(1024)
-k_mig_scan(unsigned int *__restrict__ block_sums, int nb, int n_host, const int *__restrict__ d_n, int cap, int *__restrict__ mig_hdr,
-           int *__restrict__ hdr_dn, int *__restrict__ hdr_up, int *overflow) {
-    __shared__ unsigned int s_warp[32];
-    __shared__ unsigned int s_carry;
+/* Pack: a block covers the same 1024 agents as in k_mig_count (256 threads x 4 rounds).  Its offsets in the two send
+ * buffers are the sums of the counts of the blocks before it, which every block adds up for itself (a few thousand
+ * values from L2; no scan launch, no chain between blocks); the last block also publishes the totals: the send
+ * headers and {n_old, holes}.  Leavers are written in list order (stable), their slots go to holes[] (ascending). */
+__global__ void __launch_bounds__(256)
+k_mig_pack(const char *__restrict__ list, char *__restrict__ dn, char *__restrict__ up, const ColSet cols, const ColSet bcols,
+           const float *__restrict__ coord, int n_host, const int *__restrict__ d_n, float minb, float maxb, int nplanes, int ppr,
+           int rank, int world, const unsigned int *__restrict__ block_sums, int nb, int cap, unsigned int *__restrict__ holes,
+           int *__restrict__ mig_hdr, int *__restrict__ hdr_dn, int *__restrict__ hdr_up, int *overflow) {
+    pdl_wait();
+    constexpr int ROUNDS = COMPACT_THREADS / 256;
+    __shared__ unsigned int s_off[2];
+    __shared__ unsigned int s_cnt[2][ROUNDS * 8];
+    const int n = d_n ? *d_n : n_host;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned int totals[2];
-    for (int a = 0; a < 2; ++a) {
-        unsigned int *arr = block_sums + (size_t)a * nb;
-        if (threadIdx.x == 0) s_carry = 0;
-        __syncthreads();
-        for (int base = 0; base < nb; base += 1024) {
-            const int i = base + threadIdx.x;
-            const unsigned int v = (i < nb) ? arr[i] : 0u;
-            unsigned int inc = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
-            }
-            if (lane == 31) s_warp[warp] = inc;
-            __syncthreads();
-            if (warp == 0) {
-                unsigned int w = s_warp[lane];
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned int t = __shfl_up_sync(0xffffffffu, w, o);
-                    if (lane >= o) w += t;
-                }
-                s_warp[lane] = w;
-            }
-            __syncthreads();
-            const unsigned int wbase = warp ? s_warp[warp - 1] : 0u;
-            const unsigned int carry = s_carry;
-            if (i < nb) arr[i] = carry + wbase + inc - v;
-            __syncthreads();
-            if (threadIdx.x == 1023) s_carry = carry + wbase + inc;
-            __syncthreads();
+    const unsigned int mine_dn = block_sums[blockIdx.x], mine_up = block_sums[nb + blockIdx.x];
+    const bool last = blockIdx.x == (unsigned int)nb - 1;
+    if (mine_dn + mine_up == 0 && !last) return; /* nothing leaves from these 1024 agents */
+    if (threadIdx.x < 2) s_off[threadIdx.x] = 0;
+    __syncthreads();
+    {
+        unsigned int p0 = 0, p1 = 0;
+        for (int b = threadIdx.x; b < (int)blockIdx.x; b += 256) {
+            p0 += block_sums[b];
+            p1 += block_sums[nb + b];
         }
-        totals[a] = s_carry;
-        __syncthreads();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+        }
+        if (lane == 0) {
+            if (p0) atomicAdd(&s_off[0], p0);
+            if (p1) atomicAdd(&s_off[1], p1);
+        }
     }
-    if (threadIdx.x == 0) {
-        const int dn = (int)totals[0], up = (int)totals[1];
-        if (dn > cap || up > cap) atomicExch(overflow, 1);
-        const int sdn = min(dn, cap), sup = min(up, cap);
-        hdr_dn[0] = sdn; hdr_dn[1] = dn > cap; hdr_dn[2] = 0; hdr_dn[3] = 0;
-        hdr_up[0] = sup; hdr_up[1] = up > cap; hdr_up[2] = 0; hdr_up[3] = 0;
-        mig_hdr[0] = d_n ? *d_n : n_host;
-        mig_hdr[1] = dn + up;     /* on overflow the status flag aborts the run: the hole list is then not used */
+    __syncthreads();
+    const unsigned int off_dn = s_off[0], off_up = s_off[1];
+    if (last && threadIdx.x == 0) {
+        const int tdn = (int)(off_dn + mine_dn), tup = (int)(off_up + mine_up);
+        if (tdn > cap || tup > cap) atomicExch(overflow, 1);
+        hdr_dn[0] = min(tdn, cap); hdr_dn[1] = tdn > cap; hdr_dn[2] = 0; hdr_dn[3] = 0;
+        hdr_up[0] = min(tup, cap); hdr_up[1] = tup > cap; hdr_up[2] = 0; hdr_up[3] = 0;
+        mig_hdr[0] = n;
+        mig_hdr[1] = tdn + tup;   /* on overflow the status flag aborts the run: the hole list is then not used */
         mig_hdr[2] = 0;
         mig_hdr[3] = 0;
     }
-}
-
-__global__ void __launch_bounds__(COMPACT_THREADS)
-k_mig_pack(const char *__restrict__ list, char *__restrict__ dn, char *__restrict__ up, const ColSet cols, const ColSet bcols,
-           const float *__restrict__ coord, int n_host, const int *__restrict__ d_n, float minb, float maxb, int nplanes, int ppr,
-           int rank, int world, const unsigned int *__restrict__ block_offs, int nb, int cap, unsigned int *__restrict__ holes) {
-    __shared__ unsigned int s_warp[2][32];
-    const int n = d_n ? *d_n : n_host;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (mine_dn + mine_up == 0) return;
     const int lo_rank = (rank + world - 1) % world, hi_rank = (rank + 1) % world;
-    const int f = (i < n) ? owner_class(coord[i], minb, __fsub_rn(maxb, minb), (float)nplanes, nplanes, ppr, rank, world, lo_rank, hi_rank) : 0;
-    const unsigned int b2 = __ballot_sync(0xffffffffu, f == 2), b3 = __ballot_sync(0xffffffffu, f == 3);
-    if (__syncthreads_or(f == 2 || f == 3) == 0) return; /* most blocks hold no leaver */
-    if (lane == 0) {
-        s_warp[0][warp] = __popc(b2);
-        s_warp[1][warp] = __popc(b3);
+    const float scale = (float)nplanes, range = __fsub_rn(maxb, minb);
+    int f[ROUNDS];
+    unsigned int b2[ROUNDS], b3[ROUNDS];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const int i = blockIdx.x * COMPACT_THREADS + r * 256 + threadIdx.x;
+        f[r] = (i < n) ? owner_class(coord[i], minb, range, scale, nplanes, ppr, rank, world, lo_rank, hi_rank) : 0;
+        b2[r] = __ballot_sync(0xffffffffu, f[r] == 2);
+        b3[r] = __ballot_sync(0xffffffffu, f[r] == 3);
+        if (lane == 0) {
+            s_cnt[0][r * 8 + warp] = __popc(b2[r]);
+            s_cnt[1][r * 8 + warp] = __popc(b3[r]);
+        }
     }
     __syncthreads();
-    if (warp < 2) {
-        const unsigned int v = s_warp[warp][lane];
+    if (warp < 2) { /* exclusive prefix over (round, warp) = list order inside the block */
+        const unsigned int v = (lane < ROUNDS * 8) ? s_cnt[warp][lane] : 0u;
         unsigned int inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += t;
         }
-        s_warp[warp][lane] = inc - v;
+        if (lane < ROUNDS * 8) s_cnt[warp][lane] = inc - v;
     }
     __syncthreads();
-    if (f != 2 && f != 3) return;
     const unsigned int lt = (1u << lane) - 1u;
-    const unsigned int dn_before = block_offs[blockIdx.x] + s_warp[0][warp] + __popc(b2 & lt);
-    const unsigned int up_before = block_offs[nb + blockIdx.x] + s_warp[1][warp] + __popc(b3 & lt);
-    const unsigned int hole = dn_before + up_before;             /* leavers with a smaller list index */
-    if (hole < 2u * (unsigned int)cap) holes[hole] = (unsigned int)i;
-    const unsigned int out = (f == 2) ? dn_before : up_before;
-    if (out >= (unsigned int)cap) return;                        /* overflow was flagged by k_mig_scan */
-    char *dst = (f == 2) ? dn : up;
-    for (int c = 0; c < cols.ncols; ++c) {
-        if (cols.size[c] == 4)
-            ((unsigned int *)(dst + bcols.off[c]))[out] = ((const unsigned int *)(list + cols.off[c]))[i];
-        else
-            ((unsigned long long *)(dst + bcols.off[c]))[out] = ((const unsigned long long *)(list + cols.off[c]))[i];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        if (f[r] != 2 && f[r] != 3) continue;
+        const int i = blockIdx.x * COMPACT_THREADS + r * 256 + threadIdx.x;
+        const unsigned int dn_before = off_dn + s_cnt[0][r * 8 + warp] + __popc(b2[r] & lt);
+        const unsigned int up_before = off_up + s_cnt[1][r * 8 + warp] + __popc(b3[r] & lt);
+        const unsigned int hole = dn_before + up_before;             /* leavers with a smaller list index */
+        if (hole < 2u * (unsigned int)cap) holes[hole] = (unsigned int)i;
+        const unsigned int out = (f[r] == 2) ? dn_before : up_before;
+        if (out >= (unsigned int)cap) continue;                      /* overflow was flagged above */
+        char *dst = (f[r] == 2) ? dn : up;
+        for (int c = 0; c < cols.ncols; ++c) {
+            if (cols.size[c] == 4)
+                ((unsigned int *)(dst + bcols.off[c]))[out] = ((const unsigned int *)(list + cols.off[c]))[i];
+            else
+                ((unsigned long long *)(dst + bcols.off[c]))[out] = ((const unsigned long long *)(list + cols.off[c]))[i];
+        }
     }
 }
 
@@ -1196,14 +1209,21 @@ __device__ __forceinline__ void copy_agent(const char *src, const ColSet &scols,
     }
 }
 
-/* arrivals (lower neighbour's first): arrival j takes hole j; those beyond the holes go to the end of the list */
-__global__ void __launch_bounds__(256)
+/* After the exchange, one kernel.  Arrivals (lower neighbour's first): arrival j takes hole j, those beyond the holes
+ * go to the end of the list (all blocks, grid-stride).  Holes the arrivals do not fill are filled with the live agents
+ * of the tail, ascending hole <- ascending tail agent, by block 0, which also publishes the new population; the two
+ * jobs touch disjoint slots (the arrivals take the smallest holes, the tail job the largest ones and the tail itself). */
+__global__ void __launch_bounds__(1024)
 k_mig_fill(const char *__restrict__ rlo, const char *__restrict__ rhi, char *__restrict__ list, const ColSet scols, const ColSet dcols,
-           const int *__restrict__ mig_hdr, const unsigned int *__restrict__ holes, int dst_cap, int *status) {
+           const int *__restrict__ mig_hdr, const unsigned int *__restrict__ holes, int *__restrict__ n_new_out, int dst_cap, int *status) {
+    pdl_wait();
+    __shared__ unsigned int s_warp[32];
+    __shared__ unsigned int s_carry;
     const int *hlo = (const int *)rlo, *hhi = (const int *)rhi;
     const int clo = hlo[0], chi = hhi[0], n_old = mig_hdr[0], nh = mig_hdr[1];
+    const int arrivals = clo + chi;
     if (blockIdx.x == 0 && threadIdx.x == 0 && (hlo[1] || hhi[1])) atomicExch(status, 3);
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < clo + chi; j += gridDim.x * blockDim.x) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < arrivals; j += gridDim.x * blockDim.x) {
         const char *src = (j < clo) ? rlo : rhi;
         const int sj = (j < clo) ? j : j - clo;
         const long long dst = (j < nh) ? (long long)holes[j] : (long long)n_old + (j - nh);
@@ -1213,16 +1233,7 @@ k_mig_fill(const char *__restrict__ rlo, const char *__restrict__ rhi, char *__r
         }
         copy_agent(src, scols, (size_t)sj, list, dcols, (size_t)dst);
     }
-}
-
-/* one block: holes the arrivals did not fill are filled with the live agents of the tail (ascending hole <- ascending
- * tail agent), and the new population is published */
-__global__ void __launch_bounds__(1024)
-k_mig_tail(const char *__restrict__ rlo, const char *__restrict__ rhi, char *__restrict__ list, const ColSet cols,
-           const int *__restrict__ mig_hdr, const unsigned int *__restrict__ holes, int *__restrict__ n_new_out, int dst_cap) {
-    __shared__ unsigned int s_warp[32];
-    __shared__ unsigned int s_carry;
-    const int arrivals = ((const int *)rlo)[0] + ((const int *)rhi)[0], n_old = mig_hdr[0], nh = mig_hdr[1];
+    if (blockIdx.x != 0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (arrivals >= nh) {
         if (threadIdx.x == 0) *n_new_out = min(n_old + (arrivals - nh), dst_cap);
@@ -1238,8 +1249,7 @@ k_mig_tail(const char *__restrict__ rlo, const char *__restrict__ rhi, char *__r
         const int pos = n_new + t;                    /* tail slot */
         bool live = false;
         if (t < T) {
-            /* is `pos` a hole?  binary search in the ascending hole list */
-            int lo = arrivals, hi = nh;
+            int lo = arrivals, hi = nh;               /* is `pos` a hole?  binary search in the ascending hole list */
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
                 if (holes[mid] < (unsigned int)pos) lo = mid + 1;
@@ -1264,7 +1274,7 @@ k_mig_tail(const char *__restrict__ rlo, const char *__restrict__ rhi, char *__r
         const unsigned int carry = s_carry;
         if (live) {
             const unsigned int r = carry + s_warp[warp] + __popc(bal & ((1u << lane) - 1u));
-            copy_agent(list, cols, (size_t)pos, list, cols, (size_t)holes[arrivals + r]);
+            copy_agent(list, dcols, (size_t)pos, list, dcols, (size_t)holes[arrivals + r]);
         }
         __syncthreads();
         if (threadIdx.x == 1023) s_carry = carry + s_warp[31] + __popc(bal);

@@ -77,6 +77,23 @@ extern "C" const char *fgpu_get_output_dir(void) { return g_output_dir.c_str(); 
 extern "C" void fgpu_set_exit_early(int flag) { g_exit_early = flag ? 1 : 0; }
 extern "C" int fgpu_get_exit_early(void) { return g_exit_early; }
 
+/* Kernel launch with the programmatic-dependent-launch attribute (see fgpu::pdl_wait): every kernel launched this way
+ * starts with pdl_wait().  Captured into a CUDA graph the attribute becomes a programmatic dependency edge. */
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 /* ------------------------------------------------------------------------- */
 /* runtime objects                                                            */
 /* ------------------------------------------------------------------------- */
@@ -223,6 +240,7 @@ struct fgpu_sim {
     cudaStream_t stream2 = nullptr;
     int side_priority = 0;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int opt_pdl = 1;          /* programmatic dependent launch between the kernels of an iteration */
     int opt_slab_inplace = 1; /* migration: 1 = leavers leave holes that arrivals / tail agents fill; 0 = stable three-way re-compaction */
     /* the reference's compile-time -DINSTRUMENT_* switches (simulation.xslt:370-377), as run-time options: each prints
      * the reference's own "Instrumentation: ... = %f (ms)" lines */
@@ -990,6 +1008,7 @@ static int run_function(fgpu_sim *s, int fi) {
             L.out_base = 0;
         }
     }
+    L.pdl = s->opt_pdl;
     if (F.rng) {
         L.seeds = s->seeds;
         L.Ax = s->Ax;
@@ -1249,6 +1268,7 @@ static std::vector<int> current_counts(fgpu_sim *s) {
     c.push_back(s->opt_radix_bits);
     c.push_back(s->opt_carry);
     c.push_back(s->opt_msd);
+    c.push_back(s->opt_pdl);
     return c;
 }
 
@@ -1492,6 +1512,49 @@ extern "C" int fgpu_debug_sort_pairs(const unsigned int *keys, int n, int key_bi
         CU(cudaMemcpy(keys_out, k[in], sizeof(unsigned int) * (size_t)n, cudaMemcpyDeviceToHost));
         CU(cudaMemcpy(vals_out, v[in], sizeof(unsigned int) * (size_t)n, cudaMemcpyDeviceToHost));
     }
+    cudaFree(kin);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(k[i]);
+        cudaFree(v[i]);
+    }
+    cudaFree(scratch);
+    return rc;
+}
+
+/* device time of the LSD sort of n keys of key_bits (digits of at most max_digit_bits), averaged over reps: a tuning aid */
+extern "C" int fgpu_debug_sort_time(int n, int key_bits, int max_digit_bits, int reps, float *ms_out) {
+    if (n <= 0 || key_bits < 1 || key_bits > 32 || reps < 1 || !ms_out) return set_err(FGPU_ERR_ARG, "bad argument");
+    const int max_bits = std::min(std::max(max_digit_bits, 1), SORT_MAXBITS);
+    unsigned int *kin, *k[2], *v[2], *scratch;
+    CU(cudaMalloc(&kin, sizeof(unsigned int) * (size_t)n));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaMalloc(&k[i], sizeof(unsigned int) * (size_t)n));
+        CU(cudaMalloc(&v[i], sizeof(unsigned int) * (size_t)n));
+    }
+    CU(cudaMalloc(&scratch, sizeof(unsigned int) * ((size_t)SCR_TILEHIST + (size_t)((n + SORT_TILE - 1) / SORT_TILE) * SORT_MAX_BINS)));
+    std::vector<unsigned int> h((size_t)n);
+    unsigned long long x = 0x9E3779B97F4A7C15ull;
+    for (int i = 0; i < n; ++i) {
+        x = x * 6364136223846793005ull + 1442695040888963407ull;
+        h[i] = (unsigned int)(x >> 33) & (key_bits == 32 ? 0xffffffffu : ((1u << key_bits) - 1u));
+    }
+    CU(cudaMemcpy(kin, h.data(), sizeof(unsigned int) * (size_t)n, cudaMemcpyHostToDevice));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    int in = 0, rc = FGPU_OK;
+    long long launches = 0;
+    for (int r = 0; r < reps + 2 && rc == FGPU_OK; ++r) {
+        if (r == 2) CU(cudaEventRecord(a, nullptr));
+        rc = radix_sort_pairs(nullptr, kin, n, key_bits, max_bits, k, v, scratch, &in, &launches);
+    }
+    CU(cudaEventRecord(b, nullptr));
+    CU(cudaEventSynchronize(b));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    *ms_out = ms / reps;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
     cudaFree(kin);
     for (int i = 0; i < 2; ++i) {
         cudaFree(k[i]);

@@ -60,7 +60,7 @@ template <int BITS>
 static cudaError_t launch_scatter(int tiles, cudaStream_t st, const unsigned int *kin, const unsigned int *vin, unsigned int *kout,
                                   unsigned int *vout, int n, const int *d_n, int shift, int digit_bits, const unsigned int *tile_hist,
                                   const unsigned int *totals, unsigned int key_base, const uint4 *pay_in = nullptr, uint4 *pay_out = nullptr,
-                                  int pay_quads = 0) {
+                                  int pay_quads = 0, bool pdl = false) {
     /* the opt-in above 48 KB is per device: one flag per device of the process */
     static bool configured[64] = {};
     const size_t smem = sizeof(SortSmem<BITS>);
@@ -71,9 +71,8 @@ static cudaError_t launch_scatter(int tiles, cudaStream_t st, const unsigned int
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    k_radix_scatter<BITS><<<tiles, SORT_THREADS, smem, st>>>(kin, vin, kout, vout, n, d_n, shift, digit_bits, tile_hist, totals, tiles, key_base,
-                                                             pay_in, pay_out, pay_quads);
-    return cudaGetLastError();
+    return launch_k(pdl, k_radix_scatter<BITS>, dim3(tiles), dim3(SORT_THREADS), smem, st, kin, vin, kout, vout, n, d_n, shift, digit_bits, tile_hist,
+                    totals, tiles, key_base, pay_in, pay_out, pay_quads);
 }
 
 template <int BITS>
@@ -128,7 +127,7 @@ static int build_spatial_msd(fgpu_sim *s, MsgRT &M, int n, int key_bits, unsigne
     cudaStream_t st = s->stream;
     s->prof_begin(std::string("sort:") + M.d->name);
     k_tile_hist<<<tiles, SORT_THREADS, sizeof(unsigned int) * (size_t)nbins, st>>>(M.keys_in, n, M.d_count, L, H, tile_hist, tiles, key_base, key_span,
-                                                                                   range_error);
+                                                                                   range_error, nullptr);
     LAUNCH_CHECK();
     k_row_scan<<<nbins, SORT_THREADS, 0, st>>>(tile_hist, tiles, totals);
     LAUNCH_CHECK();
@@ -169,7 +168,7 @@ static int build_spatial_msd(fgpu_sim *s, MsgRT &M, int n, int key_bits, unsigne
 static int radix_sort_pairs(cudaStream_t st, const unsigned int *keys_in, int n, int key_bits, int max_bits,
                             unsigned int *keys[2], unsigned int *vals[2], unsigned int *scratch, int *sorted_in,
                             long long *launches, const int *d_n = nullptr, unsigned int key_base = 0, unsigned int key_span = 0,
-                            int *range_error = nullptr) {
+                            int *range_error = nullptr, bool pdl = false, unsigned int *zero2 = nullptr) {
     int passes = 1;
     const int digit_bits = choose_digit_bits(key_bits, max_bits, &passes);
     if (passes > SORT_MAX_PASSES) return set_err(FGPU_ERR_MODEL, "%d key bits need %d radix passes", key_bits, passes);
@@ -180,14 +179,14 @@ static int radix_sort_pairs(cudaStream_t st, const unsigned int *keys_in, int n,
         const unsigned int *kin = p == 0 ? keys_in : keys[(p - 1) & 1];
         const unsigned int *vin = p == 0 ? nullptr : vals[(p - 1) & 1];
         const int shift = p * digit_bits;
-        k_tile_hist<<<tiles, SORT_THREADS, sizeof(unsigned int) * (size_t)nbins, st>>>(kin, n, d_n, shift, digit_bits, tile_hist, tiles, key_base,
-                                                                                       key_span, p == 0 ? range_error : nullptr);
-        k_row_scan<<<nbins, SORT_THREADS, 0, st>>>(tile_hist, tiles, totals);
-        cudaError_t e;
-        if (digit_bits <= 8) e = launch_scatter<8>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals, key_base);
-        else if (digit_bits == 9) e = launch_scatter<9>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals, key_base);
-        else if (digit_bits == 10) e = launch_scatter<10>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals, key_base);
-        else e = launch_scatter<11>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals, key_base);
+        cudaError_t e = launch_k(pdl, k_tile_hist, dim3(tiles), dim3(SORT_THREADS), sizeof(unsigned int) * (size_t)nbins, st, kin, n, d_n, shift, digit_bits,
+                                 tile_hist, tiles, key_base, key_span, p == 0 ? range_error : (int *)nullptr, p == 0 ? zero2 : (unsigned int *)nullptr);
+        if (e == cudaSuccess) e = launch_k(pdl, k_row_scan, dim3(nbins), dim3(SORT_THREADS), 0, st, tile_hist, tiles, totals);
+        if (e != cudaSuccess) return set_err(FGPU_ERR_CUDA, "radix pass launch -> %s", cudaGetErrorString(e));
+        if (digit_bits <= 8) e = launch_scatter<8>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals, key_base, nullptr, nullptr, 0, pdl);
+        else if (digit_bits == 9) e = launch_scatter<9>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals, key_base, nullptr, nullptr, 0, pdl);
+        else if (digit_bits == 10) e = launch_scatter<10>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals, key_base, nullptr, nullptr, 0, pdl);
+        else e = launch_scatter<11>(tiles, st, kin, vin, keys[p & 1], vals[p & 1], n, d_n, shift, digit_bits, tile_hist, totals, key_base, nullptr, nullptr, 0, pdl);
         if (e != cudaSuccess) return set_err(FGPU_ERR_CUDA, "radix pass launch -> %s", cudaGetErrorString(e));
         (*launches) += 3;
     }
@@ -226,11 +225,11 @@ static int build_spatial(fgpu_sim *s, MsgRT &M) {
         }
     }
     s->prof_begin(std::string("sort:") + M.d->name);
-    CU(cudaMemsetAsync(gap_count, 0, 2 * sizeof(unsigned int), s->stream));
     if (sizeof(unsigned int) * sort_scratch_words(n, key_bits, max_bits) > M.scratch_bytes)
         return set_err(FGPU_ERR_MODEL, "message %s: sort scratch too small for %d keys of %d bits", M.d->name, n, key_bits);
+    const bool pdl = s->opt_pdl != 0;
     int rc = radix_sort_pairs(s->stream, M.keys_in, n, key_bits, max_bits, M.keys, M.vals, M.scratch, &in, &s->launches, M.d_count, key_base,
-                              key_span, range_error);
+                              key_span, range_error, pdl, gap_count /* zeroed by the first kernel of the sort */);
     if (rc) return rc;
     s->prof_end();
     M.sorted_in = in;
@@ -241,10 +240,9 @@ static int build_spatial(fgpu_sim *s, MsgRT &M) {
     switch (M.d->rec_quads) {
 #define GATHER_CASE(Q)                                                                                                   \
     case Q:                                                                                                              \
-        k_gather_pbm<Q><<<g, 256, 0, s->stream>>>(M.keys[in], M.vals[in], M.unsorted, M.sorted + (size_t)M.local_at * Q, n, M.d_count, M.cell_start, \
-                                                  key_base, key_base + (key_span ? key_span : (unsigned int)M.d->grid_size),        \
-                                                  (unsigned int)M.local_at, M.gap_queue, gap_count,                            \
-                                                  carry ? M.carry_unsorted : nullptr, M.carry_sorted, carry ? M.carry_quads : 0); \
+        launch_k(pdl, k_gather_pbm<Q>, dim3(g), dim3(256), 0, s->stream, M.keys[in], M.vals[in], M.unsorted, M.sorted + (size_t)M.local_at * Q, n, \
+                 M.d_count, M.cell_start, key_base, key_base + (key_span ? key_span : (unsigned int)M.d->grid_size), (unsigned int)M.local_at,    \
+                 M.gap_queue, gap_count, carry ? M.carry_unsorted : (uint4 *)nullptr, M.carry_sorted, carry ? M.carry_quads : 0);               \
         break;
         GATHER_CASE(1)
         GATHER_CASE(2)
@@ -259,7 +257,7 @@ static int build_spatial(fgpu_sim *s, MsgRT &M) {
             return set_err(FGPU_ERR_MODEL, "message %s: record of %d quads is not supported", M.d->name, M.d->rec_quads);
     }
     LAUNCH_CHECK();
-    k_fill_gaps<<<148 * 2, 256, 0, s->stream>>>(M.cell_start, M.gap_queue, gap_count);
+    launch_k(pdl, k_fill_gaps, dim3(148 * 2), dim3(256), 0, s->stream, M.cell_start, M.gap_queue, gap_count);
     LAUNCH_CHECK();
     s->prof_end();
     return FGPU_OK;

@@ -328,15 +328,24 @@ static int slab_exchange_halo(fgpu_sim *s, int mi, cudaStream_t st) {
      * that kernel's remaining blocks, so the launches carry the priority explicitly (a captured kernel node keeps the
      * attribute) */
     const int gp = std::min(PUSH_BLOCKS * 2, g);
-    cudaLaunchAttribute pri_attr[1];
-    pri_attr[0].id = cudaLaunchAttributePriority;
-    pri_attr[0].val.priority = s->side_priority;
+    cudaLaunchAttribute pri_attr[2];
+    int nattr = 0;
+    if (s->opt_pdl) {
+        pri_attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pri_attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+        ++nattr;
+    }
+    if (st == s->stream2) {
+        pri_attr[nattr].id = cudaLaunchAttributePriority;
+        pri_attr[nattr].val.priority = s->side_priority;
+        ++nattr;
+    }
     cudaLaunchConfig_t cfg_push = {}, cfg_merge = {};
     cfg_push.gridDim = dim3(gp, 2);
     cfg_push.blockDim = dim3(256);
     cfg_push.stream = st;
     cfg_push.attrs = pri_attr;
-    cfg_push.numAttrs = (st == s->stream2) ? 1 : 0;
+    cfg_push.numAttrs = nattr;
     cfg_merge = cfg_push;
     cfg_merge.gridDim = dim3(g);
     if (S.p2p) {
@@ -495,15 +504,15 @@ static int slab_migrate(fgpu_sim *s) {
             int *mhdr = X.mig_hdr + MIG_HDR * st;
             if (inplace) {
                 s->prof_begin("mig:flags");
-                k_mig_count<<<nb, 256, 0, s->stream>>>(coord, n, d_n, S.axis_min, S.axis_max, S.nplanes, S.ppr, S.rank, S.world, A.block_sums, nb,
-                                                       S.d_status);
-                LAUNCH_CHECK();
-                k_mig_scan<<<1, 1024, 0, s->stream>>>(A.block_sums, nb, n, d_n, S.mig_cap, mhdr, (int *)X.send_dn, (int *)X.send_up, S.d_status + 1);
+                const bool pdl = s->opt_pdl != 0;
+                launch_k(pdl, k_mig_count, dim3(nb), dim3(256), 0, s->stream, coord, n, d_n, S.axis_min, S.axis_max, S.nplanes, S.ppr, S.rank, S.world,
+                         A.block_sums, nb, S.d_status);
                 LAUNCH_CHECK();
                 s->prof_end();
                 s->prof_begin("mig:scatter");
-                k_mig_pack<<<nb, COMPACT_THREADS, 0, s->stream>>>(list, X.send_dn, X.send_up, A.cols, X.bufcols, coord, n, d_n, S.axis_min, S.axis_max,
-                                                                  S.nplanes, S.ppr, S.rank, S.world, A.block_sums, nb, S.mig_cap, holes);
+                launch_k(pdl, k_mig_pack, dim3(nb), dim3(256), 0, s->stream, (const char *)list, X.send_dn, X.send_up, A.cols, X.bufcols, coord, n, d_n,
+                         S.axis_min, S.axis_max, S.nplanes, S.ppr, S.rank, S.world, (const unsigned int *)A.block_sums, nb, S.mig_cap, holes, mhdr,
+                         (int *)X.send_dn, (int *)X.send_up, S.d_status + 1);
                 LAUNCH_CHECK();
                 s->prof_end();
             } else {
@@ -530,7 +539,7 @@ static int slab_migrate(fgpu_sim *s) {
                 in_lo = S.xbuf + S.agent_off[a] + (0 + par) * A4;
                 in_hi = S.xbuf + S.agent_off[a] + (2 + par) * A4;
                 /* I am the lower neighbour's upper neighbour: my "down" migrants land in its recv_hi */
-                k_push<<<dim3(PUSH_BLOCKS, 2), 256, 0, s->stream>>>(X.send_dn, X.send_up, S.peer_lo + S.agent_off[a] + (2 + par) * A4,
+                launch_k(s->opt_pdl != 0, k_push, dim3(PUSH_BLOCKS, 2), dim3(256), 0, s->stream, (const char *)X.send_dn, (const char *)X.send_up, S.peer_lo + S.agent_off[a] + (2 + par) * A4,
                                                                     S.peer_hi + S.agent_off[a] + (0 + par) * A4, PLY, S.d_done + 32 + a,
                                                                     (int *)(S.peer_lo + 2048 + 16 * a) + 1,
                                                                     (int *)(S.peer_hi + 2048 + 16 * a) + 0,
@@ -550,10 +559,8 @@ static int slab_migrate(fgpu_sim *s) {
             s->prof_end();
             s->prof_begin("mig:append");
             if (inplace) {
-                k_mig_fill<<<std::min(148, (2 * S.mig_cap + 255) / 256), 256, 0, s->stream>>>(in_lo, in_hi, list, X.bufcols, A.cols, mhdr, holes, A.d->buffer_size,
-                                                                               S.d_status + 2);
-                LAUNCH_CHECK();
-                k_mig_tail<<<1, 1024, 0, s->stream>>>(in_lo, in_hi, list, A.cols, mhdr, holes, A.d_state_count + st, A.d->buffer_size);
+                launch_k(s->opt_pdl != 0, k_mig_fill, dim3(std::min(37, (2 * S.mig_cap + 1023) / 1024)), dim3(1024), 0, s->stream, in_lo, in_hi, list, X.bufcols,
+                         A.cols, (const int *)mhdr, (const unsigned int *)holes, A.d_state_count + st, A.d->buffer_size, S.d_status + 2);
                 LAUNCH_CHECK();
             } else {
                 k_append_both<<<(2 * S.mig_cap + 255) / 256, 256, 0, s->stream>>>(in_lo, in_hi, A.swap, X.bufcols, A.cols, cnt,

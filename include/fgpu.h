@@ -190,6 +190,8 @@ int fgpu_sim_profile_iterations(fgpu_sim *sim, int iters, const char **names, fl
  * digits of at most `max_digit_bits` bits; host in, host out. */
 int fgpu_debug_sort_pairs(const unsigned int *keys, int n, int key_bits, int max_digit_bits,
                           unsigned int *keys_out, unsigned int *vals_out);
+/* device milliseconds of one such sort of n pseudo-random keys (average of reps): a tuning aid */
+int fgpu_debug_sort_time(int n, int key_bits, int max_digit_bits, int reps, float *ms_out);
 /* Stable compaction of payload[i] where flags[i] == 1 (scatter_<A>_Agents, kernals.xslt:239-257). */
 int fgpu_debug_compact(const int *flags, const unsigned int *payload, int n, unsigned int *out, int *count_out);
 

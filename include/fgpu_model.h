@@ -105,6 +105,8 @@ typedef struct fgpu_launch {
     int win_mode;
     unsigned int win_cell_lo, win_cell_hi, win_base;
     int launch_n;                 /* win_mode != 0: number of threads to launch (a host-side upper bound) */
+    int pdl;                      /* launch with the programmatic-stream-serialization attribute (the wrapper kernel starts
+                                     with griddepcontrol.wait, so it is safe either way) */
 } fgpu_launch;
 
 typedef void (*fgpu_launch_fn)(const fgpu_launch *args, void *cuda_stream);
