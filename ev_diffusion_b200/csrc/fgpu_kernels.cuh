@@ -521,6 +521,12 @@ k_fill_gaps(unsigned int *__restrict__ cell_start, const unsigned int *__restric
     }
 }
 
+/* A column filled with one value (an agent variable the caller did not supply: its XMML defaultValue or 0) */
+template <typename T>
+__global__ void __launch_bounds__(256) k_fill_column(T *__restrict__ dst, T value, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = value;
+}
+
 /* Unpack one 32-bit word column of the sorted records to a dense array
  * (host read-back path only). */
 __global__ void k_unpack_words(const unsigned int *__restrict__ recs, int rec_words, int n, int word, unsigned int *__restrict__ out) {

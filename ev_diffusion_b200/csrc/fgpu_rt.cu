@@ -634,20 +634,34 @@ static int upload_columns(fgpu_sim *s, int agent, int state, int offset, int cou
         if (columns && columns[v]) {
             CU(cudaMemcpyAsync(dst, columns[v], (size_t)count * V.size, cudaMemcpyHostToDevice, s->stream));
         } else {
-            /* defaultValue or 0 (io.xslt:276-291) */
-            std::vector<char> tmp((size_t)count * V.size);
-            for (int i = 0; i < count; ++i) {
+            /* defaultValue or 0 (io.xslt:276-291), written on the device: no host buffer, no copy over PCIe */
+            if (count > 0) {
+                const int g = std::min(148 * 8, (count + 255) / 256);
                 if (V.size == 8) {
-                    if (V.is_float) ((double *)tmp.data())[i] = V.default_value;
-                    else ((long long *)tmp.data())[i] = (long long)V.default_value;
+                    unsigned long long bits;
+                    if (V.is_float) {
+                        const double d = V.default_value;
+                        memcpy(&bits, &d, 8);
+                    } else {
+                        const long long l = (long long)V.default_value;
+                        memcpy(&bits, &l, 8);
+                    }
+                    k_fill_column<unsigned long long><<<g, 256, 0, s->stream>>>((unsigned long long *)dst, bits, count);
                 } else {
-                    if (V.is_float) ((float *)tmp.data())[i] = (float)V.default_value;
-                    else if (!strcmp(V.ctype, "unsigned int")) ((unsigned int *)tmp.data())[i] = (unsigned int)V.default_value;
-                    else ((int *)tmp.data())[i] = (int)V.default_value;
+                    unsigned int bits;
+                    if (V.is_float) {
+                        const float f = (float)V.default_value;
+                        memcpy(&bits, &f, 4);
+                    } else if (!strcmp(V.ctype, "unsigned int")) {
+                        bits = (unsigned int)V.default_value;
+                    } else {
+                        const int i = (int)V.default_value;
+                        memcpy(&bits, &i, 4);
+                    }
+                    k_fill_column<unsigned int><<<g, 256, 0, s->stream>>>((unsigned int *)dst, bits, count);
                 }
+                CU(cudaGetLastError());
             }
-            CU(cudaMemcpyAsync(dst, tmp.data(), tmp.size(), cudaMemcpyHostToDevice, s->stream));
-            CU(cudaStreamSynchronize(s->stream));
         }
     }
     const bool same_count = (A.h_state_count[state] == offset + count);

@@ -85,8 +85,8 @@ int fgpu_sim_load_snapshot(fgpu_sim *sim, const char *path);
 int fgpu_sim_set_agents(fgpu_sim *sim, int agent, int state, int count, const void *const *columns);
 
 /* The same upload without the final synchronisation: the copies are enqueued on the simulation stream and the call
- * returns (every column must be given, from pinned host memory that stays untouched until fgpu_sim_sync, for the
- * copies to be asynchronous).  With fgpu_sim_step_async and fgpu_sim_read_agents_async, two simulations can be
+ * returns (columns should come from pinned host memory that stays untouched until fgpu_sim_sync, for the copies to
+ * be asynchronous; a NULL column is filled with its default value by a kernel, no traffic over PCIe).  With fgpu_sim_step_async and fgpu_sim_read_agents_async, two simulations can be
  * driven in alternation so that one's upload and read-back overlap the other's iteration (both PCIe directions and
  * the SMs busy at once); the reference's initialise / singleIteration / get_host_* sequence is strictly serial. */
 int fgpu_sim_set_agents_async(fgpu_sim *sim, int agent, int state, int count, const void *const *columns);
