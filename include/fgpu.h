@@ -173,9 +173,14 @@ long long fgpu_sim_launch_count(const fgpu_sim *sim);
 /* Device milliseconds of the last fgpu_sim_step call (cudaEvent pair on the
  * simulation stream, like main.xslt:405-436). */
 float fgpu_sim_last_step_ms(const fgpu_sim *sim);
-/* Tuning knobs: "order" (0/1 cell-coherent processing of message consumers),
- * "graph" (0/1 CUDA-graph replay), "radix_bits" (4..11), "nvtx" (0/1: every stage of an iteration
- * is an NVTX range on the enqueueing thread, like PROFILE_SCOPED_RANGE of the reference), "slab_p2p", "slab_async". */
+/* Options (int values).  Behaviour: "instrument_iterations", "instrument_agent_functions", "instrument_init_functions",
+ * "instrument_step_functions", "instrument_exit_functions" (0/1: the reference's -DINSTRUMENT_* output lines,
+ * simulation.xslt:370-377,714,796,913,945,973), "nvtx" (0/1: every stage of an iteration is an NVTX range on the
+ * enqueueing thread, like PROFILE_SCOPED_RANGE), "xml_float_digits" (0 = the reference's "%f"; n = "%.<n>g").
+ * Tuning, never changing a result: "order" (0/1 cell-coherent processing of message consumers), "graph" (0/1 CUDA-graph
+ * replay), "pdl" (0/1 programmatic dependent launch), "radix_bits" (4..11), "msd" (0/1 MSD message build), "carry" (0/1
+ * carried agent records), "l2_fetch" (32/64/128).  Slab mode, before fgpu_sim_slab_init: "slab_p2p", "slab_async";
+ * any time: "slab_inplace" (0 = stable re-compaction at migration: another list order), "slab_overlap". */
 int fgpu_sim_set_option(fgpu_sim *sim, const char *key, int value);
 /* Per-kernel-class device time of the most recent profiled iteration.
  * Writes up to `cap` (name,ms) pairs; returns the number written. */
@@ -204,9 +209,15 @@ int fgpu_debug_compact(const int *flags, const unsigned int *payload, int n, uns
  * the wrap pair 0 <-> world-1, because message_<M>_hash sends out-of-range
  * neighbour cells to the opposite face, kernals.xslt:880-885); after every
  * function that moves agents, agents whose plane left the slab migrate to the
- * owning neighbour.  Transport: NCCL send/recv over NVLink on the simulation
- * stream, fixed-capacity buffers (halo_cap messages / mig_cap agents per
- * direction; 0 = automatic), true counts in a device-side header.
+ * owning neighbour (in place: leavers leave holes that arrivals and tail agents
+ * fill).  Transport, default: PEER MEMORY -- the receive buffers are exchanged as
+ * CUDA IPC handles at init and the push kernels (k_push_planes, k_push) store
+ * straight into the neighbours' buffers over NVLink, publishing a sequence number
+ * with st.release.sys and waiting (bounded) for the neighbours'; NCCL is then used
+ * once, to exchange the handles.  Fallback (IPC unavailable, or option
+ * "slab_p2p" = 0): NCCL grouped send/recv of the fixed-capacity buffers on the
+ * simulation stream.  Buffers hold halo_cap messages / mig_cap agents per
+ * direction (0 = automatic), true counts in a device-side header.
  * `nccl_unique_id` is the 128-byte ncclUniqueId made by rank 0
  * (fgpu_nccl_unique_id) and broadcast by the host program. */
 int fgpu_nccl_unique_id(void *out128);
