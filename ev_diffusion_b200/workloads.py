@@ -224,6 +224,10 @@ MODEL_WORKLOADS = {
                            _SPH_XML, {"<gpu:bufferSize>131072</gpu:bufferSize>": "<gpu:bufferSize>2097152</gpu:bufferSize>",
                                       "<gpu:radius>0.02</gpu:radius>": "<gpu:radius>0.0078125</gpu:radius>"},
                            "FluidParticle", "default", 1 << 21, 556.0, 10),
+    # ... and 1 000 000 particles at the SHIPPED radius 0.02 (50^3 cells, 8 particles per cell): the parity case at scale
+    "c4_1m": ModelWorkload("c4_1m", "SPH_1M", "SmoothedParticleHydrodynamics, 1 000 000 particles, shipped radius 0.02 (50^3 cells)",
+                           _SPH_XML, {"<gpu:bufferSize>131072</gpu:bufferSize>": "<gpu:bufferSize>1048576</gpu:bufferSize>"},
+                           "FluidParticle", "default", 1000000, 556.0, 10),
     # C5': BirthDeath (authored): death compaction + births + rand48 on the spatial path, 524 288 -> <= 2 097 152 agents
     "c5p": ModelWorkload("c5p", "BirthDeath", "C5' BirthDeath (authored), 524 288 agents growing in a 2 097 152 buffer, 32^3 cells, "
                          "death compaction + births + rand48", _BD_XML, {}, "Cell", "default", 1 << 19, 170.0, 200),
@@ -237,6 +241,8 @@ def model_state(w: ModelWorkload) -> Dict[str, np.ndarray]:
         return _sph_state(256)
     if w.key == "c4_2m":
         return _sph_state(128)
+    if w.key == "c4_1m":
+        return _sph_state(100)
     if w.key == "c5p":
         return _birthdeath_state(w.n)
     raise KeyError(w.key)

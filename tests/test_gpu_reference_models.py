@@ -131,11 +131,17 @@ def test_every_function_against_live_oracle(name):
     orc.close()
 
 
-def test_keratinocyte_integer_state_and_order():
-    """C5: 598 cells, 200 iterations.  sinf/cosf/powf differ between CUDA's libdevice
-    and glibc, so float state is compared with a tolerance; what must be identical
-    is the integer state: per-state counts after births, the id ORDER of every list
-    (newborns before parents), cell types, and the rand48 seeds."""
+def test_keratinocyte_integer_state_order_and_floats():
+    """C5: 598 cells, 200 iterations.  sinf/cosf/powf differ between CUDA's libdevice and glibc, so float state is
+    compared with a stated tolerance; what must be identical is the integer state: per-state counts after births, the
+    id ORDER of every list (newborns before parents), cell types, and the rand48 seeds.
+
+    Floats: while the id order agrees, every float variable of every list must agree with the oracle within
+    |a - b| <= 1e-3 + 1e-3 |b| (positions are O(100), forces O(1); a libm difference of 1 ulp per call and a few
+    hundred calls per cell per iteration stay orders of magnitude below that), checked EVERY iteration; and a run
+    whose id order never diverged must land on the committed fixture of iteration 200 within the same tolerance.
+    A stochastic branch (`rnd() < f(float state)`) may flip on a last-bit difference; that shows as an id-order
+    divergence, is reported with its iteration, and must not happen before iteration 50."""
     name = "Keratinocyte"
     so = gen_oracle.oracle_path(name)
     if not os.path.exists(so):
@@ -144,7 +150,7 @@ def test_keratinocyte_integer_state_and_order():
     orc = OracleSimulation(so)
     _start(sim, name)
     _start(orc, name)
-    diverged = None
+    diverged, worst = None, 0.0
     for it in range(200):
         sim.step(1)
         orc.step(1)
@@ -152,14 +158,39 @@ def test_keratinocyte_integer_state_and_order():
             for s in a.states:
                 n = orc.agent_count(a.name, s)
                 assert sim.agent_count(a.name, s) == n, (it, s)
-                ids_g = sim.agent_var(a.name, s, "id", n)
-                ids_o = orc.agent_var(a.name, s, "id", n)
-                if not np.array_equal(ids_g, ids_o) and diverged is None:
-                    diverged = it
+                if n == 0:
+                    continue
+                g, o = sim.agents(a.name, s), orc.agents(a.name, s)
+                if not np.array_equal(g["id"], o["id"]):
+                    diverged = it if diverged is None else diverged
+                    continue
+                for v in a.vars:
+                    if v.dtype.kind in "iu":
+                        assert np.array_equal(g[v.name], o[v.name]), (it, s, v.name)
+                    else:
+                        err = np.abs(g[v.name].astype(np.float64) - o[v.name]) / (1.0 + np.abs(o[v.name].astype(np.float64)))
+                        worst = max(worst, float(err.max()))
+                        assert err.max() <= 1e-3, (it, s, v.name, float(err.max()))
         if diverged is not None:
             break
-    # float round-off (libm) may flip a stochastic branch eventually; require a long identical prefix
     assert diverged is None or diverged >= 50, f"id order diverged at iteration {diverged}"
+    if diverged is None:
+        assert np.array_equal(sim.seeds(), orc.seeds())
+        want = np.load(os.path.join(GOLDEN, "Keratinocyte_iter200.npz"))
+        for a in sim.model.agents:
+            for s in a.states:
+                n = int(want[f"count/{a.name}/{s}"])
+                assert sim.agent_count(a.name, s) == n
+                if n == 0:
+                    continue
+                g = sim.agents(a.name, s)
+                for v in a.vars:
+                    w = want[f"agent/{a.name}/{s}/{v.name}"]
+                    if v.dtype.kind in "iu":
+                        assert np.array_equal(g[v.name], w), (s, v.name)
+                    else:
+                        assert (np.abs(g[v.name].astype(np.float64) - w) <= 1e-3 + 1e-3 * np.abs(w)).all(), (s, v.name)
+    print(f"Keratinocyte: id order diverged at {diverged}, worst float error {worst:.3g} (|a-b| / (1+|b|))")
     sim.close()
     orc.close()
 
