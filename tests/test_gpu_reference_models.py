@@ -137,8 +137,8 @@ def test_keratinocyte_integer_state_order_and_floats():
     id ORDER of every list (newborns before parents), cell types, and the rand48 seeds.
 
     Floats: while the id order agrees, every float variable of every list must agree with the oracle within
-    |a - b| <= 1e-3 + 1e-3 |b| (positions are O(100), forces O(1); a libm difference of 1 ulp per call and a few
-    hundred calls per cell per iteration stay orders of magnitude below that), checked EVERY iteration; and a run
+    |a - b| <= 1e-5 (1 + |b|) (measured on B200: 4.2e-8 over the 200 iterations, with the id order never diverging),
+    checked EVERY iteration; and a run
     whose id order never diverged must land on the committed fixture of iteration 200 within the same tolerance.
     A stochastic branch (`rnd() < f(float state)`) may flip on a last-bit difference; that shows as an id-order
     divergence, is reported with its iteration, and must not happen before iteration 50."""
@@ -170,7 +170,7 @@ def test_keratinocyte_integer_state_order_and_floats():
                     else:
                         err = np.abs(g[v.name].astype(np.float64) - o[v.name]) / (1.0 + np.abs(o[v.name].astype(np.float64)))
                         worst = max(worst, float(err.max()))
-                        assert err.max() <= 1e-3, (it, s, v.name, float(err.max()))
+                        assert err.max() <= 1e-5, (it, s, v.name, float(err.max()))
         if diverged is not None:
             break
     assert diverged is None or diverged >= 50, f"id order diverged at iteration {diverged}"
@@ -189,7 +189,7 @@ def test_keratinocyte_integer_state_order_and_floats():
                     if v.dtype.kind in "iu":
                         assert np.array_equal(g[v.name], w), (s, v.name)
                     else:
-                        assert (np.abs(g[v.name].astype(np.float64) - w) <= 1e-3 + 1e-3 * np.abs(w)).all(), (s, v.name)
+                        assert (np.abs(g[v.name].astype(np.float64) - w) <= 1e-5 * (1.0 + np.abs(w))).all(), (s, v.name)
     print(f"Keratinocyte: id order diverged at {diverged}, worst float error {worst:.3g} (|a-b| / (1+|b|))")
     sim.close()
     orc.close()
