@@ -105,3 +105,51 @@ def unpack_fixed(buf: np.ndarray) -> np.ndarray:
     if buf[0, 1] != 0:
         raise OverflowError("exchange buffer overflow on the sending rank")
     return buf[1:1 + n]
+
+
+# ---- numpy reference of the in-place migration (csrc/fgpu_kernels.cuh: k_mig_count / k_mig_pack / k_mig_fill) ---------
+def leaver_class(coord: np.ndarray, plan: SlabPlan) -> np.ndarray:
+    """1 = stays, 2 = goes to the lower neighbour, 3 = to the upper neighbour, 4 = further than one slab away."""
+    owner = owner_of(coord, plan)
+    plane = plane_of(coord, plan)
+    cls = np.full(len(owner), 4, dtype=np.int32)
+    cls[owner == plan.rank] = 1
+    if plan.lo_rank == plan.hi_rank:                       # two slabs: the same peer on both sides
+        other = owner == plan.lo_rank
+        cls[other & (plane < plan.p0)] = 2
+        cls[other & (plane >= plan.p0)] = 3
+        cls[owner == plan.rank] = 1
+    else:
+        cls[owner == plan.lo_rank] = 2
+        cls[owner == plan.hi_rank] = 3
+    return cls
+
+
+def migrate_in_place(cols: Dict[str, np.ndarray], cls: np.ndarray, from_lower: Dict[str, np.ndarray],
+                     from_upper: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+    """The list after a migration, exactly as the device path leaves it: the leavers' slots are holes (ascending);
+    arrival j -- the lower neighbour's migrants first, each group in its sender's list order -- takes hole j; arrivals
+    beyond the holes are appended; holes beyond the arrivals are filled, ascending, with the live agents of the tail
+    that is cut off, ascending."""
+    names = list(cols.keys())
+    n_old = len(cols[names[0]])
+    holes = np.flatnonzero((cls == 2) | (cls == 3))
+    arrivals = {k: np.concatenate([from_lower[k], from_upper[k]]) for k in names}
+    na, nh = len(arrivals[names[0]]), len(holes)
+    n_new = n_old + na - nh
+    out = {k: np.concatenate([cols[k], np.zeros(max(0, na - nh), dtype=cols[k].dtype)]) for k in names}
+    m = min(na, nh)
+    for k in names:
+        out[k][holes[:m]] = arrivals[k][:m]
+    if na >= nh:
+        for k in names:
+            out[k][n_old:n_old + (na - nh)] = arrivals[k][nh:]
+    else:
+        rest = holes[na:]                                   # the largest holes
+        tail = np.arange(n_new, n_old)
+        live = tail[~np.isin(tail, rest)]
+        targets = rest[rest < n_new]
+        assert len(live) == len(targets)
+        for k in names:
+            out[k][targets] = cols[k][live]
+    return {k: out[k][:n_new].copy() for k in names}

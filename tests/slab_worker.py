@@ -98,6 +98,41 @@ def main():
             pl = slabs.make_plan(m.dims, m.min_bounds, m.max_bounds, m.is_2d, r, world)
             assert (slabs.owner_of(after["z"][owner == r], pl) == r).all(), f"it {it}: misplaced agent on rank {r}"
     moved = int((after["z"] != state["z"][ids_a]).sum())
+    # List order after a migration, rank by rank, against the numpy statement of the in-place scheme
+    # (slabs.migrate_in_place): function-by-function stepping so that the lists can be read between `move` and the
+    # migration, which runs at the head of the next output function.
+    order_bad = 0
+    if "slab_inplace=0" not in os.environ.get("SLAB_OPTIONS", ""):
+        names = ("id", "x", "y", "z", "nbr")
+        sim.begin_iteration()
+        for f in ("output_location", "count_neighbours", "move"):
+            sim.run_function(f)
+        for it in range(4):
+            pre, own_pre = gather_cols(sim, names, device)
+            sim.begin_iteration()
+            sim.run_function("output_location")               # migrates first
+            post, own_post = gather_cols(sim, names, device)
+            lists, leave = [], []
+            for r in range(world):
+                pl = slabs.make_plan(m.dims, m.min_bounds, m.max_bounds, m.is_2d, r, world)
+                cols = {k: pre[k][own_pre == r] for k in names}
+                cls = slabs.leaver_class(cols["z"].astype(np.float32), pl)
+                lists.append((pl, cols, cls))
+            for r, (pl, cols, cls) in enumerate(lists):
+                lo_cols, lo_cls = lists[pl.lo_rank][1], lists[pl.lo_rank][2]
+                hi_cols, hi_cls = lists[pl.hi_rank][1], lists[pl.hi_rank][2]
+                from_lower = {k: lo_cols[k][lo_cls == 3] for k in names}      # the lower neighbour's "up" migrants
+                from_upper = {k: hi_cols[k][hi_cls == 2] for k in names}      # the upper neighbour's "down" migrants
+                want = slabs.migrate_in_place(cols, cls, from_lower, from_upper)
+                got = {k: post[k][own_post == r] for k in names}
+                for k in ("id", "x", "y", "z"):
+                    if len(want[k]) != len(got[k]) or not np.array_equal(want[k], got[k]):
+                        order_bad += 1
+            sim.run_function("count_neighbours")
+            sim.run_function("move")
+        if rank == 0:
+            print(f"SLAB_ORDER mismatching lists={order_bad}")
+    assert order_bad == 0, f"{order_bad} per-rank lists differ from slabs.migrate_in_place"
     # a few more iterations in one call (replayed graphs in the default mode), then a digest of the global state in
     # rank order: every transport / scheduling mode must produce the same bits
     sim.step(7)

@@ -90,6 +90,73 @@ def test_halo_exchange_over_gloo(world):
     assert all(results[r][2] > 0 for r in range(world))
 
 
+def _mig_worker(rank, world, port, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        plan = slabs.make_plan(DIMS, (0, 0, 0), DIMS, False, rank, world)
+        st = slabs.partition_state(_global_state(), plan)
+        rng = np.random.default_rng(100 + rank)
+        for it in range(6):
+            # a random step along z, shorter than a slab; the hash wraps out-of-range planes to the opposite face
+            st["z"] = (st["z"] + rng.uniform(-1.5, 1.5, len(st["z"])).astype(np.float32)).astype(np.float32)
+            cls = slabs.leaver_class(st["z"], plan)
+            assert (cls != 4).all()
+            names = list(st.keys())
+            def pack(sel):
+                rows = np.stack([st[k][sel].astype(np.float64) for k in names], 1)
+                buf = np.zeros((CAP + 1, len(names)))
+                buf[0, 0] = len(rows)
+                buf[1:1 + len(rows)] = rows
+                return torch.from_numpy(buf)
+            down, up = pack(cls == 2), pack(cls == 3)
+            r_lo, r_hi = torch.zeros_like(down), torch.zeros_like(down)
+            # my "down" migrants arrive in the lower neighbour's from-upper buffer, my "up" ones in the upper's from-lower
+            ops = [dist.isend(down, plan.lo_rank, tag=0), dist.isend(up, plan.hi_rank, tag=1),
+                   dist.irecv(r_hi, plan.hi_rank, tag=0), dist.irecv(r_lo, plan.lo_rank, tag=1)]
+            for op in ops:
+                op.wait()
+            def unpack(buf):
+                n = int(buf[0, 0])
+                return {k: buf[1:1 + n, i].numpy().astype(st[k].dtype) for i, k in enumerate(names)}
+            before = len(st["id"])
+            st = slabs.migrate_in_place(st, cls, unpack(r_lo), unpack(r_hi))
+            assert (slabs.owner_of(st["z"], plan) == rank).all(), f"rank {rank} it {it}: a foreign agent stayed"
+            results[(rank, it)] = (sorted(st["id"].tolist()), before)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_in_place_migration_over_gloo(world):
+    """The hole-filling migration (slabs.migrate_in_place, the numpy statement of k_mig_pack / k_mig_fill): over six
+    random moves every agent ends on its owner, ids are conserved globally, and no slot is lost or duplicated."""
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_mig_worker, args=(world, 29653 + world, results), nprocs=world, join=True)
+    for it in range(6):
+        ids = sum((results[(r, it)][0] for r in range(world)), [])
+        assert sorted(ids) == list(range(N)), f"iteration {it}: id multiset not conserved"
+
+
+def test_in_place_migration_cases():
+    """arrivals > holes (append), arrivals < holes (tail agents fill the remaining holes, holes inside the tail are
+    dropped), no arrivals at all, and a leaver in the last slot."""
+    ids = np.arange(10, dtype=np.int32)
+    cols = {"id": ids.copy()}
+    cls = np.ones(10, dtype=np.int32)
+    cls[[2, 5, 9]] = [2, 3, 2]
+    A = lambda *v: {"id": np.array(v, dtype=np.int32)}  # noqa: E731
+    assert slabs.migrate_in_place(cols, cls, A(100, 101), A(200, 201))["id"].tolist() == [0, 1, 100, 3, 4, 101, 6, 7, 8, 200, 201]
+    # one arrival for three holes: hole 2 <- 100; holes 5 and 9 remain, the list shrinks to 8: slot 9 is a hole in the
+    # tail (dropped), slot 8 is live and moves into hole 5
+    assert slabs.migrate_in_place(cols, cls, A(100), A())["id"].tolist() == [0, 1, 100, 3, 4, 8, 6, 7]
+    # no arrival: the list shrinks to 7; tail slots 7, 8 are live (9 is a hole) and fill holes 2, 5 in ascending order
+    assert slabs.migrate_in_place(cols, cls, A(), A())["id"].tolist() == [0, 1, 7, 3, 4, 8, 6]
+    none = np.ones(10, dtype=np.int32)
+    assert slabs.migrate_in_place(cols, none, A(), A(7))["id"].tolist() == list(range(10)) + [7]
+
+
 def test_plan_and_ownership_rules():
     plan = slabs.make_plan((64, 64, 512), (0, 0, 0), (64, 64, 512), False, 3, 8)
     assert (plan.p0, plan.p1, plan.lo_rank, plan.hi_rank, plan.plane_cells) == (192, 256, 2, 4, 4096)
