@@ -399,12 +399,102 @@ def _all_states(sim):
     return out
 
 
+def run_model_workload_slabs(args, w, st, base, rank, world, local):
+    """The same model and population cut into `world` z-slabs (strong scaling), one process per GPU: BASELINE config C4 is
+    SPH "with slab domain decomposition at 2/4/8 B200".  Models with function conditions run the synchronous slab mode
+    (populations read back after every compaction, like the reference's own scans)."""
+    import torch
+    import torch.distributed as dist
+    from ev_diffusion_b200 import check, slabs
+    from ev_diffusion_b200.runtime import Simulation, nccl_unique_id
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=device)
+    sim = Simulation(B.model_path(w.name), device=local)
+    for kv in args.option:
+        k, v = kv.split("=")
+        sim.set_option(k, int(v))
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(uid, 0)
+    sim.slab_init(rank, world, uid.cpu().numpy().tobytes())
+    m = next(x for x in sim.model.messages if x.partitioning == 1)
+    plan = slabs.make_plan(m.dims, m.min_bounds, m.max_bounds, m.is_2d, rank, world)
+    sim.set_agents(w.agent, w.state, slabs.partition_state(st, plan))
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+        sim.sync()
+
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        t = torch.tensor([x], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        return int(t.item())
+
+    sim.step(args.warmup)
+    barrier()
+    n0 = allsum(_population(sim))
+    launches0 = sim.launch_count
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_each = sim.step_timed(args.steps, FLUSH_BYTES)
+    barrier()
+    clocks = sampler.stop()
+    total_ms = allmax(float(ms_each.sum()))
+    n1 = allsum(_population(sim))
+    value = 0.5 * (n0 + n1) * args.steps / (total_ms * 1e-3)
+    reps = min(args.steps, 5)
+    sim.profile_iterations(reps)
+    stage = dict(sim.profile_iterations(reps))
+    peak, peak_src = peaks()
+    ach = w.b_alg * value / world / 1e9
+    # correctness of the final state: ids conserved over the ranks, every particle on the rank that owns its plane
+    ids, zs = [], []
+    for a in sim.model.agents:
+        for si in range(len(a.states)):
+            if sim.agent_count(a.name, si) > 0:
+                cols = sim.agents(a.name, si)
+                ids.append(cols["id"])
+                zs.append(cols["z" if plan.axis == 2 else "y"])
+    ids = np.concatenate(ids) if ids else np.zeros(0, np.int32)
+    zs = np.concatenate(zs) if zs else np.zeros(0, np.float32)
+    mine_ok = bool((slabs.owner_of(zs, plan) == rank).all())
+    seen = torch.zeros(w.n, dtype=torch.int32, device="cuda")
+    seen[torch.from_numpy(ids.astype(np.int64)).cuda()] += 1
+    dist.all_reduce(seen)
+    ids_ok = bool((seen == 1).all().item())
+    own = torch.tensor([1 if mine_ok else 0], device="cuda")
+    dist.all_reduce(own, op=dist.ReduceOp.MIN)
+    parity = {"ids_conserved": ids_ok, "agents_on_owner": bool(own.item() == 1)}
+    line = dict(base, value=value, n_gpus=world, scaling="strong", steps=args.steps, warmup=args.warmup, ms_per_step=total_ms / args.steps,
+                clocks=clocks, gpu_launches=int(sim.launch_count - launches0),
+                roofline={"bound": "hbm", "kernel": "whole iteration", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                          "traffic": None, "peak_source": peak_src, "alg_bytes_per_agent_step": w.b_alg,
+                          "stage_ms": {k: round(v, 5) for k, v in stage.items()}},
+                parity_checked=bool(ids_ok and own.item() == 1), parity=parity, population={"start": n0, "end": n1},
+                e2e=None)
+    line["config"] = dict(line["config"], parallelism=f"{world} z-slabs of {m.dims[plan.axis] // world} cell planes (strong scaling), "
+                          + ("peer-memory transport" if sim.slab_info().get("p2p") else "NCCL send/recv"),
+                          l2="flushed between timed iterations (256 MiB scratch rewrite, untimed)")
+    if rank == 0:
+        print(json.dumps(line))
+    sim.close()
+    dist.destroy_process_group()
+
+
 def run_model_workload(args):
     from oracle import gen_oracle
     from oracle.oracle import OracleSimulation
     w = W.MODEL_WORKLOADS[args.workload]
     rank, world, local = dist_env()
-    if rank != 0:
+    if rank != 0 and (args.impl == "reference" or world == 1):
         return
     cores = os.cpu_count() or 1
     st = W.model_state(w)
@@ -439,6 +529,9 @@ def run_model_workload(args):
     plugin = B.model_path(w.name)
     if not os.path.exists(plugin):
         raise SystemExit(f"{plugin} missing: run `python -c 'import __graft_entry__ as g; g.build()'` first (needs /root/reference)")
+    if world > 1:
+        run_model_workload_slabs(args, w, st, base, rank, world, local)
+        return
     sim = Simulation(plugin, device=local)
     for kv in args.option:
         k, v = kv.split("=")

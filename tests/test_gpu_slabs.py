@@ -60,3 +60,17 @@ def test_more_slabs_distinct_neighbours(world):
     assert transport == "transport=p2p"
     d, _ = _run_worker("graph=0", 29650 + world, world)
     assert d == digest
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs (run under `gpurun --gpus 2`)")
+def test_sph_two_slabs_match_single_gpu():
+    """BASELINE config C4's model in slab mode (two spatial messages, function conditions, migration after a
+    conditional function): every particle, keyed by id, agrees with a single-GPU run within 1e-4 of each variable's
+    maximum (the model has no random numbers; only the order of float sums inside a cell differs)."""
+    from common import build
+    if not os.path.exists(build.model_path("SmoothedParticleHydrodynamics_exact")):
+        pytest.skip("SmoothedParticleHydrodynamics_exact is not prebuilt (needs the reference tree at build time)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29671", os.path.join(ROOT, "tests", "slab_worker_sph.py")]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert proc.returncode == 0 and "SPH_SLAB_OK" in proc.stdout, proc.stdout[-4000:]
