@@ -410,7 +410,7 @@ static int sim_alloc(fgpu_sim *s) {
         }
         const int nb = (A.d->buffer_size + COMPACT_THREADS - 1) / COMPACT_THREADS;
         CU(cudaMalloc(&A.block_sums, sizeof(unsigned int) * 3 * (size_t)(nb + 1)));
-        CU(cudaMalloc(&A.d_total, sizeof(int)));
+        CU(cudaMalloc(&A.d_total, sizeof(int) * 2)); /* [1]: second count of a function with both death and birth */
         CU(cudaMalloc(&A.d_state_count, sizeof(int) * (size_t)A.d->nstates));
         CU(cudaMemsetAsync(A.d_state_count, 0, sizeof(int) * (size_t)A.d->nstates, s->stream));
     }
@@ -1102,14 +1102,18 @@ static int run_function(fgpu_sim *s, int fi) {
     }
 
     const int pre_death_count = A.h_count;
+    /* A function with death AND birth into its own agent type pays one count read-back, not two: the survivors'
+     * scan + scatter and the newborns' scan are enqueued first, both totals come back with one synchronisation
+     * (the reference blocks on two D2H copies per scan, e.g. sim:1476-1477). */
+    const bool both = F.reallocate && F.xagent_output >= 0 && F.xagent_output == F.agent;
     if (F.reallocate) {
         /* sim:1763-1792 */
         s->prof_begin(std::string("death:") + F.name);
         int alive = 0;
-        int rc = compact(s, A, A.work, A.swap, 0, A.h_count, (const int *)(A.work + A.d->scan_offset), true, &alive);
+        int rc = compact(s, A, A.work, A.swap, 0, A.h_count, (const int *)(A.work + A.d->scan_offset), true, both ? nullptr : &alive);
         if (rc) return rc;
         std::swap(A.work, A.swap);
-        A.h_count = alive;
+        if (!both) A.h_count = alive;
         s->prof_end();
     }
     if (F.xagent_output >= 0) {
@@ -1118,8 +1122,19 @@ static int run_function(fgpu_sim *s, int fi) {
         const int st = F.xagent_output_state;
         s->prof_begin(std::string("birth:") + F.name);
         int born = 0;
-        int rc = compact(s, B, nullptr, nullptr, 0, pre_death_count, (const int *)(B.newl + B.d->scan_offset), false, &born);
-        if (rc) return rc;
+        if (both) {
+            int rc = compact(s, B, nullptr, nullptr, 0, pre_death_count, (const int *)(B.newl + B.d->scan_offset), false, nullptr, 1, nullptr,
+                             0x7fffffff, nullptr, nullptr, A.d_total + 1);
+            if (rc) return rc;
+            int two[2] = {0, 0};
+            CU(cudaMemcpyAsync(two, A.d_total, sizeof(two), cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaStreamSynchronize(s->stream));
+            A.h_count = two[0];
+            born = two[1];
+        } else {
+            int rc = compact(s, B, nullptr, nullptr, 0, pre_death_count, (const int *)(B.newl + B.d->scan_offset), false, &born);
+            if (rc) return rc;
+        }
         if (B.h_state_count[st] + born > B.d->buffer_size)
             return set_err(FGPU_ERR_OVERFLOW, "Error: Buffer size of %s agents in state %s will be exceeded writing new agents in function %s",
                            B.d->name, B.d->states[st], F.name);

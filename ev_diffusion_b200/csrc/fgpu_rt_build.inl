@@ -17,19 +17,22 @@
  * the two 4-byte D2H copies after every cub scan, e.g. simulation.xslt:1476). */
 static int compact(fgpu_sim *s, AgentRT &A, const char *src, char *dst, int dst_offset, int n, const int *flags,
                    bool scatter, int *count_out, int match = 1, const ColSet *dcols = nullptr, int dst_cap = 0x7fffffff,
-                   int *overflow = nullptr, const int *d_n = nullptr) {
+                   int *overflow = nullptr, const int *d_n = nullptr, int *d_total = nullptr) {
+    /* d_total: where the survivor count goes on the device (default A.d_total); a caller that passes its own slot and
+     * no count_out reads several counts back with one synchronisation */
+    int *total = d_total ? d_total : A.d_total;
     if (n <= 0) {
         if (count_out) *count_out = 0;
-        CU(cudaMemsetAsync(A.d_total, 0, sizeof(int), s->stream));
+        CU(cudaMemsetAsync(total, 0, sizeof(int), s->stream));
         return FGPU_OK;
     }
     const int nb = (n + COMPACT_THREADS - 1) / COMPACT_THREADS;
     k_flag_blocksum<<<nb, COMPACT_THREADS, 0, s->stream>>>(flags, n, d_n, A.block_sums, match);
     LAUNCH_CHECK();
-    k_scan_blocksums<<<1, 1024, 0, s->stream>>>(A.block_sums, nb, A.d_total);
+    k_scan_blocksums<<<1, 1024, 0, s->stream>>>(A.block_sums, nb, total);
     LAUNCH_CHECK();
     if (count_out) {
-        CU(cudaMemcpyAsync(count_out, A.d_total, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(count_out, total, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
     }
     if (scatter) {
