@@ -653,7 +653,7 @@ def _cuda_carry_struct(a: Agent) -> str:
 def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
     a = model.agent(f.agent)
     A = a.name
-    bs = 128 if f.input_message else 256
+    bs = int(os.environ.get("FGPU_CONSUMER_BLOCK", "128")) if f.input_message else 256   # tuning hook for A/B builds
     carry = _carry_vars(a)
     out = [f"/* GPUFLAME_{f.name} (krn:1320-1387) */",
            f"__global__ void __launch_bounds__({bs}) fgpu_k_{f.name}(const fgpu_launch L)\n{{",

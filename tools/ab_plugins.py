@@ -1,15 +1,19 @@
 """A/B helper: steady-state stage times of several builds of the C2 Brownian plugin on one GPU.
 
 usage: python tools/ab_plugins.py Brownian Brownian_generic:sm_local=0 ...   (plugin[:option=value]...)
+       AB_WORKLOAD=c2_16m python tools/ab_plugins.py Brownian_16M Brownian_16M_pf
 """
+import os
 import sys
 
 import numpy as np
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ev_diffusion_b200 import build as B, workloads as W
 from ev_diffusion_b200.runtime import Simulation
 
-cfg = W.BROWNIAN["c2"]
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+cfg = W.BROWNIAN[os.environ.get("AB_WORKLOAD", "c2")]
 state = W.brownian_state(cfg)
 ref = None
 for spec in sys.argv[1:]:
@@ -22,7 +26,7 @@ for spec in sys.argv[1:]:
     sim.step(5)
     sim.profile_iterations(5)
     st = sim.profile_iterations(20)
-    ms = sim.step_timed(50, 256 << 20)
+    ms = sim.step_timed(30, 256 << 20)
     nbr = sim.agent_var("Particle", "default", "nbr")
     x = sim.agent_var("Particle", "default", "x")
     if ref is None:
