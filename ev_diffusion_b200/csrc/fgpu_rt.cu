@@ -920,15 +920,32 @@ static int run_function(fgpu_sim *s, int fi) {
         s->prof_begin(std::string("cond:") + F.name);
         F.filter(&fa, s->stream);
         LAUNCH_CHECK();
-        int kept = 0, working = 0;
-        int rc = compact(s, A, A.state[cur], A.swap, 0, A.h_count, (const int *)(A.state[cur] + A.d->scan_offset), true, &kept);
+        /* The filter flags every agent in exactly one of the two lists, so ONE count (and one read-back) gives both
+         * populations; and when every agent passes -- or none -- both compactions are the identity: the filter wrote
+         * the passing agents at their own indices, in order (the reference scans and scatters both lists regardless,
+         * sim:1459-1528). */
+        const int n_all = A.h_count;
+        int working = 0;
+        int rc = compact(s, A, nullptr, nullptr, 0, n_all, (const int *)(A.work + A.d->scan_offset), false, &working);
         if (rc) return rc;
+        const int kept = n_all - working;
+        if (working == n_all) {
+            s->touch(A.work);
+        } else if (working > 0) {
+            const int nb = (n_all + COMPACT_THREADS - 1) / COMPACT_THREADS;
+            k_compact_scatter<<<nb, COMPACT_THREADS, 0, s->stream>>>(A.work, A.swap, A.cols, A.cols, (const int *)(A.work + A.d->scan_offset),
+                                                                     A.block_sums, 0, n_all, nullptr, 1, 0x7fffffff, nullptr);
+            LAUNCH_CHECK();
+            std::swap(A.work, A.swap);
+            s->touch(A.work);
+        }
+        if (kept > 0 && kept < n_all) {
+            rc = compact(s, A, A.state[cur], A.swap, 0, n_all, (const int *)(A.state[cur] + A.d->scan_offset), true, nullptr);
+            if (rc) return rc;
+            std::swap(A.state[cur], A.swap);
+        }
         A.h_state_count[cur] = kept;
-        std::swap(A.state[cur], A.swap);
-        rc = compact(s, A, A.work, A.swap, 0, A.h_count, (const int *)(A.work + A.d->scan_offset), true, &working);
-        if (rc) return rc;
         A.h_count = working;
-        std::swap(A.work, A.swap);
         s->prof_end();
         if (A.h_count == 0) return FGPU_OK;
     } else if (F.condition == FGPU_COND_GLOBAL) {
@@ -1173,6 +1190,11 @@ static int run_function(fgpu_sim *s, int fi) {
                        F.name, A.d->states[nxt], F.name);
     if (F.swappable) {
         std::swap(A.work, A.state[cur]);
+    } else if (A.h_count > 0 && A.h_state_count[nxt] == 0) {
+        /* appending to an empty list is a pointer swap (same agents, same order) */
+        std::swap(A.work, A.state[nxt]);
+        s->touch(A.state[nxt]);
+        s->touch(A.work);
     } else if (A.h_count > 0) {
         s->prof_begin(std::string("append:") + F.name);
         k_append<<<(A.h_count + 255) / 256, 256, 0, s->stream>>>(A.work, A.state[nxt], A.cols, A.h_state_count[nxt], A.h_count);
