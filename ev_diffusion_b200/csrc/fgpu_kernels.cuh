@@ -1153,7 +1153,7 @@ k_mig_pack(const char *__restrict__ list, char *__restrict__ dn, char *__restric
         hdr_dn[0] = min(tdn, cap); hdr_dn[1] = tdn > cap; hdr_dn[2] = 0; hdr_dn[3] = 0;
         hdr_up[0] = min(tup, cap); hdr_up[1] = tup > cap; hdr_up[2] = 0; hdr_up[3] = 0;
         mig_hdr[0] = n;
-        mig_hdr[1] = tdn + tup;   /* on overflow the status flag aborts the run: the hole list is then not used */
+        mig_hdr[1] = min(tdn + tup, 2 * cap);   /* never beyond the hole list; on overflow the status flag aborts the run */
         mig_hdr[2] = 0;
         mig_hdr[3] = 0;
     }
