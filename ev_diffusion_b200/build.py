@@ -93,9 +93,37 @@ def build_runtime(force: bool = False, verbose: bool = False) -> str:
     return out
 
 
+IF_CONVERT_DEFAULT = int(os.environ.get("FGPU_IF_CONVERT", "16"))
+_if_convert_ok: Optional[bool] = None
+
+
+def if_convert_flags(threshold: int) -> List[str]:
+    """nvcc flags that raise NVVM's if-conversion budget (SimplifyCFG's two-entry-phi folding threshold, default 4
+    instructions) to `threshold`.  A message-loop body of the usual shape -- `if (msg->id != agent->id) { a dozen float
+    operations; if (d2 < r2) count++; }` -- is otherwise compiled as a branch per message: BSSY/BSYNC + BRA and a
+    three-instruction conditional increment at the reconvergence point, 35 SASS instructions per pair of messages on
+    C2 against 27 when the body is predicated (lanes of a warp almost never skip the body together, so the branch
+    saves nothing).  Arithmetic and results are unchanged (same operations, same order).  The option goes to cicc's
+    optimiser (`--Xopt`); a toolchain that rejects it builds without (probe below), so it is tuning, never a dependency."""
+    global _if_convert_ok
+    if threshold <= 0:
+        return []
+    flags = ["-Xcicc", "--Xopt", "-Xcicc", "-two-entry-phi-node-folding-threshold=%d" % threshold]
+    if _if_convert_ok is None:
+        import tempfile
+        with tempfile.TemporaryDirectory() as td:
+            src = os.path.join(td, "probe.cu")
+            with open(src, "w") as fh:
+                fh.write("__global__ void k(int* p){ if (p[0]) p[1] += 1; }\n")
+            proc = subprocess.run([NVCC] + ARCH_FLAGS + flags + ["-ptx", src, "-o", os.path.join(td, "probe.ptx")],
+                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            _if_convert_ok = proc.returncode == 0
+    return flags if _if_convert_ok else []
+
+
 def build_model(xml_path: str, name: str, fmad: bool = True, force: bool = False, verbose: bool = False,
                 function_files: Optional[List[str]] = None, extra_flags: Optional[List[str]] = None,
-                rewrite_loops: bool = True, loop_unroll: Optional[int] = 2) -> str:
+                rewrite_loops: bool = True, loop_unroll: Optional[int] = 2, if_convert: Optional[int] = None) -> str:
     """Generate and compile the plugin of one model.
 
     ``fmad=False`` builds the exact-arithmetic variant (no FMA contraction) whose
@@ -107,6 +135,7 @@ def build_model(xml_path: str, name: str, fmad: bool = True, force: bool = False
     best on C2 (count_neighbours 162 us; 1: 185, 3: 175, compiler's choice 4: 170,
     8: 181 -- a row holds ~12 messages and the lanes of a warp sit in ~8 cells
     with different row lengths, so short unrolled bodies waste fewer lanes).
+    ``if_convert`` is the if-conversion budget of `if_convert_flags` (None: IF_CONVERT_DEFAULT, 0: the compiler's own).
     """
     build_runtime()   # the plugin's Face-2 shim links against libfgpu_rt.so
     model = xmml.parse_model(xml_path)
@@ -126,7 +155,9 @@ def build_model(xml_path: str, name: str, fmad: bool = True, force: bool = False
     files = codegen.emit_cuda(model, function_files, gen, rewrite_loops=rewrite_loops, loop_unroll=loop_unroll)
     os.makedirs(os.path.join(LIB, "models"), exist_ok=True)
     out = model_path(name)
-    cmd = [NVCC] + ARCH_FLAGS + COMMON + list(extra_flags or []) + ["-Xptxas", "-v", "-fmad=" + ("true" if fmad else "false"),
+    cmd = [NVCC] + ARCH_FLAGS + COMMON + list(extra_flags or []) + \
+          if_convert_flags(IF_CONVERT_DEFAULT if if_convert is None else if_convert) + \
+          ["-Xptxas", "-v", "-fmad=" + ("true" if fmad else "false"),
                                           "-I", gen, "-I", INCLUDE, "-I", CSRC, "-I", mdir,
                                           files["model_glue.cu"], "-o", out,
                                           "-L", LIB, "-lfgpu_rt", "-Xlinker", "-rpath=$ORIGIN/.."]
