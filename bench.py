@@ -752,11 +752,21 @@ def main():
                  "frac": rec["warp_instructions"] / (dom_ms * 1e-3) / slots,
                  "ncu": {k: rec[k] for k in ("issue_active_frac", "active_lanes_per_instruction", "l1_sector_hit_rate",
                                              "l2_sector_hit_rate", "source", "commit") if k in rec}}
+    l1_pipe = None
+    if rec and "l1_wavefronts_per_sm" in rec and dom_ms > 0:
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        # every LDG.128 of a message record delivers 32 lanes x 16 bytes to the register file = 4 wavefronts of the
+        # SM's 128-byte/clock L1 data pipe, whatever the hit rate: the second bound of the neighbourhood walk
+        l1_pipe = {"bound": "L1 data pipe (1 wavefront of 128 bytes / clock / SM)", "wavefronts_per_sm": rec["l1_wavefronts_per_sm"],
+                   "achieved": rec["l1_wavefronts_per_sm"] / (dom_ms * 1e-3) / 1e9, "peak": sm_hz / 1e9, "unit": "G wavefronts/s/SM",
+                   "frac": rec["l1_wavefronts_per_sm"] / (dom_ms * 1e-3) / sm_hz,
+                   "ncu": {k: rec[k] for k in ("l1_data_pipe_frac", "lsu_writeback_frac", "global_load_requests", "source", "commit") if k in rec}}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_agent": B_ALG[dom], "kernel_ms": dom_ms, "agents_per_launch": n_kernel,
                 # the bound that actually limits this kernel (user script over ~115 messages per agent): issue slots
                 "issue": issue,
+                "l1_data_pipe": l1_pipe,
                 "stage_ms": {k: round(v, 5) for k, v in stage.items()},
                 "iteration": {"alg_bytes_per_agent_step": B_ALG_ITERATION,
                               "achieved_per_gpu": B_ALG_ITERATION * n_global / world * args.steps / (total_ms * 1e-3) / 1e9,

@@ -13,7 +13,11 @@ KEYS = {"dram__bytes_read.sum": "dram_read_bytes", "dram__bytes_write.sum": "dra
         "smsp__inst_executed.sum": "warp_instructions", "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_frac",
         "smsp__thread_inst_executed_per_inst_executed.ratio": "active_lanes_per_instruction",
         "l1tex__t_sector_hit_rate.pct": "l1_sector_hit_rate", "lts__t_sector_hit_rate.pct": "l2_sector_hit_rate",
-        "launch__registers_per_thread": "registers", "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_frac"}
+        "launch__registers_per_thread": "registers", "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_frac",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed": "l1_data_pipe_frac",
+        "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed": "lsu_writeback_frac",
+        "SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts.avg": "l1_wavefronts_per_sm",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum": "global_load_requests"}
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6, "%": 0.01}
 
 
@@ -34,6 +38,7 @@ def main():
     out["_comment"] = ("per-launch figures from `ncu --set full --clock-control none` reports (tools/ncu_traffic.py); bench.py copies "
                        "them into roofline.traffic / roofline.issue -- they are not measured inside bench.py")
     wl = out.setdefault(a.workload, {})
+    seen = set()
     for r in rows[2:]:
         name = r[kn].split("(")[0].replace("void ", "").replace("fgpu::", "")
         stage = "func:" + name[len("fgpu_k_"):] if name.startswith("fgpu_k_") else name.split("<")[0]
@@ -48,7 +53,9 @@ def main():
         for k in ("dram_read_bytes", "dram_write_bytes", "warp_instructions", "registers"):
             if k in rec:
                 rec[k] = int(round(rec[k]))
-        wl.setdefault(stage, rec)            # the first launch of each kernel in the report
+        if stage not in seen:                # the first launch of each kernel in the report (replaces an older capture)
+            seen.add(stage)
+            wl[stage] = rec
     json.dump(out, open(a.out, "w"), indent=1)
     print("wrote", a.out, {k: sorted(v) for k, v in out.items() if not k.startswith("_")})
 
