@@ -145,12 +145,6 @@ def build_model(xml_path: str, name: str, fmad: bool = True, force: bool = False
     for f in function_files:
         if not os.path.exists(f):
             raise BuildError(f"function file {f} not found")
-    # the runtime moves one element per variable in compaction / append / migration / I/O: an agent array variable
-    # (header.xslt:476-492) would be truncated silently, so such models are refused instead of built
-    for a in model.agents:
-        for v in a.variables:
-            if v.array_length:
-                raise BuildError(f"agent '{a.name}': array variable '{v.name}[{v.array_length}]' is not supported by the CUDA runtime")
     gen = os.path.join(GEN, name)
     files = codegen.emit_cuda(model, function_files, gen, rewrite_loops=rewrite_loops, loop_unroll=loop_unroll)
     os.makedirs(os.path.join(LIB, "models"), exist_ok=True)

@@ -332,11 +332,12 @@ FGPU_DEV void add_{a.name}_agent(xmachine_memory_{a.name}_list* agents, {_agent_
     out.append(f"FGPU_DEV void add_{a.name}_agent(xmachine_memory_{a.name}_list* agents, {_agent_args(a)}){{")
     out.append(f"    add_{a.name}_agent<DISCRETE_2D>(agents, {', '.join(v.name for v in scal)});\n}}")
     if any(v.array_length for v in a.variables):
-        out.append(f"""template<typename T> FGPU_DEV T get_{a.name}_agent_array_value(T *array, uint index){{
-    return array[(size_t)index * xmachine_memory_{a.name}_MAX];
+        out.append(f"""/* krn:336-367: `array` points at element 0 of this agent; elements are xmachine_memory_{a.name}_MAX apart */
+template<typename T> FGPU_DEV T get_{a.name}_agent_array_value(T *array, uint index){{
+    return array != nullptr ? array[(size_t)index * xmachine_memory_{a.name}_MAX] : T(0);
 }}
 template<typename T> FGPU_DEV void set_{a.name}_agent_array_value(T *array, uint index, T value){{
-    array[(size_t)index * xmachine_memory_{a.name}_MAX] = value;
+    if (array != nullptr) array[(size_t)index * xmachine_memory_{a.name}_MAX] = value;
 }}""")
     return "\n".join(out) + "\n"
 
@@ -406,6 +407,8 @@ def _host_api_decls(model: Model) -> str:
             out.append(f"extern xmachine_memory_{a.name}_list* get_host_{a.name}_{s}_agents();")
             out.append(f"void sort_{a.name}s_{s}(void (*generate_key_value_pairs)(unsigned int* keys, unsigned int* values, xmachine_memory_{a.name}_list* agents));")
             for v in a.variables:
+                if v.array_length:   # header.xslt:648-658
+                    out.append(f"{v.type} get_{a.name}_{s}_variable_{v.name}(unsigned int index, unsigned int element);")
                 if not v.array_length:
                     out.append(f"{v.type} get_{a.name}_{s}_variable_{v.name}(unsigned int index);")
                     # analytics (header.xslt:729-751): sum for every scalar, count for integers, min/max for non-vectors
@@ -445,9 +448,16 @@ def _host_list_defs(model: Model) -> List[str]:
     fill: List[str] = []
     for ai, a in enumerate(model.agents):
         cols = ", ".join(("nullptr" if v.array_length else f"(void*)h->{v.name}") for v in a.variables)
+        # array variables arrive as `length` blocks of `count` values; the host list keeps the device layout
+        # (element e of agent i at var[e * MAX + i], header.xslt:187-194)
+        arrays = "".join(f"""
+    if (count > 0) {{ std::vector<{v.type}> t((size_t)count * {v.array_length});
+        if (fgpu_sim_read_agent_var(fgpu_cur, {ai}, state, {vi}, t.data(), count) != FGPU_OK) fgpu_die();
+        for (int e = 0; e < {v.array_length}; ++e) memcpy(h->{v.name} + (size_t)e * xmachine_memory_{a.name}_MAX, t.data() + (size_t)e * count, sizeof({v.type}) * (size_t)count); }}"""
+                         for vi, v in enumerate(a.variables) if v.array_length)
         out.append(f"""static void fgpu_fill_host_{a.name}(xmachine_memory_{a.name}_list* h, int state, int count){{
     void* const columns[] = {{{cols}}};
-    if (count > 0 && fgpu_sim_read_agents(fgpu_cur, {ai}, state, count, columns) != FGPU_OK) fgpu_die();
+    if (count > 0 && fgpu_sim_read_agents(fgpu_cur, {ai}, state, count, columns) != FGPU_OK) fgpu_die();{arrays}
 }}""")
         for si, st in enumerate(a.states):
             out.append(f"""xmachine_memory_{a.name}_list* get_host_{a.name}_{st}_agents(){{
@@ -502,14 +512,16 @@ def _host_creation_defs(model: Model, add_call: str, count_call: str) -> List[st
     """h_allocate_/h_free_/h_add_agent(s)_<A>_<S> (simulation.xslt:1192-1320): host structs with the XML default
     values, unpacked AoS -> SoA columns and appended to the state list through
     `add_call`(agent, state, count, const void* const* columns); `count_call`(agent, state) is the current
-    population for the reference's buffer-size guard (message + exit).  Agents with array variables get
-    the allocation helpers only (their h_add_ functions report the missing support)."""
+    population for the reference's buffer-size guard (message + exit).  Array variables travel as `length` blocks of
+    `count` values."""
     out = []
     for ai, a in enumerate(model.agents):
         A = a.name
-        has_arrays = any(v.array_length for v in a.variables)
         inits = "".join(f" agent->{v.name} = ({v.type}){v.default};" for v in a.variables if v.default is not None and not v.array_length)
-        arr_alloc = "".join(f" agent->{v.name} = ({v.type}*)calloc({v.array_length}, sizeof({v.type}));" for v in a.variables if v.array_length)
+        arr_alloc = "".join(f" agent->{v.name} = ({v.type}*)calloc({v.array_length}, sizeof({v.type}));"
+                            + (f" for (unsigned int index = 0; index < {v.array_length}; index++) agent->{v.name}[index] = ({v.type}){v.default};"
+                               if v.default is not None else "")      # simulation.xslt:1200-1207
+                            for v in a.variables if v.array_length)
         arr_free = "".join(f" free((*agent)->{v.name});" for v in a.variables if v.array_length)
         out.append(f"xmachine_memory_{A}* h_allocate_agent_{A}(){{ xmachine_memory_{A}* agent = (xmachine_memory_{A}*)malloc(sizeof(xmachine_memory_{A})); "
                    f"memset(agent, 0, sizeof(xmachine_memory_{A}));{inits}{arr_alloc} return agent; }}")
@@ -519,10 +531,12 @@ def _host_creation_defs(model: Model, add_call: str, count_call: str) -> List[st
         out.append(f"void h_free_agent_{A}_array(xmachine_memory_{A}*** agents, unsigned int count){{ for (unsigned int i = 0; i < count; i++) "
                    f"h_free_agent_{A}(&((*agents)[i])); free(*agents); *agents = NULL; }}")
         for si, st in enumerate(a.states):
-            if has_arrays:
-                body = (f'{{ (void)agents; (void)count; fprintf(stderr, "h_add_agents_{A}_{st}: agent array variables are not supported\\n"); exit(EXIT_FAILURE); }}')
-            else:
-                cols = "".join(f" std::vector<{v.type}> c_{v.name}(count); for (unsigned int i = 0; i < count; i++) c_{v.name}[i] = agents[i]->{v.name};"
+            if True:
+                # arrays: `length` blocks of `count` values (simulation.xslt:1238-1241 unpacks them element by element too)
+                cols = "".join((f" std::vector<{v.type}> c_{v.name}((size_t)count * {v.array_length}); for (unsigned int i = 0; i < count; i++) "
+                                f"for (unsigned int j = 0; j < {v.array_length}; j++) c_{v.name}[(size_t)j * count + i] = agents[i]->{v.name}[j];")
+                               if v.array_length else
+                               f" std::vector<{v.type}> c_{v.name}(count); for (unsigned int i = 0; i < count; i++) c_{v.name}[i] = agents[i]->{v.name};"
                                for v in a.variables)
                 ptrs = ", ".join(f"c_{v.name}.data()" for v in a.variables)
                 body = (f"{{ if (count == 0) return; if ({count_call}({ai}, {si}) + (int)count > xmachine_memory_{A}_MAX){{ "
@@ -810,7 +824,7 @@ def _descriptor_tables(model: Model, mode: str, launch_prefix: str, sources: Opt
         for v in a.variables:
             dv = v.default_literal()
             rows.append(f'    {{"{v.name}", "{v.type}", {v.size}, {1 if v.type in ("float", "double") else 0}, '
-                        f'offsetof(xmachine_memory_{a.name}_list, {v.name}), (double)({dv})}},')
+                        f'offsetof(xmachine_memory_{a.name}_list, {v.name}), (double)({dv}), {max(1, v.array_length)}}},')
         out.append(f"static const fgpu_var fgpu_vars_agent_{a.name}[] = {{\n" + "\n".join(rows) + "\n};")
         states = ", ".join(f'"{s}"' for s in a.states)
         out.append(f"static const char* const fgpu_states_{a.name}[] = {{{states}}};")
@@ -818,7 +832,7 @@ def _descriptor_tables(model: Model, mode: str, launch_prefix: str, sources: Opt
         rows = []
         for v in m.variables:
             rows.append(f'    {{"{v.name}", "{v.type}", {v.size}, {1 if v.type in ("float", "double") else 0}, '
-                        f'offsetof(xmachine_message_{m.name}{"_list" if mode == "oracle" else ""}, {v.name}), 0.0}},')
+                        f'offsetof(xmachine_message_{m.name}{"_list" if mode == "oracle" else ""}, {v.name}), 0.0, 1}},')
         out.append(f"static const fgpu_var fgpu_vars_message_{m.name}[] = {{\n" + "\n".join(rows) + "\n};")
     rows = []
     for a in model.agents:
@@ -946,6 +960,9 @@ void cleanup(){ fgpu_sim_run_exit_functions(fgpu_cur); fgpu_sim_destroy(fgpu_cur
                 if not v.array_length:
                     out.append(f"{v.type} get_{a.name}_{st}_variable_{v.name}(unsigned int index){{ {v.type} t = 0; "
                                f"if (fgpu_sim_read_agent_value(fgpu_cur, {ai}, {si}, {vi}, index, &t) != FGPU_OK) fgpu_die(); return t; }}")
+                else:   # simulation.xslt:1093-1140
+                    out.append(f"{v.type} get_{a.name}_{st}_variable_{v.name}(unsigned int index, unsigned int element){{ {v.type} t = 0; "
+                               f"if (fgpu_sim_read_agent_element(fgpu_cur, {ai}, {si}, {vi}, index, element, &t) != FGPU_OK) fgpu_die(); return t; }}")
     out += _host_list_defs(model)
     out.append("static int fgpu_reduce_cur(int a, int s, int v, int op, const void* cv, void* r){ return fgpu_sim_reduce_agent_var(fgpu_cur, a, s, v, op, cv, r); }")
     out += _reduction_defs(model, "fgpu_reduce_cur")

@@ -541,9 +541,30 @@ __global__ void k_unpack_words(const unsigned int *__restrict__ recs, int rec_wo
 constexpr int MAX_COLS = 48;
 struct ColSet {
     int ncols;
+    unsigned int stride;              /* elements between two consecutive elements of an array variable = the list's capacity
+                                         (xmachine_memory_<A>_MAX: element e of agent i lives at var[e * MAX + i], hdr:187-194) */
     int size[MAX_COLS];               /* 4 or 8 bytes */
+    unsigned short len[MAX_COLS];     /* 1 for a scalar, arrayLength for an agent array variable */
     unsigned long long off[MAX_COLS]; /* byte offset of the column in the list struct */
 };
+
+/* every variable of agent `i` of one list to position `o` of another: scalars, and array variables element by element
+ * (scatter_<A>_Agents / append_<A>_Agents / reorder_<A>_agents copy arrays with the same loop, krn:251-254,274-277,328-331) */
+__device__ __forceinline__ void copy_cols(const char *__restrict__ src, const ColSet &sc, size_t i, char *__restrict__ dst,
+                                          const ColSet &dc, size_t o) {
+    for (int c = 0; c < sc.ncols; ++c) {
+        const int L = sc.len[c];
+        if (sc.size[c] == 4) {
+            const unsigned int *sp = (const unsigned int *)(src + sc.off[c]) + i;
+            unsigned int *dp = (unsigned int *)(dst + dc.off[c]) + o;
+            for (int e = 0; e < L; ++e) dp[(size_t)e * dc.stride] = sp[(size_t)e * sc.stride];
+        } else {
+            const unsigned long long *sp = (const unsigned long long *)(src + sc.off[c]) + i;
+            unsigned long long *dp = (unsigned long long *)(dst + dc.off[c]) + o;
+            for (int e = 0; e < L; ++e) dp[(size_t)e * dc.stride] = sp[(size_t)e * sc.stride];
+        }
+    }
+}
 
 constexpr int COMPACT_THREADS = 1024;
 
@@ -626,12 +647,7 @@ k_compact_scatter(const char *__restrict__ src, char *__restrict__ dst, const Co
         if (overflow) atomicExch(overflow, 1);
         return;
     }
-    for (int c = 0; c < cols.ncols; ++c) {
-        if (cols.size[c] == 4)
-            ((unsigned int *)(dst + dcols.off[c]))[out] = ((const unsigned int *)(src + cols.off[c]))[i];
-        else
-            ((unsigned long long *)(dst + dcols.off[c]))[out] = ((const unsigned long long *)(src + cols.off[c]))[i];
-    }
+    copy_cols(src, cols, (size_t)i, dst, dcols, out);
 }
 
 /* optional_message outputs (scatter_optional_<M>_messages, krn:411-428): stable compaction of the flagged
@@ -674,12 +690,7 @@ k_reorder_agents(const char *__restrict__ src, char *__restrict__ dst, const Col
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const size_t old_pos = values[order[i]];
-    for (int c = 0; c < cols.ncols; ++c) {
-        if (cols.size[c] == 4)
-            ((unsigned int *)(dst + cols.off[c]))[i] = ((const unsigned int *)(src + cols.off[c]))[old_pos];
-        else
-            ((unsigned long long *)(dst + cols.off[c]))[i] = ((const unsigned long long *)(src + cols.off[c]))[old_pos];
-    }
+    copy_cols(src, cols, old_pos, dst, cols, (size_t)i);
 }
 
 /* append_<A>_Agents (krn:265-280) */
@@ -688,12 +699,7 @@ k_append(const char *__restrict__ src, char *__restrict__ dst, const ColSet cols
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const size_t out = (size_t)dst_offset + i;
-    for (int c = 0; c < cols.ncols; ++c) {
-        if (cols.size[c] == 4)
-            ((unsigned int *)(dst + cols.off[c]))[out] = ((const unsigned int *)(src + cols.off[c]))[i];
-        else
-            ((unsigned long long *)(dst + cols.off[c]))[out] = ((const unsigned long long *)(src + cols.off[c]))[i];
-    }
+    copy_cols(src, cols, (size_t)i, dst, cols, out);
 }
 
 /* ------------------------------------------------------------------------- */

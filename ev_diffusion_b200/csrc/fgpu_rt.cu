@@ -97,6 +97,9 @@ static cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 
 /* ------------------------------------------------------------------------- */
 /* runtime objects                                                            */
 /* ------------------------------------------------------------------------- */
+/* number of elements of an agent variable: 1 for a scalar, arrayLength for an array (fgpu_var.length) */
+static inline int var_len(const fgpu_var &v) { return v.length > 1 ? v.length : 1; }
+
 struct AgentRT {
     const fgpu_agent *d = nullptr;
     char *work = nullptr;  /* d_<A>s */
@@ -404,9 +407,12 @@ static int sim_alloc(fgpu_sim *s) {
             CU(cudaMemsetAsync(A.state[st], 0, A.d->list_bytes, s->stream));
         }
         A.cols.ncols = A.d->nvars;
+        A.cols.stride = (unsigned int)A.d->buffer_size;
         for (int v = 0; v < A.d->nvars; ++v) {
             A.cols.size[v] = A.d->vars[v].size;
+            A.cols.len[v] = (unsigned short)var_len(A.d->vars[v]);
             A.cols.off[v] = A.d->vars[v].list_offset;
+            if (var_len(A.d->vars[v]) > 65535) return set_err(FGPU_ERR_MODEL, "agent %s: array variable %s is longer than 65535", A.d->name, A.d->vars[v].name);
         }
         const int nb = (A.d->buffer_size + COMPACT_THREADS - 1) / COMPACT_THREADS;
         CU(cudaMalloc(&A.block_sums, sizeof(unsigned int) * 3 * (size_t)(nb + 1)));
@@ -628,11 +634,12 @@ static int upload_columns(fgpu_sim *s, int agent, int state, int offset, int cou
                        A.d->buffer_size, A.d->name); /* io.xslt:406, without its off-by-one */
     CU(cudaSetDevice(s->device));
     char *list = A.state[state];
-    for (int v = 0; v < A.d->nvars; ++v) {
+    for (int v = 0; v < A.d->nvars; ++v)
+      for (int e = 0; e < var_len(A.d->vars[v]); ++e) {   /* an array variable arrives element-major: columns[v] = length blocks of `count` values */
         const fgpu_var &V = A.d->vars[v];
-        char *dst = list + V.list_offset + (size_t)offset * V.size;
+        char *dst = list + V.list_offset + ((size_t)e * A.d->buffer_size + (size_t)offset) * V.size;
         if (columns && columns[v]) {
-            CU(cudaMemcpyAsync(dst, columns[v], (size_t)count * V.size, cudaMemcpyHostToDevice, s->stream));
+            CU(cudaMemcpyAsync(dst, (const char *)columns[v] + (size_t)e * count * V.size, (size_t)count * V.size, cudaMemcpyHostToDevice, s->stream));
         } else {
             /* defaultValue or 0 (io.xslt:276-291), written on the device: no host buffer, no copy over PCIe */
             if (count > 0) {
@@ -708,7 +715,9 @@ extern "C" int fgpu_sim_read_agent_var(fgpu_sim *s, int agent, int state, int va
     if (count < 0 || count > A.d->buffer_size) return set_err(FGPU_ERR_ARG, "bad count");
     CU(cudaSetDevice(s->device));
     const fgpu_var &V = A.d->vars[var];
-    CU(cudaMemcpyAsync(dst, A.state[state] + V.list_offset, (size_t)count * V.size, cudaMemcpyDeviceToHost, s->stream));
+    for (int e = 0; e < var_len(V); ++e)   /* an array variable: `length` blocks of `count` values, element-major */
+        CU(cudaMemcpyAsync((char *)dst + (size_t)e * count * V.size, A.state[state] + V.list_offset + (size_t)e * A.d->buffer_size * V.size,
+                           (size_t)count * V.size, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return FGPU_OK;
 }
@@ -729,7 +738,9 @@ static int read_agents(fgpu_sim *s, int agent, int state, int count, void *const
     for (int v = 0; v < A.d->nvars; ++v) {
         if (!columns[v]) continue;
         const fgpu_var &V = A.d->vars[v];
-        CU(cudaMemcpyAsync(columns[v], A.state[state] + V.list_offset, (size_t)count * V.size, cudaMemcpyDeviceToHost, s->stream));
+        for (int e = 0; e < var_len(V); ++e)
+            CU(cudaMemcpyAsync((char *)columns[v] + (size_t)e * count * V.size, A.state[state] + V.list_offset + (size_t)e * A.d->buffer_size * V.size,
+                               (size_t)count * V.size, cudaMemcpyDeviceToHost, s->stream));
     }
     if (!async) CU(cudaStreamSynchronize(s->stream));
     return FGPU_OK;
@@ -743,6 +754,19 @@ extern "C" int fgpu_sim_read_agent_value(fgpu_sim *s, int agent, int state, int 
     CU(cudaSetDevice(s->device));
     const fgpu_var &V = A.d->vars[var];
     CU(cudaMemcpyAsync(dst, A.state[state] + V.list_offset + (size_t)index * V.size, V.size, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FGPU_OK;
+}
+
+extern "C" int fgpu_sim_read_agent_element(fgpu_sim *s, int agent, int state, int var, unsigned int index, unsigned int element, void *dst) {
+    if (!s || !dst || agent < 0 || agent >= (int)s->agents.size()) return set_err(FGPU_ERR_ARG, "bad argument");
+    AgentRT &A = s->agents[agent];
+    if (state < 0 || state >= A.d->nstates || var < 0 || var >= A.d->nvars) return set_err(FGPU_ERR_ARG, "bad index");
+    if (index >= (unsigned int)A.h_state_count[state]) return set_err(FGPU_ERR_ARG, "agent index %u out of range", index);
+    const fgpu_var &V = A.d->vars[var];
+    if (element >= (unsigned int)var_len(V)) return set_err(FGPU_ERR_ARG, "element %u of %s[%d] out of range", element, V.name, var_len(V));
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(dst, A.state[state] + V.list_offset + ((size_t)element * A.d->buffer_size + index) * V.size, V.size, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return FGPU_OK;
 }
@@ -1632,7 +1656,9 @@ extern "C" int fgpu_debug_compact(const int *flags, const unsigned int *payload,
     CU(cudaMemcpy(d_in, payload, sizeof(unsigned int) * (size_t)n, cudaMemcpyHostToDevice));
     ColSet cols;
     cols.ncols = 1;
+    cols.stride = 0;
     cols.size[0] = 4;
+    cols.len[0] = 1;
     cols.off[0] = 0;
     k_flag_blocksum<<<nb, COMPACT_THREADS>>>(d_flags, n, nullptr, d_bs, 1);
     k_scan_blocksums<<<1, 1024>>>(d_bs, nb, d_total);

@@ -6,9 +6,18 @@
 /* ------------------------------------------------------------------------- */
 namespace {
 struct XmlAgentBuf {
-    std::vector<std::vector<char>> cols; /* per variable, raw bytes */
+    std::vector<std::vector<char>> cols; /* per variable, raw bytes; an array variable holds `length` values per agent */
     int count = 0;
 };
+
+/* element-major copy (`length` blocks of `count` values, the order of the list on the device) of an agent-major buffer */
+std::vector<char> element_major(const std::vector<char> &rows, int count, int length, int size) {
+    std::vector<char> out(rows.size());
+    for (int i = 0; i < count; ++i)
+        for (int e = 0; e < length; ++e)
+            memcpy(out.data() + ((size_t)e * count + i) * size, rows.data() + ((size_t)i * length + e) * size, (size_t)size);
+    return out;
+}
 
 void store_value(const fgpu_var &V, const char *text, char *dst) {
     if (V.is_float) {
@@ -34,6 +43,23 @@ void default_value(const fgpu_var &V, char *dst) {
         *(long long *)dst = (long long)V.default_value;
     }
 }
+/* readArrayInput (io.xslt:69-93): comma-separated items; too many items is fatal in the reference (exit), a short
+ * list leaves the remaining elements at their default and warns on stderr */
+int store_array(const fgpu_var &V, const char *agent_name, const std::string &text, char *dst) {
+    const int expected = V.length;
+    std::string buf = text;
+    char *save = nullptr;
+    int i = 0;
+    for (char *tok = strtok_r(&buf[0], ",", &save); tok != nullptr; tok = strtok_r(nullptr, ",", &save)) {
+        if (i >= expected)
+            return set_err(FGPU_ERR_IO, "Error: variable array %s->%s has too many items (%d), expected %d!", agent_name, V.name, i, expected);
+        store_value(V, tok, dst + (size_t)i * V.size);
+        ++i;
+    }
+    if (i != expected) fprintf(stderr, "Warning: variable array %s->%s has %d items, expected %d!\n", agent_name, V.name, i, expected);
+    return FGPU_OK;
+}
+
 /* The parser proper: host code only.  Fills one column buffer per agent variable with the agents of the file (each
  * under the agent type named by its <name>); <environment> values go to the model's constant setters when
  * `apply_environment` is set (fgpu_sim_load_states) and are skipped otherwise (fgpu_states_file_*: no device). */
@@ -48,8 +74,9 @@ int parse_states_file(const fgpu_model *m, const char *xml_path, std::vector<Xml
         for (int a = 0; a < m->nagents; ++a) {
             cur[a].resize(m->agents[a].nvars);
             for (int v = 0; v < m->agents[a].nvars; ++v) {
-                cur[a][v].assign(8, 0);
-                default_value(m->agents[a].vars[v], cur[a][v].data());
+                const fgpu_var &V = m->agents[a].vars[v];
+                cur[a][v].assign((size_t)8 * var_len(V), 0);
+                for (int e = 0; e < var_len(V); ++e) default_value(V, cur[a][v].data() + (size_t)e * V.size);
             }
         }
     };
@@ -95,7 +122,7 @@ int parse_states_file(const fgpu_model *m, const char *xml_path, std::vector<Xml
                         break;
                     }
                     for (int v = 0; v < m->agents[a].nvars; ++v) {
-                        const int sz = m->agents[a].vars[v].size;
+                        const int sz = m->agents[a].vars[v].size * var_len(m->agents[a].vars[v]);
                         bufs[a].cols[v].insert(bufs[a].cols[v].end(), cur[a][v].data(), cur[a][v].data() + sz);
                     }
                     bufs[a].count++;
@@ -119,7 +146,14 @@ int parse_states_file(const fgpu_model *m, const char *xml_path, std::vector<Xml
                 /* every agent type that has a variable of this name receives the value */
                 for (int a = 0; a < m->nagents; ++a)
                     for (int v = 0; v < m->agents[a].nvars; ++v)
-                        if (open_var == m->agents[a].vars[v].name) store_value(m->agents[a].vars[v], buffer.c_str(), cur[a][v].data());
+                        if (open_var == m->agents[a].vars[v].name) {
+                            if (var_len(m->agents[a].vars[v]) > 1) {
+                                rc = store_array(m->agents[a].vars[v], m->agents[a].name, buffer, cur[a][v].data());
+                                if (rc != FGPU_OK) reading = false;
+                            } else {
+                                store_value(m->agents[a].vars[v], buffer.c_str(), cur[a][v].data());
+                            }
+                        }
             } else if (in_env && apply_environment) {
                 for (int k = 0; k < m->nconstants; ++k)
                     if (open_var == m->constants[k].name && m->constants[k].length == 1) {
@@ -158,7 +192,11 @@ extern "C" int fgpu_sim_load_states(fgpu_sim *s, const char *xml_path) {
     if (rc != FGPU_OK) return rc;
     for (int a = 0; a < m->nagents; ++a) {
         std::vector<const void *> cols(m->agents[a].nvars);
-        for (int v = 0; v < m->agents[a].nvars; ++v) cols[v] = bufs[a].cols[v].data();
+        for (int v = 0; v < m->agents[a].nvars; ++v) {
+            const fgpu_var &V = m->agents[a].vars[v];
+            if (var_len(V) > 1) bufs[a].cols[v] = element_major(bufs[a].cols[v], bufs[a].count, var_len(V), V.size);
+            cols[v] = bufs[a].cols[v].data();
+        }
         /* other states start empty */
         for (int st = 0; st < m->agents[a].nstates; ++st) s->agents[a].h_state_count[st] = 0;
         rc = upload_columns(s, a, m->agents[a].initial_state, 0, bufs[a].count, bufs[a].count ? cols.data() : nullptr);
@@ -187,6 +225,13 @@ extern "C" int fgpu_states_file_read_var(const fgpu_model *model, const char *xm
     const int rc = parse_states_file(model, xml_path, bufs, false);
     if (rc != FGPU_OK) return rc;
     if (count < 0 || count > bufs[agent].count) return set_err(FGPU_ERR_ARG, "the file holds %d agents of type %s", bufs[agent].count, model->agents[agent].name);
-    memcpy(dst, bufs[agent].cols[var].data(), (size_t)count * model->agents[agent].vars[var].size);
+    const fgpu_var &V = model->agents[agent].vars[var];
+    if (var_len(V) > 1) {   /* element-major, like fgpu_sim_read_agent_var: `length` blocks of `count` values */
+        std::vector<char> rows(bufs[agent].cols[var].begin(), bufs[agent].cols[var].begin() + (size_t)count * var_len(V) * V.size);
+        const std::vector<char> em = element_major(rows, count, var_len(V), V.size);
+        memcpy(dst, em.data(), em.size());
+        return FGPU_OK;
+    }
+    memcpy(dst, bufs[agent].cols[var].data(), (size_t)count * V.size);
     return FGPU_OK;
 }

@@ -182,11 +182,17 @@ extern "C" int fgpu_sim_slab_init(fgpu_sim *s, int rank, int world, const void *
         for (int v = 0; v < A.d->nvars; ++v)
             if (!strcmp(A.d->vars[v].name, axis_name) && A.d->vars[v].is_float && A.d->vars[v].size == 4) X.axis_var = v;
         if (X.axis_var < 0) continue; /* agents without a position never migrate */
+        for (int v = 0; v < A.d->nvars; ++v)   /* the migrant buffers and their kernels move one value per variable */
+            if (var_len(A.d->vars[v]) > 1)
+                return set_err(FGPU_ERR_MODEL, "slab mode: agent %s has the array variable %s[%d]; migrating agents with array variables is not supported",
+                               A.d->name, A.d->vars[v].name, var_len(A.d->vars[v]));
         size_t off = 16;
         X.bufcols.ncols = A.d->nvars;
+        X.bufcols.stride = (unsigned int)S.mig_cap;
         for (int v = 0; v < A.d->nvars; ++v) {
             off = (off + 15) & ~(size_t)15;
             X.bufcols.size[v] = A.d->vars[v].size;
+            X.bufcols.len[v] = 1;
             X.bufcols.off[v] = off;
             off += (size_t)A.d->vars[v].size * S.mig_cap;
         }

@@ -29,9 +29,12 @@ int download_states(fgpu_sim *s, int a, std::vector<std::vector<std::vector<char
     for (int st = 0; st < A.d->nstates; ++st)
         for (int v = 0; v < A.d->nvars; ++v) {
             const fgpu_var &V = A.d->vars[v];
-            cols[st][v].resize((size_t)A.h_state_count[st] * V.size);
-            if (!cols[st][v].empty())
-                CU(cudaMemcpyAsync(cols[st][v].data(), A.state[st] + V.list_offset, cols[st][v].size(), cudaMemcpyDeviceToHost, s->stream));
+            /* an array variable: `length` blocks of `count` values (element-major, the order of the list) */
+            const size_t block = (size_t)A.h_state_count[st] * V.size;
+            cols[st][v].resize(block * var_len(V));
+            for (int e = 0; block && e < var_len(V); ++e)
+                CU(cudaMemcpyAsync(cols[st][v].data() + (size_t)e * block, A.state[st] + V.list_offset + (size_t)e * A.d->buffer_size * V.size, block,
+                                   cudaMemcpyDeviceToHost, s->stream));
         }
     CU(cudaStreamSynchronize(s->stream));
     return FGPU_OK;
@@ -93,7 +96,11 @@ extern "C" int fgpu_sim_save_states(fgpu_sim *s, const char *outputpath, int ite
                 for (int v = 0; v < A.d->nvars; ++v) {
                     const fgpu_var &V = A.d->vars[v];
                     fprintf(f, "<%s>", V.name);
-                    write_value(f, V.ctype, V.size, V.is_float != 0, cols[st][v].data() + (size_t)i * V.size, s->opt_xml_digits);
+                    for (int e = 0; e < var_len(V); ++e) {   /* arrays: comma-separated (io.xslt:176-186) */
+                        write_value(f, V.ctype, V.size, V.is_float != 0, cols[st][v].data() + ((size_t)e * A.h_state_count[st] + i) * V.size,
+                                    s->opt_xml_digits);
+                        if (e != var_len(V) - 1) fputc(',', f);
+                    }
                     fprintf(f, "</%s>\n", V.name);
                 }
                 fputs("</xagent>\n", f);
@@ -123,7 +130,7 @@ extern "C" int fgpu_sim_save_snapshot(fgpu_sim *s, const char *path) {
         }
         const AgentRT &A = s->agents[a];
         ok = put_str(f, A.d->name) && put_u32(f, (unsigned int)A.d->nvars) && put_u32(f, (unsigned int)A.d->nstates);
-        for (int v = 0; ok && v < A.d->nvars; ++v) ok = put_str(f, A.d->vars[v].name) && put_u32(f, (unsigned int)A.d->vars[v].size);
+        for (int v = 0; ok && v < A.d->nvars; ++v) ok = put_str(f, A.d->vars[v].name) && put_u32(f, (unsigned int)(A.d->vars[v].size * var_len(A.d->vars[v])));
         for (int st = 0; ok && st < A.d->nstates; ++st) {
             ok = put_str(f, A.d->states[st]) && put_u32(f, (unsigned int)A.h_state_count[st]);
             for (int v = 0; ok && v < A.d->nvars; ++v) ok = put(f, cols[st][v].data(), cols[st][v].size());
@@ -167,7 +174,7 @@ extern "C" int fgpu_sim_load_snapshot(fgpu_sim *s, const char *path) {
             return fail("agent layout differs");
         for (int v = 0; v < A.d->nvars; ++v) {
             unsigned int size = 0;
-            if (!get_str(f, &name) || name != A.d->vars[v].name || !get_u32(f, &size) || (int)size != A.d->vars[v].size)
+            if (!get_str(f, &name) || name != A.d->vars[v].name || !get_u32(f, &size) || (int)size != A.d->vars[v].size * var_len(A.d->vars[v]))
                 return fail("variable layout differs");
         }
         for (int st = 0; st < A.d->nstates; ++st) {
@@ -177,8 +184,9 @@ extern "C" int fgpu_sim_load_snapshot(fgpu_sim *s, const char *path) {
             std::vector<std::vector<char>> cols(A.d->nvars);
             std::vector<const void *> ptrs(A.d->nvars);
             for (int v = 0; v < A.d->nvars; ++v) {
-                cols[v].resize((size_t)count * A.d->vars[v].size + 1);
-                if (!get(f, cols[v].data(), (size_t)count * A.d->vars[v].size)) return fail("truncated");
+                const size_t bytes = (size_t)count * A.d->vars[v].size * var_len(A.d->vars[v]);
+                cols[v].resize(bytes + 1);
+                if (!get(f, cols[v].data(), bytes)) return fail("truncated");
                 ptrs[v] = cols[v].data();
             }
             const int rc = upload_columns(s, a, st, 0, (int)count, ptrs.data());
@@ -251,6 +259,7 @@ extern "C" int fgpu_sim_reduce_agent_var(fgpu_sim *s, int agent, int state, int 
     if (rc) return rc;
     const fgpu_var &V = A.d->vars[var];
     const int n = A.h_state_count[state];
+    if (var_len(V) > 1) return set_err(FGPU_ERR_ARG, "reductions are not defined for agent array variables (header.xslt:724)");
     if (op == FGPU_REDUCE_COUNT && V.is_float) return set_err(FGPU_ERR_ARG, "count_ is defined for integer variables only (header.xslt:735)");
     if (n == 0) {
         if (op == FGPU_REDUCE_MIN || op == FGPU_REDUCE_MAX) return set_err(FGPU_ERR_ARG, "min/max of an empty %s list", A.d->name);

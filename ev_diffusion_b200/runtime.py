@@ -33,7 +33,7 @@ class FgpuError(RuntimeError):
 # ---- ctypes mirrors of include/fgpu_model.h --------------------------------
 class _Var(C.Structure):
     _fields_ = [("name", C.c_char_p), ("ctype", C.c_char_p), ("size", C.c_int), ("is_float", C.c_int),
-                ("list_offset", C.c_size_t), ("default_value", C.c_double)]
+                ("list_offset", C.c_size_t), ("default_value", C.c_double), ("length", C.c_int)]
 
 
 class _Agent(C.Structure):
@@ -92,6 +92,7 @@ class VarInfo:
         self.size = v.size
         self.dtype = np.dtype(_NP_TYPES[self.ctype])
         self.default = v.default_value
+        self.length = max(1, int(v.length))   # > 1: an agent array variable; its columns are (count, length) arrays here
 
 
 class AgentInfo:
@@ -246,6 +247,10 @@ class SimBase:
                     n = arr.shape[0]
                 if arr.shape[0] != n:
                     raise FgpuError(f"column {v.name}: {arr.shape[0]} rows, expected {n}")
+                if v.length > 1:   # (count, length) here; the C ABI takes `length` blocks of `count` values
+                    if arr.shape != (n, v.length):
+                        raise FgpuError(f"column {v.name}: shape {arr.shape}, expected ({n}, {v.length})")
+                    arr = np.ascontiguousarray(arr.T)
                 arrs.append(arr)
             else:
                 arrs.append(None)
@@ -308,9 +313,10 @@ class SimBase:
         vi = a.var_index(var) if isinstance(var, str) else int(var)
         if count is None:
             count = self.agent_count(agent, state)
-        out = np.empty(count, dtype=a.vars[vi].dtype)
+        L = a.vars[vi].length
+        out = np.empty(count * L, dtype=a.vars[vi].dtype)
         self._check(self._fn("sim_read_agent_var")(self._h, agent, state, vi, out.ctypes.data, count))
-        return out
+        return np.ascontiguousarray(out.reshape(L, count).T) if L > 1 else out
 
     def agents(self, agent, state=0) -> Dict[str, np.ndarray]:
         agent = self._agent(agent)
@@ -480,10 +486,10 @@ def read_states_file(plugin_path: str, xml_path: str) -> Dict[str, Dict[str, np.
             raise FgpuError(lib.fgpu_last_error().decode())
         out[a.name] = {}
         for vi, v in enumerate(a.vars):
-            col = np.empty(n, dtype=v.dtype)
+            col = np.empty(n * v.length, dtype=v.dtype)
             if lib.fgpu_states_file_read_var(model, os.fsencode(xml_path), ai, vi, col.ctypes.data, n) != 0:
                 raise FgpuError(lib.fgpu_last_error().decode())
-            out[a.name][v.name] = col
+            out[a.name][v.name] = np.ascontiguousarray(col.reshape(v.length, n).T) if v.length > 1 else col
     return out
 
 
@@ -531,7 +537,8 @@ class Simulation(SimBase):
         ptrs = (C.c_void_p * len(a.vars))()
         for name, arr in out.items():
             vi = a.var_index(name)
-            if arr.dtype != a.vars[vi].dtype or arr.size < count or not arr.flags["C_CONTIGUOUS"]:
+            # an array variable is delivered as `length` blocks of `count` values (the C ABI's element-major layout)
+            if arr.dtype != a.vars[vi].dtype or arr.size < count * a.vars[vi].length or not arr.flags["C_CONTIGUOUS"]:
                 raise ValueError(f"read_agents: bad destination for '{name}'")
             ptrs[vi] = arr.ctypes.data
         if _async:

@@ -81,7 +81,10 @@ int fgpu_sim_load_snapshot(fgpu_sim *sim, const char *path);
 
 /* Direct upload of one state list from host SoA columns (one pointer per
  * agent variable, XML order; NULL = defaultValue).  Replaces the malloc +
- * cudaMemcpy H2D of the whole list struct (simulation.xslt:568-581). */
+ * cudaMemcpy H2D of the whole list struct (simulation.xslt:568-581).
+ * An agent array variable (arrayLength L, header.xslt:187-194) is one column of L blocks of `count` values,
+ * element-major: element e of agent i at column[e * count + i] -- the order of the list on the device with
+ * `count` in place of xmachine_memory_<A>_MAX.  Every call that moves columns uses this layout. */
 int fgpu_sim_set_agents(fgpu_sim *sim, int agent, int state, int count, const void *const *columns);
 
 /* The same upload without the final synchronisation: the copies are enqueued on the simulation stream and the call
@@ -138,6 +141,9 @@ int fgpu_sim_read_agents(fgpu_sim *sim, int agent, int state, int count, void *c
 int fgpu_sim_read_agents_async(fgpu_sim *sim, int agent, int state, int count, void *const *columns);
 /* get_<A>_<S>_variable_<v>(index) (header.xslt:645): one element of a state list. */
 int fgpu_sim_read_agent_value(fgpu_sim *sim, int agent, int state, int var, unsigned int index, void *dst);
+/* get_<A>_<S>_variable_<v>(index, element) (header.xslt:648-658, simulation.xslt:1093-1140): one element of an
+ * agent array variable. */
+int fgpu_sim_read_agent_element(fgpu_sim *sim, int agent, int state, int var, unsigned int index, unsigned int element, void *dst);
 /* reduce_/min_/max_/count_<A>_<S>_<v>_variable() (header.xslt:729-751, simulation.xslt:1325-1357): one scalar
  * agent variable of a state list folded on the device.  `result` (and `count_value`, FGPU_REDUCE_COUNT only)
  * have the variable's own C type; the count is returned in that type too, like the reference.  Integer results

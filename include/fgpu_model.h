@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FGPU_MODEL_ABI_VERSION 10
+#define FGPU_MODEL_ABI_VERSION 11
 
 /* One agent or message variable.  Agent lists keep the reference's SoA struct
  * layout (header.xslt:187-194): int _position[MAX]; int _scan_input[MAX];
@@ -33,6 +33,8 @@ typedef struct fgpu_var {
     size_t list_offset;      /* agents: byte offset of the column in the list struct;
                                 messages: byte offset inside the packed record */
     double default_value;    /* XMML defaultValue or 0 (io.xslt:276-291) */
+    int length;              /* 1 for a scalar; arrayLength of an agent array variable (header.xslt:187-194:
+                                T var[MAX * length], element e of agent i at var[e * MAX + i]) */
 } fgpu_var;
 
 typedef struct fgpu_agent {

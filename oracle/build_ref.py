@@ -208,7 +208,11 @@ def emit_shim(model) -> str:
     for ai, a in enumerate(model.agents):
         for si, s in enumerate(a.states):
             for vi, v in enumerate(a.variables):
-                if v.array_length:
+                if v.array_length:     # `length` blocks of `count` values (element e of agent i at var[e * MAX + i])
+                    L.append(f"    case {(ai * 64 + si) * 256 + vi}: for (int e = 0; e < {v.array_length}; ++e) "
+                             f"std::memcpy((char*)dst + sizeof({v.type}) * (size_t)e * h_xmachine_memory_{a.name}_{s}_count, "
+                             f"d_{a.name}s_{s}->{v.name} + (size_t)e * xmachine_memory_{a.name}_MAX, "
+                             f"sizeof({v.type}) * h_xmachine_memory_{a.name}_{s}_count); return 0;")
                     continue
                 L.append(f"    case {(ai * 64 + si) * 256 + vi}: std::memcpy(dst, d_{a.name}s_{s}->{v.name}, "
                          f"sizeof({v.type}) * h_xmachine_memory_{a.name}_{s}_count); return 0;")

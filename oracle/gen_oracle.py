@@ -284,7 +284,12 @@ def _filter(model: Model, f: Function) -> str:
     A = a.name
     if f.condition is not None:
         expr = f.condition.c_expr("currentState->{0}[index]")
-        copies = "\n".join(f"            nextState->{v.name}[index] = currentState->{v.name}[index];" for v in a.variables if not v.array_length)
+        # krn:172-173 copies `var[index]` for every variable, i.e. only element 0 of an array variable, and leaves the rest of
+        # the working list's arrays as allocated (uninitialised in the reference).  Both back ends of this repository copy
+        # the whole array -- what scatter/append/reorder do (krn:251-254) -- so that the result is defined.
+        copies = "\n".join(
+            (f"            for (int i = 0; i < {v.array_length}; i++) nextState->{v.name}[(i*xmachine_memory_{A}_MAX)+index] = currentState->{v.name}[(i*xmachine_memory_{A}_MAX)+index];"
+             if v.array_length else f"            nextState->{v.name}[index] = currentState->{v.name}[index];") for v in a.variables)
         return f"""/* {f.name}_function_filter, krn:162-184 */
 static void orc_filter_{f.name}(const fgpu_filter* F, void*){{
     xmachine_memory_{A}_list* currentState = (xmachine_memory_{A}_list*)F->current;
@@ -395,6 +400,15 @@ template <int AGENT_TYPE> void add_{a.name}_agent(xmachine_memory_{a.name}_list*
         out.append("}")
         out.append(f"void add_{a.name}_agent(xmachine_memory_{a.name}_list* agents, {codegen._agent_args(a)}){{")
         out.append(f"    add_{a.name}_agent<DISCRETE_2D>(agents, {', '.join(v.name for v in scal)});\n}}")
+        if any(v.array_length for v in a.variables):
+            out.append(f"""/* get/set_{a.name}_agent_array_value, krn:336-367 */
+template<typename T> T get_{a.name}_agent_array_value(T *array, uint index){{
+    if (array != nullptr) return array[index*xmachine_memory_{a.name}_MAX];
+    return T(0);
+}}
+template<typename T> void set_{a.name}_agent_array_value(T *array, uint index, T value){{
+    if (array != nullptr) array[index*xmachine_memory_{a.name}_MAX] = value;
+}}""")
     for p in function_files:
         out.append(f'#include "{os.path.abspath(p)}"')
     for f in model.all_functions():

@@ -210,10 +210,16 @@ static int orc_scan_count(OrcAgent &A, char *list, int n) {
     return (scan[n - 1] == 1) ? pos[n - 1] + 1 : pos[n - 1];
 }
 
+/* elements of an agent variable: 1, or arrayLength (element e of agent i at var[e * MAX + i], hdr:187-194) */
+static inline int orc_var_len(const fgpu_var &V) { return V.length > 1 ? V.length : 1; }
+
+/* every variable of one agent; array variables element by element like krn:251-254,274-277 */
 static void orc_copy_agent(OrcAgent &A, char *dst, int di, const char *src, int si) {
+    const size_t MAX = (size_t)A.d->buffer_size;
     for (int v = 0; v < A.d->nvars; ++v) {
         const fgpu_var &V = A.d->vars[v];
-        memcpy(dst + V.list_offset + (size_t)di * V.size, src + V.list_offset + (size_t)si * V.size, V.size);
+        for (int e = 0; e < orc_var_len(V); ++e)
+            memcpy(dst + V.list_offset + (e * MAX + (size_t)di) * V.size, src + V.list_offset + (e * MAX + (size_t)si) * V.size, V.size);
     }
 }
 
@@ -555,11 +561,12 @@ static int orc_upload(orc_sim *s, int agent, int state, int offset, int count, c
     OrcAgent &A = s->agents[agent];
     if (state < 0 || state >= A.d->nstates) return orc_set_err(-1, "bad state");
     if (count < 0 || offset + count > A.d->buffer_size) return orc_set_err(-3, "ERROR: MAX Buffer size (%i) for agent %s exceeded whilst reading data", A.d->buffer_size, A.d->name);
-    for (int v = 0; v < A.d->nvars; ++v) {
+    for (int v = 0; v < A.d->nvars; ++v)
+      for (int e = 0; e < orc_var_len(A.d->vars[v]); ++e) {   /* array variables: `length` blocks of `count` values */
         const fgpu_var &V = A.d->vars[v];
-        char *dst = A.state[state] + V.list_offset + (size_t)offset * V.size;
+        char *dst = A.state[state] + V.list_offset + ((size_t)e * A.d->buffer_size + (size_t)offset) * V.size;
         if (columns && columns[v]) {
-            memcpy(dst, columns[v], (size_t)count * V.size);
+            memcpy(dst, (const char *)columns[v] + (size_t)e * count * V.size, (size_t)count * V.size);
         } else {
             for (int i = 0; i < count; ++i) {
                 if (V.size == 8) {
@@ -622,7 +629,8 @@ int orc_sim_read_agent_var(void *p, int agent, int state, int var, void *dst, in
     OrcAgent &A = s->agents[agent];
     if (state < 0 || state >= A.d->nstates || var < 0 || var >= A.d->nvars) return orc_set_err(-1, "bad index");
     const fgpu_var &V = A.d->vars[var];
-    memcpy(dst, A.state[state] + V.list_offset, (size_t)count * V.size);
+    for (int e = 0; e < orc_var_len(V); ++e)
+        memcpy((char *)dst + (size_t)e * count * V.size, A.state[state] + V.list_offset + (size_t)e * A.d->buffer_size * V.size, (size_t)count * V.size);
     return 0;
 }
 int orc_sim_message_count(void *p, int message) {

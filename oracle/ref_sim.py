@@ -76,10 +76,11 @@ class RefSimulation:
         si = self._state(ai, state)
         a = self.model.agents[ai]
         vi = var if isinstance(var, int) else [v.name for v in a.variables].index(var)
-        out = np.empty(self.agent_count(ai, si), dtype=_DTYPES[a.variables[vi].type])
+        n, L = self.agent_count(ai, si), max(1, a.variables[vi].array_length)
+        out = np.empty(n * L, dtype=_DTYPES[a.variables[vi].type])
         if self.lib.ref_read_var(ai, si, vi, out.ctypes.data) != 0:
             raise KeyError((agent, state, var))
-        return out
+        return np.ascontiguousarray(out.reshape(L, n).T) if L > 1 else out     # array variables: (count, length)
 
     def message_count(self, message) -> int:
         mi = message if isinstance(message, int) else [m.name for m in self.model.messages].index(message)

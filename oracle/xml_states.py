@@ -40,13 +40,21 @@ def _parse(ctype: str, text: str):
 
 
 def read_states(path: str, agents: List[Tuple[str, List[Tuple[str, str, float]]]], constants: List[Tuple[str, str]] = ()):
-    """agents: [(agent name, [(var name, ctype, default)])].  Returns
-    ({agent: {var: array}}, {constant: value})."""
+    """agents: [(agent name, [(var name, ctype, default[, arrayLength])])].  Returns
+    ({agent: {var: array}}, {constant: value}); an array variable comes back as a (count, arrayLength) array."""
     data = open(path, "rb").read().decode("latin-1")
+    agents = [(a, [(tuple(v) + (0,))[:4] for v in vs]) for a, vs in agents]
+    lengths = {a: {v: int(l or 0) for v, _, _, l in vs} for a, vs in agents}
+    agents = [(a, [v[:3] for v in vs]) for a, vs in agents]
     out = {a: {v: [] for v, _, _ in vs} for a, vs in agents}
-    defaults = {a: {v: _parse(t, repr(d) if t in ("float", "double") else str(int(d))) for v, t, d in vs} for a, vs in agents}
+    scalar_defaults = {a: {v: _parse(t, repr(d) if t in ("float", "double") else str(int(d))) for v, t, d in vs} for a, vs in agents}
+
+    def _fresh():
+        return {a: {v: (np.full(lengths[a][v], scalar_defaults[a][v]) if lengths[a][v] > 1 else scalar_defaults[a][v])
+                    for v in scalar_defaults[a]} for a in scalar_defaults}
+    defaults = _fresh()
     types = {a: {v: t for v, t, _ in vs} for a, vs in agents}
-    cur = {a: dict(defaults[a]) for a, _ in agents}
+    cur = _fresh()
     env: Dict[str, object] = {}
     ctypes_env = dict(constants)
     buf: List[str] = []
@@ -80,7 +88,7 @@ def read_states(path: str, agents: List[Tuple[str, List[Tuple[str, str, float]]]
                 if agentname in out:
                     for v in out[agentname]:
                         out[agentname][v].append(cur[agentname][v])
-                cur = {a: dict(defaults[a]) for a, _ in agents}
+                cur = _fresh()
                 in_xagent = False
             if tag.startswith("/"):
                 if open_var == tag[1:]:
@@ -97,7 +105,15 @@ def read_states(path: str, agents: List[Tuple[str, List[Tuple[str, str, float]]]
             elif in_xagent:
                 for a, vs in agents:
                     if open_var in types[a]:
-                        cur[a][open_var] = _parse(types[a][open_var], text)
+                        if lengths[a][open_var] > 1:      # readArrayInput (io.xslt:69-93): strtok on ","
+                            items = [t for t in text.split(",") if t != ""]
+                            if len(items) > lengths[a][open_var]:
+                                raise ValueError("Error: variable array %s->%s has too many items (%d), expected %d!"
+                                                 % (a, open_var, lengths[a][open_var], lengths[a][open_var]))
+                            for i, t in enumerate(items):
+                                cur[a][open_var][i] = _parse(types[a][open_var], t)
+                        else:
+                            cur[a][open_var] = _parse(types[a][open_var], text)
             elif in_env:
                 if open_var in ctypes_env:
                     env[open_var] = _parse(ctypes_env[open_var], text)
@@ -144,7 +160,8 @@ def write_states(path: str, iteration: int, agents, states, constants=()) -> Non
             for i in range(n):
                 out.append("<xagent>\n<name>%s</name>\n" % aname)
                 for vname, ctype in variables:
-                    out.append("<%s>%s</%s>\n" % (vname, _format(ctype, cols[vname][i]), vname))
+                    vals = np.atleast_1d(cols[vname][i])      # an array variable: comma-separated (io.xslt:176-186)
+                    out.append("<%s>%s</%s>\n" % (vname, ",".join(_format(ctype, v) for v in vals), vname))
                 out.append("</xagent>\n")
     out.append("</states>\n")
     with open(path, "w") as fh:

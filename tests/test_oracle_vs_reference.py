@@ -210,8 +210,9 @@ def _write_input(path, states):
             for i in range(len(cols[names[0]])):
                 fh.write(f"<xagent>\n<name>{agent}</name>\n")
                 for k in names:
-                    v = cols[k][i]
-                    fh.write(f"<{k}>{float(v):.9g}</{k}>\n" if np.issubdtype(cols[k].dtype, np.floating) else f"<{k}>{int(v)}</{k}>\n")
+                    isf = np.issubdtype(cols[k].dtype, np.floating)
+                    vals = np.atleast_1d(cols[k][i])          # an array variable: comma-separated (io.xslt:176-186)
+                    fh.write(f"<{k}>" + ",".join(f"{float(v):.9g}" if isf else f"{int(v)}" for v in vals) + f"</{k}>\n")
                 fh.write("</xagent>\n")
         fh.write("</states>\n")
     return str(path)
@@ -254,13 +255,19 @@ def _authored(key):
         from test_gpu_sph import lattice
         d = f"{REFERENCE}/examples/{key}/src/model"
         return key, f"{d}/XMLModelFile.xml", d, {"FluidParticle": lattice(12, 12, 12)}, 5
+    if key == "ArrayLedger":     # agent array variables through death compaction and both appends of a state change
+        n = 3000
+        st = {"id": np.arange(n, dtype=np.int32), "x": W.uniform24(5, n) * np.float32(10),
+              "hist": (np.arange(n * 8, dtype=np.int32).reshape(n, 8) * 3) % 11, "steps": (np.arange(n, dtype=np.int32) % 5),
+              "trail": W.uniform24(6, n * 4).reshape(n, 4), "sum": np.zeros(n, np.int32)}
+        return key, os.path.join(m, key, "src", "model", "XMLModelFile.xml"), os.path.join(m, key, "src", "model"), {"Walker": st}, 30
     if key == "HostCreate":      # population comes from the init function (h_add_agents_*), then 3 more per step function
         return key, os.path.join(m, key, "src", "model", "XMLModelFile.xml"), os.path.join(m, key, "src", "model"), {}, 8
     raise KeyError(key)
 
 
 @pytest.mark.parametrize("key", ["Brownian_small", "BirthDeath", "OptionalSignal", "TwoStage", "GlobalGate", "HostCreate",
-                                 "SmoothedParticleHydrodynamics"])
+                                 "SmoothedParticleHydrodynamics", "ArrayLedger"])
 def test_authored_model_matches_the_reference_build(key, tmp_path):
     name, xml, fdir, states, iters = _authored(key)
     model_files = [os.path.join(fdir, f) for f in __import__("ev_diffusion_b200.xmml", fromlist=["x"]).parse_model(xml).function_files]
