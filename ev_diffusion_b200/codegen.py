@@ -333,10 +333,10 @@ FGPU_DEV void add_{a.name}_agent(xmachine_memory_{a.name}_list* agents, {_agent_
     out.append(f"    add_{a.name}_agent<DISCRETE_2D>(agents, {', '.join(v.name for v in scal)});\n}}")
     if any(v.array_length for v in a.variables):
         out.append(f"""/* krn:336-367: `array` points at element 0 of this agent; elements are xmachine_memory_{a.name}_MAX apart */
-template<typename T> FGPU_DEV T get_{a.name}_agent_array_value(T *array, uint index){{
+template<typename T> FGPU_DEV T get_{a.name}_agent_array_value(T *array, unsigned int index){{
     return array != nullptr ? array[(size_t)index * xmachine_memory_{a.name}_MAX] : T(0);
 }}
-template<typename T> FGPU_DEV void set_{a.name}_agent_array_value(T *array, uint index, T value){{
+template<typename T> FGPU_DEV void set_{a.name}_agent_array_value(T *array, unsigned int index, T value){{
     if (array != nullptr) array[(size_t)index * xmachine_memory_{a.name}_MAX] = value;
 }}""")
     return "\n".join(out) + "\n"

@@ -402,11 +402,11 @@ template <int AGENT_TYPE> void add_{a.name}_agent(xmachine_memory_{a.name}_list*
         out.append(f"    add_{a.name}_agent<DISCRETE_2D>(agents, {', '.join(v.name for v in scal)});\n}}")
         if any(v.array_length for v in a.variables):
             out.append(f"""/* get/set_{a.name}_agent_array_value, krn:336-367 */
-template<typename T> T get_{a.name}_agent_array_value(T *array, uint index){{
+template<typename T> T get_{a.name}_agent_array_value(T *array, unsigned int index){{
     if (array != nullptr) return array[index*xmachine_memory_{a.name}_MAX];
     return T(0);
 }}
-template<typename T> void set_{a.name}_agent_array_value(T *array, uint index, T value){{
+template<typename T> void set_{a.name}_agent_array_value(T *array, unsigned int index, T value){{
     if (array != nullptr) array[index*xmachine_memory_{a.name}_MAX] = value;
 }}""")
     for p in function_files:

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(f"{REFERENCE}/FLAMEGPU/templat
 # does not provide: none since round 2 (generate_<A>_id / set_initial_<A>_id and sort_<A>s_<S> were the last two)
 NOT_PROVIDED = {}
 MODELS = ["CirclesPartitioning_float", "CirclesBruteForce_double", "Boids_Partitioning", "SmoothedParticleHydrodynamics",
-          "Keratinocyte", "SocialParticleSimulation", "MonteCarlo_MSMPR", "Analytics", "EmptyExample"]
+          "Keratinocyte", "SocialParticleSimulation", "MonteCarlo_MSMPR", "Analytics", "EmptyExample", "StableMarriage"]
 QUALIFIERS = ("extern", "__FLAME_GPU_HOST_FUNC__", "__FLAME_GPU_FUNC__", "__host__", "__device__", "FGPU_DEV", "FGPU_HD", "inline",
               "static", "__forceinline__")
 
@@ -106,7 +106,8 @@ def _structs(text: str):
             for m in re.finditer(r"struct\s+(?:__align__\(\d+\)\s*)?(\w+)\s*\{([^{}]*)\}\s*;", masked)}
 
 
-@pytest.mark.parametrize("name", ["CirclesPartitioning_float", "Keratinocyte", "SmoothedParticleHydrodynamics", "CirclesBruteForce_double"])
+@pytest.mark.parametrize("name", ["CirclesPartitioning_float", "Keratinocyte", "SmoothedParticleHydrodynamics", "CirclesBruteForce_double",
+                                  "StableMarriage"])
 def test_struct_layouts_seen_by_scripts_and_drivers(name):
     """What user code can touch has the reference's layout: the agent struct handed to every agent function and the
     SoA agent list a driver gets from get_device_/get_host_<A>_<S>_agents() are member for member the reference's

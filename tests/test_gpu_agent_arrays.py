@@ -167,7 +167,7 @@ def marriage_state(n, seed=3):
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(SM_XML) and not os.path.exists(build.model_path("StableMarriage_exact")),
                     reason="StableMarriage plugin is not prebuilt and the reference tree (its model) is not mounted")
-@pytest.mark.parametrize("n", [64, 1024])
+@pytest.mark.parametrize("n", [64, 400])
 def test_stable_marriage_reference_example(n):
     """examples/StableMarriage (scripts compiled where they lie): int[1024] arrays moved by two function conditions per
     iteration.  The function filter copies whole arrays here (the reference copies element 0 only, krn:172-173, and leaves
