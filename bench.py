@@ -497,6 +497,8 @@ def run_model_workload(args):
     if rank != 0 and (args.impl == "reference" or world == 1):
         return
     cores = os.cpu_count() or 1
+    if w.n < 100000:
+        cores = 1          # a 1024-agent iteration is microseconds of work: OpenMP fork/join over many threads only slows it down
     st = W.model_state(w)
     base = {"metric": METRIC, "unit": "agent-steps/s", "n_gpus": 1, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -504,7 +506,7 @@ def run_model_workload(args):
 
     def cpu_run(steps, warm):
         orc = OracleSimulation(gen_oracle.oracle_path(w.name), threads=cores)
-        orc.set_agents(w.agent, w.state, st)
+        W.start_model(orc, w, st)
         if warm:
             orc.step(warm)
         n0 = _population(orc)
@@ -530,13 +532,15 @@ def run_model_workload(args):
     if not os.path.exists(plugin):
         raise SystemExit(f"{plugin} missing: run `python -c 'import __graft_entry__ as g; g.build()'` first (needs /root/reference)")
     if world > 1:
+        if w.golden:
+            raise SystemExit(f"--workload {w.key} is a shipped-size single-GPU config")
         run_model_workload_slabs(args, w, st, base, rank, world, local)
         return
     sim = Simulation(plugin, device=local)
     for kv in args.option:
         k, v = kv.split("=")
         sim.set_option(k, int(v))
-    sim.set_agents(w.agent, w.state, st)
+    W.start_model(sim, w, st)
     sim.step(args.warmup)
     n0 = _population(sim)
     launches0 = sim.launch_count
@@ -554,22 +558,29 @@ def run_model_workload(args):
     stage = dict(sim.profile_iterations(reps))
     dom = max(stage, key=lambda k: stage[k])
     peak, peak_src = peaks()
-    ach = w.b_alg * value / 1e9
+    ach = w.b_alg * value / 1e9      # b_alg 0: a config SURVEY.md 8(d) lists without a byte count (C5), no roofline claim
     roofline = {"bound": "hbm", "kernel": "whole iteration (sum of its kernels; dominant stage: %s)" % dom, "achieved": ach, "peak": peak,
                 "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src, "alg_bytes_per_agent_step": w.b_alg,
                 "stage_ms": {k: round(v, 5) for k, v in stage.items()}, "dominant_stage": dom, "dominant_stage_ms": stage[dom]}
     # end to end: upload of the initial population, one iteration, read-back of every variable (host buffers)
     import torch
-    pin = {k: torch.from_numpy(v.copy()).pin_memory().numpy() for k, v in st.items()}
+    pin = {k: torch.from_numpy(np.ascontiguousarray(v).copy()).pin_memory().numpy() for k, v in st.items() if not k.startswith("env/")}
     h2d = sum(v.nbytes for v in pin.values())
     e2e_steps = min(args.steps, 5)
     sim2 = Simulation(plugin, device=local)
-    sim2.set_agents(w.agent, w.state, pin)
+
+    def upload(s_):
+        if w.golden:      # the shipped input: every agent type into its initial state
+            for a in s_.model.agents:
+                s_.set_agents(a.name, a.states[a.initial_state], {v.name: pin[f"{a.name}/{v.name}"] for v in a.vars})
+        else:
+            s_.set_agents(w.agent, w.state, pin)
+    W.start_model(sim2, w, st)
     sim2.step(1)
     t0 = time.perf_counter()
     d2h = 0
     for _ in range(e2e_steps):
-        sim2.set_agents(w.agent, w.state, pin)
+        upload(sim2)
         sim2.step(1)
         got = _all_states(sim2)
         d2h = sum(v.nbytes for cols in got.values() for v in cols.values())
@@ -584,7 +595,7 @@ def run_model_workload(args):
         orc = OracleSimulation(gen_oracle.oracle_path(w.name), threads=cores)
         g = Simulation(exact, device=local)
         for s_ in (orc, g):
-            s_.set_agents(w.agent, w.state, st)
+            W.start_model(s_, w, st)
             s_.step(iters)
         a, b = _all_states(g), _all_states(orc)
         parity = {"iterations": iters, "lists": {}}
@@ -617,7 +628,7 @@ def run_model_workload(args):
                 population={"start": n0, "end": n1})
     line["config"]["l2"] = "flushed between timed iterations (256 MiB scratch rewrite, untimed)"
     if not args.no_cpu_baseline:
-        v, dt, k = cpu_run(1 if w.n > (1 << 22) else 2, 1)
+        v, dt, k = cpu_run(1 if w.n > (1 << 22) else 2 if w.n > 100000 else w.iterations, 1)
         line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
                                 "sample": f"{k} full iteration(s) of the workload ({dt:.1f} s), OpenMP {cores} threads"}
     print(json.dumps(line))

@@ -162,6 +162,7 @@ class ModelWorkload:
     b_alg: float              # algorithmic bytes per agent-step
     iterations: int           # iterations the BASELINE row asks for
     function_files: tuple = ()
+    golden: str = ""          # shipped-input configs: tests/golden/<golden>_initial.npz (the example's own 0.xml as arrays)
 
     def xml(self) -> str:
         if not self.replacements:
@@ -228,6 +229,17 @@ MODEL_WORKLOADS = {
     "c4_1m": ModelWorkload("c4_1m", "SPH_1M", "SmoothedParticleHydrodynamics, 1 000 000 particles, shipped radius 0.02 (50^3 cells)",
                            _SPH_XML, {"<gpu:bufferSize>131072</gpu:bufferSize>": "<gpu:bufferSize>1048576</gpu:bufferSize>"},
                            "FluidParticle", "default", 1000000, 556.0, 10),
+    # C1: CirclesPartitioning_float exactly as shipped (1024 agents, 8x8x1 cells; the reference's own CPU-runnable case --
+    # launch-latency-bound at this size: reported, no roofline expectation)
+    "c1": ModelWorkload("c1", "CirclesPartitioning_float", "C1 CirclesPartitioning_float (reference model, scripts and shipped 0.xml), "
+                        "1024 agents, 8x8x1 cells", os.path.join(REFERENCE_EXAMPLES, "CirclesPartitioning_float", "src", "model", "XMLModelFile.xml"),
+                        {}, "Circle", "default", 1024, 157.0, 100, golden="CirclesPartitioning_float"),
+    # C5 at its shipped size (598 keratinocytes, growing): globalCondition, births, rand48, two spatial messages.  The 2M-cell
+    # variant the BASELINE table names is degenerate on this script (its hard-coded 500-unit surface makes every cell read
+    # ~40 % of all messages), so the shipped case is what is timed; no roofline claim
+    "c5": ModelWorkload("c5", "Keratinocyte", "C5 Keratinocyte (reference model, scripts and shipped 0.xml), 598 cells growing, "
+                        "two spatial messages, globalCondition, births", os.path.join(REFERENCE_EXAMPLES, "Keratinocyte", "src", "model", "XMLModelFile.xml"),
+                        {}, "keratinocyte", "default", 598, 0.0, 200, golden="Keratinocyte"),
     # C5': BirthDeath (authored): death compaction + births + rand48 on the spatial path, 524 288 -> <= 2 097 152 agents
     "c5p": ModelWorkload("c5p", "BirthDeath", "C5' BirthDeath (authored), 524 288 agents growing in a 2 097 152 buffer, 32^3 cells, "
                          "death compaction + births + rand48", _BD_XML, {}, "Cell", "default", 1 << 19, 170.0, 200),
@@ -235,6 +247,9 @@ MODEL_WORKLOADS = {
 
 
 def model_state(w: ModelWorkload) -> Dict[str, np.ndarray]:
+    if w.golden:
+        path = os.path.join(build.ROOT, "tests", "golden", w.golden + "_initial.npz")
+        return dict(np.load(path))
     if w.key == "c3":
         return _boids_state(w.n)
     if w.key == "c4":
@@ -246,3 +261,16 @@ def model_state(w: ModelWorkload) -> Dict[str, np.ndarray]:
     if w.key == "c5p":
         return _birthdeath_state(w.n)
     raise KeyError(w.key)
+
+
+def start_model(sim, w: ModelWorkload, st: Dict[str, np.ndarray]) -> None:
+    """Initial population of a model workload on a simulation object (CUDA path or oracle)."""
+    if not w.golden:
+        sim.set_agents(w.agent, w.state, st)
+        return
+    for k, v in st.items():            # the shipped 0.xml: environment values, every agent type, then the init functions
+        if k.startswith("env/"):
+            sim.set_constant(k[4:], v)
+    for a in sim.model.agents:
+        sim.set_agents(a.name, a.states[a.initial_state], {v.name: st[f"{a.name}/{v.name}"] for v in a.vars})
+    sim.run_init_functions()
