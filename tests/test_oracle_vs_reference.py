@@ -470,3 +470,43 @@ def test_reader_restatement_on_awkward_input(tmp_path):
     assert theirs["id"].tolist() == [31, -12, 15, 2147483647]
     for v in model.agents[0].variables:
         assert np.array_equal(theirs[v.name].view(np.uint8), mine["Circle"][v.name].view(np.uint8)), (v.name, theirs[v.name], mine["Circle"][v.name])
+
+
+def test_array_variables_in_a_states_file_against_the_reference_reader_and_writer(tmp_path):
+    """Agent array variables in 0.xml: the reference's own reader (readArrayInput, io.xslt:69-93 -- full arrays, a short
+    one that keeps the defaultValue of the rest, a variable left out, empty items, hex and octal items) against the
+    numpy restatement and the CUDA path's C++ parser; then the reference's own writer (io.xslt:176-186, comma-separated)
+    against the numpy restatement, byte for byte."""
+    from oracle.xml_states import read_states, write_states
+    from ev_diffusion_b200.runtime import read_states_file
+    xml = os.path.join(build.MODELS, "ArrayLedger", "src", "model", "XMLModelFile.xml")
+    fdir = os.path.dirname(xml)
+    text = ("<states><itno>0</itno><environment></environment>\n"
+            "<xagent><name>Walker</name><id>7</id><x>1.5</x><hist>1,2,3,4,5,6,7,8</hist><steps>2</steps><trail>0.25,0.5,0.75,1</trail></xagent>\n"
+            "<xagent><name>Walker</name><id>8</id><hist>9,0x10,,011</hist><trail>1e-3</trail></xagent>\n"
+            "<xagent><name>Walker</name><id>9</id></xagent>\n</states>\n")
+    inp = tmp_path / "0.xml"
+    inp.write_text(text)
+    lib = _ref_library("ArrayLedger", xml, fdir)
+    worker = ("import sys, os, numpy as np\nsys.path.insert(0, sys.argv[1])\nfrom oracle.ref_sim import RefSimulation\n"
+              "sim = RefSimulation(sys.argv[2], sys.argv[3], sys.argv[4])\n"
+              "np.savez(sys.argv[5], **{v.name: sim.agent_var('Walker', 'active', v.name) for v in sim.model.agents[0].variables})\n"
+              "sim.save_iteration(sys.argv[6], 3)\n")
+    out = tmp_path / "read.npz"
+    subprocess.run([sys.executable, "-c", worker, ROOT, lib, xml, str(inp), str(out), str(tmp_path) + "/"], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    theirs = np.load(out)
+    spec = [("Walker", [("id", "int", 0), ("x", "float", 0), ("hist", "int", -1, 8), ("steps", "int", 0), ("trail", "float", 0, 4), ("sum", "int", 0)])]
+    mine, _ = read_states(str(inp), spec, [])
+    assert theirs["hist"].tolist() == [[1, 2, 3, 4, 5, 6, 7, 8], [9, 16, 9, -1, -1, -1, -1, -1], [-1] * 8]
+    plugin = build.model_path("ArrayLedger_exact")
+    cuda_side = read_states_file(plugin, str(inp))["Walker"] if os.path.exists(plugin) else None
+    for k in theirs.files:
+        assert np.array_equal(theirs[k].view(np.uint8), mine["Walker"][k].view(np.uint8)), k
+        if cuda_side is not None:
+            assert np.array_equal(theirs[k].view(np.uint8), cuda_side[k].view(np.uint8)), k
+    variables = [("id", "int"), ("x", "float"), ("hist", "int"), ("steps", "int"), ("trail", "float"), ("sum", "int")]
+    empty = {k: v[:0] for k, v in mine["Walker"].items()}
+    write_states(str(tmp_path / "mine.xml"), 3, [("Walker", [("active", variables), ("resting", variables)])],
+                 {("Walker", "active"): mine["Walker"], ("Walker", "resting"): empty}, [("DEATH_P", "float", np.float32(0.05))])
+    assert open(tmp_path / "3.xml").read() == open(tmp_path / "mine.xml").read()
