@@ -792,7 +792,7 @@ def main():
         pin = {k: v for k, v in pin.items() if k != "nbr"}
     h2d = sum(v.nbytes for v in pin.values())
     d2h = 0
-    for _ in range(2):   # untimed: first-touch of the pinned pages, graph capture
+    for _ in range(2 if world == 1 else 4):   # untimed: first-touch of the pinned pages, graph capture (slab mode replays up to 4 graphs)
         sim.set_agents("Particle", "default", pin)
         sim.step(1)
         sim.read_agents("Particle", "default", out)
