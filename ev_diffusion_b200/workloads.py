@@ -163,6 +163,10 @@ class ModelWorkload:
     iterations: int           # iterations the BASELINE row asks for
     function_files: tuple = ()
     golden: str = ""          # shipped-input configs: tests/golden/<golden>_initial.npz (the example's own 0.xml as arrays)
+    tiles: int = 0            # > 0: the shipped population replicated on a tiles x tiles grid of its own domain (x, y shifted per tile)
+    tile_width: float = 0.0
+    script_patch: tuple = ()  # ((regex, replacement), ...): constants of the script that XML-only scaling cannot reach; applied to a
+                              # transient copy under _gen/ that is compiled and removed (never committed, SURVEY.md 8d "documented deviation")
 
     def xml(self) -> str:
         if not self.replacements:
@@ -173,7 +177,27 @@ class ModelWorkload:
     def functions(self):
         if self.function_files:
             return list(self.function_files)
-        return [os.path.join(os.path.dirname(self.xml_source), "functions.c")]
+        src = os.path.join(os.path.dirname(self.xml_source), "functions.c")
+        if not self.script_patch:
+            return [src]
+        import re
+        text = open(src, errors="replace").read()
+        for pattern, repl in self.script_patch:
+            text, hits = re.subn(pattern, repl, text)
+            if hits != 1:
+                raise build.BuildError(f"{self.key}: script patch /{pattern}/ matched {hits} times in {src}")
+        dst = self.patched_script()
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        with open(dst, "w") as fh:
+            fh.write(text)
+        return [dst]
+
+    def patched_script(self) -> str:
+        return os.path.join(build.GEN, self.name, "src", "model", "functions.c")
+
+    def remove_patched_script(self) -> None:
+        if self.script_patch and os.path.exists(self.patched_script()):
+            os.remove(self.patched_script())
 
 
 def _boids_state(n: int, seed: int = 43) -> Dict[str, np.ndarray]:
@@ -240,6 +264,17 @@ MODEL_WORKLOADS = {
     "c5": ModelWorkload("c5", "Keratinocyte", "C5 Keratinocyte (reference model, scripts and shipped 0.xml), 598 cells growing, "
                         "two spatial messages, globalCondition, births", os.path.join(REFERENCE_EXAMPLES, "Keratinocyte", "src", "model", "XMLModelFile.xml"),
                         {}, "keratinocyte", "default", 598, 0.0, 200, golden="Keratinocyte"),
+    # C5 at the size the BASELINE table names: the shipped colony (598 cells on a 500-unit surface) replicated on a 58 x 58 grid of
+    # surfaces = 2 011 672 cells on a 29 000-unit surface.  XML-only: bufferSize, message bounds (location: 232 x 232 x 4 cells, force:
+    # 1856 x 1856 x 32 = 110 M cells, 27-bit keys).  The surface width is a #define of the script, so the plugin is compiled from a
+    # transient copy with that one constant changed -- the deviation SURVEY.md 8(d) documents for a physically sane 2M run.
+    "c5_2m": ModelWorkload("c5_2m", "Keratinocyte_2M", "C5 Keratinocyte (reference model and scripts, SURFACE_WIDTH scaled), 2 011 672 cells = the shipped "
+                           "colony tiled 58 x 58, two spatial messages (force grid 1856 x 1856 x 32 cells), globalCondition, births",
+                           os.path.join(REFERENCE_EXAMPLES, "Keratinocyte", "src", "model", "XMLModelFile.xml"),
+                           {"<gpu:bufferSize>8192</gpu:bufferSize>": "<gpu:bufferSize>4194304</gpu:bufferSize>",
+                            "<gpu:xmax>500</gpu:xmax>": "<gpu:xmax>29000</gpu:xmax>", "<gpu:ymax>500</gpu:ymax>": "<gpu:ymax>29000</gpu:ymax>"},
+                           "keratinocyte", "default", 58 * 58 * 598, 0.0, 10, golden="Keratinocyte", tiles=58, tile_width=500.0,
+                           script_patch=((r"#define\s+SURFACE_WIDTH\s+500\.0f", "#define SURFACE_WIDTH 29000.0f"),)),
     # C5': BirthDeath (authored): death compaction + births + rand48 on the spatial path, 524 288 -> <= 2 097 152 agents
     "c5p": ModelWorkload("c5p", "BirthDeath", "C5' BirthDeath (authored), 524 288 agents growing in a 2 097 152 buffer, 32^3 cells, "
                          "death compaction + births + rand48", _BD_XML, {}, "Cell", "default", 1 << 19, 170.0, 200),
@@ -249,7 +284,20 @@ MODEL_WORKLOADS = {
 def model_state(w: ModelWorkload) -> Dict[str, np.ndarray]:
     if w.golden:
         path = os.path.join(build.ROOT, "tests", "golden", w.golden + "_initial.npz")
-        return dict(np.load(path))
+        st = dict(np.load(path))
+        if w.tiles:
+            T = w.tiles
+            n0 = len(st[f"{w.agent}/id"])
+            tile = np.repeat(np.arange(T * T, dtype=np.int64), n0)
+            out = {k: v for k, v in st.items() if not k.startswith(w.agent + "/")}
+            for k, v in st.items():
+                if k.startswith(w.agent + "/"):
+                    out[k] = np.tile(v, T * T)
+            out[f"{w.agent}/x"] = (out[f"{w.agent}/x"] + (tile % T).astype(np.float32) * np.float32(w.tile_width)).astype(np.float32)
+            out[f"{w.agent}/y"] = (out[f"{w.agent}/y"] + (tile // T).astype(np.float32) * np.float32(w.tile_width)).astype(np.float32)
+            out[f"{w.agent}/id"] = (out[f"{w.agent}/id"].astype(np.int64) + tile * 8192).astype(np.int32)   # shipped ids are < 8192
+            st = out
+        return st
     if w.key == "c3":
         return _boids_state(w.n)
     if w.key == "c4":
