@@ -668,9 +668,11 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
     a = model.agent(f.agent)
     A = a.name
     bs = int(os.environ.get("FGPU_CONSUMER_BLOCK", "128")) if f.input_message else 256   # tuning hook for A/B builds
+    minb = int(os.environ.get("FGPU_CONSUMER_MINBLOCKS", "0")) if f.input_message else 0    # ... and a register cap through min blocks per SM
+    bounds = f"{bs}, {minb}" if minb else f"{bs}"
     carry = _carry_vars(a)
     out = [f"/* GPUFLAME_{f.name} (krn:1320-1387) */",
-           f"__global__ void __launch_bounds__({bs}) fgpu_k_{f.name}(const fgpu_launch L)\n{{",
+           f"__global__ void __launch_bounds__({bounds}) fgpu_k_{f.name}(const fgpu_launch L)\n{{",
            '    asm volatile("griddepcontrol.wait;" ::: "memory");   /* programmatic dependent launch: the previous kernel of the iteration has completed */',
            "    int t = blockIdx.x * blockDim.x + threadIdx.x;"]
     if f.input_message and model.message(f.input_message).partitioning == "spatial":
