@@ -146,6 +146,77 @@ def written_variables(func: Function, agent: Agent, sources: List[str]) -> Set[s
     return allv
 
 
+def message_mirror(func: Function, agent: Agent, message, sources: List[str]) -> Dict[str, str]:
+    """Agent variables whose value a producer's message carries unchanged: {agent variable: message variable}.
+
+    A script of the usual shape ends with ``add_<M>_message(messages, agent->id, agent->x, agent->y, agent->z)``.  When the call is
+    the function's one unconditional output, an argument is literally ``agent->v``, the types agree and the function never
+    writes ``v``, message k holds the value variable v of list index k has when the function returns.  A consumer that runs in
+    cell order right behind it (thread t <-> sorted message t <-> list index order[t]) can then take v from its own message
+    -- one coalesced 16-byte load -- instead of one random 4-byte gather per variable (fgpu_launch.mirror).  Anything that
+    cannot be proved from the text gives an empty map: macros hiding member accesses, a conditional or repeated call, a
+    ``return`` before the call, an argument that is any other expression."""
+    if func.output_message != message.name or (func.output_type or "single_message") != "single_message":
+        return {}
+    written = written_variables(func, agent, sources)
+    scalars = {v.name: v for v in agent.variables if not v.array_length}
+    if written >= set(scalars):
+        return {}
+    for raw in sources:
+        src = _strip(raw)
+        found = find_function_body(src, func.name)
+        if not found:
+            continue
+        params, body = found
+        pm = re.search(r"([A-Za-z_]\w*)\s*$", params.split(",")[0].strip())
+        if not pm:
+            return {}
+        p = pm.group(1)
+        calls = list(re.finditer(r"\badd_" + re.escape(message.name) + r"_message\s*\(", body))
+        if len(calls) != 1:
+            return {}
+        c = calls[0]
+        before = body[:c.start()]
+        # the call is a top-level statement of the function body (brace depth 1) and nothing returns before it
+        if before.count("{") - before.count("}") != 1 or re.search(r"\breturn\b", before):
+            return {}
+        i, depth = c.end(), 1
+        while i < len(body) and depth:
+            depth += {"(": 1, ")": -1}.get(body[i], 0)
+            i += 1
+        args, cur, depth = [], "", 0
+        for ch in body[c.end():i - 1] + ",":
+            if ch == "," and depth == 0:
+                args.append(cur.strip())
+                cur = ""
+                continue
+            depth += ch in "([{"
+            depth -= ch in ")]}"
+            cur += ch
+        if len(args) != len(message.variables) + 1:
+            return {}
+        out: Dict[str, str] = {}
+        for arg, mv in zip(args[1:], message.variables):
+            m = re.fullmatch(re.escape(p) + r"\s*->\s*([A-Za-z_]\w*)", arg)
+            if m and m.group(1) in scalars and m.group(1) not in written and scalars[m.group(1)].type == mv.type \
+                    and m.group(1) not in out:
+                out[m.group(1)] = mv.name
+        return out
+    return {}
+
+
+def mirror_producer(model: Model, f: Function, sources: List[str]) -> Tuple[Optional[Function], Dict[str, str]]:
+    """The one function whose message `f` consumes and the variables of f's agent that message carries (see message_mirror);
+    (None, {}) unless the message is spatially partitioned and has exactly one producer, on f's own agent type."""
+    if not f.input_message or model.message(f.input_message).partitioning != "spatial":
+        return None, {}
+    producers = [g for g in model.all_functions() if g.output_message == f.input_message]
+    if len(producers) != 1 or producers[0].agent != f.agent:
+        return None, {}
+    m = message_mirror(producers[0], model.agent(f.agent), model.message(f.input_message), sources)
+    return (producers[0], m) if m else (None, {})
+
+
 # --------------------------------------------------------------------------
 # shared header pieces
 # --------------------------------------------------------------------------
@@ -664,7 +735,7 @@ def _cuda_carry_struct(a: Agent) -> str:
     return "\n".join(out) + "\n"
 
 
-def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
+def _cuda_kernel(model: Model, f: Function, written: Set[str], mirror: Optional[Dict[str, str]] = None) -> str:
     a = model.agent(f.agent)
     A = a.name
     bs = int(os.environ.get("FGPU_CONSUMER_BLOCK", "128")) if f.input_message else 256   # tuning hook for A/B builds
@@ -685,6 +756,19 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
             "    const int index = L.order ? (int)__ldg(L.order + t) : t;",
             f"    xmachine_memory_{A}_list* __restrict__ agents = (xmachine_memory_{A}_list*)L.agents;",
             f"    xmachine_memory_{A} agent;"]
+    def mirror_branch(indent: str) -> List[str]:
+        # cell order, straight behind the message's producer: sorted message t is this agent's own, and it carries these
+        # variables unchanged (codegen.message_mirror) -- one coalesced record load instead of a random gather per variable
+        M = f.input_message
+        lines = [f"{indent}const xmachine_message_{M} fgpu_self = fgpu::load_message((const xmachine_message_{M}*)L.in_recs + ((size_t)L.mirror_base + (size_t)t));"]
+        for v in a.variables:
+            if v.name in mirror:
+                lines.append(f"{indent}agent.{v.name} = fgpu_self.{mirror[v.name]};")
+            elif v.array_length:
+                lines.append(f"{indent}agent.{v.name} = &(agents->{v.name}[index]);")
+            else:
+                lines.append(f"{indent}agent.{v.name} = agents->{v.name}[index];")
+        return lines
     if carry and f.input_message:
         out.append(f"    if (L.carry_in) {{   /* cell order: the producer's packed records, moved by the message build */")
         out.append(f"        constexpr int CQ = (int)(sizeof(fgpu_carry_{A}) / 16);")
@@ -692,9 +776,22 @@ def _cuda_kernel(model: Model, f: Function, written: Set[str]) -> str:
         out.append(f"        for (int _q = 0; _q < CQ; ++_q) r.q[_q] = __ldg((const uint4*)L.carry_in + (size_t)t * CQ + _q);")
         for v in carry:
             out.append(f"        agent.{v.name} = r.c.{v.name};")
+        if mirror:
+            out.append("    } else if (L.mirror) {")
+            out += mirror_branch("        ")
         out.append("    } else {")
         for v in a.variables:
             out.append(f"        agent.{v.name} = agents->{v.name}[index];")
+        out.append("    }")
+    elif mirror:
+        out.append("    if (L.mirror) {")
+        out += mirror_branch("        ")
+        out.append("    } else {")
+        for v in a.variables:
+            if v.array_length:
+                out.append(f"        agent.{v.name} = &(agents->{v.name}[index]);")
+            else:
+                out.append(f"        agent.{v.name} = agents->{v.name}[index];")
         out.append("    }")
     else:
         for v in a.variables:
@@ -879,7 +976,10 @@ def _descriptor_tables(model: Model, mode: str, launch_prefix: str, sources: Opt
             f'{model.agent(f.xagent_output).states.index(f.xagent_output_state) if f.xagent_output else -1}, '
             f'{int(f.reallocate)}, {swappable}, {int(f.rng)}, {cond}, {f.gc_max_iterations}, {int(f.gc_must_evaluate_to)}, '
             f'{launch_prefix}{f.name}, {filt}, {128 if f.input_message else 256}, '
-            f'{int(bool(written_variables(f, a, sources or []) & {"x", "y", "z"}))}}},')
+            f'{int(bool(written_variables(f, a, sources or []) & {"x", "y", "z"}))}, '
+            # the wrapper can take agent variables from the agent's own message when this function produced it
+            # (cuda back end only: the oracle reads the list)
+            + (str(fidx[mirror_producer(model, f, sources or [])[0].name]) if mode == "cuda" and mirror_producer(model, f, sources or [])[0] else "-1") + '},')
     out.append("static const fgpu_function fgpu_functions[] = {\n" + "\n".join(rows) + "\n};")
     lrows = []
     for i, layer in enumerate(model.layers):
@@ -1021,7 +1121,7 @@ def emit_cuda_glue(model: Model, function_files: List[str], include_files: Optio
         out.append(_cuda_carry_struct(a))
     for f in model.all_functions():
         a = model.agent(f.agent)
-        out.append(_cuda_kernel(model, f, written_variables(f, a, sources)))
+        out.append(_cuda_kernel(model, f, written_variables(f, a, sources), mirror_producer(model, f, sources)[1]))
         if f.condition is not None or f.global_condition is not None:
             out.append(_cuda_filter(model, f))
     out.append(_constants_code(model, cuda=True))

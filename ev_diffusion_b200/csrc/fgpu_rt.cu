@@ -149,6 +149,8 @@ struct MsgRT {
     bool carry_pending = false;   /* the producer of this iteration wrote carry_unsorted */
     bool carry_valid = false;     /* carry_sorted matches the sorted list */
     unsigned long long carry_content = 0; /* content epoch of the producer list when the records were written */
+    int producer_fn = -1;                 /* the function that produced the list (single producer), for the own-message shortcut */
+    unsigned long long producer_content = 0; /* content epoch of its list right after it ran */
     const int *d_count = nullptr; /* slab mode: exact message count on the device (h_count is an upper bound) */
 };
 
@@ -244,6 +246,7 @@ struct fgpu_sim {
     int side_priority = 0;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int opt_pdl = 1;          /* programmatic dependent launch between the kernels of an iteration */
+    int opt_mirror = 1;       /* a cell-order consumer reads the variables its own message carries from that message (fgpu_launch.mirror) */
     int opt_slab_inplace = 1; /* migration: 1 = leavers leave holes that arrivals / tail agents fill; 0 = stable three-way re-compaction */
     /* the reference's compile-time -DINSTRUMENT_* switches (simulation.xslt:370-377), as run-time options: each prints
      * the reference's own "Instrumentation: ... = %f (ms)" lines */
@@ -1043,6 +1046,11 @@ static int run_function(fgpu_sim *s, int fi) {
             /* ... and the variables themselves in cell order, if the producer left them and nothing ran on the list since */
             if (s->opt_carry && Min->carry_valid && Min->carry_quads == A.d->carry_quads && Min->carry_content == s->content[A.work])
                 L.carry_in = Min->carry_sorted;
+            /* ... or from the agent's own message, when the producer passed them through and nothing ran on the list since */
+            if (s->opt_mirror && F.mirror_producer >= 0 && Min->producer_fn == F.mirror_producer && Min->producer_content == s->content[A.work]) {
+                L.mirror = 1;
+                L.mirror_base = (unsigned int)Min->local_at;
+            }
         }
     }
     if (Mout) {
@@ -1133,6 +1141,8 @@ static int run_function(fgpu_sim *s, int fi) {
             Mout->producers = 1;
             Mout->producer_buf = A.work;
             Mout->producer_epoch = s->epoch_of(A.work);
+            Mout->producer_fn = fi;
+            Mout->producer_content = s->content[A.work];
             Mout->d_count = slab_async ? L.d_n : nullptr;
         } else {
             Mout->producers++;
@@ -1344,6 +1354,7 @@ static std::vector<int> current_counts(fgpu_sim *s) {
     c.push_back(s->opt_carry);
     c.push_back(s->opt_msd);
     c.push_back(s->opt_pdl);
+    c.push_back(s->opt_mirror);
     return c;
 }
 

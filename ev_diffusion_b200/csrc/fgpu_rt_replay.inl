@@ -26,6 +26,7 @@ static std::vector<unsigned long long> slab_graph_key(fgpu_sim *s) {
     k.push_back((unsigned long long)s->opt_slab_inplace);
     k.push_back((unsigned long long)s->opt_slab_overlap);
     k.push_back((unsigned long long)s->opt_pdl);
+    k.push_back((unsigned long long)s->opt_mirror);
     return k;
 }
 

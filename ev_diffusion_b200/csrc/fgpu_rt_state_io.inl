@@ -286,6 +286,7 @@ extern "C" int fgpu_sim_set_option(fgpu_sim *s, const char *key, int value) {
     else if (!strcmp(key, "instrument_exit_functions")) s->opt_instr_exit_functions = value ? 1 : 0;
     else if (!strcmp(key, "pdl")) s->opt_pdl = value ? 1 : 0;
     else if (!strcmp(key, "msd")) s->opt_msd = value ? 1 : 0;
+    else if (!strcmp(key, "mirror")) s->opt_mirror = value ? 1 : 0;
     else if (!strcmp(key, "l2_fetch")) {
         /* device-wide hint: bytes the L2 fetches from HBM per miss (32, 64 or 128).  The random 16-byte record
          * gather of the message build wastes most of a 64-byte fetch. */

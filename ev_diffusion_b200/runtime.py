@@ -57,7 +57,7 @@ class _Function(C.Structure):
                 ("xagent_output", C.c_int), ("xagent_output_state", C.c_int), ("reallocate", C.c_int),
                 ("swappable", C.c_int), ("rng", C.c_int), ("condition", C.c_int), ("gc_max_iterations", C.c_int),
                 ("gc_must_evaluate_to", C.c_int), ("launch", C.c_void_p), ("filter", C.c_void_p),
-                ("block_size", C.c_int), ("writes_position", C.c_int)]
+                ("block_size", C.c_int), ("writes_position", C.c_int), ("mirror_producer", C.c_int)]
 
 
 class _Layer(C.Structure):

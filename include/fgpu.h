@@ -185,7 +185,8 @@ float fgpu_sim_last_step_ms(const fgpu_sim *sim);
  * enqueueing thread, like PROFILE_SCOPED_RANGE), "xml_float_digits" (0 = the reference's "%f"; n = "%.<n>g").
  * Tuning, never changing a result: "order" (0/1 cell-coherent processing of message consumers), "graph" (0/1 CUDA-graph
  * replay), "pdl" (0/1 programmatic dependent launch), "radix_bits" (4..11), "msd" (0/1 MSD message build), "carry" (0/1
- * carried agent records), "l2_fetch" (32/64/128).  Slab mode, before fgpu_sim_slab_init: "slab_p2p", "slab_async";
+ * carried agent records), "mirror" (0/1: a cell-order consumer takes the variables its own message carries from that
+ * message, fgpu_launch.mirror; on by default), "l2_fetch" (32/64/128).  Slab mode, before fgpu_sim_slab_init: "slab_p2p", "slab_async";
  * any time: "slab_inplace" (0 = stable re-compaction at migration: another list order), "slab_overlap". */
 int fgpu_sim_set_option(fgpu_sim *sim, const char *key, int value);
 /* Per-kernel-class device time of the most recent profiled iteration.

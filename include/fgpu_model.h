@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FGPU_MODEL_ABI_VERSION 11
+#define FGPU_MODEL_ABI_VERSION 12
 
 /* One agent or message variable.  Agent lists keep the reference's SoA struct
  * layout (header.xslt:187-194): int _position[MAX]; int _scan_input[MAX];
@@ -109,6 +109,11 @@ typedef struct fgpu_launch {
     int launch_n;                 /* win_mode != 0: number of threads to launch (a host-side upper bound) */
     int pdl;                      /* launch with the programmatic-stream-serialization attribute (the wrapper kernel starts
                                      with griddepcontrol.wait, so it is safe either way) */
+    /* own-message shortcut (fgpu_function.mirror_producer): sorted message mirror_base + t is the message list index
+     * order[t] emitted, and it carries some of the agent's variables unchanged -- the wrapper reads those from that one
+     * record (coalesced) instead of gathering them from the SoA list at a random index */
+    int mirror;
+    unsigned int mirror_base;     /* record index of the local block inside in_recs (0 on one GPU; slab mode: behind the low halo) */
 } fgpu_launch;
 
 typedef void (*fgpu_launch_fn)(const fgpu_launch *args, void *cuda_stream);
@@ -145,6 +150,10 @@ typedef struct fgpu_function {
     fgpu_filter_fn filter;        /* NULL unless condition != NONE */
     int block_size;               /* threads per block the launcher uses */
     int writes_position;          /* the script may modify x, y or z (slab mode: agents may change owner) */
+    int mirror_producer;          /* >= 0: index of the one function whose (spatial, single_message) output this function consumes
+                                     AND whose add_<M>_message call passes variables of this agent type through unchanged: when
+                                     that function ran last on the list this one runs on, the runtime may set fgpu_launch.mirror.
+                                     -1: never */
 } fgpu_function;
 
 typedef struct fgpu_layer {
