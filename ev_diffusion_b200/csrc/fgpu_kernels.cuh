@@ -45,6 +45,9 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
  * tiles took ~20 us per wave -- profiles/r01_notes.md -- so the chain-free form is
  * both faster and free of spin-waits.)
  * Digits are up to 11 bits wide; the digit width is balanced over the passes. */
+#ifndef FGPU_SCATTER_MINB_WIDE
+#define FGPU_SCATTER_MINB_WIDE 3   /* resident blocks per SM asked of the scatter pass for 10- and 11-bit digits: 80 registers, 4 bytes spilled; 2.1M keys of 19 bits 89.6 -> 86.4 us, 4.2M of 20 bits 137.7 -> 127.7 (tools/sort_tune.py) */
+#endif
 constexpr int SORT_MAXBITS = 11;
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
@@ -143,7 +146,7 @@ struct SortSmem {
  * ascending input index; tiles are in input order.  BITS is the compile-time digit
  * capacity (bins per thread = 2^BITS / 256); digit_bits <= BITS is the width in use. */
 template <int BITS>
-__global__ void __launch_bounds__(SORT_THREADS, (BITS <= 9 ? 3 : 2))
+__global__ void __launch_bounds__(SORT_THREADS, (BITS <= 9 ? 3 : FGPU_SCATTER_MINB_WIDE))
 k_radix_scatter(const unsigned int *__restrict__ keys_in, const unsigned int *__restrict__ vals_in,
                 unsigned int *__restrict__ keys_out, unsigned int *__restrict__ vals_out, int n_host,
                 const int *__restrict__ d_n, int shift, int digit_bits, const unsigned int *__restrict__ tile_hist,

@@ -3,7 +3,7 @@
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ev_diffusion_b200.runtime import load_runtime
-lib = load_runtime()
+lib = C.CDLL(os.environ["FGPU_RT_ALT"]) if os.environ.get("FGPU_RT_ALT") else load_runtime()
 lib.fgpu_debug_sort_time.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
 for n, bits in ((1 << 20, 18), (2162688, 19), (4194304 + 65536, 20), (8 << 20, 21), (1 << 24, 22), (1 << 22, 21), (1 << 24, 24), (1 << 19, 15)):
     row = []
