@@ -1122,12 +1122,11 @@ k_mig_count(const float *__restrict__ coord, int n_host, const int *__restrict__
  * buffers are the sums of the counts of the blocks before it, which every block adds up for itself (a few thousand
  * values from L2; no scan launch, no chain between blocks); the last block also publishes the totals: the send
  * headers and {n_old, holes}.  Leavers are written in list order (stable), their slots go to holes[] (ascending). */
-__global__ void __launch_bounds__(256)
-k_mig_pack(const char *__restrict__ list, char *__restrict__ dn, char *__restrict__ up, const ColSet cols, const ColSet bcols,
-           const float *__restrict__ coord, int n_host, const int *__restrict__ d_n, float minb, float maxb, int nplanes, int ppr,
-           int rank, int world, const unsigned int *__restrict__ block_sums, int nb, int cap, unsigned int *__restrict__ holes,
-           int *__restrict__ mig_hdr, int *__restrict__ hdr_dn, int *__restrict__ hdr_up, int *overflow) {
-    pdl_wait();
+__device__ __forceinline__ void
+mig_pack_body(const char *__restrict__ list, char *__restrict__ dn, char *__restrict__ up, const ColSet &cols, const ColSet &bcols,
+              const float *__restrict__ coord, int n_host, const int *__restrict__ d_n, float minb, float maxb, int nplanes, int ppr,
+              int rank, int world, const unsigned int *__restrict__ block_sums, int nb, int cap, unsigned int *__restrict__ holes,
+              int *__restrict__ mig_hdr, int *__restrict__ hdr_dn, int *__restrict__ hdr_up, int *overflow) {
     constexpr int ROUNDS = COMPACT_THREADS / 256;
     __shared__ unsigned int s_off[2];
     __shared__ unsigned int s_cnt[2][ROUNDS * 8];
@@ -1214,6 +1213,23 @@ k_mig_pack(const char *__restrict__ list, char *__restrict__ dn, char *__restric
         }
     }
 }
+
+__global__ void __launch_bounds__(256)
+k_mig_pack(const char *__restrict__ list, char *__restrict__ dn, char *__restrict__ up, const ColSet cols, const ColSet bcols,
+           const float *__restrict__ coord, int n_host, const int *__restrict__ d_n, float minb, float maxb, int nplanes, int ppr,
+           int rank, int world, const unsigned int *__restrict__ block_sums, int nb, int cap, unsigned int *__restrict__ holes,
+           int *__restrict__ mig_hdr, int *__restrict__ hdr_dn, int *__restrict__ hdr_up, int *overflow,
+           /* direct mode (done_counter != nullptr): dn / up / hdr_* are the NEIGHBOURS' arrival buffers (peer memory), so the
+            * leavers cross NVLink as they are packed; the last block to finish publishes the exchange number to both neighbours
+            * and waits for theirs -- what k_push did in a kernel of its own */
+           unsigned int *done_counter, int *peer_flag_lo, int *peer_flag_hi, const int *my_flag_a, const int *my_flag_b,
+           int *seq_counter, int *status) {
+    pdl_wait();
+    mig_pack_body(list, dn, up, cols, bcols, coord, n_host, d_n, minb, maxb, nplanes, ppr, rank, world, block_sums, nb, cap, holes, mig_hdr,
+                  hdr_dn, hdr_up, overflow);
+    if (done_counter != nullptr) push_signal_and_wait(done_counter, peer_flag_lo, peer_flag_hi, my_flag_a, my_flag_b, seq_counter, status);
+}
+
 
 __device__ __forceinline__ void copy_agent(const char *src, const ColSet &scols, size_t si, char *dst, const ColSet &dcols, size_t di) {
     for (int c = 0; c < scols.ncols; ++c) {

@@ -246,6 +246,9 @@ struct fgpu_sim {
     int side_priority = 0;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int opt_pdl = 1;          /* programmatic dependent launch between the kernels of an iteration */
+    int opt_slab_direct = 0;  /* slab mode, peer-memory transport: 1 = migrants are packed straight into the neighbours' buffers (no k_push launch).
+                                 Off: measured slower at 2 ranks (1.445 vs 1.411 ms per iteration of C2-16M): the pack's scattered 4-byte stores cross
+                                 NVLink one by one (pack 27 -> 75 us), which costs more than the saved launch and bulk copy (19 us) */
     int opt_mirror = 1;       /* a cell-order consumer reads the variables its own message carries from that message (fgpu_launch.mirror) */
     int opt_slab_inplace = 1; /* migration: 1 = leavers leave holes that arrivals / tail agents fill; 0 = stable three-way re-compaction */
     /* the reference's compile-time -DINSTRUMENT_* switches (simulation.xslt:370-377), as run-time options: each prints

@@ -27,6 +27,7 @@ static std::vector<unsigned long long> slab_graph_key(fgpu_sim *s) {
     k.push_back((unsigned long long)s->opt_slab_overlap);
     k.push_back((unsigned long long)s->opt_pdl);
     k.push_back((unsigned long long)s->opt_mirror);
+    k.push_back((unsigned long long)s->opt_slab_direct);
     return k;
 }
 

@@ -516,9 +516,21 @@ static int slab_migrate(fgpu_sim *s) {
                 LAUNCH_CHECK();
                 s->prof_end();
                 s->prof_begin("mig:scatter");
-                launch_k(pdl, k_mig_pack, dim3(nb), dim3(256), 0, s->stream, (const char *)list, X.send_dn, X.send_up, A.cols, X.bufcols, coord, n, d_n,
-                         S.axis_min, S.axis_max, S.nplanes, S.ppr, S.rank, S.world, (const unsigned int *)A.block_sums, nb, S.mig_cap, holes, mhdr,
-                         (int *)X.send_dn, (int *)X.send_up, S.d_status + 1);
+                if (S.p2p && s->opt_slab_direct) {
+                    /* leavers are packed straight into the neighbours' arrival buffers; the kernel's last block signals and waits
+                     * (I am the lower neighbour's upper neighbour: my "down" migrants land in its recv_hi) */
+                    char *pdn = S.peer_lo + S.agent_off[a] + (2 + par) * A4, *pup = S.peer_hi + S.agent_off[a] + (0 + par) * A4;
+                    launch_k(pdl, k_mig_pack, dim3(nb), dim3(256), 0, s->stream, (const char *)list, pdn, pup, A.cols, X.bufcols, coord, n, d_n,
+                             S.axis_min, S.axis_max, S.nplanes, S.ppr, S.rank, S.world, (const unsigned int *)A.block_sums, nb, S.mig_cap, holes, mhdr,
+                             (int *)pdn, (int *)pup, S.d_status + 1, S.d_done + 32 + a, (int *)(S.peer_lo + 2048 + 16 * a) + 1,
+                             (int *)(S.peer_hi + 2048 + 16 * a) + 0, (const int *)(S.xbuf + 2048 + 16 * a), (const int *)(S.xbuf + 2048 + 16 * a) + 1,
+                             S.d_seq + 32 + a, S.d_status + 3);
+                } else {
+                    launch_k(pdl, k_mig_pack, dim3(nb), dim3(256), 0, s->stream, (const char *)list, X.send_dn, X.send_up, A.cols, X.bufcols, coord, n, d_n,
+                             S.axis_min, S.axis_max, S.nplanes, S.ppr, S.rank, S.world, (const unsigned int *)A.block_sums, nb, S.mig_cap, holes, mhdr,
+                             (int *)X.send_dn, (int *)X.send_up, S.d_status + 1, (unsigned int *)nullptr, (int *)nullptr, (int *)nullptr,
+                             (const int *)nullptr, (const int *)nullptr, (int *)nullptr, (int *)nullptr);
+                }
                 LAUNCH_CHECK();
                 s->prof_end();
             } else {
@@ -534,7 +546,10 @@ static int slab_migrate(fgpu_sim *s) {
                 s->prof_end();
             }
             s->prof_begin("mig:xfer");
-            if (S.p2p) {
+            if (S.p2p && inplace && s->opt_slab_direct) {
+                in_lo = S.xbuf + S.agent_off[a] + (0 + par) * A4;   /* already there: k_mig_pack of the neighbours wrote and signalled */
+                in_hi = S.xbuf + S.agent_off[a] + (2 + par) * A4;
+            } else if (S.p2p) {
                 PushLayout PLY;
                 PLY.fixed_bytes = 16;
                 PLY.nseg = X.bufcols.ncols;

@@ -311,6 +311,8 @@ extern "C" int fgpu_sim_set_option(fgpu_sim *s, const char *key, int value) {
     else if (!strcmp(key, "slab_p2p")) {
         if (s->slab.on) return set_err(FGPU_ERR_ARG, "slab_p2p must be set before fgpu_sim_slab_init");
         s->opt_slab_p2p = value ? 1 : 0;
+    } else if (!strcmp(key, "slab_direct")) {
+        s->opt_slab_direct = value ? 1 : 0;
     } else if (!strcmp(key, "slab_overlap")) {
         s->opt_slab_overlap = value ? 1 : 0;
     } else if (!strcmp(key, "slab_inplace")) {

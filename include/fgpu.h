@@ -187,7 +187,8 @@ float fgpu_sim_last_step_ms(const fgpu_sim *sim);
  * replay), "pdl" (0/1 programmatic dependent launch), "radix_bits" (4..11), "msd" (0/1 MSD message build), "carry" (0/1
  * carried agent records), "mirror" (0/1: a cell-order consumer takes the variables its own message carries from that
  * message, fgpu_launch.mirror; on by default), "l2_fetch" (32/64/128).  Slab mode, before fgpu_sim_slab_init: "slab_p2p", "slab_async";
- * any time: "slab_inplace" (0 = stable re-compaction at migration: another list order), "slab_overlap". */
+ * any time: "slab_inplace" (0 = stable re-compaction at migration: another list order), "slab_overlap", "slab_direct" (1 = migrants
+ * are packed straight into the neighbours' arrival buffers over NVLink, 0 = into a local buffer that a second kernel pushes; 0 by default, measured faster). */
 int fgpu_sim_set_option(fgpu_sim *sim, const char *key, int value);
 /* Per-kernel-class device time of the most recent profiled iteration.
  * Writes up to `cap` (name,ms) pairs; returns the number written. */
