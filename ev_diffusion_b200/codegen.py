@@ -173,7 +173,7 @@ def message_mirror(func: Function, agent: Agent, message, sources: List[str]) ->
             return {}
         p = pm.group(1)
         calls = list(re.finditer(r"\badd_" + re.escape(message.name) + r"_message\s*\(", body))
-        if len(calls) != 1:
+        if len(calls) != 1 or re.search(r"^[ \t]*#", body, re.M):     # conditional compilation inside the body: the text is not the program
             return {}
         c = calls[0]
         before = body[:c.start()]

@@ -54,6 +54,8 @@ def test_plain_pass_through_is_mirrored():
     (" for (int i = 0; i < 1; i++) { add_location_message(location_messages, agent->id, agent->x, agent->y, agent->z); } return 0; ", {}),
     # the agent pointer escapes: every variable counts as written
     (" helper(agent); add_location_message(location_messages, agent->id, agent->x, agent->y, agent->z); return 0; ", {}),
+    # conditional compilation inside the body: what is compiled is not what the text shows
+    ("\n#ifdef EMIT\n add_location_message(location_messages, agent->id, agent->x, agent->y, agent->z);\n#endif\n return 0; ", {}),
     # comments and strings do not count
     (" /* add_location_message(a, b, c, d, e); */ add_location_message(location_messages, agent->id, agent->x, agent->y, agent->z); return 0; ",
      {"id": "id", "x": "x", "y": "y", "z": "z"}),
