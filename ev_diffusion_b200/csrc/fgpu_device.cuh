@@ -45,11 +45,28 @@ namespace fgpu {
  * The (float) casts and the single rounding per operation are kept by
  * forbidding contraction on these expressions (no a*b+c pattern is present:
  * sub, mul, div). */
+__host__ __device__ constexpr bool is_power_of_two(float v) {
+    if (!(v > 0.0f) || v > 1e30f || v < 1e-30f) return false;
+    while (v > 1.0f) v *= 0.5f;   /* exact for a power of two; any other value never reaches 1 */
+    while (v < 1.0f) v *= 2.0f;
+    return v == 1.0f;
+}
+
+/* a / extent, correctly rounded.  The extent (max - min of the partitioning bounds) is a compile-time constant; when it is a power of
+ * two the quotient is an exact scaling, so the product with the (exact) reciprocal is the same correctly rounded value for every a --
+ * one FMUL instead of the IEEE division sequence (FCHK + reciprocal + 3 FFMA + a slow-path call) the intrinsic compiles to. */
+template <int AXIS, class T>
+FGPU_DEV float div_extent(float a) {
+    constexpr float ext = AXIS == 0 ? T::MAXX - T::MINX : AXIS == 1 ? T::MAXY - T::MINY : T::MAXZ - T::MINZ;
+    if constexpr (is_power_of_two(ext)) return __fmul_rn(a, 1.0f / ext);
+    else return __fdiv_rn(a, ext);
+}
+
 template <class T>
 FGPU_DEV void grid_position(float x, float y, float z, int &cx, int &cy, int &cz) {
-    cx = (int)floorf(__fdiv_rn(__fmul_rn(__fsub_rn(x, T::MINX), (float)T::DIMX), __fsub_rn(T::MAXX, T::MINX)));
-    cy = (int)floorf(__fdiv_rn(__fmul_rn(__fsub_rn(y, T::MINY), (float)T::DIMY), __fsub_rn(T::MAXY, T::MINY)));
-    cz = (int)floorf(__fdiv_rn(__fmul_rn(__fsub_rn(z, T::MINZ), (float)T::DIMZ), __fsub_rn(T::MAXZ, T::MINZ)));
+    cx = (int)floorf(div_extent<0, T>(__fmul_rn(__fsub_rn(x, T::MINX), (float)T::DIMX)));
+    cy = (int)floorf(div_extent<1, T>(__fmul_rn(__fsub_rn(y, T::MINY), (float)T::DIMY)));
+    cz = (int)floorf(div_extent<2, T>(__fmul_rn(__fsub_rn(z, T::MINZ), (float)T::DIMZ)));
 }
 
 /* message_<M>_hash, krn:877-889: out-of-range jumps to the opposite face. */
