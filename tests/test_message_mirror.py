@@ -116,3 +116,25 @@ def test_results_do_not_depend_on_the_shortcut(key):
     assert a["nbr"].max() > 0
     on.close()
     off.close()
+
+
+def test_division_by_a_power_of_two_extent_is_an_exact_scaling():
+    """fgpu::div_extent (csrc/fgpu_device.cuh) replaces the IEEE division of grid_position (krn:860-871) by a multiplication with
+    the reciprocal when the extent of the partitioning bounds is a power of two.  Both are the correctly rounded value of the same
+    real number, so they agree in every bit -- checked here in binary32 over values that include subnormal quotients, negative and
+    huge numerators, infinities and NaN."""
+    rng = np.random.default_rng(11)
+    a = np.concatenate([
+        rng.standard_normal(200000).astype(np.float32) * np.float32(1e3),
+        (rng.random(200000).astype(np.float32) * np.float32(16384.0)),
+        np.float32(2.0) ** rng.integers(-149, 127, 20000).astype(np.float32) * rng.standard_normal(20000).astype(np.float32),
+        np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 3.4028235e38, 1.17549435e-38, 16383.999], dtype=np.float32)])
+    with np.errstate(all="ignore"):
+        for ext in (np.float32(1.0), np.float32(8.0), np.float32(64.0), np.float32(128.0), np.float32(256.0), np.float32(0.5), np.float32(1024.0)):
+            q = (a / ext).astype(np.float32)
+            m = (a * (np.float32(1.0) / ext)).astype(np.float32)
+            same = (q.view(np.uint32) == m.view(np.uint32)) | (np.isnan(q) & np.isnan(m))
+            assert same.all(), (ext, a[~same][:5])
+        # ... and it is NOT an identity for other extents, which is why those keep the division
+        ext = np.float32(500.0)
+        assert ((a / ext).astype(np.float32).view(np.uint32) != (a * (np.float32(1.0) / ext)).astype(np.float32).view(np.uint32)).any()
