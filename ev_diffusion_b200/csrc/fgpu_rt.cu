@@ -28,6 +28,7 @@
  *   fgpu_rt_state_io.inl   iteration-file writer, binary snapshot, host analytics reductions
  */
 #include <cuda_runtime.h>
+#include <charconv>
 #include <nvtx3/nvToolsExt.h>
 #include <dlfcn.h>
 

@@ -75,3 +75,45 @@ def test_generated_file_round_trip_and_errors(tmp_path):
     big = W.write_states_xml(str(tmp_path / "big.xml"), "Particle", W.brownian_state(cfg, cfg.buffer_size + 1))
     with pytest.raises(FgpuError, match="MAX Buffer size"):
         read_states_file(plugin, big)
+
+
+def test_fast_decimal_path_equals_atof(tmp_path):
+    """The parser's decimal fast path (std::from_chars) against libc's atof (what the reference calls, io.xslt:55-64) on values
+    chosen to be awkward: long mantissas, halfway cases of binary32, exponents at both ends of the double range, subnormals,
+    overflow to infinity, forms the fast path must leave to strtod (leading blanks, '+', hex floats, inf / nan, trailing text)."""
+    import ctypes
+    libc = ctypes.CDLL(None)
+    libc.atof.restype = ctypes.c_double
+    libc.atof.argtypes = [ctypes.c_char_p]
+    rng = np.random.default_rng(5)
+    texts = []
+    for _ in range(16000):          # Brownian_small holds 16 384 agents
+        k = rng.integers(0, 6)
+        if k == 0:
+            texts.append("%.9g" % np.float32(rng.standard_normal() * 10.0 ** rng.integers(-30, 30)))
+        elif k == 1:
+            texts.append("%d.%s" % (rng.integers(-10 ** 6, 10 ** 6), "".join(str(d) for d in rng.integers(0, 10, rng.integers(1, 40)))))
+        elif k == 2:
+            texts.append("%.17ge%d" % (rng.standard_normal(), rng.integers(-340, 320)))
+        elif k == 3:      # exactly between two binary32 neighbours, as a long decimal
+            f = np.float32(rng.random() * 100)
+            mid = (np.float64(f) + np.float64(np.nextafter(f, np.float32(np.inf)))) / 2
+            texts.append("%.40f" % mid)
+        elif k == 4:
+            texts.append("%se%d" % (rng.integers(1, 10 ** 9), rng.integers(-60, -30)))      # binary32 subnormal range
+        else:
+            texts.append(["  1.5", "+2.25", "0x1.8p3", "inf", "-inf", "nan", "1.5abc", "1e", "1e+", ".", "-", "", "1e400", "-1e400", "1e-400",
+                          "00012.5000", "-.5", "5.", "1E5", "1.e-2"][rng.integers(0, 20)])
+    path = tmp_path / "0.xml"
+    with open(path, "w") as fh:
+        fh.write("<states><itno>0</itno>\n")
+        for t in texts:
+            fh.write("<xagent><name>Particle</name><id>1</id><x>%s</x></xagent>\n" % t)
+        fh.write("</states>\n")
+    got = read_states_file(_plugin("Brownian_small"), str(path))["Particle"]["x"]
+    want = np.array([libc.atof(t.encode()) for t in texts], dtype=np.float64)
+    with np.errstate(over="ignore"):
+        want = want.astype(np.float32)
+    assert len(got) == len(texts)
+    same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+    assert same.all(), [(texts[i], got[i], want[i]) for i in np.flatnonzero(~same)[:10]]
