@@ -57,3 +57,20 @@ def test_reference_cuda_leg_never_raises():
     if os.path.exists(exe) and not _cuda_device_present():
         failed = bench.reference_cuda(W.BROWNIAN["c2"], iterations=1, timeout_s=120)
         assert set(failed) == {"unavailable"} and "CUDA" in failed["unavailable"]
+
+
+def test_reference_arm_of_the_shipped_size_configs():
+    """`--workload c1 / c5` (the examples' own 0.xml from tests/golden/): the CPU arm prints the same contract line, on one
+    thread (an iteration of a thousand agents is microseconds of work), with the population the fixture holds."""
+    import pytest
+    from oracle import gen_oracle
+    for wl, agents in (("c1", 1024), ("c5", 598)):
+        name = {"c1": "CirclesPartitioning_float", "c5": "Keratinocyte"}[wl]
+        if not os.path.exists(gen_oracle.oracle_path(name)):
+            pytest.skip("oracle library of %s is not prebuilt" % name)
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--workload", wl],
+                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, cwd=ROOT)
+        assert out.returncode == 0, out.stderr[-2000:]
+        d = json.loads([l for l in out.stdout.splitlines() if l.strip()][-1])
+        assert REQUIRED <= set(d), REQUIRED - set(d)
+        assert d["impl"] == "reference" and d["config"]["agents"] == agents and d["cpu_baseline"]["cores"] == 1 and d["value"] > 0
